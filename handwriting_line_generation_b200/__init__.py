@@ -1,0 +1,9 @@
+"""handwriting_line_generation_b200 — sm_100a implementation of the HWWithStyle
+training-step hot path (generator, recognizer, CTC) of herobd/handwriting_line_generation.
+
+The CUDA lives in lib/libhwg_b200.so (C-ABI: include/hwg_b200.h); this package is the
+host-side mirror of the reference's PyTorch surface."""
+from . import _lib  # noqa: F401
+from .ctc import CTCLoss, ctc_greedy_decode, naive_decode  # noqa: F401
+
+__all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode"]

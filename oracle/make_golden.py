@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE — writes tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, CPU, torch 2.11.0) on deterministic synthetic inputs.
+
+Run in the build container:  python -m oracle.make_golden [ctc|hwr|gen|all]
+The GPU box has no /root/reference: tests there read the committed fixtures only.
+Inputs come from oracle/synth.py (numpy RandomState, reproducible everywhere), so the
+full-size cases store only outputs (loss, nll, gradient digests), not the inputs."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shim, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+# name -> (T, B, C, S, seed, ragged)
+CTC_CASES = {
+    "small": (20, 3, 7, 5, 11, True),
+    "cfg1": (250, 8, 80, 60, 12, False),      # BASELINE.json configs[0]: IAM charset, S=60
+    "cfg1_ragged": (250, 8, 80, 90, 13, True),
+    "cfg5": (506, 64, 78, 120, 14, False),    # configs[4]: RIMES charset, S=120, W=2048
+    "odd_c": (64, 5, 37, 9, 15, True),        # C not a multiple of 2: 4-byte cp.async path
+    "empty_target": (30, 4, 10, 6, 16, True),  # one sequence with target length 0
+    "repeats": (40, 4, 6, 12, 17, True),      # few classes -> many repeated labels
+}
+
+
+def grad_digest(g):
+    """Position-weighted digests + a strided sample: enough to pin a [T,B,C] gradient."""
+    flat = g.reshape(-1).astype(np.float64)
+    w = np.cos(np.arange(flat.size) * 0.37) + 1.5
+    idx = np.arange(0, flat.size, max(1, flat.size // 4096))
+    return np.array([flat.sum(), np.abs(flat).sum(), (flat * w).sum(), np.abs(flat).max()]), flat[idx].astype(np.float32)
+
+
+def make_ctc():
+    ref_shim.install()
+    from model.loss import CTCLoss  # the reference's wrapper, model/loss.py:28
+    from utils.string_utils import naive_decode  # utils/string_utils.py:51
+    out = {}
+    for name, (T, B, C, S, seed, ragged) in CTC_CASES.items():
+        lp, tg, il, tl = synth.ctc_case(T, B, C, S, seed, ragged)
+        if name == "empty_target":
+            tl[1] = 0
+            tg[1, :] = 0
+        lpt = torch.from_numpy(lp).requires_grad_()
+        # the trainer's call pattern: label [S,B] int32 -> label.permute(1,0); CPU IntTensors
+        label = torch.from_numpy(np.ascontiguousarray(tg.T))
+        loss = CTCLoss(lpt, label.permute(1, 0), torch.from_numpy(il), torch.from_numpy(tl))
+        (loss * 1.0).backward()
+        nll = torch.nn.functional.ctc_loss(lpt.detach(), label.permute(1, 0), torch.from_numpy(il),
+                                           torch.from_numpy(tl), reduction="none")
+        g = lpt.grad.numpy()
+        dig, samp = grad_digest(g)
+        out[f"{name}/loss"] = np.float32(loss.item())
+        out[f"{name}/nll"] = nll.numpy().astype(np.float32)
+        out[f"{name}/grad_digest"] = dig
+        out[f"{name}/grad_sample"] = samp
+        # fp64 run of the same call: measures the fp32 rounding noise of the reference itself
+        lp64 = torch.from_numpy(lp).double().requires_grad_()
+        torch.nn.functional.ctc_loss(lp64, label.permute(1, 0), torch.from_numpy(il),
+                                     torch.from_numpy(tl)).backward()
+        _, samp64 = grad_digest(lp64.grad.numpy())
+        out[f"{name}/grad_fp32_noise"] = np.float64(np.abs(samp.astype(np.float64) - samp64).max())
+        if T * B * C <= 20000:
+            out[f"{name}/grad"] = g
+        dec = [naive_decode(lp[:, b, :])[0] for b in range(B)]
+        out[f"{name}/decoded_len"] = np.array([len(d) for d in dec], np.int32)
+        out[f"{name}/decoded"] = np.array([x for d in dec for x in d], np.int32)
+        print(f"ctc/{name}: T={T} B={B} C={C} S={S} loss={loss.item():.6f}")
+    np.savez_compressed(os.path.join(GOLD, "ctc.npz"), **out)
+
+
+def main(argv):
+    what = argv[1] if len(argv) > 1 else "all"
+    os.makedirs(GOLD, exist_ok=True)
+    if what in ("ctc", "all"):
+        make_ctc()
+    if what in ("hwr", "all") and "make_hwr" in globals():
+        globals()["make_hwr"]()
+    if what in ("gen", "all") and "make_gen" in globals():
+        globals()["make_gen"]()
+
+
+if __name__ == "__main__":
+    main(sys.argv)
