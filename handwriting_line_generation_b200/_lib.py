@@ -26,7 +26,27 @@ _SIGNATURES = {
     "hwg_ctc_backward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_int,
                                  c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "hwg_ctc_greedy_decode": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
+
+
+HWG_MAX_TAPS = 16
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_LOGSOFTMAX = 0, 1, 2, 3
+DT_BF16, DT_F32 = 0, 1
+
+
+class ConvDesc(ctypes.Structure):
+    """struct hwgConvDesc (include/hwg_b200.h)."""
+    _fields_ = [
+        ("N", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+        ("Cin", ctypes.c_int32), ("x_pitch", ctypes.c_int32), ("Cout", ctypes.c_int32),
+        ("Ho", ctypes.c_int32), ("Wo", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+        ("tap_dh", ctypes.c_int32 * HWG_MAX_TAPS), ("tap_dw", ctypes.c_int32 * HWG_MAX_TAPS),
+        ("y_stride_n", ctypes.c_int64), ("y_stride_h", ctypes.c_int64), ("y_stride_w", ctypes.c_int64),
+        ("y_dtype", ctypes.c_int32), ("act", ctypes.c_int32), ("slope", ctypes.c_float),
+        ("tile_w", ctypes.c_int32),
+        ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
+    ]
 
 
 def exported_symbols():

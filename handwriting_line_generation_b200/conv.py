@@ -1,0 +1,90 @@
+"""Host side of the tcgen05 implicit-GEMM convolution (hwg_conv_fprop).
+
+Activations cross the kernels as NHWC bf16 tensors ([N,H,W,C], C contiguous); weights as
+tap-major packed bf16 [ntaps, Cout, Cin] (`pack_taps`).  A "tap" is an input-pixel offset
+(dh, dw); every convolution flavour of the hot path is a tap list (see include/hwg_b200.h).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def conv_taps(kh, kw, pad_h, pad_w, dil_h=1, dil_w=1):
+    """Tap list of a stride-1 cross-correlation (nn.Conv2d): tap (i,j) reads x[ho+i*dil-pad, ...]."""
+    return [(i * dil_h - pad_h, j * dil_w - pad_w) for i in range(kh) for j in range(kw)]
+
+
+def pack_taps(mats, cin_pad=None):
+    """mats: list of [Cout, Cin] fp32 matrices, one per tap -> bf16 [ntaps, Cout, Cin_pad]."""
+    w = torch.stack(list(mats), 0)
+    cin = w.size(2)
+    cin_pad = cin_pad or ((cin + 15) // 16) * 16
+    if cin_pad != cin:
+        w = torch.nn.functional.pad(w, (0, cin_pad - cin))
+    return w.to(torch.bfloat16).contiguous()
+
+
+def pack_conv2d_weight(weight, cin_pad=None):
+    """nn.Conv2d weight [Cout, Cin, kh, kw] -> packed taps in conv_taps() order."""
+    co, ci, kh, kw = weight.shape
+    return pack_taps([weight[:, :, i, j] for i in range(kh) for j in range(kw)], cin_pad)
+
+
+def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
+               out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, stats=None,
+               cin=None, tile_w=0):
+    """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
+
+    x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
+    out_view  optional (tensor, stride_n, stride_h, stride_w, element_offset): write into an existing
+              tensor with custom pixel strides (used by the parity/phase launches of the
+              up-sampling convolutions); otherwise a fresh [N,Ho,Wo,Cout] tensor is returned
+    noise     optional fp32 [N,Ho,Wo,Cout] NHWC tensor added as noise_w[c]*noise before the activation
+    stats     optional zeroed fp32 [N,Cout,2]; receives per-(n,c) sum and sum of squares of the output
+    """
+    _lib.require_cuda(x, w_packed)
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+    assert w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
+    N, H, W, Cp = x.shape
+    ntaps, Cout, Cin = w_packed.shape
+    cin = cin or Cin
+    assert cin == Cin and Cin <= Cp and ntaps == len(taps)
+    d = _lib.ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps = N, H, W, Cin, Cp, Cout, Ho, Wo, ntaps
+    for i, (dh, dw) in enumerate(taps):
+        d.tap_dh[i], d.tap_dw[i] = dh, dw
+    if out_view is None:
+        if out is None:
+            out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=out_dtype)
+        y, sn, sh, sw, off = out, Ho * Wo * Cout, Wo * Cout, Cout, 0
+    else:
+        y, sn, sh, sw, off = out_view
+        out = y
+    d.y_stride_n, d.y_stride_h, d.y_stride_w = sn, sh, sw
+    d.y_dtype = _lib.DT_F32 if y.dtype == torch.float32 else _lib.DT_BF16
+    assert y.dtype in (torch.float32, torch.bfloat16)
+    d.act, d.slope, d.tile_w = act, slope, tile_w
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (N, Ho, Wo, Cout)
+        d.nz_stride_n, d.nz_stride_h, d.nz_stride_w = Ho * Wo * Cout, Wo * Cout, Cout
+        assert noise_w is not None and noise_w.dtype == torch.float32
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cout
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.numel() == N * Cout * 2
+    _lib.call("hwg_conv_fprop", ctypes.addressof(d), x.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias),
+              _lib.ptr(noise), _lib.ptr(noise_w), _lib.ptr(stats), y.data_ptr() + off * y.element_size(),
+              _lib.stream())
+    return out
+
+
+def to_nhwc_bf16(x, c_pad=None):
+    """[N,C,H,W] float -> [N,H,W,Cp] bf16 (plumbing used at the module boundary and in tests)."""
+    n, c, h, w = x.shape
+    c_pad = c_pad or ((c + 15) // 16) * 16
+    y = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    if c_pad != c:
+        y = torch.nn.functional.pad(y, (0, c_pad - c))
+    return y.contiguous()

@@ -1,0 +1,374 @@
+// Implicit-GEMM convolution forward on tcgen05 (sm_100a).
+//
+//   GEMM view:  D[M = 128 output pixels][N = BN output channels]
+//               += A[M][K] * B[N][K]^T,  K = taps x Cin, walked in chunks of CK channels
+//
+//   A chunk  = the CK-channel slice of the 128 input pixels that tap t pairs with the tile's
+//              output pixels: ONE 4-D TMA box {CK, TW, TH, 1} of the NHWC tensor at
+//              (c0, wo0+dw[t], ho0+dh[t], n).  Out-of-bounds pixels arrive as zeros, which
+//              is the reference's zero padding — there is no im2col buffer and no halo code.
+//   B chunk  = w[t][n0:n0+BN][c0:c0+CK]: one 2-D TMA box of the [ntaps*... ] weight matrix.
+//   Both land K-major with the 128/64/32-byte swizzle that matches CK = 64/32/16, which is
+//   exactly the canonical UMMA shared-memory layout, so the MMA descriptors point straight at
+//   the TMA destination.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane issues tcgen05.mma, tcgen05.commit releases smem stages / signals the
+// epilogue), warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns -> registers -> bias,
+// noise, activation or log-softmax, per-(n,c) statistics by a register butterfly + one atomic
+// per channel per warp, vectorised NHWC stores).
+// Pipeline: STAGES-deep ring of {A,B} buffers with full/empty mbarriers; the accumulator
+// (128 lanes x BN fp32 columns) lives in TMEM.
+#include "common.cuh"
+#include "sm100.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+#include <mutex>
+#include <string.h>
+
+namespace hwg {
+using namespace sm100;
+
+struct ConvKParams {
+  int N, Ho, Wo, Cout;
+  int TW, TH, tiles_w, tiles_h;
+  int CK, BN, kchunks, ntaps, stages;
+  int a_bytes, b_bytes;  // per stage (b rounded up to 1 KiB)
+  int tmem_cols;
+  int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
+  long long ysn, ysh, ysw;
+  long long zsn, zsh, zsw;
+  int y_f32, act;
+  float slope;
+  const float* bias;
+  const float* noise;
+  const float* noise_w;
+  float* stats;
+  void* y;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == HWG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HWG_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
+// Recursive halving: 31 shuffles instead of 32*5.
+__device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      // lanes with bit `half` set keep the upper half of the surviving registers
+      float send = upper ? v[i] : v[i + half];
+      float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ ConvKParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // the swizzled TMA/UMMA tiles need 1 KiB alignment; the host over-allocates by 1 KiB
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+  const int n = tile;
+  const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH;
+  const int n0 = blockIdx.y * p.BN;
+  const int kiters = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int t = it / p.kchunks, kc = it - t * p.kchunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        unsigned char* a_dst = smem + (size_t)stage * stage_bytes;
+        unsigned char* b_dst = a_dst + p.a_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(128 * p.CK * 2 + p.BN * p.CK * 2));
+        tma_load_4d(a_dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[t], ho0 + p.tap_dh[t], n);
+        tma_load_2d(b_dst, &tmap_w, &full_bar[stage], kc * p.CK, t * p.Cout + n0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      const uint32_t row_bytes = (uint32_t)p.CK * 2u;
+      const int kk_n = p.CK / 16;
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
+        const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
+        const uint64_t db = umma_desc_kmajor(b_addr, row_bytes);
+        for (int kk = 0; kk < kk_n; ++kk) {
+          // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
+          umma_bf16(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                    (it | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);            // frees this smem stage when the MMAs retire
+        if (it == kiters - 1) umma_commit(tmem_full);  // accumulator complete
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int hl = m / p.TW, wl = m - hl * p.TW;
+    const int ho = ho0 + hl, wo = wo0 + wl;
+    const bool valid = (ho < p.Ho) && (wo < p.Wo);
+    const int nvalid_c = min(p.BN, p.Cout - n0);  // channels of this N tile that exist
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const long long yoff = (long long)n * p.ysn + (long long)ho * p.ysh + (long long)wo * p.ysw + n0;
+    const long long zoff = (long long)n * p.zsn + (long long)ho * p.zsh + (long long)wo * p.zsw + n0;
+
+    float lse = 0.f;
+    if (p.act == HWG_ACT_LOGSOFTMAX) {
+      // pass 1: online max / sum-exp over this pixel's channels
+      float mx = -CUDART_INF_F, se = 0.f;
+      for (int c0 = 0; c0 < nvalid_c; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(trow + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int nc = min(32, nvalid_c - c0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < nc) {
+            float v = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c0 + j] : 0.f);
+            float nm = fmaxf(mx, v);
+            se = se * expf(mx - nm) + expf(v - nm);
+            mx = nm;
+          }
+        }
+      }
+      lse = mx + logf(se);
+    }
+
+    for (int c0 = 0; c0 < nvalid_c; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(trow + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int nc = min(32, nvalid_c - c0);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        const bool cv = j < nc;
+        if (p.bias && cv) x += p.bias[n0 + c0 + j];
+        if (p.noise && cv && valid) x += p.noise_w[n0 + c0 + j] * p.noise[zoff + c0 + j];
+        if (p.act == HWG_ACT_LOGSOFTMAX) x -= lse;
+        else x = apply_act(x, p.act, p.slope);
+        v[j] = (cv && valid) ? x : 0.f;
+      }
+      if (valid) {
+        if (p.y_f32) {
+          float* yp = reinterpret_cast<float*>(p.y) + yoff + c0;
+          if (nc == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0;
+          if ((nc & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < nc) {
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(yp + j) = pk;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      if (p.stats) {
+        // per-(n,c) sum and sum of squares over this warp's 32 pixels (invalid lanes hold 0)
+        float sq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+        float s1 = butterfly_reduce32(v, lane);
+        float s2 = butterfly_reduce32(sq, lane);
+        if (lane < nc) {
+          float* st = p.stats + ((size_t)n * p.Cout + n0 + c0 + lane) * 2;
+          atomicAdd(st, s1);
+          atomicAdd(st + 1, s2);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace hwg
+
+using namespace hwg;
+
+extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w, const float* bias,
+                              const float* noise, const float* noise_w, float* stats, void* y,
+                              void* stream) {
+  HWG_REQUIRE(d && x && w && y, "hwg_conv_fprop: null pointer");
+  HWG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "hwg_conv_fprop: empty extent");
+  HWG_REQUIRE(d->Cin >= 16 && d->Cin % 16 == 0, "hwg_conv_fprop: Cin=%d must be a multiple of 16", d->Cin);
+  HWG_REQUIRE(d->x_pitch >= d->Cin && d->x_pitch % 8 == 0, "hwg_conv_fprop: x_pitch=%d invalid", d->x_pitch);
+  HWG_REQUIRE(d->Cout >= 1, "hwg_conv_fprop: Cout=%d", d->Cout);
+  HWG_REQUIRE(d->ntaps >= 1 && d->ntaps <= HWG_MAX_TAPS, "hwg_conv_fprop: ntaps=%d", d->ntaps);
+  HWG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+              "hwg_conv_fprop: x and w must be 16-byte aligned");
+  HWG_REQUIRE((noise == nullptr) == (noise_w == nullptr), "hwg_conv_fprop: noise and noise_w go together");
+  HWG_REQUIRE(d->y_dtype == HWG_DT_BF16 || d->y_dtype == HWG_DT_F32, "hwg_conv_fprop: bad y_dtype");
+  HWG_REQUIRE(d->act >= 0 && d->act <= HWG_ACT_LOGSOFTMAX, "hwg_conv_fprop: bad act");
+  HWG_REQUIRE(d->act != HWG_ACT_LOGSOFTMAX || d->Cout <= 256, "hwg_conv_fprop: log-softmax needs Cout <= 256");
+  PFN_encodeTiled encode = get_encode();
+  if (!encode) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return HWG_ERR_CUDA; }
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
+  p.CK = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+  p.kchunks = d->Cin / p.CK;
+  p.ntaps = d->ntaps;
+  // N tile: all of Cout if it fits one UMMA (<= 256), else 256 / 128 splits
+  int cout16 = round_up(d->Cout, 16);
+  if (cout16 <= 256) p.BN = cout16;
+  else if (cout16 % 256 == 0) p.BN = 256;
+  else p.BN = 128;
+  const int n_tiles = (d->Cout + p.BN - 1) / p.BN;
+  // output tile TW x TH = 128 pixels
+  int TW = d->tile_w;
+  if (TW == 0) {
+    // widest power of two that wastes the least; prefer wide tiles (longer contiguous rows)
+    long best = -1; TW = 128;
+    for (int tw = 128; tw >= 8; tw >>= 1) {
+      int th = 128 / tw;
+      long padded = (long)round_up(d->Wo, tw) * round_up(d->Ho, th);
+      if (best < 0 || padded < best) { best = padded; TW = tw; }
+    }
+  }
+  HWG_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "hwg_conv_fprop: tile_w=%d", TW);
+  p.TW = TW; p.TH = 128 / TW;
+  p.tiles_w = (d->Wo + p.TW - 1) / p.TW;
+  p.tiles_h = (d->Ho + p.TH - 1) / p.TH;
+  p.a_bytes = 128 * p.CK * 2;
+  p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  int kiters = p.ntaps * p.kchunks;
+  p.stages = (196 * 1024) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages > kiters) p.stages = kiters < 2 ? 2 : kiters;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  for (int t = 0; t < d->ntaps; ++t) { p.tap_dh[t] = d->tap_dh[t]; p.tap_dw[t] = d->tap_dw[t]; }
+  p.ysn = d->y_stride_n; p.ysh = d->y_stride_h; p.ysw = d->y_stride_w;
+  p.zsn = d->nz_stride_n; p.zsh = d->nz_stride_h; p.zsw = d->nz_stride_w;
+  p.y_f32 = d->y_dtype == HWG_DT_F32; p.act = d->act; p.slope = d->slope;
+  p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.stats = stats; p.y = y;
+
+  const CUtensorMapSwizzle swz = p.CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (p.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmx, tmw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
+                             (cuuint64_t)d->H * d->W * d->x_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.CK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(x) failed (%d)", (int)r); return HWG_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->ntaps * d->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.CK, (cuuint32_t)p.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return HWG_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  HWG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * d->N), (unsigned)n_tiles);
+  conv_fprop_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  return check_launch("conv_fprop_kernel");
+}

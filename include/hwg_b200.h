@@ -92,6 +92,70 @@ int hwg_ctc_greedy_decode(const float* log_probs, int T, int B, int C,
                           int32_t* raw, int32_t* decoded, int32_t* decoded_len,
                           void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in
+ * TMEM), TMA-staged NHWC tiles.  One entry point covers every dense
+ * convolution of the hot path, because a launch is described by a list of
+ * taps (input-pixel offsets) rather than by kernel/stride/padding:
+ *
+ *   y[n, ho, wo, co] = epilogue( sum_t sum_ci x[n, ho+dh[t], wo+dw[t], ci]
+ *                                             * w[t][co][ci] )
+ *
+ * with x read as zero outside [0,H)x[0,W) (TMA out-of-bounds fill = the
+ * reference's zero padding).  Replaces, in the reference:
+ *   nn.Conv2d 3x3 (pure_gen.py:181-183,197; cnn_only_hwr.py:31) : 9 taps
+ *   nn.Conv1d k3 dilated (cnn_only_hwr.py:78-90)                : 3 taps, H=1
+ *   nn.Upsample(2,1)+Conv2d (pure_gen.py:176-186)   : 2 launches (row parity),
+ *       6 taps each, weights pre-summed over the duplicated rows
+ *   FusedUpsample conv_transpose2d 4x4 s2 (pure_gen.py:259-279) : 4 launches
+ *       (output parity), 4 taps each
+ *   nn.ConvTranspose2d (4,3) on H=1 (pure_gen.py:161-163)        : 4 launches
+ *       (output row), 3 taps each
+ * The y strides/pointer select the output rows/columns a launch writes.
+ *
+ * x        bf16 NHWC, channel pitch x_pitch (elements, multiple of 8)
+ * w        bf16 [ntaps][Cout][Cin] (Cin contiguous), Cin multiple of 16
+ * y        bf16 or fp32; element (n,ho,wo,c) at y[n*y_stride_n + ho*y_stride_h
+ *          + wo*y_stride_w + c]
+ * Epilogue, in this order: + bias[co]; + noise_w[co]*noise[n,ho,wo,co];
+ * activation; accumulate per-(n,co) sum / sum of squares into stats; store.
+ * HWG_EPI_LOGSOFTMAX replaces the activation by log-softmax over co
+ * (cnn_only_hwr.py:91 + the permute at :105 via the y strides); needs
+ * Cout <= 256.
+ * ---------------------------------------------------------------------- */
+#define HWG_MAX_TAPS 16
+#define HWG_ACT_NONE 0
+#define HWG_ACT_RELU 1
+#define HWG_ACT_LRELU 2
+#define HWG_ACT_LOGSOFTMAX 3
+#define HWG_DT_BF16 0
+#define HWG_DT_F32 1
+
+typedef struct hwgConvDesc {
+  int32_t N, H, W;        /* input extent */
+  int32_t Cin;            /* channels contracted (multiple of 16) */
+  int32_t x_pitch;        /* channel pitch of x, elements */
+  int32_t Cout;           /* output channels */
+  int32_t Ho, Wo;         /* output grid computed by this launch */
+  int32_t ntaps;
+  int32_t tap_dh[HWG_MAX_TAPS];
+  int32_t tap_dw[HWG_MAX_TAPS];
+  int64_t y_stride_n, y_stride_h, y_stride_w; /* elements */
+  int32_t y_dtype;        /* HWG_DT_* */
+  int32_t act;            /* HWG_ACT_* */
+  float slope;            /* LeakyReLU negative slope */
+  int32_t tile_w;         /* 0 = auto; else output-tile width (8..128, power of 2) */
+  int64_t nz_stride_n, nz_stride_h, nz_stride_w; /* noise tensor strides, elements */
+} hwgConvDesc;
+
+/* bias [Cout] fp32 or NULL; noise fp32 + noise_w [Cout] fp32, or both NULL;
+ * stats [N][Cout][2] fp32 (sum, sum of squares; accumulated with atomics, the
+ * caller zeroes it) or NULL. */
+int hwg_conv_fprop(const hwgConvDesc* desc, const void* x, const void* w, const float* bias,
+                   const float* noise, const float* noise_w, float* stats, void* y,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
