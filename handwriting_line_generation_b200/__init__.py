@@ -5,5 +5,7 @@ The CUDA lives in lib/libhwg_b200.so (C-ABI: include/hwg_b200.h); this package i
 host-side mirror of the reference's PyTorch surface."""
 from . import _lib  # noqa: F401
 from .ctc import CTCLoss, ctc_greedy_decode, naive_decode  # noqa: F401
+from .pure_gen import SpacedGenerator  # noqa: F401
+from .cnn_only_hwr import CNNOnlyHWR  # noqa: F401
 
-__all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode"]
+__all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR"]

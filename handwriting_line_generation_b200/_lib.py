@@ -27,6 +27,18 @@ _SIGNATURES = {
                                  c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "hwg_ctc_greedy_decode": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_linear_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp]),
+    "hwg_pixelnorm_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "hwg_gen_pack_input": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "hwg_adain_coeffs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f, c_vp, c_vp]),
+    "hwg_bn_coeffs": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_int, c_vp, c_vp, c_vp]),
+    "hwg_scale_shift_act": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_f, c_vp]),
+    "hwg_blur_noise_act_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, ctypes.c_uint64,
+                                         ctypes.c_uint64, c_int, c_f, c_vp, c_vp]),
+    "hwg_gen_output": (c_int, [c_vp, c_vp, c_vp, c_f, c_int, c_i64, c_int, c_vp, c_vp]),
+    "hwg_hwr_stem": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "hwg_maxpool_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_vp]),
 }
 
 
@@ -46,6 +58,7 @@ class ConvDesc(ctypes.Structure):
         ("y_dtype", ctypes.c_int32), ("act", ctypes.c_int32), ("slope", ctypes.c_float),
         ("tile_w", ctypes.c_int32),
         ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
+        ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64),
     ]
 
 

@@ -33,8 +33,8 @@ def pack_conv2d_weight(weight, cin_pad=None):
 
 
 def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
-               out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, stats=None,
-               cin=None, tile_w=0):
+               out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, noise_view=None,
+               noise_seed=None, noise_subseq=0, stats=None, cin=None, tile_w=0):
     """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
 
     x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
@@ -42,6 +42,8 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
               tensor with custom pixel strides (used by the parity/phase launches of the
               up-sampling convolutions); otherwise a fresh [N,Ho,Wo,Cout] tensor is returned
     noise     optional fp32 [N,Ho,Wo,Cout] NHWC tensor added as noise_w[c]*noise before the activation
+              (or noise_view=(tensor, sn, sh, sw, element_offset) for a strided one); with noise_w and
+              noise_seed but no tensor, N(0,1) is drawn inside the kernel (Philox)
     stats     optional zeroed fp32 [N,Cout,2]; receives per-(n,c) sum and sum of squares of the output
     """
     _lib.require_cuda(x, w_packed)
@@ -66,16 +68,26 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
     d.y_dtype = _lib.DT_F32 if y.dtype == torch.float32 else _lib.DT_BF16
     assert y.dtype in (torch.float32, torch.bfloat16)
     d.act, d.slope, d.tile_w = act, slope, tile_w
+    nz_ptr = None
     if noise is not None:
         assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (N, Ho, Wo, Cout)
         d.nz_stride_n, d.nz_stride_h, d.nz_stride_w = Ho * Wo * Cout, Wo * Cout, Cout
-        assert noise_w is not None and noise_w.dtype == torch.float32
+        nz_ptr = noise.data_ptr()
+    elif noise_view is not None:
+        nz, d.nz_stride_n, d.nz_stride_h, d.nz_stride_w, nz_off = noise_view
+        assert nz.dtype == torch.float32
+        nz_ptr = nz.data_ptr() + 4 * nz_off
+    if noise_w is not None:
+        assert noise_w.dtype == torch.float32 and noise_w.numel() == Cout
+        if nz_ptr is None:
+            assert noise_seed is not None, "noise_w without a noise tensor needs noise_seed"
+            d.noise_seed, d.noise_subseq = noise_seed, noise_subseq
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.numel() == N * Cout * 2
     _lib.call("hwg_conv_fprop", ctypes.addressof(d), x.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias),
-              _lib.ptr(noise), _lib.ptr(noise_w), _lib.ptr(stats), y.data_ptr() + off * y.element_size(),
+              nz_ptr, _lib.ptr(noise_w), _lib.ptr(stats), y.data_ptr() + off * y.element_size(),
               _lib.stream())
     return out
 

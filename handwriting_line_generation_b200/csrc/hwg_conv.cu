@@ -21,6 +21,7 @@
 // (128 lanes x BN fp32 columns) lives in TMEM.
 #include "common.cuh"
 #include "sm100.cuh"
+#include "philox.cuh"
 #include <cuda.h>
 #include <math_constants.h>
 #include <mutex>
@@ -45,6 +46,7 @@ struct ConvKParams {
   const float* noise_w;
   float* stats;
   void* y;
+  unsigned long long noise_seed, noise_subseq;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -190,12 +192,30 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tmem_ld_wait();
       const int nc = min(32, nvalid_c - c0);
       float v[32];
+      float z[32];
+      const bool philox = (p.noise == nullptr) && (p.noise_w != nullptr);
+      if (philox && valid) {
+        // element index in the launch's logical [N,Ho,Wo,Cout] output
+        const unsigned long long e0 =
+            (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.Cout + n0 + c0;
+        if ((e0 & 3ull) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 g = normal4(p.noise_seed, p.noise_subseq, (e0 + j) >> 2);
+            z[j] = g.x; z[j + 1] = g.y; z[j + 2] = g.z; z[j + 3] = g.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = normal1(p.noise_seed, p.noise_subseq, e0 + j);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(r[j]);
         const bool cv = j < nc;
         if (p.bias && cv) x += p.bias[n0 + c0 + j];
         if (p.noise && cv && valid) x += p.noise_w[n0 + c0 + j] * p.noise[zoff + c0 + j];
+        if (philox && cv && valid) x += p.noise_w[n0 + c0 + j] * z[j];
         if (p.act == HWG_ACT_LOGSOFTMAX) x -= lse;
         else x = apply_act(x, p.act, p.slope);
         v[j] = (cv && valid) ? x : 0.f;
@@ -293,7 +313,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   HWG_REQUIRE(d->ntaps >= 1 && d->ntaps <= HWG_MAX_TAPS, "hwg_conv_fprop: ntaps=%d", d->ntaps);
   HWG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
               "hwg_conv_fprop: x and w must be 16-byte aligned");
-  HWG_REQUIRE((noise == nullptr) == (noise_w == nullptr), "hwg_conv_fprop: noise and noise_w go together");
+  HWG_REQUIRE(noise == nullptr || noise_w != nullptr, "hwg_conv_fprop: noise needs noise_w");
   HWG_REQUIRE(d->y_dtype == HWG_DT_BF16 || d->y_dtype == HWG_DT_F32, "hwg_conv_fprop: bad y_dtype");
   HWG_REQUIRE(d->act >= 0 && d->act <= HWG_ACT_LOGSOFTMAX, "hwg_conv_fprop: bad act");
   HWG_REQUIRE(d->act != HWG_ACT_LOGSOFTMAX || d->Cout <= 256, "hwg_conv_fprop: log-softmax needs Cout <= 256");
@@ -341,6 +361,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.zsn = d->nz_stride_n; p.zsh = d->nz_stride_h; p.zsw = d->nz_stride_w;
   p.y_f32 = d->y_dtype == HWG_DT_F32; p.act = d->act; p.slope = d->slope;
   p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.stats = stats; p.y = y;
+  p.noise_seed = d->noise_seed; p.noise_subseq = d->noise_subseq;
 
   const CUtensorMapSwizzle swz = p.CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : (p.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -1,0 +1,458 @@
+// HBM-bound fused passes around the convolutions (sm_100a): every kernel moves 16-byte
+// vectors of 8 bf16 channels, NHWC, and touches each activation once.
+#include "common.cuh"
+#include "philox.cuh"
+#include <math_constants.h>
+
+namespace hwg {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ float act_fn(float v, int act, float slope) {
+  if (act == HWG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HWG_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+constexpr int EW_THREADS = 256;
+constexpr int EW_ITER = 8;  // vectors per thread per block
+
+// ---- small dense layers ---------------------------------------------------------------------
+__global__ void linear_f32_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                  const float* __restrict__ bias, float* __restrict__ out, int B, int K,
+                                  int O, int act, float slope) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * O) return;
+  const int b = gw / O, o = gw - b * O;
+  const float* x = in + (size_t)b * K;
+  const float* w = W + (size_t)o * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(x[k], w[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[(size_t)b * O + o] = act_fn(acc + (bias ? bias[o] : 0.f), act, slope);
+}
+
+__global__ void pixelnorm_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int K) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B) return;
+  const float* x = in + (size_t)gw * K;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s += x[k] * x[k];
+  s = warp_sum(s);
+  const float r = rsqrtf(s / (float)K + 1e-8f);
+  for (int k = lane; k < K; k += 32) out[(size_t)gw * K + k] = x[k] * r;
+}
+
+__global__ void gen_pack_input_kernel(const float* __restrict__ content, long long cs_t, long long cs_b,
+                                      long long cs_c, const float* __restrict__ style, int T, int B, int C,
+                                      int S, int Cp, uint4* __restrict__ x) {
+  const int CV = Cp / 8;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)B * T * CV) return;
+  const int cv = (int)(item % CV);
+  const long long pix = item / CV;
+  const int t = (int)(pix % T), b = (int)(pix / T);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    float v = 0.f;
+    if (c < C) v = content[t * cs_t + b * cs_b + c * cs_c];
+    else if (c < C + S) v = style[(size_t)b * S + (c - C)];
+    f[j] = v;
+  }
+  x[item] = pack8(f);
+}
+
+// ---- normalisation coefficients -------------------------------------------------------------
+__global__ void adain_coeffs_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, long long gbs, int N, int C, float inv_hw,
+                                    float eps, float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const float mean = stats[2 * i] * inv_hw;
+  const float var = fmaxf(stats[2 * i + 1] * inv_hw - mean * mean, 0.f);
+  const float a = gamma[n * gbs + c] * rsqrtf(var + eps);
+  coef[2 * i] = a;
+  coef[2 * i + 1] = beta[n * gbs + c] - mean * a;
+}
+
+__global__ void bn_coeffs_kernel(const float* __restrict__ stats, int N, int C, float count,
+                                 const float* __restrict__ weight, const float* __restrict__ bias,
+                                 float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                 int use_batch, float* __restrict__ coef, float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (use_batch) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int n = 0; n < N; ++n) { s1 += stats[((size_t)n * C + c) * 2]; s2 += stats[((size_t)n * C + c) * 2 + 1]; }
+    mean = s1 / count;
+    var = fmaxf(s2 / count - mean * mean, 0.f);
+    if (rmean) {
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+    }
+  } else {
+    mean = rmean[c]; var = rvar[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float a = (weight ? weight[c] : 1.f) * rstd;
+  coef[2 * c] = a;
+  coef[2 * c + 1] = (bias ? bias[c] : 0.f) - mean * a;
+  if (save) { save[2 * c] = mean; save[2 * c + 1] = rstd; }
+}
+
+// ---- y = act(a*x+b) ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+scale_shift_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ coef,
+                       int per_sample, long long HW, int C, int act, float slope) {
+  extern __shared__ float cs[];  // [C][2]
+  const int n = blockIdx.y, CV = C / 8;
+  const float* cf = coef + (per_sample ? (size_t)n * C * 2 : 0);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) cs[i] = cf[i];
+  __syncthreads();
+  const long long total = HW * CV;
+  const long long base = (long long)blockIdx.x * EW_THREADS * EW_ITER;
+  const uint4* xn = x + (size_t)n * total;
+  uint4* yn = y + (size_t)n * total;
+#pragma unroll
+  for (int it = 0; it < EW_ITER; ++it) {
+    const long long item = base + it * EW_THREADS + threadIdx.x;
+    if (item < total) {
+      const int cv = (int)(item % CV);
+      float f[8];
+      unpack8(xn[item], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 ab = *reinterpret_cast<const float2*>(&cs[2 * (cv * 8 + j)]);
+        f[j] = act_fn(fmaf(ab.x, f[j], ab.y), act, slope);
+      }
+      yn[item] = pack8(f);
+    }
+  }
+}
+
+// ---- blur + noise + activation + statistics ---------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
+                            const float* __restrict__ noise, const float* __restrict__ noise_w,
+                            unsigned long long seed, unsigned long long subseq, int act, float slope,
+                            float* __restrict__ stats) {
+  extern __shared__ float sacc[];  // [C][2] block-level statistics
+  const int n = blockIdx.y, CV = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)H * W * CV;
+  const long long base = (long long)blockIdx.x * EW_THREADS * EW_ITER;
+  const uint4* xn = x + (size_t)n * total;
+  uint4* yn = y + (size_t)n * total;
+  const int cv = threadIdx.x % CV;  // CV divides EW_THREADS: fixed per thread
+  float nw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+
+  for (int it = 0; it < EW_ITER; ++it) {
+    const long long item = base + it * EW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    const long long pix = item / CV;
+    const int h = (int)(pix / W), w = (int)(pix - (long long)h * W);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        const float k = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
+        float f[8];
+        unpack8(xn[((long long)hh * W + ww) * CV + cv], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
+      }
+    }
+    if (noise_w) {
+      float z[8];
+      if (noise) {
+        const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
+        float4 z0 = zp[0], z1 = zp[1];
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+      } else {
+        const unsigned long long e4 = ((unsigned long long)n * total + item) * 2ull;
+        float4 z0 = normal4(seed, subseq, e4), z1 = normal4(seed, subseq, e4 + 1);
+        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = act_fn(acc[j], act, slope);
+      s1[j] += acc[j]; s2[j] += acc[j] * acc[j];
+    }
+    yn[item] = pack8(acc);
+  }
+  if (stats) {
+    // lanes congruent mod CV hold the same channels: fold them, then one shared atomic per warp
+    if (CV <= 32) {
+      for (int off = 16; off >= CV; off >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+        }
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    if (CV > 32 || lane < CV) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sacc[2 * (cv * 8 + j)], s1[j]);
+        atomicAdd(&sacc[2 * (cv * 8 + j) + 1], s2[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(size_t)n * C * 2 + i], sacc[i]);
+  }
+}
+
+// ---- generator output: AdaIN apply + 1x1 conv + tanh -------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+gen_output_kernel(const uint4* __restrict__ x, const float* __restrict__ coef, const float* __restrict__ w,
+                  float b0, long long HW, int C, float* __restrict__ out) {
+  extern __shared__ float wa[];  // [C] w*a, then [1] constant
+  const int n = blockIdx.y, CV = C / 8;
+  if (threadIdx.x < 32) {
+    float cst = 0.f;
+    for (int c = threadIdx.x; c < C; c += 32) {
+      const float a = coef[((size_t)n * C + c) * 2], b = coef[((size_t)n * C + c) * 2 + 1];
+      wa[c] = w[c] * a;
+      cst += w[c] * b;
+    }
+    cst = warp_sum(cst);
+    if (threadIdx.x == 0) wa[C] = cst + b0;
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const uint4* xp = x + ((size_t)n * HW + pix) * CV;
+  float acc = wa[C];
+  for (int v = 0; v < CV; ++v) {
+    float f[8];
+    unpack8(xp[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(wa[v * 8 + j], f[j], acc);
+  }
+  out[(size_t)n * HW + pix] = tanhf(acc);
+}
+
+// ---- recognizer stem: conv 1->Cout 3x3 pad 1 + ReLU + maxpool 2x2 --------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+hwr_stem_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b, int N,
+                int H, int W, int Cout, uint4* __restrict__ y) {
+  extern __shared__ float ws[];  // [Cout][9] then [Cout]
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[Cout * 9 + i] = b[i];
+  __syncthreads();
+  const int CV = Cout / 8, Hp = H / 2, Wp = W / 2;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)N * Hp * Wp * CV) return;
+  const int cv = (int)(item % CV);
+  long long pix = item / CV;
+  const int wp = (int)(pix % Wp); pix /= Wp;
+  const int hp = (int)(pix % Hp);
+  const int n = (int)(pix / Hp);
+  float patch[4][4];
+  const float* im = img + (size_t)n * H * W;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int hh = 2 * hp - 1 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ww = 2 * wp - 1 + j;
+      patch[i][j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? im[(size_t)hh * W + ww] : 0.f;
+    }
+  }
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* k = ws + (cv * 8 + j) * 9;
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        float a = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(k[ky * 3 + kx], patch[oy + ky][ox + kx], a);
+        m = fmaxf(m, a);
+      }
+    f[j] = fmaxf(m + ws[Cout * 9 + cv * 8 + j], 0.f);
+  }
+  y[item] = pack8(f);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+maxpool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C, int kh, int kw,
+                    int sh, int sw, int ph, int pw, int Ho, int Wo) {
+  const int CV = C / 8;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)N * Ho * Wo * CV) return;
+  const int cv = (int)(item % CV);
+  long long pix = item / CV;
+  const int wo = (int)(pix % Wo); pix /= Wo;
+  const int ho = (int)(pix % Ho);
+  const int n = (int)(pix / Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;
+  for (int i = 0; i < kh; ++i) {
+    const int hh = ho * sh - ph + i;
+    if (hh < 0 || hh >= H) continue;
+    for (int j2 = 0; j2 < kw; ++j2) {
+      const int ww = wo * sw - pw + j2;
+      if (ww < 0 || ww >= W) continue;
+      float f[8];
+      unpack8(x[(((size_t)n * H + hh) * W + ww) * CV + cv], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  y[item] = pack8(m);
+}
+
+static inline unsigned blocks_for(long long items, int per_block) {
+  return (unsigned)((items + per_block - 1) / per_block);
+}
+static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace hwg
+
+using namespace hwg;
+
+extern "C" int hwg_linear_f32(const float* in, const float* W, const float* bias, float* out, int B, int K,
+                              int O, int act, float slope, void* stream) {
+  HWG_REQUIRE(in && W && out && B > 0 && K > 0 && O > 0, "hwg_linear_f32: bad argument");
+  const long long warps = (long long)B * O;
+  linear_f32_kernel<<<blocks_for(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, W, bias, out, B, K, O, act, slope);
+  return check_launch("linear_f32_kernel");
+}
+
+extern "C" int hwg_pixelnorm_f32(const float* in, float* out, int B, int K, void* stream) {
+  HWG_REQUIRE(in && out && B > 0 && K > 0, "hwg_pixelnorm_f32: bad argument");
+  pixelnorm_kernel<<<blocks_for((long long)B * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, K);
+  return check_launch("pixelnorm_kernel");
+}
+
+extern "C" int hwg_gen_pack_input(const float* content, int64_t cs_t, int64_t cs_b, int64_t cs_c,
+                                  const float* style, int T, int B, int C, int S, int Cp, void* x,
+                                  void* stream) {
+  HWG_REQUIRE(content && x && T > 0 && B > 0 && C > 0 && S >= 0, "hwg_gen_pack_input: bad argument");
+  HWG_REQUIRE(S == 0 || style, "hwg_gen_pack_input: null style");
+  HWG_REQUIRE(Cp % 8 == 0 && Cp >= C + S, "hwg_gen_pack_input: Cp=%d too small for C+S=%d", Cp, C + S);
+  const long long items = (long long)B * T * (Cp / 8);
+  gen_pack_input_kernel<<<blocks_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      content, cs_t, cs_b, cs_c, style, T, B, C, S, Cp, reinterpret_cast<uint4*>(x));
+  return check_launch("gen_pack_input_kernel");
+}
+
+extern "C" int hwg_adain_coeffs(const float* stats, const float* gamma, const float* beta,
+                                int64_t gb_stride_n, int N, int C, int HW, float eps, float* coef,
+                                void* stream) {
+  HWG_REQUIRE(stats && gamma && beta && coef && N > 0 && C > 0 && HW > 0, "hwg_adain_coeffs: bad argument");
+  adain_coeffs_kernel<<<blocks_for((long long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      stats, gamma, beta, gb_stride_n, N, C, 1.0f / (float)HW, eps, coef);
+  return check_launch("adain_coeffs_kernel");
+}
+
+extern "C" int hwg_bn_coeffs(const float* stats, int N, int C, int64_t count_per_n, const float* weight,
+                             const float* bias, float* running_mean, float* running_var, float momentum,
+                             float eps, int use_batch_stats, float* coef, float* save_mean_rstd,
+                             void* stream) {
+  HWG_REQUIRE(coef && C > 0, "hwg_bn_coeffs: bad argument");
+  HWG_REQUIRE(use_batch_stats ? (stats && N > 0 && count_per_n > 0) : (running_mean && running_var),
+              "hwg_bn_coeffs: missing statistics");
+  bn_coeffs_kernel<<<blocks_for(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      stats, N, C, (float)((double)N * (double)count_per_n), weight, bias, running_mean, running_var, momentum,
+      eps, use_batch_stats, coef, save_mean_rstd);
+  return check_launch("bn_coeffs_kernel");
+}
+
+extern "C" int hwg_scale_shift_act(const void* x, void* y, const float* coef, int per_sample, int N,
+                                   int64_t HW, int C, int act, float slope, void* stream) {
+  HWG_REQUIRE(x && y && coef && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "hwg_scale_shift_act: bad argument");
+  const long long total = HW * (C / 8);
+  dim3 grid(blocks_for(total, EW_THREADS * EW_ITER), N);
+  scale_shift_act_kernel<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), coef, per_sample, HW, C, act, slope);
+  return check_launch("scale_shift_act_kernel");
+}
+
+extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, int W, int C,
+                                        const float* noise, const float* noise_w, uint64_t noise_seed,
+                                        uint64_t noise_subseq, int act, float slope, float* stats,
+                                        void* stream) {
+  HWG_REQUIRE(x && y && x != y && N > 0 && H > 0 && W > 0, "hwg_blur_noise_act_stats: bad argument");
+  HWG_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= EW_THREADS,
+              "hwg_blur_noise_act_stats: C=%d must be 8 x a power of two", C);
+  HWG_REQUIRE(noise == nullptr || noise_w != nullptr, "hwg_blur_noise_act_stats: noise needs noise_w");
+  const long long total = (long long)H * W * (C / 8);
+  dim3 grid(blocks_for(total, EW_THREADS * EW_ITER), N);
+  blur_noise_act_stats_kernel<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, noise, noise_w, noise_seed,
+      noise_subseq, act, slope, stats);
+  return check_launch("blur_noise_act_stats_kernel");
+}
+
+extern "C" int hwg_gen_output(const void* x, const float* coef, const float* w, float b0, int N, int64_t HW,
+                              int C, float* out, void* stream) {
+  HWG_REQUIRE(x && coef && w && out && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "hwg_gen_output: bad argument");
+  dim3 grid(blocks_for(HW, EW_THREADS), N);
+  gen_output_kernel<<<grid, EW_THREADS, (size_t)(C + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), coef, w, b0, HW, C, out);
+  return check_launch("gen_output_kernel");
+}
+
+extern "C" int hwg_hwr_stem(const float* img, const float* w, const float* b, int N, int H, int W, int Cout,
+                            void* y, void* stream) {
+  HWG_REQUIRE(img && w && b && y && N > 0, "hwg_hwr_stem: bad argument");
+  HWG_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cout % 8 == 0, "hwg_hwr_stem: H=%d W=%d must be even, Cout=%d a multiple of 8", H, W, Cout);
+  const long long items = (long long)N * (H / 2) * (W / 2) * (Cout / 8);
+  hwr_stem_kernel<<<blocks_for(items, EW_THREADS), EW_THREADS, (size_t)Cout * 10 * sizeof(float), (cudaStream_t)stream>>>(
+      img, w, b, N, H, W, Cout, reinterpret_cast<uint4*>(y));
+  return check_launch("hwr_stem_kernel");
+}
+
+extern "C" int hwg_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh, int kw, int sh,
+                                int sw, int ph, int pw, int Ho, int Wo, void* stream) {
+  HWG_REQUIRE(x && y && N > 0 && C % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0, "hwg_maxpool_nhwc: bad argument");
+  HWG_REQUIRE(Ho == (H + 2 * ph - kh) / sh + 1 && Wo == (W + 2 * pw - kw) / sw + 1,
+              "hwg_maxpool_nhwc: Ho/Wo do not match the pooling geometry");
+  const long long items = (long long)N * Ho * Wo * (C / 8);
+  maxpool_nhwc_kernel<<<blocks_for(items, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), N, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo);
+  return check_launch("maxpool_nhwc_kernel");
+}

@@ -1,0 +1,90 @@
+"""Thin python entry points of the fused memory-bound kernels (hwg_fused.cu)."""
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_LRELU  # noqa: F401
+
+
+def linear(x, W, b, act=ACT_NONE, slope=0.0):
+    B, K = x.shape
+    O = W.size(0)
+    out = torch.empty((B, O), device=x.device, dtype=torch.float32)
+    _lib.call("hwg_linear_f32", x.data_ptr(), W.data_ptr(), _lib.ptr(b), out.data_ptr(), B, K, O, act, slope,
+              _lib.stream())
+    return out
+
+
+def pixelnorm(x):
+    out = torch.empty_like(x)
+    _lib.call("hwg_pixelnorm_f32", x.data_ptr(), out.data_ptr(), x.size(0), x.size(1), _lib.stream())
+    return out
+
+
+def gen_pack_input(content, style, Cp):
+    """content [T,B,C] fp32 (any strides), style [B,S] fp32 -> [B,1,T,Cp] bf16."""
+    T, B, C = content.shape
+    S = 0 if style is None else style.size(1)
+    x = torch.empty((B, 1, T, Cp), device=content.device, dtype=torch.bfloat16)
+    _lib.call("hwg_gen_pack_input", content.data_ptr(), content.stride(0), content.stride(1), content.stride(2),
+              _lib.ptr(style), T, B, C, S, Cp, x.data_ptr(), _lib.stream())
+    return x
+
+
+def adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps=1e-5):
+    coef = torch.empty((N, C, 2), device=stats.device, dtype=torch.float32)
+    _lib.call("hwg_adain_coeffs", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gb_stride, N, C, HW, eps,
+              coef.data_ptr(), _lib.stream())
+    return coef
+
+
+def bn_coeffs(stats, N, C, count_per_n, weight, bias, running_mean, running_var, momentum, eps, use_batch_stats):
+    dev = weight.device
+    coef = torch.empty((C, 2), device=dev, dtype=torch.float32)
+    save = torch.empty((C, 2), device=dev, dtype=torch.float32)
+    _lib.call("hwg_bn_coeffs", _lib.ptr(stats), N, C, count_per_n, _lib.ptr(weight), _lib.ptr(bias),
+              _lib.ptr(running_mean), _lib.ptr(running_var), momentum, eps, int(use_batch_stats), coef.data_ptr(),
+              save.data_ptr(), _lib.stream())
+    return coef, save
+
+
+def scale_shift_act(x, coef, per_sample, act=ACT_NONE, slope=0.0, out=None):
+    """x [N,H,W,C] bf16 -> act(a*x+b); in place when out is None."""
+    N, H, W, C = x.shape
+    out = x if out is None else out
+    _lib.call("hwg_scale_shift_act", x.data_ptr(), out.data_ptr(), coef.data_ptr(), int(per_sample), N, H * W, C, act,
+              slope, _lib.stream())
+    return out
+
+
+def blur_noise_act_stats(x, noise, noise_w, stats, act=ACT_LRELU, slope=0.2, seed=0, subseq=0):
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    _lib.call("hwg_blur_noise_act_stats", x.data_ptr(), y.data_ptr(), N, H, W, C, _lib.ptr(noise), _lib.ptr(noise_w),
+              seed, subseq, act, slope, _lib.ptr(stats), _lib.stream())
+    return y
+
+
+def gen_output(x, coef, w, b0):
+    N, H, W, C = x.shape
+    out = torch.empty((N, 1, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("hwg_gen_output", x.data_ptr(), coef.data_ptr(), w.data_ptr(), float(b0), N, H * W, C, out.data_ptr(),
+              _lib.stream())
+    return out
+
+
+def hwr_stem(img, w, b):
+    N, _, H, W = img.shape
+    Cout = w.size(0)
+    y = torch.empty((N, H // 2, W // 2, Cout), device=img.device, dtype=torch.bfloat16)
+    _lib.call("hwg_hwr_stem", img.data_ptr(), w.data_ptr(), b.data_ptr(), N, H, W, Cout, y.data_ptr(), _lib.stream())
+    return y
+
+
+def maxpool_nhwc(x, k, s, p):
+    N, H, W, C = x.shape
+    Ho = (H + 2 * p[0] - k[0]) // s[0] + 1
+    Wo = (W + 2 * p[1] - k[1]) // s[1] + 1
+    y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("hwg_maxpool_nhwc", x.data_ptr(), y.data_ptr(), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo,
+              _lib.stream())
+    return y

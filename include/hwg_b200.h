@@ -147,14 +147,80 @@ typedef struct hwgConvDesc {
   float slope;            /* LeakyReLU negative slope */
   int32_t tile_w;         /* 0 = auto; else output-tile width (8..128, power of 2) */
   int64_t nz_stride_n, nz_stride_h, nz_stride_w; /* noise tensor strides, elements */
+  uint64_t noise_seed;    /* in-kernel Philox N(0,1) when noise == NULL and noise_w != NULL */
+  uint64_t noise_subseq;  /* distinguishes launches that share a seed */
 } hwgConvDesc;
 
-/* bias [Cout] fp32 or NULL; noise fp32 + noise_w [Cout] fp32, or both NULL;
+/* bias [Cout] fp32 or NULL; noise_w [Cout] fp32 or NULL (no noise); noise fp32 tensor or NULL
+ * (NULL with noise_w set: draw N(0,1) in the kernel, Philox4x32-10 keyed by noise_seed);
  * stats [N][Cout][2] fp32 (sum, sum of squares; accumulated with atomics, the
  * caller zeroes it) or NULL. */
 int hwg_conv_fprop(const hwgConvDesc* desc, const void* x, const void* w, const float* bias,
                    const float* noise, const float* noise_w, float* stats, void* y,
                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused memory-bound passes around the convolutions.  Activations are NHWC
+ * bf16 with C a multiple of 8; `HW` below is pixels per image.
+ * ---------------------------------------------------------------------- */
+
+/* out[b,o] = act(sum_k in[b,k]*W[o,k] + bias[o]) in fp32 — the style MLP
+ * Linear+LeakyReLU(0.2) layers (pure_gen.py:31-39) and the AdaIN style
+ * projections (pure_gen.py:57,63), all ten concatenated into one call. */
+int hwg_linear_f32(const float* in, const float* W, const float* bias, float* out,
+                   int B, int K, int O, int act, float slope, void* stream);
+
+/* PixelNorm (pure_gen.py:306-311): out = in / sqrt(mean_k(in^2) + 1e-8), [B,K] fp32. */
+int hwg_pixelnorm_f32(const float* in, float* out, int B, int K, void* stream);
+
+/* Generator input (pure_gen.py:43-48): content [T,B,C] fp32 (element (t,b,c) at
+ * content[t*cs_t + b*cs_b + c*cs_c]) and style [B,S] fp32 -> x [B,1,T,Cp] bf16 with
+ * channels [0,C) = content, [C,C+S) = style broadcast over t, rest 0. */
+int hwg_gen_pack_input(const float* content, int64_t cs_t, int64_t cs_b, int64_t cs_c,
+                       const float* style, int T, int B, int C, int S, int Cp, void* x,
+                       void* stream);
+
+/* AdaIN coefficients (pure_gen.py:62-69): from per-(n,c) sum/sumsq over HW pixels
+ * (biased variance, eps) and gamma/beta rows: coef[n,c] = (a, b) with
+ * a = gamma*rstd, b = beta - mean*a, so that AdaIN(x) = a*x + b. */
+int hwg_adain_coeffs(const float* stats, const float* gamma, const float* beta,
+                     int64_t gb_stride_n, int N, int C, int HW, float eps, float* coef,
+                     void* stream);
+
+/* BatchNorm coefficients (nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79): training
+ * (use_batch_stats=1): reduce stats over n, biased variance to normalise,
+ * running_mean/var updated with `momentum` and the unbiased variance;
+ * eval: running stats.  coef[c] = (a, b). */
+int hwg_bn_coeffs(const float* stats, int N, int C, int64_t count_per_n,
+                  const float* weight, const float* bias, float* running_mean,
+                  float* running_var, float momentum, float eps, int use_batch_stats,
+                  float* coef, float* save_mean_rstd, void* stream);
+
+/* y = act(a*x + b) on NHWC bf16; coef is [N,C,2] (per_sample=1) or [C,2]. In place allowed. */
+int hwg_scale_shift_act(const void* x, void* y, const float* coef, int per_sample, int N,
+                        int64_t HW, int C, int act, float slope, void* stream);
+
+/* Blur 3x3 [1,2,1]x[1,2,1]/16 with zero padding (pure_gen.py:80-137) fused with
+ * NoiseInjection (:72-79), LeakyReLU and the InstanceNorm statistics of the
+ * result.  x, y [N,H,W,C] bf16; noise fp32 NHWC or NULL (NULL + noise_w: Philox). */
+int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, int W, int C,
+                             const float* noise, const float* noise_w, uint64_t noise_seed,
+                             uint64_t noise_subseq, int act, float slope, float* stats,
+                             void* stream);
+
+/* Generator output (pure_gen.py:29,50): AdaIN apply (coef [N,C,2]) + 1x1 conv C->1
+ * (weight w[C], bias b0) + tanh; x [N,H,W,C] bf16 -> out [N,1,H,W] fp32. */
+int hwg_gen_output(const void* x, const float* coef, const float* w, float b0, int N,
+                   int64_t HW, int C, float* out, void* stream);
+
+/* Recognizer stem (cnn_only_hwr.py:44-46): Conv2d(1,64,3,pad 1)+ReLU+MaxPool2d(2,2)
+ * in one pass.  img [N,1,H,W] fp32 -> y [N,H/2,W/2,Cout] bf16; w [Cout,9], b [Cout]. */
+int hwg_hwr_stem(const float* img, const float* w, const float* b, int N, int H, int W,
+                 int Cout, void* y, void* stream);
+
+/* MaxPool2d on NHWC bf16 with -inf padding (cnn_only_hwr.py:48,51-52,55-56). */
+int hwg_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh, int kw,
+                     int sh, int sw, int ph, int pw, int Ho, int Wo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,106 @@ def make_ctc():
     np.savez_compressed(os.path.join(GOLD, "ctc.npz"), **out)
 
 
+# name -> (T, B, dense content, weight seed, input seed)
+GEN_CASES = {
+    "tiny": (8, 2, False, 100, 101),
+    "small": (32, 3, False, 100, 102),
+    "dense": (24, 2, True, 100, 103),
+    "odd_T": (37, 2, False, 104, 105),   # width not a multiple of any tile
+}
+GEN_ARGS = dict(n_class=80, style_size=128, dim=256, n_style_trans=6, emb_dropout=False, append_style=True,
+                small=False)
+
+# name -> (B, W, weight seed, input seed, training)
+HWR_CASES = {
+    "train_w128": (2, 128, 200, 201, True),
+    "train_w260": (3, 260, 200, 202, True),   # W/4+1 etc. not multiples of the tile
+    "eval_w128": (2, 128, 200, 203, False),
+}
+
+
+def digest(t):
+    """Digests + a strided sample of a float tensor (full tensor when small)."""
+    flat = t.reshape(-1).astype(np.float64)
+    w = np.cos(np.arange(flat.size) * 0.37) + 1.5
+    idx = np.arange(0, flat.size, max(1, flat.size // 8192))
+    return np.array([flat.sum(), np.abs(flat).sum(), (flat * w).sum(), np.abs(flat).max()]), flat[idx].astype(np.float32)
+
+
+def weights_digest(sd):
+    """One number per state_dict: catches any difference in init order or key naming."""
+    tot = 0.0
+    for i, k in enumerate(sorted(sd)):
+        v = sd[k].double().reshape(-1)
+        tot += float((v * torch.cos(torch.arange(v.numel(), dtype=torch.float64) * 0.11 + i)).sum())
+    return np.float64(tot)
+
+
+def keys_fixture(sd):
+    return np.array([f"{k}:{'x'.join(str(d) for d in v.shape)}" for k, v in sd.items()])
+
+
+def make_gen():
+    ref_shim.install()
+    from model.pure_gen import SpacedGenerator
+    out = {}
+    for name, (T, B, dense, wseed, iseed) in GEN_CASES.items():
+        m, sd = synth.state_dict_from_seed(lambda: SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False,
+                                                                   append_style=True, small=False), wseed)
+        m.eval()
+        out[f"{name}/weights_digest"] = weights_digest(sd)
+        out["state_dict_keys"] = keys_fixture(sd)
+        content, style = synth.gen_case(T, B, 80, 128, iseed, dense)
+        noise = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(T, B), iseed + 7)]
+        it = iter(noise)
+        orig = torch.randn_like
+
+        def fake_randn_like(x, **kw):
+            z = next(it)
+            assert z.shape == x.shape, (z.shape, x.shape)
+            return z
+
+        torch.randn_like = fake_randn_like   # the reference draws its noise here (pure_gen.py:206,212)
+        try:
+            with torch.no_grad():
+                img = m(torch.from_numpy(content), torch.from_numpy(style))
+        finally:
+            torch.randn_like = orig
+        dig, samp = digest(img.numpy())
+        out[f"{name}/digest"], out[f"{name}/sample"] = dig, samp
+        out[f"{name}/shape"] = np.array(img.shape)
+        if img.numel() <= 40000:
+            out[f"{name}/image"] = img.numpy()
+        print(f"gen/{name}: T={T} B={B} -> {tuple(img.shape)} absmax {dig[3]:.4f}")
+    np.savez_compressed(os.path.join(GOLD, "gen.npz"), **out)
+
+
+def make_hwr():
+    ref_shim.install()
+    from model.cnn_only_hwr import CNNOnlyHWR
+    out = {}
+    for name, (B, W, wseed, iseed, training) in HWR_CASES.items():
+        m, sd = synth.state_dict_from_seed(lambda: CNNOnlyHWR(80, norm='batch'), wseed)
+        m.train(training)
+        out[f"{name}/weights_digest"] = weights_digest(sd)
+        out["state_dict_keys"] = keys_fixture(sd)
+        img = synth.hwr_case(B, W, iseed)
+        with torch.no_grad():
+            lp = m(torch.from_numpy(img))
+        dig, samp = digest(lp.numpy())
+        out[f"{name}/digest"], out[f"{name}/sample"] = dig, samp
+        out[f"{name}/shape"] = np.array(lp.shape)
+        if lp.numel() <= 40000:
+            out[f"{name}/log_probs"] = lp.numpy()
+        out[f"{name}/argmax"] = lp.argmax(2).numpy().astype(np.int32)
+        sd2 = m.state_dict()
+        for k in ("cnn.batchnorm2.running_mean", "cnn.batchnorm6.running_var", "cnn1d.10.running_mean",
+                  "cnn1d.1.running_var"):
+            out[f"{name}/{k}"] = sd2[k].numpy()
+        print(f"hwr/{name}: B={B} W={W} train={training} -> {tuple(lp.shape)}")
+    np.savez_compressed(os.path.join(GOLD, "hwr.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)

@@ -19,3 +19,72 @@ def ctc_case(T, B, C, S, seed, ragged=True, min_frac=0.5, sharp=3.0):
         tg[b, tl[b]:] = 0
     il = np.full(B, T, np.int32)
     return lp, tg, il, tl
+
+
+def gen_case(T, B, n_class=80, style_dim=128, seed=0, dense=False):
+    """Generator inputs: spaced one-hot content [T,B,C] built from random text —
+    each character index ~U{1..C-1} emitted twice, separated by two blanks (class 0), truncated to T —
+    or, with dense=True, softmax(randn) content as generate.py:834 feeds; style ~ N(0,1) [B,S]."""
+    r = np.random.RandomState(seed)
+    content = np.zeros((T, B, n_class), np.float32)
+    if dense:
+        x = r.standard_normal((T, B, n_class)).astype(np.float32)
+        e = np.exp(x - x.max(2, keepdims=True))
+        content = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    else:
+        for b in range(B):
+            seq = []
+            while len(seq) < T:
+                ch = int(r.randint(1, n_class))
+                seq += [ch, ch, 0, 0]
+            content[np.arange(T), b, np.array(seq[:T])] = 1.0
+    style = r.standard_normal((B, style_dim)).astype(np.float32)
+    return content, style
+
+
+def gen_noise(shapes, seed):
+    """The ten N(0,1) tensors NoiseInjection consumes, [B,C,H,W] each, in call order."""
+    r = np.random.RandomState(seed)
+    return [r.standard_normal(s).astype(np.float32) for s in shapes]
+
+
+def gen_noise_shapes(T, B, dim=256):
+    shapes = []
+    H, W = 4, T
+    for i, c in enumerate([dim, dim // 2, dim // 4, dim // 8, dim // 16]):
+        if i in (1, 2):
+            H *= 2
+        elif i in (3, 4):
+            H, W = H * 2, W * 2
+        shapes += [(B, c, H, W)] * 2
+    return shapes
+
+
+def hwr_case(B, W, seed, H=64):
+    r = np.random.RandomState(seed)
+    return (r.rand(B, 1, H, W).astype(np.float32) * 2 - 1)
+
+
+def state_dict_from_seed(make_module, seed):
+    """Random-init weights, reproducible from the seed (torch CPU generator)."""
+    import torch
+    torch.manual_seed(seed)
+    m = make_module()
+    # BatchNorm affine/running stats and biases away from their trivial init, so parity is not vacuous
+    g = torch.Generator().manual_seed(seed + 1)
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.75)
+        elif "batchnorm" in k or (k.startswith("cnn1d") and k.split(".")[1] in ("1", "4", "7", "10")):
+            if k.endswith("weight"):
+                v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.75)
+            elif k.endswith("bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif "noise" in k and k.endswith("weight_orig"):
+            v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.25)   # make the noise path matter
+        elif k.endswith("conv1.0.bias") or k.endswith("out.0.conv.bias"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+    return m, sd
