@@ -10,6 +10,10 @@ import torch
 
 from . import _lib
 
+# bench.py sets this to a list to time every launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, issued_flops)
+PROFILE = None
+
 
 def conv_taps(kh, kw, pad_h, pad_w, dil_h=1, dil_w=1):
     """Tap list of a stride-1 cross-correlation (nn.Conv2d): tap (i,j) reads x[ho+i*dil-pad, ...]."""
@@ -86,9 +90,15 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
         assert bias.dtype == torch.float32 and bias.numel() == Cout
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.numel() == N * Cout * 2
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("hwg_conv_fprop", ctypes.addressof(d), x.data_ptr(), w_packed.data_ptr(), _lib.ptr(bias),
               nz_ptr, _lib.ptr(noise_w), _lib.ptr(stats), y.data_ptr() + off * y.element_size(),
               _lib.stream())
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * Cout * Cin * ntaps))
     return out
 
 

@@ -7,18 +7,22 @@
 //              output pixels: ONE 4-D TMA box {CK, TW, TH, 1} of the NHWC tensor at
 //              (c0, wo0+dw[t], ho0+dh[t], n).  Out-of-bounds pixels arrive as zeros, which
 //              is the reference's zero padding — there is no im2col buffer and no halo code.
-//   B chunk  = w[t][n0:n0+BN][c0:c0+CK]: one 2-D TMA box of the [ntaps*... ] weight matrix.
+//   B chunk  = w[t][n0:n0+BN][c0:c0+CK]: one 2-D TMA box of the [ntaps*Cout, Cin] weight matrix.
 //   Both land K-major with the 128/64/32-byte swizzle that matches CK = 64/32/16, which is
 //   exactly the canonical UMMA shared-memory layout, so the MMA descriptors point straight at
 //   the TMA destination.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane issues tcgen05.mma, tcgen05.commit releases smem stages / signals the
-// epilogue), warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns -> registers -> bias,
-// noise, activation or log-softmax, per-(n,c) statistics by a register butterfly + one atomic
-// per channel per warp, vectorised NHWC stores).
-// Pipeline: STAGES-deep ring of {A,B} buffers with full/empty mbarriers; the accumulator
-// (128 lanes x BN fp32 columns) lives in TMEM.
+// Persistent CTAs: each CTA walks a contiguous range of output tiles.  Warp roles (192 threads):
+//   warp 0    TMA producer (one lane): STAGES-deep {A,B} ring, full/empty mbarriers
+//   warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees smem
+//             stages and signals the epilogue)
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> bias, noise, activation
+//             or log-softmax, per-(n,c) statistics, vectorised NHWC stores
+// The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM, so the epilogue of
+// tile i overlaps the TMA/MMA main loop of tile i+1.
+// Statistics: a register butterfly folds the 32 pixels of a warp, shared-memory accumulators fold
+// the tiles a CTA processes for one image, and one global atomic per channel flushes them when
+// the image (or the CTA) ends.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "philox.cuh"
@@ -32,14 +36,15 @@ using namespace sm100;
 
 struct ConvKParams {
   int N, Ho, Wo, Cout;
-  int TW, TH, tiles_w, tiles_h;
+  int TW, TH, tiles_w, tiles_h, tiles_m, n_tiles, total_tiles, tiles_per_cta;
   int CK, BN, kchunks, ntaps, stages;
   int a_bytes, b_bytes;  // per stage (b rounded up to 1 KiB)
-  int tmem_cols;
+  int tmem_cols, acc_stride;
+  int cpad;              // floats reserved per staged per-channel vector
   int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
   long long ysn, ysh, ysw;
   long long zsn, zsh, zsw;
-  int y_f32, act;
+  int y_f32, act, noise_mode, has_stats;  // noise_mode: 0 none, 1 tensor, 2 Philox
   float slope;
   const float* bias;
   const float* noise;
@@ -49,12 +54,6 @@ struct ConvKParams {
   unsigned long long noise_seed, noise_subseq;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  if (act == HWG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == HWG_ACT_LRELU) return v > 0.f ? v : v * slope;
-  return v;
-}
-
 // Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
 // Recursive halving: 31 shuffles instead of 32*5.
 __device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
@@ -63,7 +62,6 @@ __device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
     const bool upper = (lane & half) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
-      // lanes with bit `half` set keep the upper half of the surviving registers
       float send = upper ? v[i] : v[i + half];
       float keep = upper ? v[i + half] : v[i];
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
@@ -72,7 +70,12 @@ __device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Template parameters >= 0 fix an epilogue option at compile time; -1 leaves it to the runtime
+// value in ConvKParams (generic fallback used by uncommon combinations).
+template <int ACT_T, int NOISE_T, int STATS_T, int F32_T>
+__global__ void __launch_bounds__(192)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ ConvKParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -81,30 +84,37 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  float* bias_s = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);  // [cpad]
+  float* nw_s = bias_s + p.cpad;                                                    // [cpad]
+  float* stat_s = nw_s + p.cpad;                                                    // [256][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat_s + 512);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  // tile coordinates
-  int tile = blockIdx.x;
-  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
-  const int n = tile;
-  const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH;
-  const int n0 = blockIdx.y * p.BN;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(p.total_tiles, t_begin + p.tiles_per_cta);
   const int kiters = p.ntaps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;
+    for (int c = e; c < p.cpad; c += 128) {
+      bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
+      nw_s[c] = (p.noise_w && c < p.Cout) ? p.noise_w[c] : 0.f;
+    }
+    for (int c = e; c < 512; c += 128) stat_s[c] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -115,15 +125,21 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int t = it / p.kchunks, kc = it - t * p.kchunks;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        unsigned char* a_dst = smem + (size_t)stage * stage_bytes;
-        unsigned char* b_dst = a_dst + p.a_bytes;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(128 * p.CK * 2 + p.BN * p.CK * 2));
-        tma_load_4d(a_dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[t], ho0 + p.tap_dh[t], n);
-        tma_load_2d(b_dst, &tmap_w, &full_bar[stage], kc * p.CK, t * p.Cout + n0);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      const uint32_t tx = (uint32_t)(128 * p.CK * 2 + p.BN * p.CK * 2);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
+        const int tw_i = pt % p.tiles_w, r = pt / p.tiles_w;
+        const int th_i = r % p.tiles_h, n = r / p.tiles_h;
+        const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH, n0 = nt * p.BN;
+        for (int it = 0; it < kiters; ++it) {
+          const int tp = it / p.kchunks, kc = it - tp * p.kchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          unsigned char* a_dst = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], tx);
+          tma_load_4d(a_dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[tp], ho0 + p.tap_dh[tp], n);
+          tma_load_2d(a_dst + p.a_bytes, &tmap_w, &full_bar[stage], kc * p.CK, tp * p.Cout + n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -133,138 +149,202 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t row_bytes = (uint32_t)p.CK * 2u;
       const int kk_n = p.CK / 16;
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < kiters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      int ti = 0;
+      for (int t = t_begin; t < t_end; ++t, ++ti) {
+        const int a = ti & 1;
+        mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
-        const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
-        const uint64_t db = umma_desc_kmajor(b_addr, row_bytes);
-        for (int kk = 0; kk < kk_n; ++kk) {
-          // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
-          umma_bf16(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                    (it | kk) != 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
+          const uint64_t db = umma_desc_kmajor(a_addr + (uint32_t)p.a_bytes, row_bytes);
+          for (int kk = 0; kk < kk_n; ++kk) {
+            // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
+            umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (it | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&empty_bar[stage]);            // frees this smem stage when the MMAs retire
-        if (it == kiters - 1) umma_commit(tmem_full);  // accumulator complete
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        umma_commit(&tmem_full[a]);        // accumulator complete
       }
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int act = ACT_T >= 0 ? ACT_T : p.act;
+    const int noise_mode = NOISE_T >= 0 ? NOISE_T : p.noise_mode;
+    const bool has_stats = STATS_T >= 0 ? (STATS_T != 0) : (p.has_stats != 0);
+    const bool y_f32 = F32_T >= 0 ? (F32_T != 0) : (p.y_f32 != 0);
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m / p.TW, wl = m - hl * p.TW;
-    const int ho = ho0 + hl, wo = wo0 + wl;
-    const bool valid = (ho < p.Ho) && (wo < p.Wo);
-    const int nvalid_c = min(p.BN, p.Cout - n0);  // channels of this N tile that exist
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const long long yoff = (long long)n * p.ysn + (long long)ho * p.ysh + (long long)wo * p.ysw + n0;
-    const long long zoff = (long long)n * p.zsn + (long long)ho * p.zsh + (long long)wo * p.zsw + n0;
+    int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
+    int ti = 0;
+    for (int t = t_begin; t < t_end; ++t, ++ti) {
+      const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
+      const int tw_i = pt % p.tiles_w, rr = pt / p.tiles_w;
+      const int th_i = rr % p.tiles_h, n = rr / p.tiles_h;
+      const int n0 = nt * p.BN;
+      const int ho = th_i * p.TH + hl, wo = tw_i * p.TW + wl;
+      const bool valid = (ho < p.Ho) && (wo < p.Wo);
+      const int nvalid_c = min(p.BN, p.Cout - n0);  // channels of this N tile that exist
+      const int a = ti & 1;
+      if (has_stats && (n != stat_n || n0 != stat_n0)) {
+        // flush the statistics of the previous image / channel tile (all four epilogue warps)
+        epi_bar_sync();
+        if (stat_n >= 0) {
+          const int e = threadIdx.x - 64;
+          for (int c = e; c < 2 * p.BN; c += 128) {
+            const int ch = stat_n0 + (c >> 1);
+            if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
+            stat_s[c] = 0.f;
+          }
+        }
+        epi_bar_sync();
+        stat_n = n; stat_n0 = n0;
+      }
+      mbar_wait(&tmem_full[a], (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_stride);
+      const long long yoff = (long long)n * p.ysn + (long long)ho * p.ysh + (long long)wo * p.ysw + n0;
+      const long long zoff = (long long)n * p.zsn + (long long)ho * p.zsh + (long long)wo * p.zsw + n0;
 
-    float lse = 0.f;
-    if (p.act == HWG_ACT_LOGSOFTMAX) {
-      // pass 1: online max / sum-exp over this pixel's channels
-      float mx = -CUDART_INF_F, se = 0.f;
+      float lse = 0.f;
+      if (act == HWG_ACT_LOGSOFTMAX) {
+        // pass 1: online max / sum-exp over this pixel's channels
+        float mx = -CUDART_INF_F, se = 0.f;
+        for (int c0 = 0; c0 < nvalid_c; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int nc = min(32, nvalid_c - c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nc) {
+              float v = __uint_as_float(r[j]) + bias_s[n0 + c0 + j];
+              float nm = fmaxf(mx, v);
+              se = se * __expf(mx - nm) + __expf(v - nm);
+              mx = nm;
+            }
+          }
+        }
+        lse = mx + __logf(se);
+      }
+
       for (int c0 = 0; c0 < nvalid_c; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(trow + (uint32_t)c0, r);
         tmem_ld_wait();
+        if (c0 + 32 >= nvalid_c) {
+          // last TMEM read of this tile: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[a]);
+        }
         const int nc = min(32, nvalid_c - c0);
+        float v[32];
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nc) {
-            float v = __uint_as_float(r[j]) + (p.bias ? p.bias[n0 + c0 + j] : 0.f);
-            float nm = fmaxf(mx, v);
-            se = se * expf(mx - nm) + expf(v - nm);
-            mx = nm;
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = b4[j >> 2];
+          v[j] = __uint_as_float(r[j]) + bb.x; v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bb.z; v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
         }
-      }
-      lse = mx + logf(se);
-    }
-
-    for (int c0 = 0; c0 < nvalid_c; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(trow + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int nc = min(32, nvalid_c - c0);
-      float v[32];
-      float z[32];
-      const bool philox = (p.noise == nullptr) && (p.noise_w != nullptr);
-      if (philox && valid) {
-        // element index in the launch's logical [N,Ho,Wo,Cout] output
-        const unsigned long long e0 =
-            (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.Cout + n0 + c0;
-        if ((e0 & 3ull) == 0) {
+        if (noise_mode == 2) {
+          // element index in the launch's logical [N,Ho,Wo,Cout] output
+          const unsigned long long e0 =
+              (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.Cout + n0 + c0;
+          const float4* w4 = reinterpret_cast<const float4*>(nw_s + n0 + c0);
+          if ((e0 & 3ull) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 g = normal4(p.noise_seed, p.noise_subseq, (e0 + j) >> 2);
-            z[j] = g.x; z[j + 1] = g.y; z[j + 2] = g.z; z[j + 3] = g.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = normal1(p.noise_seed, p.noise_subseq, e0 + j);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]);
-        const bool cv = j < nc;
-        if (p.bias && cv) x += p.bias[n0 + c0 + j];
-        if (p.noise && cv && valid) x += p.noise_w[n0 + c0 + j] * p.noise[zoff + c0 + j];
-        if (philox && cv && valid) x += p.noise_w[n0 + c0 + j] * z[j];
-        if (p.act == HWG_ACT_LOGSOFTMAX) x -= lse;
-        else x = apply_act(x, p.act, p.slope);
-        v[j] = (cv && valid) ? x : 0.f;
-      }
-      if (valid) {
-        if (p.y_f32) {
-          float* yp = reinterpret_cast<float*>(p.y) + yoff + c0;
-          if (nc == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0;
-          if ((nc & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 32; j += 4) {
               if (j < nc) {
-                uint4 pk;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                *reinterpret_cast<uint4*>(yp + j) = pk;
+                const float4 g = normal4(p.noise_seed, p.noise_subseq, (e0 + j) >> 2);
+                const float4 ww = w4[j >> 2];
+                v[j] = fmaf(ww.x, g.x, v[j]); v[j + 1] = fmaf(ww.y, g.y, v[j + 1]);
+                v[j + 2] = fmaf(ww.z, g.z, v[j + 2]); v[j + 3] = fmaf(ww.w, g.w, v[j + 3]);
               }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], normal1(p.noise_seed, p.noise_subseq, e0 + j), v[j]);
+          }
+        } else if (noise_mode == 1) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], p.noise[zoff + c0 + j], v[j]);
+          }
+        }
+        if (act == HWG_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (act == HWG_ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        } else if (act == HWG_ACT_LOGSOFTMAX) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] -= lse;
+        }
+        if (valid) {
+          if (y_f32) {
+            float* yp = reinterpret_cast<float*>(p.y) + yoff + c0;
+            if (nc == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0;
+            if ((nc & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < nc) {
+                  uint4 pk;
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                  __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                  __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                  *reinterpret_cast<uint4*>(yp + j) = pk;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nc) yp[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+        if (has_stats) {
+          // per-(n,c) sum and sum of squares over this warp's 32 pixels
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = valid ? v[j] : 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          const float s1 = butterfly_reduce32(v, lane);
+          const float s2 = butterfly_reduce32(sq, lane);
+          if (lane < nc) {
+            atomicAdd(&stat_s[2 * (c0 + lane)], s1);
+            atomicAdd(&stat_s[2 * (c0 + lane) + 1], s2);
           }
         }
       }
-      if (p.stats) {
-        // per-(n,c) sum and sum of squares over this warp's 32 pixels (invalid lanes hold 0)
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        float s1 = butterfly_reduce32(v, lane);
-        float s2 = butterfly_reduce32(sq, lane);
-        if (lane < nc) {
-          float* st = p.stats + ((size_t)n * p.Cout + n0 + c0 + lane) * 2;
-          atomicAdd(st, s1);
-          atomicAdd(st + 1, s2);
-        }
+    }
+    if (has_stats && stat_n >= 0) {
+      epi_bar_sync();
+      const int e = threadIdx.x - 64;
+      for (int c = e; c < 2 * p.BN; c += 128) {
+        const int ch = stat_n0 + (c >> 1);
+        if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
       }
     }
     tc_fence_before();
@@ -296,7 +376,31 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+typedef void (*ConvKernel)(const CUtensorMap, const CUtensorMap, const ConvKParams);
+
+// epilogue specialisations that the hot path uses; anything else runs the runtime-generic kernel
+static ConvKernel pick_kernel(const ConvKParams& p) {
+  const int a = p.act, nz = p.noise_mode, st = p.has_stats, f = p.y_f32;
+  if (!f && nz == 0 && !st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 0, 0>;
+  if (!f && nz == 0 && st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 1, 0>;
+  if (!f && nz == 0 && !st && a == HWG_ACT_RELU) return conv_fprop_kernel<HWG_ACT_RELU, 0, 0, 0>;
+  if (!f && nz == 2 && st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 1, 0>;
+  if (f && nz == 0 && !st && a == HWG_ACT_LOGSOFTMAX) return conv_fprop_kernel<HWG_ACT_LOGSOFTMAX, 0, 0, 1>;
+  return conv_fprop_kernel<-1, -1, -1, -1>;
+}
 
 }  // namespace hwg
 
@@ -331,11 +435,11 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   if (cout16 <= 256) p.BN = cout16;
   else if (cout16 % 256 == 0) p.BN = 256;
   else p.BN = 128;
-  const int n_tiles = (d->Cout + p.BN - 1) / p.BN;
+  p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
   // output tile TW x TH = 128 pixels
   int TW = d->tile_w;
   if (TW == 0) {
-    // widest power of two that wastes the least; prefer wide tiles (longer contiguous rows)
+    // the power of two that wastes the fewest pixels; ties go to the wider tile
     long best = -1; TW = 128;
     for (int tw = 128; tw >= 8; tw >>= 1) {
       int th = 128 / tw;
@@ -347,19 +451,33 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.TW = TW; p.TH = 128 / TW;
   p.tiles_w = (d->Wo + p.TW - 1) / p.TW;
   p.tiles_h = (d->Ho + p.TH - 1) / p.TH;
+  p.tiles_m = p.tiles_w * p.tiles_h * d->N;
+  p.total_tiles = p.tiles_m * p.n_tiles;
   p.a_bytes = 128 * p.CK * 2;
   p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  int kiters = p.ntaps * p.kchunks;
-  p.stages = (196 * 1024) / stage_bytes;
+  p.cpad = round_up(d->Cout, 32) + 32;
+  const size_t fixed = (size_t)(2 * p.cpad + 512) * sizeof(float) + (2 * 8 + 4) * sizeof(uint64_t) + 16 + 1024;
+  // two CTAs per SM when the ring is small (the small-channel, memory-bound layers): more epilogue
+  // warps in flight; otherwise one CTA with as deep a ring as fits
+  const int sms = num_sms();
+  int ctas_per_sm = 1;
+  p.stages = (int)((200 * 1024 - fixed) / stage_bytes);
   if (p.stages > 8) p.stages = 8;
-  if (p.stages > kiters) p.stages = kiters < 2 ? 2 : kiters;
-  p.tmem_cols = 32;
-  while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+  if (p.stages >= 8 && (size_t)stage_bytes * 8 + fixed <= 100 * 1024 && p.BN <= 128) ctas_per_sm = 2;
+  if (p.stages < 2) p.stages = 2;
+  p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
+  p.tmem_cols = 2 * p.acc_stride;
+  int grid = sms * ctas_per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
+  grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   for (int t = 0; t < d->ntaps; ++t) { p.tap_dh[t] = d->tap_dh[t]; p.tap_dw[t] = d->tap_dw[t]; }
   p.ysn = d->y_stride_n; p.ysh = d->y_stride_h; p.ysw = d->y_stride_w;
   p.zsn = d->nz_stride_n; p.zsh = d->nz_stride_h; p.zsw = d->nz_stride_w;
   p.y_f32 = d->y_dtype == HWG_DT_F32; p.act = d->act; p.slope = d->slope;
+  p.noise_mode = noise_w ? (noise ? 1 : 2) : 0;
+  p.has_stats = stats != nullptr;
   p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.stats = stats; p.y = y;
   p.noise_seed = d->noise_seed; p.noise_subseq = d->noise_subseq;
 
@@ -387,9 +505,9 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return HWG_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  HWG_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * d->N), (unsigned)n_tiles);
-  conv_fprop_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  const size_t smem = (size_t)p.stages * stage_bytes + fixed;
+  ConvKernel k = pick_kernel(p);
+  HWG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<grid, 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   return check_launch("conv_fprop_kernel");
 }

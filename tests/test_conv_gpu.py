@@ -135,3 +135,45 @@ def test_phase_launch_strided_output():
                         out_view=(out, 2 * H * W * Cout, 2 * W * Cout, Cout, par * W * Cout))
     got = out.permute(0, 3, 1, 2).cpu()
     assert _rel(got, ref) <= 1e-2  # summed taps are rounded to bf16 once more than the reference
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 16, 96), (3, 16, 16, 40, 200), (2, 256, 256, 4, 130), (1, 32, 32, 33, 70)])
+def test_specialised_philox_stats_kernel_with_zero_noise_weight(shape):
+    """The generator's epilogue specialisation (LeakyReLU + in-kernel noise + statistics, bf16 out) with the noise
+    weight set to zero must equal the plain convolution: checks the persistent tile loop, the TMEM double
+    buffering and the shared-memory statistics accumulation across tiles and images."""
+    from handwriting_line_generation_b200 import conv, _lib
+    N, Cin, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.leaky_relu(_ref_conv(x, w, b, (1, 1)), 0.2)
+    stats = torch.zeros(N, Cout, 2, device="cuda")
+    y = conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), conv.pack_conv2d_weight(w.cuda()), conv.conv_taps(3, 3, 1, 1),
+                        H, W, bias=b.cuda(), act=_lib.ACT_LRELU, slope=0.2, noise_w=torch.zeros(Cout, device="cuda"),
+                        noise_seed=7, stats=stats)
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert _rel(got, ref) <= 1e-2
+    s = stats.cpu()
+    assert _rel(s[:, :, 0], ref.sum((2, 3))) <= 3e-3 * (H * W) ** 0.5
+    assert _rel(s[:, :, 1], (ref * ref).sum((2, 3))) <= 5e-3
+
+
+def test_many_tiles_per_cta_and_two_n_tiles():
+    """More tiles than CTAs (persistent loop wraps the smem ring and both TMEM buffers many times), Cout=512
+    (two N tiles), statistics on."""
+    from handwriting_line_generation_b200 import conv
+    g = torch.Generator().manual_seed(11)
+    N, Cin, Cout, H, W = 6, 64, 512, 24, 260
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / 24
+    b = torch.randn(Cout, generator=g)
+    ref = _ref_conv(x, w, b, (1, 1))
+    stats = torch.zeros(N, Cout, 2, device="cuda")
+    y = conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), conv.pack_conv2d_weight(w.cuda()), conv.conv_taps(3, 3, 1, 1),
+                        H, W, bias=b.cuda(), stats=stats)
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert _rel(got, ref) <= 1e-2
+    s = stats.cpu()
+    assert _rel(s[:, :, 1], (ref * ref).sum((2, 3))) <= 5e-3

@@ -1,0 +1,46 @@
+"""Device timing of hwg_conv_fprop on representative layer shapes (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from handwriting_line_generation_b200 import conv, _lib
+
+SHAPES = {
+    # name: (N, H, W, Cin, Cout, taps(kh,kw,ph,pw), epilogue)
+    "hwr_conv3": (8, 16, 256, 256, 256, (3, 3, 1, 1), "relu"),
+    "hwr_conv5": (8, 8, 257, 512, 512, (3, 3, 0, 0), "relu"),
+    "hwr_conv1": (8, 32, 512, 64, 128, (3, 3, 1, 1), "relu"),
+    "gen_b0c2": (32, 4, 256, 256, 256, (3, 3, 1, 1), "noise_stats"),
+    "gen_b1c2": (32, 8, 256, 128, 128, (3, 3, 1, 1), "noise_stats"),
+    "gen_b3c2": (32, 32, 512, 32, 32, (3, 3, 1, 1), "noise_stats"),
+    "gen_b4c2": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "noise_stats"),
+    "gen_b4c2_plain": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "none"),
+}
+which = sys.argv[1:] or list(SHAPES)
+reps = 10
+for name in which:
+    N, H, W, Cin, Cout, (kh, kw, ph, pw), epi = SHAPES[name]
+    x = torch.randn(N, H, W, Cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(kh * kw, Cout, Cin, device="cuda") / (Cin * kh * kw) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device="cuda")
+    taps = conv.conv_taps(kh, kw, ph, pw)
+    Ho, Wo = H + 2 * ph - kh + 1, W + 2 * pw - kw + 1
+    kw_ = dict(bias=b)
+    if epi == "relu":
+        kw_.update(act=_lib.ACT_RELU)
+    elif epi == "noise_stats":
+        kw_.update(act=_lib.ACT_LRELU, slope=0.2, noise_w=torch.ones(Cout, device="cuda"), noise_seed=1,
+                   stats=torch.zeros(N, Cout, 2, device="cuda"))
+    out = torch.empty(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        conv.conv_fprop(x, w, taps, Ho, Wo, out=out, **kw_)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        conv.conv_fprop(x, w, taps, Ho, Wo, out=out, **kw_)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    fl = 2.0 * N * Ho * Wo * Cout * Cin * kh * kw
+    by = (x.numel() + out.numel()) * 2
+    print(f"{name:16s} {us:9.1f} us  {fl / us / 1e6:8.1f} TFLOP/s  act-bytes {by / us / 1e3:8.1f} GB/s", flush=True)
