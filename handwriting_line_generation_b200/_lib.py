@@ -27,6 +27,7 @@ _SIGNATURES = {
                                  c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "hwg_ctc_greedy_decode": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_linear_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "hwg_pixelnorm_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "hwg_gen_pack_input": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
@@ -59,6 +60,16 @@ class ConvDesc(ctypes.Structure):
         ("tile_w", ctypes.c_int32),
         ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
         ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64),
+    ]
+
+
+class WgradDesc(ctypes.Structure):
+    """struct hwgWgradDesc (include/hwg_b200.h)."""
+    _fields_ = [
+        ("N", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("Cin", ctypes.c_int32),
+        ("x_pitch", ctypes.c_int32), ("Ho", ctypes.c_int32), ("Wo", ctypes.c_int32), ("Cout", ctypes.c_int32),
+        ("gy_pitch", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+        ("tap_dh", ctypes.c_int32 * HWG_MAX_TAPS), ("tap_dw", ctypes.c_int32 * HWG_MAX_TAPS),
     ]
 
 

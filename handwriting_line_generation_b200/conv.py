@@ -110,3 +110,28 @@ def to_nhwc_bf16(x, c_pad=None):
     if c_pad != c:
         y = torch.nn.functional.pad(y, (0, c_pad - c))
     return y.contiguous()
+
+
+def dgrad_pack(w_taps_f32, taps):
+    """Forward tap matrices [ntaps][Cout][Cin] (fp32) -> (packed bf16 [ntaps][Cin][Cout_pad], negated taps):
+    the input gradient is hwg_conv_fprop of the output gradient with these."""
+    mats = [w_taps_f32[t].t() for t in range(w_taps_f32.size(0))]
+    return pack_taps(mats), [(-dh, -dw) for dh, dw in taps]
+
+
+def conv_wgrad(x, gy, taps, cin, cout, out=None):
+    """dw[t][co][ci] = sum_pixels gy[n,ho,wo,co] * x[n,ho+dh_t,wo+dw_t,ci]  (fp32 [ntaps,cout,cin]).
+    x [N,H,W,Cp>=cin] bf16 NHWC, gy [N,Ho,Wo,Gp>=cout] bf16 NHWC."""
+    _lib.require_cuda(x, gy)
+    assert x.dtype == torch.bfloat16 and gy.dtype == torch.bfloat16 and x.is_contiguous() and gy.is_contiguous()
+    N, H, W, Cp = x.shape
+    N2, Ho, Wo, Gp = gy.shape
+    assert N == N2
+    d = _lib.WgradDesc()
+    d.N, d.H, d.W, d.Cin, d.x_pitch, d.Ho, d.Wo, d.Cout, d.gy_pitch, d.ntaps = N, H, W, cin, Cp, Ho, Wo, cout, Gp, len(taps)
+    for i, (dh, dw) in enumerate(taps):
+        d.tap_dh[i], d.tap_dw[i] = dh, dw
+    if out is None:
+        out = torch.zeros((len(taps), cout, cin), device=x.device, dtype=torch.float32)
+    _lib.call("hwg_conv_wgrad", ctypes.addressof(d), x.data_ptr(), gy.data_ptr(), out.data_ptr(), _lib.stream())
+    return out

@@ -222,6 +222,29 @@ int hwg_hwr_stem(const float* img, const float* w, const float* b, int N, int H,
 int hwg_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh, int kw,
                      int sh, int sw, int ph, int pw, int Ho, int Wo, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Backward of the convolutions.
+ * dgrad needs no new entry point: it is hwg_conv_fprop on the output gradient with the
+ * negated taps and transposed weight matrices (the host packs them).
+ *
+ * wgrad (replaces cudnnConvolutionBackwardFilter behind nn.Conv2d/Conv1d backward):
+ *   dw[t][co][ci] += sum_{n,ho,wo} gy[n,ho,wo,co] * x[n, ho+dh[t], wo+dw[t], ci]
+ * as a tcgen05 GEMM with M = Cout tile (128), N = Cin tile (<= 256), K = pixels, both
+ * operands MN-major straight from the NHWC tensors via TMA (zero fill outside x = padding),
+ * split over pixel ranges with fp32 vector reductions (red.global.add.v4.f32) into dw.
+ * x  bf16 NHWC [N,H,W,x_pitch], Cin multiple of 64;  gy bf16 NHWC [N,Ho,Wo,gy_pitch]
+ * dw fp32 [ntaps][Cout][Cin], ACCUMULATED into (caller zeroes it).
+ * ---------------------------------------------------------------------- */
+typedef struct hwgWgradDesc {
+  int32_t N, H, W, Cin, x_pitch;
+  int32_t Ho, Wo, Cout, gy_pitch;
+  int32_t ntaps;
+  int32_t tap_dh[HWG_MAX_TAPS];
+  int32_t tap_dw[HWG_MAX_TAPS];
+} hwgWgradDesc;
+
+int hwg_conv_wgrad(const hwgWgradDesc* desc, const void* x, const void* gy, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
