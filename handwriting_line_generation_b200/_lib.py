@@ -28,6 +28,12 @@ _SIGNATURES = {
     "hwg_ctc_greedy_decode": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_logsoftmax_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_bn_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "hwg_bn_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_relu_maxpool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_hwr_stem_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_linear_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "hwg_pixelnorm_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "hwg_gen_pack_input": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

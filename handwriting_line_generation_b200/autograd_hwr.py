@@ -1,7 +1,220 @@
-"""Training path of the recognizer (autograd.Function around the fused forward + backward kernels)."""
+"""Training path of the recognizer: one torch.autograd.Function around the fused forward and the
+backward kernels of libhwg_b200 (reference: the autograd graph PyTorch records for
+model/cnn_only_hwr.py:96-107; backward = cuDNN dgrad/wgrad + ATen batch_norm/max_pool/relu/
+log_softmax backward kernels).
+
+Backward of every convolution = dgrad (hwg_conv_fprop on the output gradient with negated taps and
+transposed weights) + wgrad (hwg_conv_wgrad, tcgen05 with MN-major operands); the memory-bound passes
+between them (log-softmax, BatchNorm+ReLU, ReLU+MaxPool, stem) emit the bias gradients on the way.
+"""
+import torch
+
+from . import conv, ops
+from ._lib import ACT_LOGSOFTMAX, ACT_NONE, ACT_RELU
+
+_T3 = conv.conv_taps(3, 3, 1, 1)
+_T3P0 = conv.conv_taps(3, 3, 0, 0)
+_CNN1D = [(0, 1, 2, 2), (3, 4, 4, 4), (6, 7, 0, 1), (9, 10, 8, 8)]
+_POOL22 = ((2, 2), (2, 2), (0, 0))
+_POOL21 = ((2, 2), (2, 1), (0, 1))
+
+
+def _taps_f32(weight4d):
+    """[Cout,Cin,kh,kw] -> fp32 tap matrices [kh*kw, Cout, Cin]."""
+    co, ci, kh, kw = weight4d.shape
+    return weight4d.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+
+
+def _dgrad_packs(m):
+    """Transposed tap matrices for every tensor-core convolution (cached with the forward packs)."""
+    c = m._packed()
+    if "dgrad" not in c:
+        d = {}
+        for i in range(1, 7):
+            taps = _T3 if i <= 4 else _T3P0
+            d[f"w{i}"] = conv.dgrad_pack(_taps_f32(getattr(m.cnn, f"conv{i}").weight), taps)
+        for ci, _, pad, dil in _CNN1D + [(12, None, 0, 1)]:
+            taps = conv.conv_taps(1, 3, 0, pad, 1, dil)
+            d[f"v{ci}"] = conv.dgrad_pack(_taps_f32(m.cnn1d[ci].weight.unsqueeze(2)), taps)
+        c["dgrad"] = d
+    return c["dgrad"]
+
+
+def _bn_train(m, y, stats, bn):
+    N, H, W, C = y.shape
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    use_batch = m.training or not bn.track_running_stats
+    coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                               bn.running_var, momentum, bn.eps, use_batch)
+    if m.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    if not use_batch:  # eval-mode BN under autograd: (mean, rstd) from the running statistics
+        save = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)], 1).contiguous()
+    a = ops.scale_shift_act(y, coef, False, ACT_RELU, out=torch.empty_like(y))
+    return a, coef, save
+
+
+def forward_train(m, x):
+    """Forward that keeps what the backward needs.  Returns (log_probs [T,B,C], ctx dict)."""
+    if m.pad is not None:
+        x = m.pad(x)
+    if m.small:
+        raise NotImplementedError("small=True is not implemented")
+    c = m._packed()
+    x = x.float().contiguous()
+    B = x.size(0)
+    dev = x.device
+    ctx = {"x": x}
+
+    def stats_for(C):
+        return torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
+
+    a0 = ops.hwr_stem(x, c["w0"], c["b0"])
+    c1 = conv.conv_fprop(a0, c["w1"], _T3, a0.size(1), a0.size(2), bias=c["b1"], act=ACT_RELU)
+    a1 = ops.maxpool_nhwc(c1, *_POOL22)
+    st = stats_for(256)
+    z2 = conv.conv_fprop(a1, c["w2"], _T3, a1.size(1), a1.size(2), bias=c["b2"], stats=st)
+    a2, coef2, save2 = _bn_train(m, z2, st, m.cnn.batchnorm2)
+    c3 = conv.conv_fprop(a2, c["w3"], _T3, a2.size(1), a2.size(2), bias=c["b3"], act=ACT_RELU)
+    a3 = ops.maxpool_nhwc(c3, *_POOL21)
+    st = stats_for(512)
+    z4 = conv.conv_fprop(a3, c["w4"], _T3, a3.size(1), a3.size(2), bias=c["b4"], stats=st)
+    a4, coef4, save4 = _bn_train(m, z4, st, m.cnn.batchnorm4)
+    c5 = conv.conv_fprop(a4, c["w5"], _T3P0, a4.size(1) - 2, a4.size(2) - 2, bias=c["b5"], act=ACT_RELU)
+    if m._save:
+        m.saved_features[0] = c5.permute(0, 3, 1, 2).float()
+    a5 = ops.maxpool_nhwc(c5, *_POOL21)
+    st = stats_for(512)
+    z6 = conv.conv_fprop(a5, c["w6"], _T3P0, a5.size(1) - 2, a5.size(2) - 2, bias=c["b6"], stats=st)
+    a6, coef6, save6 = _bn_train(m, z6, st, m.cnn.batchnorm6)
+    if a6.size(1) != 1:
+        raise RuntimeError(f"CNNOnlyHWR expects 64-px-high images (conv height {a6.size(1)} != 1)")
+    ctx.update(a0=a0, c1=c1, a1=a1, z2=z2, a2=a2, bn2=(coef2, save2), c3=c3, a3=a3, z4=z4, a4=a4, bn4=(coef4, save4),
+               c5=c5, a5=a5, z6=z6, bn6=(coef6, save6))
+    a = a6
+    ctx["head_in"] = []
+    for ci, bi, pad, dil in _CNN1D:
+        Wo = a.size(2) + 2 * pad - 2 * dil
+        st = stats_for(512)
+        z = conv.conv_fprop(a, c[f"v{ci}"], conv.conv_taps(1, 3, 0, pad, 1, dil), 1, Wo, bias=c[f"c{ci}"], stats=st)
+        an, coef, save = _bn_train(m, z, st, m.cnn1d[bi])
+        ctx["head_in"].append((a, z, coef, save))
+        a = an
+    T = a.size(2) - 2
+    C = m.nclass
+    out = torch.empty((T, B, C), device=dev, dtype=torch.float32)
+    conv.conv_fprop(a, c["v12"], conv.conv_taps(1, 3, 0, 0), 1, T, bias=c["c12"], act=ACT_LOGSOFTMAX,
+                    out_view=(out, C, 0, B * C, 0))
+    ctx["a10"] = a
+    ctx["lp"] = out
+    return out, ctx
+
+
+def _w4(dw, kh, kw):
+    """wgrad output [kh*kw, Cout, Cin] -> parameter layout [Cout, Cin, kh, kw]."""
+    t, co, ci = dw.shape
+    return dw.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
+
+
+def backward_train(m, ctx, g_lp):
+    """Returns {parameter name: gradient} for every parameter of the module."""
+    dg = _dgrad_packs(m)
+    grads = {}
+    lp = ctx["lp"]
+    T, B, C = lp.shape
+    Cp = ((C + 15) // 16) * 16
+
+    def dgrad(gz, key, H, W):
+        wd, tapsd = dg[key]
+        return conv.conv_fprop(gz, wd, tapsd, H, W)
+
+    # ---- head: log-softmax + Conv1d(512, C, 3)
+    gz, db = ops.logsoftmax_bwd(g_lp.contiguous().float(), lp, Cp)
+    a10 = ctx["a10"]
+    dw = conv.conv_wgrad(a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)
+    grads["cnn1d.12.weight"] = dw[:, :C, :].permute(1, 2, 0).contiguous()
+    grads["cnn1d.12.bias"] = db
+    g = dgrad(gz, "v12", 1, a10.size(2))
+    # ---- dilated 1-D blocks, last to first
+    for (ci, bi, pad, dil), (a_in, z, coef, save) in zip(reversed(_CNN1D), reversed(ctx["head_in"])):
+        bn = m.cnn1d[bi]
+        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach())
+        grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
+        dw = conv.conv_wgrad(a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
+        grads[f"cnn1d.{ci}.weight"] = dw.permute(1, 2, 0).contiguous()
+        grads[f"cnn1d.{ci}.bias"] = dcb
+        g = dgrad(gz, f"v{ci}", 1, a_in.size(2))
+    # ---- conv6 + BN + ReLU
+    coef, save = ctx["bn6"]
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach())
+    grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
+    a5 = ctx["a5"]
+    grads["cnn.conv6.weight"] = _w4(conv.conv_wgrad(a5, gz, _T3P0, 512, 512), 3, 3)
+    grads["cnn.conv6.bias"] = dcb
+    g = dgrad(gz, "w6", a5.size(1), a5.size(2))
+    # ---- pool + ReLU + conv5
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c5"], *_POOL21)
+    a4 = ctx["a4"]
+    grads["cnn.conv5.weight"] = _w4(conv.conv_wgrad(a4, gc, _T3P0, 512, 512), 3, 3)
+    grads["cnn.conv5.bias"] = db
+    g = dgrad(gc, "w5", a4.size(1), a4.size(2))
+    # ---- conv4 + BN + ReLU
+    coef, save = ctx["bn4"]
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach())
+    grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
+    a3 = ctx["a3"]
+    grads["cnn.conv4.weight"] = _w4(conv.conv_wgrad(a3, gz, _T3, 256, 512), 3, 3)
+    grads["cnn.conv4.bias"] = dcb
+    g = dgrad(gz, "w4", a3.size(1), a3.size(2))
+    # ---- pool + ReLU + conv3
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c3"], *_POOL21)
+    a2 = ctx["a2"]
+    grads["cnn.conv3.weight"] = _w4(conv.conv_wgrad(a2, gc, _T3, 256, 256), 3, 3)
+    grads["cnn.conv3.bias"] = db
+    g = dgrad(gc, "w3", a2.size(1), a2.size(2))
+    # ---- conv2 + BN + ReLU
+    coef, save = ctx["bn2"]
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach())
+    grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
+    a1 = ctx["a1"]
+    grads["cnn.conv2.weight"] = _w4(conv.conv_wgrad(a1, gz, _T3, 128, 256), 3, 3)
+    grads["cnn.conv2.bias"] = dcb
+    g = dgrad(gz, "w2", a1.size(1), a1.size(2))
+    # ---- pool + ReLU + conv1
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c1"], *_POOL22)
+    a0 = ctx["a0"]
+    grads["cnn.conv1.weight"] = _w4(conv.conv_wgrad(a0, gc, _T3, 64, 128), 3, 3)
+    grads["cnn.conv1.bias"] = db
+    g = dgrad(gc, "w1", a0.size(1), a0.size(2))
+    # ---- stem
+    c = m._packed()
+    dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g)
+    grads["cnn.conv0.weight"] = dw0.view(64, 1, 3, 3)
+    grads["cnn.conv0.bias"] = db0
+    return grads
+
+
+class _HWRFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, names, x, *params):
+        with torch.no_grad():
+            out, saved = forward_train(module, x)
+        ctx.module, ctx.names, ctx.saved = module, names, saved
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.x_needs_grad:
+            raise NotImplementedError("gradient w.r.t. the recognizer's input image (GAN lessons) is not built yet; "
+                                      "there is deliberately no PyTorch fallback")
+        with torch.no_grad():
+            grads = backward_train(ctx.module, ctx.saved, g)
+        ctx.saved = None
+        return (None, None, None) + tuple(grads[n] for n in ctx.names)
 
 
 def hwr_apply(module, input):
-    raise NotImplementedError(
-        "CNNOnlyHWR backward on libhwg_b200 is not built yet (round 1 ships the forward path); call under "
-        "torch.no_grad() — there is deliberately no PyTorch fallback")
+    named = [(n, p) for n, p in module.named_parameters()]
+    names = tuple(n for n, _ in named)
+    return _HWRFn.apply(module, names, input, *[p for _, p in named])

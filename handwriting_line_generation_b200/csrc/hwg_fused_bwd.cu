@@ -1,0 +1,392 @@
+// HBM-bound backward passes of the recognizer (sm_100a): NHWC bf16 gradients, 16-byte vectors of
+// 8 channels per thread, per-channel reductions folded warp -> shared -> one global atomic per block.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace hwg {
+
+__device__ __forceinline__ void unpack8b(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+constexpr int BW_THREADS = 256;
+constexpr int BW_ITER = 8;
+
+// Per-channel reduction of K x 8 per-thread partial sums.  The thread's channel vector `cv` is fixed
+// (CV divides BW_THREADS).  sacc: [K][C] shared floats (zeroed by the caller, followed by a barrier).
+template <int K>
+__device__ __forceinline__ void channel_reduce(float (&acc)[K][8], int cv, int CV, int C, float* sacc,
+                                               float* gout, int gstride) {
+  if (CV < 32) {
+    for (int off = 16; off >= CV; off >>= 1) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], off);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  if (CV >= 32 || lane < CV) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[k * C + cv * 8 + j], acc[k][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    atomicAdd(&gout[c * gstride + k], sacc[i]);
+  }
+}
+
+// ---- log-softmax backward ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+logsoftmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp, int T, int B, int C, int Cp,
+                      __nv_bfloat16* __restrict__ gz, float* __restrict__ dbias) {
+  extern __shared__ float sb[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;  // row = t*B + b
+  if (row < (long long)T * B) {
+    const int t = (int)(row / B), b = (int)(row - (long long)t * B);
+    const float* gr = g + row * C;
+    const float* lr = lp + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += gr[c];
+    s = warp_sum(s);
+    __nv_bfloat16* out = gz + ((long long)b * T + t) * Cp;
+    for (int c = lane; c < Cp; c += 32) {
+      float v = 0.f;
+      if (c < C) {
+        v = gr[c] - __expf(lr[c]) * s;
+        atomicAdd(&sb[c], v);
+      }
+      out[c] = __float2bfloat16_rn(v);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], sb[i]);
+}
+
+// ---- BatchNorm (+ReLU) backward ----------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS)
+bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
+                     const float* __restrict__ save, long long rows, int C, int relu, float* __restrict__ sums) {
+  extern __shared__ float sacc[];  // [2][C]
+  const int CV = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  float a[8], b[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    a[j] = coef[2 * c]; b[j] = coef[2 * c + 1]; mean[j] = save[2 * c]; rstd[j] = save[2 * c + 1];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long total = rows * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    float gf[8], zf[8];
+    unpack8b(g[item], gf);
+    unpack8b(z[item], zf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gy = (!relu || fmaf(a[j], zf[j], b[j]) > 0.f) ? gf[j] : 0.f;
+      acc[0][j] += gy;
+      acc[1][j] += gy * (zf[j] - mean[j]) * rstd[j];
+    }
+  }
+  channel_reduce<2>(acc, cv, CV, C, sacc, sums, 2);
+}
+
+__global__ void __launch_bounds__(BW_THREADS)
+bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
+                    const float* __restrict__ save, const float* __restrict__ weight,
+                    const float* __restrict__ sums, long long rows, int C, int relu, uint4* __restrict__ gz,
+                    float* __restrict__ dconv_bias) {
+  extern __shared__ float sacc[];  // [1][C]
+  const int CV = C / 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  const float invM = 1.f / (float)rows;
+  float a[8], b[8], mean[8], rstd[8], k0[8], k1[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    a[j] = coef[2 * c]; b[j] = coef[2 * c + 1]; mean[j] = save[2 * c]; rstd[j] = save[2 * c + 1];
+    sc[j] = (weight ? weight[c] : 1.f) * rstd[j];
+    k0[j] = sums[2 * c] * invM;       // mean of gy
+    k1[j] = sums[2 * c + 1] * invM;   // mean of gy*xhat
+  }
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  const long long total = rows * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    float gf[8], zf[8], o[8];
+    unpack8b(g[item], gf);
+    unpack8b(z[item], zf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gy = (!relu || fmaf(a[j], zf[j], b[j]) > 0.f) ? gf[j] : 0.f;
+      const float xh = (zf[j] - mean[j]) * rstd[j];
+      o[j] = sc[j] * (gy - k0[j] - xh * k1[j]);
+      acc[0][j] += o[j];
+    }
+    gz[item] = pack8b(o);
+  }
+  if (dconv_bias) channel_reduce<1>(acc, cv, CV, C, sacc, dconv_bias, 1);
+}
+
+// ---- ReLU + MaxPool backward (gather) ------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS)
+relu_maxpool_bwd_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ c, int N, int H, int W, int C,
+                        int kh, int kw, int sh, int sw, int ph, int pw, int Ho, int Wo, uint4* __restrict__ gc,
+                        float* __restrict__ dbias) {
+  extern __shared__ float sacc[];  // [1][C]
+  const int CV = C / 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  const long long total = (long long)N * H * W * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    long long pix = item / CV;
+    const int w = (int)(pix % W); pix /= W;
+    const int h = (int)(pix % H);
+    const int n = (int)(pix / H);
+    float me[8], o[8];
+    unpack8b(c[item], me);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    // pooling windows (ho,wo) that contain (h,w): ho*sh - ph <= h < ho*sh - ph + kh
+    const int ho_hi = min(Ho - 1, (h + ph) / sh);
+    const int ho_lo = max(0, (h + ph - kh + sh) / sh);   // ceil((h+ph-kh+1)/sh)
+    const int wo_hi = min(Wo - 1, (w + pw) / sw);
+    const int wo_lo = max(0, (w + pw - kw + sw) / sw);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        // is (h,w) the FIRST maximum of this window (row-major scan, strict > to replace)?
+        bool first[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) first[j] = true;
+        for (int i = 0; i < kh; ++i) {
+          const int hh = ho * sh - ph + i;
+          if (hh < 0 || hh >= H) continue;
+          for (int j2 = 0; j2 < kw; ++j2) {
+            const int ww = wo * sw - pw + j2;
+            if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
+            float f[8];
+            unpack8b(c[(((long long)n * H + hh) * W + ww) * CV + cv], f);
+            const bool before = (hh < h) || (hh == h && ww < w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) first[j] = first[j] && (before ? (f[j] < me[j]) : (f[j] <= me[j]));
+          }
+        }
+        float gf[8];
+        unpack8b(ga[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (first[j]) o[j] += gf[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = me[j] > 0.f ? o[j] : 0.f;   // ReLU mask (c is the post-ReLU activation)
+      acc[0][j] += o[j];
+    }
+    gc[item] = pack8b(o);
+  }
+  if (dbias) channel_reduce<1>(acc, cv, CV, C, sacc, dbias, 1);
+}
+
+// ---- stem backward ---------------------------------------------------------------------------------
+// thread = (pooled pixel, 8-channel group); block-level reduction of dw[c][9], db[c] in shared memory
+__global__ void __launch_bounds__(BW_THREADS)
+hwr_stem_bwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                    const uint4* __restrict__ ga, int N, int H, int W, int Cout, float* __restrict__ dw,
+                    float* __restrict__ db) {
+  extern __shared__ float sm[];  // w [Cout*9], b [Cout], acc [Cout*10]
+  float* ws = sm;
+  float* bs = sm + Cout * 9;
+  float* accs = bs + Cout;
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = b[i];
+  for (int i = threadIdx.x; i < Cout * 10; i += blockDim.x) accs[i] = 0.f;
+  __syncthreads();
+  const int CV = Cout / 8, Hp = H / 2, Wp = W / 2;
+  const long long total = (long long)N * Hp * Wp * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  const int cv = threadIdx.x % CV;
+  float acc[8][10];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[j][k] = 0.f;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    long long pix = item / CV;
+    const int wp = (int)(pix % Wp); pix /= Wp;
+    const int hp = (int)(pix % Hp);
+    const int n = (int)(pix / Hp);
+    float patch[4][4];
+    const float* im = img + (size_t)n * H * W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int hh = 2 * hp - 1 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ww = 2 * wp - 1 + j;
+        patch[i][j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? im[(size_t)hh * W + ww] : 0.f;
+      }
+    }
+    float gf[8];
+    unpack8b(ga[item], gf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* k = ws + (cv * 8 + j) * 9;
+      float m = -CUDART_INF_F; int by = 0, bx = 0;
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+          float a = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) a = fmaf(k[ky * 3 + kx], patch[oy + ky][ox + kx], a);
+          if (a > m) { m = a; by = oy; bx = ox; }   // first maximum wins, like max_pool2d
+        }
+      const float gv = (m + bs[cv * 8 + j] > 0.f) ? gf[j] : 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // patch[by+ky][bx+kx] with by,bx in {0,1}: select without dynamic indexing
+          const float p00 = patch[ky][kx], p01 = patch[ky][kx + 1], p10 = patch[ky + 1][kx], p11 = patch[ky + 1][kx + 1];
+          const float pv = by ? (bx ? p11 : p10) : (bx ? p01 : p00);
+          acc[j][ky * 3 + kx] = fmaf(gv, pv, acc[j][ky * 3 + kx]);
+        }
+      acc[j][9] += gv;
+    }
+  }
+  // fold lanes that share cv, then shared atomics, then one global atomic per value per block
+  if (CV < 32) {
+    for (int off = 16; off >= CV; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[j][k] += __shfl_xor_sync(0xffffffffu, acc[j][k], off);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  if (CV >= 32 || lane < CV) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) atomicAdd(&accs[(cv * 8 + j) * 10 + k], acc[j][k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 10; i += blockDim.x) {
+    const int c = i / 10, k = i - c * 10;
+    if (k < 9) atomicAdd(&dw[c * 9 + k], accs[i]);
+    else atomicAdd(&db[c], accs[i]);
+  }
+}
+
+static inline unsigned bw_blocks(long long items, int per_block) {
+  return (unsigned)((items + per_block - 1) / per_block);
+}
+static inline bool cv_ok(int C) {
+  const int cv = C / 8;
+  return C % 8 == 0 && cv > 0 && (cv & (cv - 1)) == 0 && cv <= BW_THREADS;
+}
+
+}  // namespace hwg
+
+using namespace hwg;
+
+extern "C" int hwg_logsoftmax_bwd(const float* g, const float* lp, int T, int B, int C, int Cp, void* gz,
+                                  float* dbias, void* stream) {
+  HWG_REQUIRE(g && lp && gz && dbias && T > 0 && B > 0 && C > 0 && Cp >= C, "hwg_logsoftmax_bwd: bad argument");
+  const long long rows = (long long)T * B;
+  logsoftmax_bwd_kernel<<<bw_blocks(rows, 8), 256, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+      g, lp, T, B, C, Cp, reinterpret_cast<__nv_bfloat16*>(gz), dbias);
+  return check_launch("logsoftmax_bwd_kernel");
+}
+
+extern "C" int hwg_bn_bwd_reduce(const void* g, const void* z, const float* coef, const float* save, int64_t rows,
+                                 int C, int relu, float* sums, void* stream) {
+  HWG_REQUIRE(g && z && coef && save && sums && rows > 0, "hwg_bn_bwd_reduce: bad argument");
+  HWG_REQUIRE(cv_ok(C), "hwg_bn_bwd_reduce: C=%d must be 8 x a power of two", C);
+  const long long total = rows * (C / 8);
+  bn_bwd_reduce_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)2 * C * sizeof(float),
+                         (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z),
+                                                 coef, save, rows, C, relu, sums);
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int hwg_bn_bwd_apply(const void* g, const void* z, const float* coef, const float* save,
+                                const float* weight, const float* sums, int64_t rows, int C, int relu, void* gz,
+                                float* dconv_bias, void* stream) {
+  HWG_REQUIRE(g && z && coef && save && sums && gz && rows > 0, "hwg_bn_bwd_apply: bad argument");
+  HWG_REQUIRE(cv_ok(C), "hwg_bn_bwd_apply: C=%d must be 8 x a power of two", C);
+  const long long total = rows * (C / 8);
+  bn_bwd_apply_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float),
+                        (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z),
+                                                coef, save, weight, sums, rows, C, relu,
+                                                reinterpret_cast<uint4*>(gz), dconv_bias);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H, int W, int C, int kh, int kw,
+                                    int sh, int sw, int ph, int pw, int Ho, int Wo, void* gc, float* dbias,
+                                    void* stream) {
+  HWG_REQUIRE(ga && c && gc && N > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0, "hwg_relu_maxpool_bwd: bad argument");
+  HWG_REQUIRE(cv_ok(C), "hwg_relu_maxpool_bwd: C=%d must be 8 x a power of two", C);
+  HWG_REQUIRE(Ho == (H + 2 * ph - kh) / sh + 1 && Wo == (W + 2 * pw - kw) / sw + 1,
+              "hwg_relu_maxpool_bwd: Ho/Wo do not match the pooling geometry");
+  const long long total = (long long)N * H * W * (C / 8);
+  relu_maxpool_bwd_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float),
+                            (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(ga),
+                                                    reinterpret_cast<const uint4*>(c), N, H, W, C, kh, kw, sh, sw, ph,
+                                                    pw, Ho, Wo, reinterpret_cast<uint4*>(gc), dbias);
+  return check_launch("relu_maxpool_bwd_kernel");
+}
+
+extern "C" int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b, const void* ga, int N, int H,
+                                int W, int Cout, float* dw, float* db, void* stream) {
+  HWG_REQUIRE(img && w && b && ga && dw && db && N > 0, "hwg_hwr_stem_bwd: bad argument");
+  HWG_REQUIRE(H % 2 == 0 && W % 2 == 0 && cv_ok(Cout), "hwg_hwr_stem_bwd: bad geometry");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (Cout / 8);
+  hwr_stem_bwd_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)Cout * 20 * sizeof(float),
+                        (cudaStream_t)stream>>>(img, w, b, reinterpret_cast<const uint4*>(ga), N, H, W, Cout, dw, db);
+  return check_launch("hwr_stem_bwd_kernel");
+}

@@ -88,3 +88,48 @@ def maxpool_nhwc(x, k, s, p):
     _lib.call("hwg_maxpool_nhwc", x.data_ptr(), y.data_ptr(), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo,
               _lib.stream())
     return y
+
+
+# ---- backward passes (hwg_fused_bwd.cu) ----------------------------------------------------------------
+def logsoftmax_bwd(g, lp, Cp):
+    """g, lp [T,B,C] fp32 -> (gz [B,1,T,Cp] bf16 NHWC, dbias [C] fp32)."""
+    T, B, C = lp.shape
+    gz = torch.empty((B, 1, T, Cp), device=lp.device, dtype=torch.bfloat16)
+    db = torch.zeros(C, device=lp.device, dtype=torch.float32)
+    _lib.call("hwg_logsoftmax_bwd", g.data_ptr(), lp.data_ptr(), T, B, C, Cp, gz.data_ptr(), db.data_ptr(), _lib.stream())
+    return gz, db
+
+
+def bn_bwd(g, z, coef, save, weight, relu=True):
+    """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C])."""
+    C = z.size(-1)
+    rows = z.numel() // C
+    sums = torch.zeros((C, 2), device=z.device, dtype=torch.float32)
+    _lib.call("hwg_bn_bwd_reduce", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), rows, C, int(relu),
+              sums.data_ptr(), _lib.stream())
+    gz = torch.empty_like(z)
+    dcb = torch.zeros(C, device=z.device, dtype=torch.float32)
+    _lib.call("hwg_bn_bwd_apply", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), weight.data_ptr(),
+              sums.data_ptr(), rows, C, int(relu), gz.data_ptr(), dcb.data_ptr(), _lib.stream())
+    return gz, sums[:, 1].contiguous(), sums[:, 0].contiguous(), dcb
+
+
+def relu_maxpool_bwd(ga, c, k, s, p):
+    """ga [N,Ho,Wo,C], c [N,H,W,C] (post-ReLU, pre-pool) -> (gc [N,H,W,C] bf16, dbias [C])."""
+    N, H, W, C = c.shape
+    Ho, Wo = ga.size(1), ga.size(2)
+    gc = torch.empty_like(c)
+    db = torch.zeros(C, device=c.device, dtype=torch.float32)
+    _lib.call("hwg_relu_maxpool_bwd", ga.data_ptr(), c.data_ptr(), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo,
+              gc.data_ptr(), db.data_ptr(), _lib.stream())
+    return gc, db
+
+
+def hwr_stem_bwd(img, w, b, ga):
+    N, _, H, W = img.shape
+    Cout = w.size(0)
+    dw = torch.zeros((Cout, 9), device=img.device, dtype=torch.float32)
+    db = torch.zeros(Cout, device=img.device, dtype=torch.float32)
+    _lib.call("hwg_hwr_stem_bwd", img.data_ptr(), w.data_ptr(), b.data_ptr(), ga.data_ptr(), N, H, W, Cout, dw.data_ptr(),
+              db.data_ptr(), _lib.stream())
+    return dw, db

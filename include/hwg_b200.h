@@ -245,6 +245,40 @@ typedef struct hwgWgradDesc {
 
 int hwg_conv_wgrad(const hwgWgradDesc* desc, const void* x, const void* gy, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Memory-bound backward passes of the recognizer (NHWC bf16 gradients).
+ * Each pass also emits the per-channel sum of the gradient it writes = the
+ * bias gradient of the convolution that produced that activation.
+ * ---------------------------------------------------------------------- */
+
+/* LogSoftmax backward (cnn_only_hwr.py:91): gz = g - exp(lp) * sum_c g, written as the NHWC bf16
+ * tensor [B,1,T,Cp] the head's dgrad/wgrad read (channels >= C zero).  g, lp are [T,B,C] fp32.
+ * dbias [C] fp32 is accumulated (caller zeroes). */
+int hwg_logsoftmax_bwd(const float* g, const float* lp, int T, int B, int C, int Cp, void* gz,
+                       float* dbias, void* stream);
+
+/* BatchNorm(+ReLU) backward, pass 1: sums[c] = (sum gy, sum gy*xhat), gy = g * (a*z+b > 0),
+ * xhat = (z-mean)*rstd.  g, z [rows,C] bf16; coef [C,2] = forward (a,b); save [C,2] = (mean,rstd).
+ * sums [C,2] fp32 accumulated (caller zeroes). */
+int hwg_bn_bwd_reduce(const void* g, const void* z, const float* coef, const float* save, int64_t rows,
+                      int C, int relu, float* sums, void* stream);
+/* pass 2: gz = weight*rstd*(gy - sums0/M - xhat*sums1/M) -> bf16 [rows,C]; dweight = sums1, dbias = sums0
+ * are read by the host from `sums`; dconv_bias [C] fp32 accumulates sum gz (caller zeroes). */
+int hwg_bn_bwd_apply(const void* g, const void* z, const float* coef, const float* save, const float* weight,
+                     const float* sums, int64_t rows, int C, int relu, void* gz, float* dconv_bias,
+                     void* stream);
+
+/* ReLU + MaxPool2d backward in gather form (no atomics): gc[n,h,w,:] = (c>0) * sum over the pooling
+ * windows that contain (h,w) and whose first maximum is (h,w) of ga[window].  c [N,H,W,C] is the
+ * saved post-ReLU pre-pool activation, ga [N,Ho,Wo,C].  dbias [C] accumulates sum gc. */
+int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H, int W, int C, int kh, int kw, int sh,
+                         int sw, int ph, int pw, int Ho, int Wo, void* gc, float* dbias, void* stream);
+
+/* Stem backward (conv0+ReLU+MaxPool, cnn_only_hwr.py:44-46): dw [Cout,9], db [Cout] fp32 accumulated
+ * from ga [N,H/2,W/2,Cout] bf16 and the fp32 image (pre-activations are recomputed). */
+int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b, const void* ga, int N, int H, int W,
+                     int Cout, float* dw, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,9 @@ CASES = [
     (3, 512, 512, 1, 254, (1, 3), (0, 4), (1, 4)),
     (2, 512, 80, 1, 100, (1, 3), (0, 0), (1, 1)),
     (2, 128, 256, 5, 9, (3, 3), (1, 1), (1, 1)),
+    (2, 512, 80, 1, 28, (1, 3), (0, 0), (1, 1)),      # head at W=128: 26 frames, 2-row pixel chunks on H=1
+    (2, 512, 512, 1, 26, (1, 3), (0, 8), (1, 8)),     # dilation wider than a chunk
+    (2, 256, 512, 3, 32, (3, 3), (0, 0), (1, 1)),
 ]
 
 
