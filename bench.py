@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 Default workload = BASELINE.json configs[1]: pure_gen generator inference, batch 32 per GPU,
-T_s=256 spaced characters -> 32 x [1,64,1024] lines per step, in-kernel Philox noise.
+T_s=256 spaced characters -> 32 x [1,64,1024] lines per step, in-kernel noise.
 A "step" is one pass of that path over one batch of synthetic input.
 
   value     lines/s with the inputs already resident in HBM (device-timed, CUDA events)
@@ -158,7 +158,7 @@ def workload_config(B):
             "batch_per_gpu": B, "line_px": [64, 4 * GEN["T"]],
             "l2": "no explicit flush: the bf16 activations one step streams (~0.7 GB at B=32) exceed the 126 MB L2; "
                   "weights (4 MB) stay cached, as in production",
-            "noise": "NoiseInjection N(0,1) drawn in-kernel (Philox), a fresh seed every step"}
+            "noise": "NoiseInjection N(0,1) drawn in-kernel (counter-based hash + Box-Muller), a fresh seed every step"}
 
 
 # ----------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
               up-sampling convolutions); otherwise a fresh [N,Ho,Wo,Cout] tensor is returned
     noise     optional fp32 [N,Ho,Wo,Cout] NHWC tensor added as noise_w[c]*noise before the activation
               (or noise_view=(tensor, sn, sh, sw, element_offset) for a strided one); with noise_w and
-              noise_seed but no tensor, N(0,1) is drawn inside the kernel (Philox)
+              noise_seed but no tensor, N(0,1) is drawn inside the kernel (counter-based hash + Box-Muller)
     stats     optional zeroed fp32 [N,Cout,2]; receives per-(n,c) sum and sum of squares of the output
     """
     _lib.require_cuda(x, w_packed)

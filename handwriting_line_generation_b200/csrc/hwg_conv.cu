@@ -12,11 +12,11 @@
 //   exactly the canonical UMMA shared-memory layout, so the MMA descriptors point straight at
 //   the TMA destination.
 //
-// Persistent CTAs: each CTA walks a contiguous range of output tiles.  Warp roles (192 threads):
+// Persistent CTAs: each CTA walks a contiguous range of output tiles.  Warp roles (192 or 320 threads):
 //   warp 0    TMA producer (one lane): STAGES-deep {A,B} ring, full/empty mbarriers
 //   warp 1    TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees smem
 //             stages and signals the epilogue)
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> bias, noise, activation
+//   warps 2-5 (and 6-9 when one CTA owns the SM) epilogue groups: tcgen05.ld (32 lanes x 32 columns) -> registers -> bias, noise, activation
 //             or log-softmax, per-(n,c) statistics, vectorised NHWC stores
 // The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM, so the epilogue of
 // tile i overlaps the TMA/MMA main loop of tile i+1.
@@ -25,7 +25,7 @@
 // the image (or the CTA) ends.
 #include "common.cuh"
 #include "sm100.cuh"
-#include "philox.cuh"
+#include "noise_rng.cuh"
 #include <cuda.h>
 #include <math_constants.h>
 #include <mutex>
@@ -38,13 +38,16 @@ struct ConvKParams {
   int N, Ho, Wo, Cout;
   int TW, TH, tiles_w, tiles_h, tiles_m, n_tiles, total_tiles, tiles_per_cta;
   int CK, BN, kchunks, ntaps, stages;
-  int a_bytes, b_bytes;  // per stage (b rounded up to 1 KiB)
+  int a_bytes, b_bytes;  // per (tap, chunk) operand tile (b rounded up to 1 KiB)
+  int gsize, ngroups;    // (tap, chunk) tiles per pipeline stage / stages per output tile
+  int wstat;             // 1: all weight tiles stay resident in shared memory (loaded once per CTA)
+  int unit_bytes;        // bytes of one (tap, chunk) slot inside a stage: a_bytes (+ b_bytes unless wstat)
   int tmem_cols, acc_stride;
   int cpad;              // floats reserved per staged per-channel vector
   int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
   long long ysn, ysh, ysw;
   long long zsn, zsh, zsw;
-  int y_f32, act, noise_mode, has_stats;  // noise_mode: 0 none, 1 tensor, 2 Philox
+  int y_f32, act, noise_mode, has_stats;  // noise_mode: 0 none, 1 tensor, 2 in-kernel RNG
   float slope;
   const float* bias;
   const float* noise;
@@ -70,12 +73,13 @@ __device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one 128-thread epilogue group (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 // Template parameters >= 0 fix an epilogue option at compile time; -1 leaves it to the runtime
 // value in ConvKParams (generic fallback used by uncommon combinations).
 template <int ACT_T, int NOISE_T, int STATS_T, int F32_T>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(320)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ ConvKParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -83,25 +87,28 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int stage_bytes = p.a_bytes + p.b_bytes;
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);  // [cpad]
+  const int stage_bytes = p.gsize * p.unit_bytes;
+  const int kiters = p.ntaps * p.kchunks;
+  unsigned char* wsmem = smem + (size_t)p.stages * stage_bytes;                      // resident weights (wstat)
+  float* bias_s = reinterpret_cast<float*>(wsmem + (p.wstat ? (size_t)kiters * p.b_bytes : 0));  // [cpad]
   float* nw_s = bias_s + p.cpad;                                                    // [cpad]
-  float* stat_s = nw_s + p.cpad;                                                    // [256][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat_s + 512);
+  float* stat_all = nw_s + p.cpad;                                                  // [2 groups][256][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat_all + 1024);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* w_bar = tmem_empty + 2;             // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(p.total_tiles, t_begin + p.tiles_per_cta);
-  const int kiters = p.ntaps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -110,11 +117,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   }
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
-    for (int c = e; c < p.cpad; c += 128) {
+    for (int c = e; c < p.cpad; c += (int)blockDim.x - 64) {
       bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
       nw_s[c] = (p.noise_w && c < p.Cout) ? p.noise_w[c] : 0.f;
     }
-    for (int c = e; c < 512; c += 128) stat_s[c] = 0.f;
+    for (int c = e; c < 1024; c += (int)blockDim.x - 64) stat_all[c] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -125,19 +132,35 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(128 * p.CK * 2 + p.BN * p.CK * 2);
+      const uint32_t a_tx = (uint32_t)(128 * p.CK * 2), b_tx = (uint32_t)(p.BN * p.CK * 2);
+      if (p.wstat) {
+        // weight-stationary: every (tap, chunk) weight tile of this CTA's channel tile, once
+        const int n0w = (t_begin / p.tiles_m) * p.BN;   // wstat implies a single channel tile
+        mbar_expect_tx(w_bar, b_tx * (uint32_t)kiters);
+        int tp = 0, kc = 0;
+        for (int it = 0; it < kiters; ++it) {
+          tma_load_2d(wsmem + (size_t)it * p.b_bytes, &tmap_w, w_bar, kc * p.CK, tp * p.Cout + n0w);
+          if (++kc == p.kchunks) { kc = 0; ++tp; }
+        }
+      }
+      const uint32_t unit_tx = a_tx + (p.wstat ? 0u : b_tx);
       for (int t = t_begin; t < t_end; ++t) {
         const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
         const int tw_i = pt % p.tiles_w, r = pt / p.tiles_w;
         const int th_i = r % p.tiles_h, n = r / p.tiles_h;
         const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH, n0 = nt * p.BN;
-        for (int it = 0; it < kiters; ++it) {
-          const int tp = it / p.kchunks, kc = it - tp * p.kchunks;
+        int tp = 0, kc = 0, it = 0;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int nsub = min(p.gsize, kiters - it);
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          unsigned char* a_dst = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], tx);
-          tma_load_4d(a_dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[tp], ho0 + p.tap_dh[tp], n);
-          tma_load_2d(a_dst + p.a_bytes, &tmap_w, &full_bar[stage], kc * p.CK, tp * p.Cout + n0);
+          unsigned char* dst = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], unit_tx * (uint32_t)nsub);
+          for (int sub = 0; sub < nsub; ++sub, ++it) {
+            tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[tp], ho0 + p.tap_dh[tp], n);
+            if (!p.wstat) tma_load_2d(dst + p.a_bytes, &tmap_w, &full_bar[stage], kc * p.CK, tp * p.Cout + n0);
+            dst += p.unit_bytes;
+            if (++kc == p.kchunks) { kc = 0; ++tp; }
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -150,20 +173,28 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int kk_n = p.CK / 16;
       int stage = 0; uint32_t phase = 0;
       int ti = 0;
+      if (p.wstat) { mbar_wait(w_bar, 0); tc_fence_after(); }
+      const uint32_t w_addr = smem_u32(wsmem);
       for (int t = t_begin; t < t_end; ++t, ++ti) {
         const int a = ti & 1;
         mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
-        for (int it = 0; it < kiters; ++it) {
+        int it = 0;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int nsub = min(p.gsize, kiters - it);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
-          const uint64_t db = umma_desc_kmajor(a_addr + (uint32_t)p.a_bytes, row_bytes);
-          for (int kk = 0; kk < kk_n; ++kk) {
-            // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
-            umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (it | kk) != 0 ? 1u : 0u);
+          uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          for (int sub = 0; sub < nsub; ++sub, ++it) {
+            const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
+            const uint64_t db = umma_desc_kmajor(p.wstat ? w_addr + (uint32_t)(it * p.b_bytes)
+                                                         : a_addr + (uint32_t)p.a_bytes, row_bytes);
+            for (int kk = 0; kk < kk_n; ++kk) {
+              // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
+              umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (it | kk) != 0 ? 1u : 0u);
+            }
+            a_addr += (uint32_t)p.unit_bytes;
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -176,13 +207,29 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int noise_mode = NOISE_T >= 0 ? NOISE_T : p.noise_mode;
     const bool has_stats = STATS_T >= 0 ? (STATS_T != 0) : (p.has_stats != 0);
+    // STATS_T == 2 (BN <= 32, one column chunk): per-thread register accumulation across tiles, folded
+    // over the warp only when the statistics are flushed — no shuffles on the per-tile path
+    constexpr bool STAT_REG = (STATS_T == 2);
+    float ts1[32], ts2[32];  // dead (optimised away) unless STAT_REG
+    if constexpr (STAT_REG) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { ts1[j] = 0.f; ts2[j] = 0.f; }
+    }
     const bool y_f32 = F32_T >= 0 ? (F32_T != 0) : (p.y_f32 != 0);
+    // one or two epilogue groups of four warps (blockDim 192 / 320); group g owns every tile with
+    // (tile iteration % groups) == g, i.e. with two groups each TMEM accumulator buffer has its own group
+    const int ngrp = ((int)blockDim.x - 64) >> 7;
+    const int grp = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64 - grp * 128;   // thread index inside the group
+    float* stat_s = stat_all + grp * 512;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m / p.TW, wl = m - hl * p.TW;
+    const uint2 nkey = noise_key(p.noise_seed, p.noise_subseq);
     int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
     int ti = 0;
     for (int t = t_begin; t < t_end; ++t, ++ti) {
+      if (ngrp == 2 && (ti & 1) != grp) continue;
       const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
       const int tw_i = pt % p.tiles_w, rr = pt / p.tiles_w;
       const int th_i = rr % p.tiles_h, n = rr / p.tiles_h;
@@ -193,16 +240,23 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int a = ti & 1;
       if (has_stats && (n != stat_n || n0 != stat_n0)) {
         // flush the statistics of the previous image / channel tile (all four epilogue warps)
-        epi_bar_sync();
+        if constexpr (STAT_REG) if (stat_n >= 0) {
+          const float s1 = butterfly_reduce32(ts1, lane);
+          const float s2 = butterfly_reduce32(ts2, lane);
+          if (lane < p.BN) { atomicAdd(&stat_s[2 * lane], s1); atomicAdd(&stat_s[2 * lane + 1], s2); }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { ts1[j] = 0.f; ts2[j] = 0.f; }
+        }
+        epi_bar_sync(grp);
         if (stat_n >= 0) {
-          const int e = threadIdx.x - 64;
+          const int e = et;
           for (int c = e; c < 2 * p.BN; c += 128) {
             const int ch = stat_n0 + (c >> 1);
             if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
             stat_s[c] = 0.f;
           }
         }
-        epi_bar_sync();
+        epi_bar_sync(grp);
         stat_n = n; stat_n0 = n0;
       }
       mbar_wait(&tmem_full[a], (uint32_t)((ti >> 1) & 1));
@@ -256,21 +310,20 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // element index in the launch's logical [N,Ho,Wo,Cout] output
           const unsigned long long e0 =
               (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.Cout + n0 + c0;
-          const float4* w4 = reinterpret_cast<const float4*>(nw_s + n0 + c0);
-          if ((e0 & 3ull) == 0) {
+          const float2* w2 = reinterpret_cast<const float2*>(nw_s + n0 + c0);
+          if ((e0 & 1ull) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 32; j += 2) {
               if (j < nc) {
-                const float4 g = normal4(p.noise_seed, p.noise_subseq, (e0 + j) >> 2);
-                const float4 ww = w4[j >> 2];
+                const float2 g = normal_pair(nkey, (e0 + j) >> 1);
+                const float2 ww = w2[j >> 1];
                 v[j] = fmaf(ww.x, g.x, v[j]); v[j + 1] = fmaf(ww.y, g.y, v[j + 1]);
-                v[j + 2] = fmaf(ww.z, g.z, v[j + 2]); v[j + 3] = fmaf(ww.w, g.w, v[j + 3]);
               }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], normal1(p.noise_seed, p.noise_subseq, e0 + j), v[j]);
+              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], normal_one(nkey, e0 + j), v[j]);
           }
         } else if (noise_mode == 1) {
           if (valid) {
@@ -284,7 +337,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         } else if (act == HWG_ACT_LRELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * p.slope);  // slope in [0,1]
         } else if (act == HWG_ACT_LOGSOFTMAX) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] -= lse;
@@ -322,7 +375,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             }
           }
         }
-        if (has_stats) {
+        if constexpr (STAT_REG) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = valid ? v[j] : 0.f;
+            ts1[j] += x; ts2[j] = fmaf(x, x, ts2[j]);
+          }
+        } else if (has_stats) {
           // per-(n,c) sum and sum of squares over this warp's 32 pixels
           float sq[32];
 #pragma unroll
@@ -340,8 +399,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     if (has_stats && stat_n >= 0) {
-      epi_bar_sync();
-      const int e = threadIdx.x - 64;
+      if constexpr (STAT_REG) {
+        const float s1 = butterfly_reduce32(ts1, lane);
+        const float s2 = butterfly_reduce32(ts2, lane);
+        if (lane < p.BN) { atomicAdd(&stat_s[2 * lane], s1); atomicAdd(&stat_s[2 * lane + 1], s2); }
+      }
+      epi_bar_sync(grp);
+      const int e = et;
       for (int c = e; c < 2 * p.BN; c += 128) {
         const int ch = stat_n0 + (c >> 1);
         if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
@@ -397,6 +461,7 @@ static ConvKernel pick_kernel(const ConvKParams& p) {
   if (!f && nz == 0 && !st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 0, 0>;
   if (!f && nz == 0 && st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 1, 0>;
   if (!f && nz == 0 && !st && a == HWG_ACT_RELU) return conv_fprop_kernel<HWG_ACT_RELU, 0, 0, 0>;
+  if (!f && nz == 2 && st && a == HWG_ACT_LRELU && p.BN <= 32) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 2, 0>;
   if (!f && nz == 2 && st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 1, 0>;
   if (f && nz == 0 && !st && a == HWG_ACT_LOGSOFTMAX) return conv_fprop_kernel<HWG_ACT_LOGSOFTMAX, 0, 0, 1>;
   return conv_fprop_kernel<-1, -1, -1, -1>;
@@ -455,16 +520,30 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.total_tiles = p.tiles_m * p.n_tiles;
   p.a_bytes = 128 * p.CK * 2;
   p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
-  const int stage_bytes = p.a_bytes + p.b_bytes;
+  const int kiters = p.ntaps * p.kchunks;
   p.cpad = round_up(d->Cout, 32) + 32;
-  const size_t fixed = (size_t)(2 * p.cpad + 512) * sizeof(float) + (2 * 8 + 4) * sizeof(uint64_t) + 16 + 1024;
-  // two CTAs per SM when the ring is small (the small-channel, memory-bound layers): more epilogue
-  // warps in flight; otherwise one CTA with as deep a ring as fits
+  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+  // Small layers: keep every weight tile resident (one load per CTA) and put several (tap, chunk) operand
+  // tiles behind one mbarrier round trip, so the single-thread producer / MMA loops are not the bottleneck.
+  p.wstat = (p.n_tiles == 1 && (size_t)kiters * p.b_bytes <= 40 * 1024) ? 1 : 0;
+  p.unit_bytes = p.a_bytes + (p.wstat ? 0 : p.b_bytes);
+  p.gsize = (24 * 1024) / p.unit_bytes;
+  if (p.gsize < 1) p.gsize = 1;
+  if (p.gsize > kiters) p.gsize = kiters;
+  p.ngroups = (kiters + p.gsize - 1) / p.gsize;
+  p.gsize = (kiters + p.ngroups - 1) / p.ngroups;   // balance the groups
+  const int stage_bytes = p.gsize * p.unit_bytes;
+  const size_t wbytes = p.wstat ? (size_t)kiters * p.b_bytes : 0;
+  // two CTAs per SM when everything is small (the memory-bound layers): more epilogue warps in flight
   const int sms = num_sms();
   int ctas_per_sm = 1;
-  p.stages = (int)((200 * 1024 - fixed) / stage_bytes);
+  p.stages = (int)((200 * 1024 - fixed - wbytes) / stage_bytes);
   if (p.stages > 8) p.stages = 8;
-  if (p.stages >= 8 && (size_t)stage_bytes * 8 + fixed <= 100 * 1024 && p.BN <= 128) ctas_per_sm = 2;
+  if (p.BN <= 128 && (size_t)stage_bytes * 3 + fixed + wbytes <= 100 * 1024) {
+    ctas_per_sm = 2;
+    p.stages = (int)((100 * 1024 - fixed - wbytes) / stage_bytes);
+    if (p.stages > 8) p.stages = 8;
+  }
   if (p.stages < 2) p.stages = 2;
   p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.tmem_cols = 2 * p.acc_stride;
@@ -505,9 +584,10 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return HWG_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + fixed;
+  const size_t smem = (size_t)p.stages * stage_bytes + wbytes + fixed;
   ConvKernel k = pick_kernel(p);
   HWG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently
+  k<<<grid, ctas_per_sm == 1 ? 320 : 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   return check_launch("conv_fprop_kernel");
 }

@@ -1,7 +1,7 @@
 // HBM-bound fused passes around the convolutions (sm_100a): every kernel moves 16-byte
 // vectors of 8 bf16 channels, NHWC, and touches each activation once.
 #include "common.cuh"
-#include "philox.cuh"
+#include "noise_rng.cuh"
 #include <math_constants.h>
 
 namespace hwg {
@@ -168,6 +168,7 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const uint2 nkey = noise_key(seed, subseq);
 
   for (int it = 0; it < EW_ITER; ++it) {
     const long long item = base + it * EW_THREADS + threadIdx.x;
@@ -199,9 +200,12 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
         float4 z0 = zp[0], z1 = zp[1];
         z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
       } else {
-        const unsigned long long e4 = ((unsigned long long)n * total + item) * 2ull;
-        float4 z0 = normal4(seed, subseq, e4), z1 = normal4(seed, subseq, e4 + 1);
-        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+        const unsigned long long e2 = ((unsigned long long)n * total + item) * 4ull;   // pair index of channel 0
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 zz = normal_pair(nkey, e2 + q);
+          z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);

@@ -245,7 +245,7 @@ class SpacedGenerator(nn.Module):
         """content [T,B,n_class] fp32 (one-hot or dense), style [B,style_size].
         `noise`: optional list of the ten [B,C,H,W] tensors the reference would have drawn with
         torch.randn_like (pure_gen.py:206,212), in call order — for parity tests.  By default the
-        noise is generated inside the kernels (Philox), seeded from torch's CPU generator."""
+        noise is generated inside the kernels (counter-based hash + Box-Muller), seeded from torch's CPU generator."""
         _lib.require_cuda(content, style)
         if torch.is_grad_enabled() and (content.requires_grad or style.requires_grad
                                         or any(p.requires_grad for p in self.parameters())):

@@ -147,12 +147,12 @@ typedef struct hwgConvDesc {
   float slope;            /* LeakyReLU negative slope */
   int32_t tile_w;         /* 0 = auto; else output-tile width (8..128, power of 2) */
   int64_t nz_stride_n, nz_stride_h, nz_stride_w; /* noise tensor strides, elements */
-  uint64_t noise_seed;    /* in-kernel Philox N(0,1) when noise == NULL and noise_w != NULL */
+  uint64_t noise_seed;    /* in-kernel N(0,1) noise (counter-based hash + Box-Muller) when noise == NULL and noise_w != NULL */
   uint64_t noise_subseq;  /* distinguishes launches that share a seed */
 } hwgConvDesc;
 
 /* bias [Cout] fp32 or NULL; noise_w [Cout] fp32 or NULL (no noise); noise fp32 tensor or NULL
- * (NULL with noise_w set: draw N(0,1) in the kernel, Philox4x32-10 keyed by noise_seed);
+ * (NULL with noise_w set: draw N(0,1) in the kernel, keyed by noise_seed and the element index);
  * stats [N][Cout][2] fp32 (sum, sum of squares; accumulated with atomics, the
  * caller zeroes it) or NULL. */
 int hwg_conv_fprop(const hwgConvDesc* desc, const void* x, const void* w, const float* bias,
@@ -202,7 +202,7 @@ int hwg_scale_shift_act(const void* x, void* y, const float* coef, int per_sampl
 
 /* Blur 3x3 [1,2,1]x[1,2,1]/16 with zero padding (pure_gen.py:80-137) fused with
  * NoiseInjection (:72-79), LeakyReLU and the InstanceNorm statistics of the
- * result.  x, y [N,H,W,C] bf16; noise fp32 NHWC or NULL (NULL + noise_w: Philox). */
+ * result.  x, y [N,H,W,C] bf16; noise fp32 NHWC or NULL (NULL + noise_w: in-kernel RNG). */
 int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, int W, int C,
                              const float* noise, const float* noise_w, uint64_t noise_seed,
                              uint64_t noise_subseq, int act, float slope, float* stats,

@@ -138,7 +138,7 @@ def test_phase_launch_strided_output():
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 16, 96), (3, 16, 16, 40, 200), (2, 256, 256, 4, 130), (1, 32, 32, 33, 70)])
-def test_specialised_philox_stats_kernel_with_zero_noise_weight(shape):
+def test_specialised_noise_stats_kernel_with_zero_noise_weight(shape):
     """The generator's epilogue specialisation (LeakyReLU + in-kernel noise + statistics, bf16 out) with the noise
     weight set to zero must equal the plain convolution: checks the persistent tile loop, the TMEM double
     buffering and the shared-memory statistics accumulation across tiles and images."""

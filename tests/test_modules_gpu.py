@@ -61,7 +61,7 @@ def test_generator_matches_golden_and_oracle(name, golden_dir):
 
 
 def test_generator_config2_shape_and_noise_statistics():
-    """BASELINE config 2 shapes (B=32, T=256 -> [32,1,64,1024]) with in-kernel Philox noise: finite, in tanh
+    """BASELINE config 2 shapes (B=32, T=256 -> [32,1,64,1024]) with in-kernel noise: finite, in tanh
     range, reproducible under torch.manual_seed, different across seeds."""
     m, _ = _gen_module(100)
     m = m.cuda().eval()
@@ -81,7 +81,7 @@ def test_generator_config2_shape_and_noise_statistics():
     assert same < 2e-2 and other > 3 * same
 
 
-def test_philox_noise_is_standard_normal():
+def test_inkernel_noise_is_standard_normal():
     """The fused NoiseInjection draws N(0,1): check mean/variance/kurtosis through a conv whose weights are zero."""
     from handwriting_line_generation_b200 import conv, _lib
     N, C, H, W = 2, 64, 32, 256
