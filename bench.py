@@ -298,11 +298,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gen_infer", choices=["gen_infer", "hwr_train"],
+                    help="gen_infer = BASELINE configs[1] (default); hwr_train = configs[0] recognizer+CTC train step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "hwr_train":
+        import bench_hwr_train
+        bench_hwr_train.main(args, rank, world, local_rank, load_peaks, ClockSampler)
+    elif args.impl == "reference":
         if args.steps > 10:
             args.steps = 10   # bounded: each step is a 4-line slice on the CPU (~0.5 s)
         run_reference(args, rank)

@@ -1,0 +1,182 @@
+"""bench.py --workload hwr_train: BASELINE configs[0] — CNNOnlyHWR + CTC train step (forward, CTC loss, backward
+through every layer, Adam) on synthetic 64x1024 IAM-shaped lines, batch 8 per GPU, 80 classes, 60-char targets.
+Same JSON contract as bench.py; data-parallel with the NCCL gradient all-reduce of
+handwriting_line_generation_b200.dp.GradBuckets when WORLD_SIZE > 1."""
+import json
+import os
+import statistics
+import time
+
+import numpy as np
+import torch
+
+HWR = dict(B=8, W=1024, S=60, C=80)
+GF_FWD_PER_LINE = 24.661  # forward conv GFLOP per 64x1024 line; fwd+dgrad+wgrad = 3x
+
+
+def config(B):
+    return {"workload": "BASELINE configs[0]: cnn_only_hwr CTC recognizer train step (fwd + CTC loss + bwd + Adam) on "
+                        f"synthetic 64x{HWR['W']} lines, IAM charset ({HWR['C']} classes), {HWR['S']}-char targets, "
+                        "random-init weights",
+            "batch_per_gpu": B, "line_px": [64, HWR["W"]],
+            "l2": "activations + gradients of one step (~0.5 GB at B=8) exceed the 126 MB L2; no explicit flush"}
+
+
+def cpu_lines_per_s(sample_B, reps):
+    """The reference's CPU path for this step: torch fp32 modules/autograd (oracle port) + F.ctc_loss + Adam."""
+    from oracle import hwr as ohwr, synth
+    from handwriting_line_generation_b200 import CNNOnlyHWR
+    torch.manual_seed(0)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in CNNOnlyHWR(HWR["C"], norm='batch').state_dict().items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    img = torch.from_numpy(synth.hwr_case(sample_B, HWR["W"], 1))
+    T = HWR["W"] // 4 - 6
+    tg = torch.randint(1, HWR["C"], (sample_B, HWR["S"]), dtype=torch.int32)
+    il, tl = torch.full((sample_B,), T, dtype=torch.int32), torch.full((sample_B,), HWR["S"], dtype=torch.int32)
+    times = []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        lp = ohwr.hwr_forward(sd, img, True, {})
+        torch.nn.functional.ctc_loss(lp, tg, il, tl).backward()
+        opt.step()
+        if i:
+            times.append(time.perf_counter() - t0)
+    return sample_B / statistics.median(times), times
+
+
+def main(args, rank, world, local_rank, load_peaks, ClockSampler):
+    B = HWR["B"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        steps = min(args.steps, 5)
+        t0 = time.time()
+        lps, times = cpu_lines_per_s(2, steps)
+        sample = (f"{len(times)} timed train steps on a 2-line slice of the batch, torch fp32 on "
+                  f"{torch.get_num_threads()} host threads, {time.time() - t0:.1f}s")
+        print(json.dumps({"impl": "reference", "metric": "train-step lines/sec", "value": lps, "unit": "lines/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(B),
+                          "cpu_baseline": {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(),
+                                           "kind": "port", "sample": sample},
+                          "e2e": {"value": lps, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
+
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import conv as hconv, dp
+    from oracle import synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = pkg.CNNOnlyHWR(HWR["C"], norm='batch').to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    buckets = dp.GradBuckets(model.parameters()) if world > 1 else None
+    T = HWR["W"] // 4 - 6
+    n_sets = 4
+    host = []
+    for i in range(n_sets):
+        img = torch.from_numpy(synth.hwr_case(B, HWR["W"], 100 * rank + i)).pin_memory()
+        tg = torch.from_numpy(np.random.RandomState(i).randint(1, HWR["C"], (B, HWR["S"])).astype(np.int32)).pin_memory()
+        host.append((img, tg))
+    devsets = [(a.to(dev), b.to(dev)) for a, b in host]
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), HWR["S"], dtype=torch.int32, device=dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def train(img, tg):
+        opt.zero_grad(set_to_none=True)
+        loss = pkg.CTCLoss(model(img), tg, il, tl)
+        loss.backward()
+        if buckets is not None:
+            buckets.reduce()
+        opt.step()
+        return loss
+
+    def step_device(i):
+        return train(*devsets[i % n_sets])
+
+    def step_e2e(i):
+        a, b = host[i % n_sets]
+        loss = train(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
+        loss_host.copy_(loss, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return dp.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for i in range(max(3, args.warmup)):
+        step_device(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    n0 = pkg._lib.launch_count()
+    t0 = time.time()
+    ms = timed(step_device, args.steps)
+    t1 = time.time()
+    launches = pkg._lib.launch_count() - n0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    prof = []
+    hconv.PROFILE = prof
+    psteps = min(args.steps, 5)
+    barrier()
+    for i in range(psteps):
+        step_device(i)
+    barrier()
+    hconv.PROFILE = None
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof) / psteps
+    peaks = load_peaks()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    lines = B * world
+    ms_step = ms / args.steps
+    conv_flops = 3 * GF_FWD_PER_LINE * 1e9 * B
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    cpu = None
+    if world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        tb = time.time()
+        lps, times = cpu_lines_per_s(2, 2)
+        cpu = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{len(times)} timed train steps on a 2-line slice, torch fp32, {time.time() - tb:.1f}s of CPU work"}
+    print(json.dumps({
+        "metric": "train-step lines/sec", "value": lines / (ms_step * 1e-3), "unit": "lines/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(B),
+        "e2e": {"value": lines / (ms_e2e / args.steps * 1e-3), "unit": "lines/s",
+                "h2d_bytes_per_step": int(B * 64 * HWR["W"] * 4 + B * HWR["S"] * 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_fprop_kernel + conv_wgrad_kernel (fprop, dgrad, wgrad)",
+                     "achieved": achieved, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"],
+                     "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
+                     "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
+                     "algorithmic_gflop_per_step": conv_flops / 1e9},
+        "cpu_baseline": cpu}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()

@@ -65,6 +65,7 @@ class ConvDesc(ctypes.Structure):
         ("y_dtype", ctypes.c_int32), ("act", ctypes.c_int32), ("slope", ctypes.c_float),
         ("tile_w", ctypes.c_int32),
         ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
+        ("in_stride_h", ctypes.c_int32), ("in_stride_w", ctypes.c_int32),
         ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64),
     ]
 
@@ -76,6 +77,8 @@ class WgradDesc(ctypes.Structure):
         ("x_pitch", ctypes.c_int32), ("Ho", ctypes.c_int32), ("Wo", ctypes.c_int32), ("Cout", ctypes.c_int32),
         ("gy_pitch", ctypes.c_int32), ("ntaps", ctypes.c_int32),
         ("tap_dh", ctypes.c_int32 * HWG_MAX_TAPS), ("tap_dw", ctypes.c_int32 * HWG_MAX_TAPS),
+        ("Hi", ctypes.c_int32), ("Wi", ctypes.c_int32), ("gy_stride_h", ctypes.c_int32),
+        ("gy_stride_w", ctypes.c_int32), ("gy_off_h", ctypes.c_int32), ("gy_off_w", ctypes.c_int32),
     ]
 
 

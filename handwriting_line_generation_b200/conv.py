@@ -38,7 +38,7 @@ def pack_conv2d_weight(weight, cin_pad=None):
 
 def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
                out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, noise_view=None,
-               noise_seed=None, noise_subseq=0, stats=None, cin=None, tile_w=0):
+               noise_seed=None, noise_subseq=0, stats=None, cin=None, tile_w=0, in_stride=(1, 1)):
     """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
 
     x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
@@ -72,6 +72,7 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
     d.y_dtype = _lib.DT_F32 if y.dtype == torch.float32 else _lib.DT_BF16
     assert y.dtype in (torch.float32, torch.bfloat16)
     d.act, d.slope, d.tile_w = act, slope, tile_w
+    d.in_stride_h, d.in_stride_w = in_stride
     nz_ptr = None
     if noise is not None:
         assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (N, Ho, Wo, Cout)
@@ -119,7 +120,7 @@ def dgrad_pack(w_taps_f32, taps):
     return pack_taps(mats), [(-dh, -dw) for dh, dw in taps]
 
 
-def conv_wgrad(x, gy, taps, cin, cout, out=None):
+def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy_offset=(0, 0)):
     """dw[t][co][ci] = sum_pixels gy[n,ho,wo,co] * x[n,ho+dh_t,wo+dw_t,ci]  (fp32 [ntaps,cout,cin]).
     x [N,H,W,Cp>=cin] bf16 NHWC, gy [N,Ho,Wo,Gp>=cout] bf16 NHWC."""
     _lib.require_cuda(x, gy)
@@ -131,7 +132,17 @@ def conv_wgrad(x, gy, taps, cin, cout, out=None):
     d.N, d.H, d.W, d.Cin, d.x_pitch, d.Ho, d.Wo, d.Cout, d.gy_pitch, d.ntaps = N, H, W, cin, Cp, Ho, Wo, cout, Gp, len(taps)
     for i, (dh, dw) in enumerate(taps):
         d.tap_dh[i], d.tap_dw[i] = dh, dw
+    if grid is not None:   # phase of an up-sampling conv: iterate the input grid, gy read with a stride
+        d.Hi, d.Wi = grid
+        d.gy_stride_h, d.gy_stride_w = gy_stride
+        d.gy_off_h, d.gy_off_w = gy_offset
     if out is None:
         out = torch.zeros((len(taps), cout, cin), device=x.device, dtype=torch.float32)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("hwg_conv_wgrad", ctypes.addressof(d), x.data_ptr(), gy.data_ptr(), out.data_ptr(), _lib.stream())
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * len(taps)))
     return out

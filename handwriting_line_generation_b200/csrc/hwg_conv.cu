@@ -40,6 +40,7 @@ struct ConvKParams {
   int CK, BN, kchunks, ntaps, stages;
   int a_bytes, b_bytes;  // per (tap, chunk) operand tile (b rounded up to 1 KiB)
   int gsize, ngroups;    // (tap, chunk) tiles per pipeline stage / stages per output tile
+  int ish, isw;          // input element strides (strided convolution)
   int wstat;             // 1: all weight tiles stay resident in shared memory (loaded once per CTA)
   int unit_bytes;        // bytes of one (tap, chunk) slot inside a stage: a_bytes (+ b_bytes unless wstat)
   int tmem_cols, acc_stride;
@@ -156,7 +157,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           unsigned char* dst = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], unit_tx * (uint32_t)nsub);
           for (int sub = 0; sub < nsub; ++sub, ++it) {
-            tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.tap_dw[tp], ho0 + p.tap_dh[tp], n);
+            tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 * p.isw + p.tap_dw[tp], ho0 * p.ish + p.tap_dh[tp], n);
             if (!p.wstat) tma_load_2d(dst + p.a_bytes, &tmap_w, &full_bar[stage], kc * p.CK, tp * p.Cout + n0);
             dst += p.unit_bytes;
             if (++kc == p.kchunks) { kc = 0; ++tp; }
@@ -513,6 +514,11 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     }
   }
   HWG_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "hwg_conv_fprop: tile_w=%d", TW);
+  p.ish = d->in_stride_h > 1 ? d->in_stride_h : 1;
+  p.isw = d->in_stride_w > 1 ? d->in_stride_w : 1;
+  HWG_REQUIRE(p.ish <= 8 && p.isw <= 8, "hwg_conv_fprop: input strides up to 8");
+  while (TW * p.isw > 256) TW >>= 1;                 // TMA box limit: 256 traversed elements per dimension
+  HWG_REQUIRE((128 / TW) * p.ish <= 256, "hwg_conv_fprop: tile does not fit the TMA box with these strides");
   p.TW = TW; p.TH = 128 / TW;
   p.tiles_w = (d->Wo + p.TW - 1) / p.TW;
   p.tiles_h = (d->Ho + p.TH - 1) / p.TH;
@@ -567,8 +573,8 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
                              (cuuint64_t)d->H * d->W * d->x_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.CK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.CK, (cuuint32_t)(p.TW * p.isw), (cuuint32_t)(p.TH * p.ish), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p.isw, (cuuint32_t)p.ish, 1};
     CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -26,19 +26,24 @@ constexpr int WG_PIX = 64;  // pixels per K chunk
 struct WgradKParams {
   int Cout, Cin, ntaps;
   int PW, PH, chunks_w, chunks_h, total_chunks, chunks_per_split;
-  int co_tiles, ci_tiles, BN;  // BN = ci tile width (multiple of 64, <= 256)
+  int co_tiles, ci_tiles, BN;  // BN = ci tile width (<= 256)
+  int CBa, CBb;                // channels per TMA box of gy / x (64, 32 or 16 -> 128/64/32-byte swizzle)
+  int gsh, gsw, goh, gow;      // where iteration-grid point (i,j) sits in gy: (i*gsh+goh, j*gsw+gow)
   int stages, a_bytes, b_bytes, tmem_cols;
   int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
   float* dw;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major operand made of TMA boxes {CB channels, 64 pixels}: a pixel row is CB*2 = 128/64/32 bytes (the
+// swizzle span), 8-pixel groups are 8 rows apart (SBO), CB-channel blocks one box apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t row_bytes, uint32_t lbo_bytes) {
+  const uint32_t mode = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // between 64-element MN blocks
-  d |= (uint64_t)(1024u >> 4) << 32;                   // between 8-row K groups
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  d |= (uint64_t)mode << 61;
   return d;
 }
 
@@ -67,8 +72,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
   const int c_begin = blockIdx.x * p.chunks_per_split;
   const int c_end = min(p.total_chunks, c_begin + p.chunks_per_split);
   const int kiters = c_end - c_begin;
-  const int nblk_b = p.BN / 64;
-  const uint32_t box_bytes = WG_PIX * 128;
+  const int nblk_a = 128 / p.CBa, nblk_b = p.BN / p.CBb;
+  const uint32_t boxa_bytes = WG_PIX * p.CBa * 2, boxb_bytes = WG_PIX * p.CBb * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_gy);
@@ -98,11 +103,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         unsigned char* a_dst = smem + (size_t)stage * stage_bytes;
         unsigned char* b_dst = a_dst + p.a_bytes;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + nblk_b) * box_bytes));
-        tma_load_4d(a_dst, &tmap_gy, &full_bar[stage], co0, w0, h0, n);
-        tma_load_4d(a_dst + box_bytes, &tmap_gy, &full_bar[stage], co0 + 64, w0, h0, n);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(nblk_a * boxa_bytes + nblk_b * boxb_bytes));
+        for (int b = 0; b < nblk_a; ++b)   // channel blocks past Cout arrive as zeros
+          tma_load_4d(a_dst + b * boxa_bytes, &tmap_gy, &full_bar[stage], co0 + p.CBa * b, w0 * p.gsw + p.gow,
+                      h0 * p.gsh + p.goh, n);
         for (int b = 0; b < nblk_b; ++b)
-          tma_load_4d(b_dst + b * box_bytes, &tmap_x, &full_bar[stage], ci0 + 64 * b, w0 + dw, h0 + dh, n);
+          tma_load_4d(b_dst + b * boxb_bytes, &tmap_x, &full_bar[stage], ci0 + p.CBb * b, w0 + dw, h0 + dh, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -116,13 +122,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
-        const uint64_t da = umma_desc_mnmajor_sw128(a_addr, box_bytes);
-        const uint64_t db = umma_desc_mnmajor_sw128(b_addr, box_bytes);
+        const uint64_t da = umma_desc_mnmajor(a_addr, (uint32_t)p.CBa * 2u, boxa_bytes);
+        const uint64_t db = umma_desc_mnmajor(b_addr, (uint32_t)p.CBb * 2u, boxb_bytes);
+        // 16 pixels = two 8-row groups = 16 rows further into the box (start address is in 16-byte units)
+        const uint64_t ka = (uint64_t)(p.CBa * 2), kb = (uint64_t)(p.CBb * 2);
 #pragma unroll
-        for (int kk = 0; kk < WG_PIX / 16; ++kk) {
-          // 16 pixels = two 8-row groups = 2 KiB further into the box (>>4 -> +128)
-          umma_bf16(tmem_base, da + (uint64_t)(kk * 128), db + (uint64_t)(kk * 128), idesc, (it | kk) != 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < WG_PIX / 16; ++kk)
+          umma_bf16(tmem_base, da + kk * ka, db + kk * kb, idesc, (it | kk) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (it == kiters - 1) umma_commit(tmem_full);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -142,8 +148,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
       if (co < p.Cout) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                     __uint_as_float(r[j + 3]));
+          if (c0 + j < p.BN)
+            red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                       __uint_as_float(r[j + 3]));
       }
     }
     tc_fence_before();
@@ -173,13 +180,15 @@ static PFN_encodeTiled wg_get_encode() {
 }
 
 static int encode_nhwc(PFN_encodeTiled encode, CUtensorMap* tm, const void* base, int C, int W, int H, int N,
-                       int pitch, int PW, int PH, const char* what) {
+                       int pitch, int CB, int PW, int PH, int sw, int sh, const char* what) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)PW, (cuuint32_t)PH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)(PW * sw), (cuuint32_t)(PH * sh), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+  const CUtensorMapSwizzle swz = CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("hwg_conv_wgrad: cuTensorMapEncodeTiled(%s) failed (%d)", what, (int)r); return HWG_ERR_CUDA; }
   return HWG_OK;
@@ -192,8 +201,10 @@ using namespace hwg;
 extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* gy, float* dw, void* stream) {
   HWG_REQUIRE(d && x && gy && dw, "hwg_conv_wgrad: null pointer");
   HWG_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Ho > 0 && d->Wo > 0, "hwg_conv_wgrad: empty extent");
-  HWG_REQUIRE(d->Cin >= 64 && d->Cin % 64 == 0, "hwg_conv_wgrad: Cin=%d must be a multiple of 64", d->Cin);
-  HWG_REQUIRE(d->Cout >= 8 && d->Cout % 8 == 0, "hwg_conv_wgrad: Cout=%d must be a multiple of 8", d->Cout);
+  HWG_REQUIRE(d->Cin == 16 || d->Cin == 32 || (d->Cin >= 64 && d->Cin % 64 == 0),
+              "hwg_conv_wgrad: Cin=%d must be 16, 32 or a multiple of 64", d->Cin);
+  HWG_REQUIRE(d->Cout == 16 || d->Cout == 32 || (d->Cout >= 64 && d->Cout % 8 == 0),
+              "hwg_conv_wgrad: Cout=%d must be 16, 32 or a multiple of 8 >= 64", d->Cout);
   HWG_REQUIRE(d->x_pitch >= d->Cin && d->x_pitch % 8 == 0 && d->gy_pitch >= d->Cout && d->gy_pitch % 8 == 0,
               "hwg_conv_wgrad: bad channel pitch");
   HWG_REQUIRE(d->ntaps >= 1 && d->ntaps <= HWG_MAX_TAPS, "hwg_conv_wgrad: ntaps=%d", d->ntaps);
@@ -206,18 +217,24 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
   memset(&p, 0, sizeof(p));
   p.Cout = d->Cout; p.Cin = d->Cin; p.ntaps = d->ntaps;
   // 64-pixel K chunks: as wide as the output row allows
+  const int Hi = d->Hi > 0 ? d->Hi : d->Ho, Wi = d->Wi > 0 ? d->Wi : d->Wo;
+  p.gsh = d->gy_stride_h > 1 ? d->gy_stride_h : 1;
+  p.gsw = d->gy_stride_w > 1 ? d->gy_stride_w : 1;
+  p.goh = d->gy_off_h; p.gow = d->gy_off_w;
+  HWG_REQUIRE(p.gsh <= 4 && p.gsw <= 4, "hwg_conv_wgrad: gy strides up to 4");
   int PW = 64;
-  while (PW > 8 && PW / 2 >= d->Wo) PW >>= 1;
+  while (PW > 8 && PW / 2 >= Wi) PW >>= 1;
   p.PW = PW; p.PH = WG_PIX / PW;
-  p.chunks_w = (d->Wo + p.PW - 1) / p.PW;
-  p.chunks_h = (d->Ho + p.PH - 1) / p.PH;
+  p.chunks_w = (Wi + p.PW - 1) / p.PW;
+  p.chunks_h = (Hi + p.PH - 1) / p.PH;
   p.total_chunks = p.chunks_w * p.chunks_h * d->N;
   p.co_tiles = (d->Cout + 127) / 128;
-  p.BN = d->Cin % 256 == 0 ? 256 : (d->Cin % 128 == 0 ? 128 : 64);
-  if (p.BN > d->Cin) p.BN = d->Cin;
+  p.BN = d->Cin % 256 == 0 ? 256 : (d->Cin % 128 == 0 ? 128 : (d->Cin >= 64 ? 64 : d->Cin));
   p.ci_tiles = d->Cin / p.BN;
-  p.a_bytes = 2 * WG_PIX * 128;
-  p.b_bytes = (p.BN / 64) * WG_PIX * 128;
+  p.CBa = d->Cout >= 64 ? 64 : d->Cout;
+  p.CBb = d->Cin >= 64 ? 64 : d->Cin;
+  p.a_bytes = 128 * WG_PIX * 2;            // always 128 output-channel rows (blocks past Cout are zero-filled)
+  p.b_bytes = p.BN * WG_PIX * 2;
   const int stage_bytes = p.a_bytes + p.b_bytes;
   p.stages = (190 * 1024) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
@@ -233,9 +250,9 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
   splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
 
   CUtensorMap tmg, tmx;
-  int rc = encode_nhwc(encode, &tmg, gy, d->Cout, d->Wo, d->Ho, d->N, d->gy_pitch, p.PW, p.PH, "gy");
+  int rc = encode_nhwc(encode, &tmg, gy, d->Cout, d->Wo, d->Ho, d->N, d->gy_pitch, p.CBa, p.PW, p.PH, p.gsw, p.gsh, "gy");
   if (rc) return rc;
-  rc = encode_nhwc(encode, &tmx, x, d->Cin, d->W, d->H, d->N, d->x_pitch, p.PW, p.PH, "x");
+  rc = encode_nhwc(encode, &tmx, x, d->Cin, d->W, d->H, d->N, d->x_pitch, p.CBb, p.PW, p.PH, 1, 1, "x");
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
   HWG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -147,6 +147,8 @@ typedef struct hwgConvDesc {
   float slope;            /* LeakyReLU negative slope */
   int32_t tile_w;         /* 0 = auto; else output-tile width (8..128, power of 2) */
   int64_t nz_stride_n, nz_stride_h, nz_stride_w; /* noise tensor strides, elements */
+  int32_t in_stride_h, in_stride_w; /* 0/1 = dense; s>1: tap t reads x[n, ho*s_h+dh[t], wo*s_w+dw[t], :]
+                                       (strided convolution = the input gradient of a stride-s transposed conv) */
   uint64_t noise_seed;    /* in-kernel N(0,1) noise (counter-based hash + Box-Muller) when noise == NULL and noise_w != NULL */
   uint64_t noise_subseq;  /* distinguishes launches that share a seed */
 } hwgConvDesc;
@@ -232,7 +234,8 @@ int hwg_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh,
  * as a tcgen05 GEMM with M = Cout tile (128), N = Cin tile (<= 256), K = pixels, both
  * operands MN-major straight from the NHWC tensors via TMA (zero fill outside x = padding),
  * split over pixel ranges with fp32 vector reductions (red.global.add.v4.f32) into dw.
- * x  bf16 NHWC [N,H,W,x_pitch], Cin multiple of 64;  gy bf16 NHWC [N,Ho,Wo,gy_pitch]
+ * x  bf16 NHWC [N,H,W,x_pitch], Cin in {16, 32} or a multiple of 64;  gy bf16 NHWC [N,Ho,Wo,gy_pitch],
+ * Cout in {16, 32} or a multiple of 8 >= 64
  * dw fp32 [ntaps][Cout][Cin], ACCUMULATED into (caller zeroes it).
  * ---------------------------------------------------------------------- */
 typedef struct hwgWgradDesc {
@@ -241,6 +244,10 @@ typedef struct hwgWgradDesc {
   int32_t ntaps;
   int32_t tap_dh[HWG_MAX_TAPS];
   int32_t tap_dw[HWG_MAX_TAPS];
+  /* Iteration grid (0 = Ho x Wo) and where grid point (i,j) sits in gy: gy[n, i*gy_stride_h+gy_off_h,
+   * j*gy_stride_w+gy_off_w, :] pairs with x[n, i+dh, j+dw, :].  Strides > 1 give the weight gradient of one
+   * output phase of an up-sampling convolution (pure_gen.py:176-186, 259-279). */
+  int32_t Hi, Wi, gy_stride_h, gy_stride_w, gy_off_h, gy_off_w;
 } hwgWgradDesc;
 
 int hwg_conv_wgrad(const hwgWgradDesc* desc, const void* x, const void* gy, float* dw, void* stream);

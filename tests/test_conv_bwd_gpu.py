@@ -50,3 +50,65 @@ def test_dgrad_and_wgrad_match_autograd(case):
     dw = conv.conv_wgrad(xc, gyc, taps, Cin, Cout)                     # [ntaps, Cout, Cin]
     got = dw.view(k[0], k[1], Cout, Cin).permute(2, 3, 0, 1).cpu().double()
     assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 32, 12, 40, (2, 2)), (1, 32, 16, 16, 64, (2, 2)), (2, 128, 64, 8, 50, (2, 1))])
+def test_strided_input_conv(case):
+    """in_stride: y[ho,wo] = sum_t x[s*ho+dh, s*wo+dw] w_t — a stride-s convolution (TMA element strides), which is
+    the input gradient of the generator's stride-2 transposed / up-sampling convolutions."""
+    from handwriting_line_generation_b200 import conv
+    N, Cin, Cout, H, W, st = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).double()
+    w = (torch.randn(Cout, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5).to(torch.bfloat16).double()
+    ref = F.conv2d(x, w, stride=st, padding=1)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    taps = [(i - 1, j - 1) for i in range(4) for j in range(4)]
+    y = conv.conv_fprop(conv.to_nhwc_bf16(x.float().cuda()), conv.pack_conv2d_weight(w.float().cuda()), taps, Ho, Wo,
+                        out_dtype=torch.float32, in_stride=st)
+    assert _rel(y.permute(0, 3, 1, 2).cpu().double(), ref) <= TOL
+
+
+@pytest.mark.parametrize("Cin,Cout", [(16, 16), (32, 16), (32, 32), (64, 32), (16, 64), (256, 128)])
+def test_wgrad_small_channels(Cin, Cout):
+    """16/32-channel operands: 32/64-byte swizzled MN-major boxes, output-channel blocks past Cout zero-filled."""
+    from handwriting_line_generation_b200 import conv
+    N, H, W = 2, 20, 72
+    g = torch.Generator().manual_seed(Cin * 100 + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).double()
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, padding=1)
+    gy = torch.randn(y.shape, generator=g).to(torch.bfloat16).double()
+    (gw_ref,) = torch.autograd.grad(y, w, gy)
+    dw = conv.conv_wgrad(conv.to_nhwc_bf16(x.float().cuda()), conv.to_nhwc_bf16(gy.float().cuda()),
+                         conv.conv_taps(3, 3, 1, 1), Cin, Cout)
+    got = dw.view(3, 3, Cout, Cin).permute(2, 3, 0, 1).cpu().double()
+    assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)
+
+
+@pytest.mark.parametrize("Cin,Cout", [(64, 32), (32, 16)])
+def test_wgrad_of_transposed_conv_phases(Cin, Cout):
+    """Weight gradient of conv_transpose2d(stride 2, pad 1, 4x4) (FusedUpsample, pure_gen.py:277) as four
+    output-parity launches reading gy with stride 2."""
+    from handwriting_line_generation_b200 import conv
+    N, H, W = 2, 10, 36
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).double()
+    w4 = torch.zeros(Cin, Cout, 4, 4, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose2d(x, w4, stride=2, padding=1)
+    gy = torch.randn(y.shape, generator=g).to(torch.bfloat16).double()
+    (gw_ref,) = torch.autograd.grad(y, w4, gy)          # [Cin, Cout, 4, 4]
+    xc, gyc = conv.to_nhwc_bf16(x.float().cuda()), conv.to_nhwc_bf16(gy.float().cuda())
+    sel = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}   # parity -> [(input offset, kernel index)]
+    got = torch.zeros_like(gw_ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            taps, idx = [], []
+            for dh, ky in sel[py]:
+                for dw, kx in sel[px]:
+                    taps.append((dh, dw))
+                    idx.append((ky, kx))
+            dw_ = conv.conv_wgrad(xc, gyc, taps, Cin, Cout, grid=(H, W), gy_stride=(2, 2), gy_offset=(py, px)).cpu().double()
+            for t, (ky, kx) in enumerate(idx):
+                got[:, :, ky, kx] = dw_[t].t()
+    assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)
