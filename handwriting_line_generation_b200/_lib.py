@@ -37,7 +37,11 @@ _SIGNATURES = {
     "hwg_linear_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "hwg_pixelnorm_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
     "hwg_gen_pack_input": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
-    "hwg_adain_coeffs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f, c_vp, c_vp]),
+    "hwg_adain_coeffs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
+    "hwg_adain_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
+    "hwg_adain_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp,
+                                    ctypes.c_uint64, ctypes.c_uint64, c_int, c_vp, c_vp, c_vp]),
+    "hwg_gen_output_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "hwg_bn_coeffs": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_int, c_vp, c_vp, c_vp]),
     "hwg_scale_shift_act": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_f, c_vp]),
     "hwg_blur_noise_act_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, ctypes.c_uint64,

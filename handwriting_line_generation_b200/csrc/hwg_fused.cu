@@ -80,15 +80,17 @@ __global__ void gen_pack_input_kernel(const float* __restrict__ content, long lo
 // ---- normalisation coefficients -------------------------------------------------------------
 __global__ void adain_coeffs_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, long long gbs, int N, int C, float inv_hw,
-                                    float eps, float* __restrict__ coef) {
+                                    float eps, float* __restrict__ coef, float* __restrict__ save) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i - n * C;
   const float mean = stats[2 * i] * inv_hw;
   const float var = fmaxf(stats[2 * i + 1] * inv_hw - mean * mean, 0.f);
-  const float a = gamma[n * gbs + c] * rsqrtf(var + eps);
+  const float rstd = rsqrtf(var + eps);
+  const float a = gamma[n * gbs + c] * rstd;
   coef[2 * i] = a;
   coef[2 * i + 1] = beta[n * gbs + c] - mean * a;
+  if (save) { save[2 * i] = mean; save[2 * i + 1] = rstd; }
 }
 
 __global__ void bn_coeffs_kernel(const float* __restrict__ stats, int N, int C, float count,
@@ -385,10 +387,10 @@ extern "C" int hwg_gen_pack_input(const float* content, int64_t cs_t, int64_t cs
 
 extern "C" int hwg_adain_coeffs(const float* stats, const float* gamma, const float* beta,
                                 int64_t gb_stride_n, int N, int C, int HW, float eps, float* coef,
-                                void* stream) {
+                                float* save_mean_rstd, void* stream) {
   HWG_REQUIRE(stats && gamma && beta && coef && N > 0 && C > 0 && HW > 0, "hwg_adain_coeffs: bad argument");
   adain_coeffs_kernel<<<blocks_for((long long)N * C, 256), 256, 0, (cudaStream_t)stream>>>(
-      stats, gamma, beta, gb_stride_n, N, C, 1.0f / (float)HW, eps, coef);
+      stats, gamma, beta, gb_stride_n, N, C, 1.0f / (float)HW, eps, coef, save_mean_rstd);
   return check_launch("adain_coeffs_kernel");
 }
 

@@ -1,6 +1,7 @@
 // HBM-bound backward passes of the recognizer (sm_100a): NHWC bf16 gradients, 16-byte vectors of
 // 8 channels per thread, per-channel reductions folded warp -> shared -> one global atomic per block.
 #include "common.cuh"
+#include "noise_rng.cuh"
 #include <math_constants.h>
 
 namespace hwg {
@@ -321,6 +322,155 @@ hwr_stem_bwd_kernel(const float* __restrict__ img, const float* __restrict__ w, 
   }
 }
 
+
+// ---- generator: AdaIN + LeakyReLU (+ noise weight) backward ------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS)
+adain_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a, const float* __restrict__ save,
+                        long long HW, int C, float* __restrict__ sums) {
+  extern __shared__ float sacc[];  // [2][C]
+  const int n = blockIdx.y, CV = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const size_t i = ((size_t)n * C + cv * 8 + j) * 2;
+    mean[j] = save[i]; rstd[j] = save[i + 1];
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const long long total = HW * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  const uint4* gn = g + (size_t)n * total;
+  const uint4* an = a + (size_t)n * total;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    float gf[8], af[8];
+    unpack8b(gn[item], gf);
+    unpack8b(an[item], af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += gf[j];
+      acc[1][j] += gf[j] * (af[j] - mean[j]) * rstd[j];
+    }
+  }
+  channel_reduce<2>(acc, cv, CV, C, sacc, sums + (size_t)n * C * 2, 2);
+}
+
+__global__ void __launch_bounds__(BW_THREADS)
+adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a, const float* __restrict__ save,
+                       const float* __restrict__ coef, const float* __restrict__ sums, int H, int W, int C,
+                       float slope, const float* __restrict__ noise, unsigned long long seed,
+                       unsigned long long subseq, int row_subseq, uint4* __restrict__ gy,
+                       float* __restrict__ dch) {
+  extern __shared__ float sacc[];  // [2][C]
+  const int n = blockIdx.y, CV = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  const long long HW = (long long)H * W;
+  const float inv = 1.f / (float)HW;
+  float mean[8], rstd[8], A[8], k0[8], k1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const size_t i = ((size_t)n * C + cv * 8 + j) * 2;
+    mean[j] = save[i]; rstd[j] = save[i + 1];
+    A[j] = coef[i];
+    k0[j] = sums[i] * inv; k1[j] = sums[i + 1] * inv;
+  }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  const uint2 nkey = noise_key(seed, subseq);
+  const long long total = HW * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  const uint4* gn = g + (size_t)n * total;
+  const uint4* an = a + (size_t)n * total;
+  uint4* yn = gy + (size_t)n * total;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    float gf[8], af[8], o[8], z[8];
+    unpack8b(gn[item], gf);
+    unpack8b(an[item], af);
+    if (noise) {
+      const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
+      const float4 z0 = zp[0], z1 = zp[1];
+      z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+    } else {
+      unsigned long long e;   // element index of channel cv*8 in the forward launch's numbering
+      uint2 key = nkey;
+      if (row_subseq) {
+        const long long pix = item / CV;
+        const int h = (int)(pix / W), w = (int)(pix - (long long)h * W);
+        key = noise_key(seed, subseq + (unsigned long long)h);
+        e = ((unsigned long long)n * W + w) * (unsigned long long)C + cv * 8;
+      } else {
+        e = ((unsigned long long)n * total + item) * 8ull;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 zz = normal_pair(key, (e >> 1) + q);
+        z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ah = (af[j] - mean[j]) * rstd[j];
+      const float ga = A[j] * (gf[j] - k0[j] - ah * k1[j]);
+      o[j] = af[j] > 0.f ? ga : ga * slope;
+      acc[0][j] += o[j];
+      acc[1][j] = fmaf(o[j], z[j], acc[1][j]);
+    }
+    yn[item] = pack8b(o);
+  }
+  channel_reduce<2>(acc, cv, CV, C, sacc, dch, 2);
+}
+
+// ---- generator output backward ----------------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS)
+gen_output_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ out, const uint4* __restrict__ a,
+                      const float* __restrict__ coef, const float* __restrict__ w, long long HW, int C,
+                      uint4* __restrict__ gx, float* __restrict__ dwb) {
+  extern __shared__ float sm[];  // A[C], B[C], w[C], acc[C+1]
+  const int n = blockIdx.y, CV = C / 8;
+  float* As = sm; float* Bs = sm + C; float* ws = sm + 2 * C; float* accs = sm + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    As[c] = coef[((size_t)n * C + c) * 2]; Bs[c] = coef[((size_t)n * C + c) * 2 + 1]; ws[c] = w[c];
+  }
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) accs[c] = 0.f;
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pix < HW;
+  float gp = 0.f;
+  if (valid) {
+    const float o = out[(size_t)n * HW + pix];
+    gp = g_out[(size_t)n * HW + pix] * (1.f - o * o);
+  }
+  const uint4* ap = a + ((size_t)n * HW + (valid ? pix : 0)) * CV;
+  uint4* gp_out = gx + ((size_t)n * HW + (valid ? pix : 0)) * CV;
+  for (int v = 0; v < CV; ++v) {   // every lane runs the same warp reductions; tail lanes contribute zeros
+    float af[8], o8[8];
+    unpack8b(ap[v], af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      o8[j] = ws[c] * gp;
+      // dw[c] += gp * x_last[c]: warp-reduce, then one shared atomic per warp
+      const float t = warp_sum(gp * fmaf(As[c], af[j], Bs[c]));
+      if ((threadIdx.x & 31) == 0) atomicAdd(&accs[c], t);
+    }
+    if (valid) gp_out[v] = pack8b(o8);
+  }
+  const float s = warp_sum(gp);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&accs[C], s);
+  __syncthreads();
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) atomicAdd(&dwb[c], accs[c]);
+}
+
 static inline unsigned bw_blocks(long long items, int per_block) {
   return (unsigned)((items + per_block - 1) / per_block);
 }
@@ -389,4 +539,37 @@ extern "C" int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b
   hwr_stem_bwd_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)Cout * 20 * sizeof(float),
                         (cudaStream_t)stream>>>(img, w, b, reinterpret_cast<const uint4*>(ga), N, H, W, Cout, dw, db);
   return check_launch("hwr_stem_bwd_kernel");
+}
+
+extern "C" int hwg_adain_bwd_reduce(const void* g, const void* a, const float* save, int N, int64_t HW, int C,
+                                    float* sums, void* stream) {
+  HWG_REQUIRE(g && a && save && sums && N > 0 && HW > 0, "hwg_adain_bwd_reduce: bad argument");
+  HWG_REQUIRE(cv_ok(C), "hwg_adain_bwd_reduce: C=%d must be 8 x a power of two", C);
+  dim3 grid(bw_blocks(HW * (C / 8), BW_THREADS * BW_ITER), N);
+  adain_bwd_reduce_kernel<<<grid, BW_THREADS, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(a), save, HW, C, sums);
+  return check_launch("adain_bwd_reduce_kernel");
+}
+
+extern "C" int hwg_adain_bwd_apply(const void* g, const void* a, const float* save, const float* coef,
+                                   const float* sums, int N, int H, int W, int C, float slope, const float* noise,
+                                   uint64_t noise_seed, uint64_t noise_subseq, int row_subseq, void* gy, float* dch,
+                                   void* stream) {
+  HWG_REQUIRE(g && a && save && coef && sums && gy && dch && N > 0 && H > 0 && W > 0, "hwg_adain_bwd_apply: bad argument");
+  HWG_REQUIRE(cv_ok(C), "hwg_adain_bwd_apply: C=%d must be 8 x a power of two", C);
+  dim3 grid(bw_blocks((long long)H * W * (C / 8), BW_THREADS * BW_ITER), N);
+  adain_bwd_apply_kernel<<<grid, BW_THREADS, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(a), save, coef, sums, H, W, C, slope, noise,
+      noise_seed, noise_subseq, row_subseq, reinterpret_cast<uint4*>(gy), dch);
+  return check_launch("adain_bwd_apply_kernel");
+}
+
+extern "C" int hwg_gen_output_bwd(const float* g_out, const float* out, const void* a, const float* coef,
+                                  const float* w, int N, int64_t HW, int C, void* gx, float* dwb, void* stream) {
+  HWG_REQUIRE(g_out && out && a && coef && w && gx && dwb && N > 0 && HW > 0 && C % 8 == 0,
+              "hwg_gen_output_bwd: bad argument");
+  dim3 grid(bw_blocks(HW, BW_THREADS), N);
+  gen_output_bwd_kernel<<<grid, BW_THREADS, (size_t)(4 * C + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, C, reinterpret_cast<uint4*>(gx), dwb);
+  return check_launch("gen_output_bwd_kernel");
 }

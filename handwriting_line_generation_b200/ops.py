@@ -30,11 +30,12 @@ def gen_pack_input(content, style, Cp):
     return x
 
 
-def adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps=1e-5):
+def adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps=1e-5, save=False):
     coef = torch.empty((N, C, 2), device=stats.device, dtype=torch.float32)
+    sv = torch.empty((N, C, 2), device=stats.device, dtype=torch.float32) if save else None
     _lib.call("hwg_adain_coeffs", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gb_stride, N, C, HW, eps,
-              coef.data_ptr(), _lib.stream())
-    return coef
+              coef.data_ptr(), _lib.ptr(sv), _lib.stream())
+    return (coef, sv) if save else coef
 
 
 def bn_coeffs(stats, N, C, count_per_n, weight, bias, running_mean, running_var, momentum, eps, use_batch_stats):
@@ -133,3 +134,28 @@ def hwr_stem_bwd(img, w, b, ga):
     _lib.call("hwg_hwr_stem_bwd", img.data_ptr(), w.data_ptr(), b.data_ptr(), ga.data_ptr(), N, H, W, Cout, dw.data_ptr(),
               db.data_ptr(), _lib.stream())
     return dw, db
+
+
+def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, row_subseq=False):
+    """Backward of x_next = AdaIN(LeakyReLU(y)), y = pre + nw*z.  g, a [N,H,W,C] bf16.
+    Returns (gy bf16, dgamma [N,C], dbeta [N,C], dbias [C] = sum gy, dnoise_w [C] = sum gy*z)."""
+    N, H, W, C = a.shape
+    sums = torch.zeros((N, C, 2), device=a.device, dtype=torch.float32)
+    _lib.call("hwg_adain_bwd_reduce", g.data_ptr(), a.data_ptr(), save.data_ptr(), N, H * W, C, sums.data_ptr(),
+              _lib.stream())
+    gy = torch.empty_like(a)
+    dch = torch.zeros((C, 2), device=a.device, dtype=torch.float32)
+    _lib.call("hwg_adain_bwd_apply", g.data_ptr(), a.data_ptr(), save.data_ptr(), coef.data_ptr(), sums.data_ptr(),
+              N, H, W, C, slope, _lib.ptr(noise), seed, subseq, int(row_subseq), gy.data_ptr(), dch.data_ptr(),
+              _lib.stream())
+    return gy, sums[:, :, 1], sums[:, :, 0], dch[:, 0], dch[:, 1]
+
+
+def gen_output_bwd(g_out, out, a, coef, w):
+    """Returns (gx [N,H,W,C] bf16, dw [C], db0 [])."""
+    N, H, W, C = a.shape
+    gx = torch.empty_like(a)
+    dwb = torch.zeros(C + 1, device=a.device, dtype=torch.float32)
+    _lib.call("hwg_gen_output_bwd", g_out.data_ptr(), out.data_ptr(), a.data_ptr(), coef.data_ptr(), w.data_ptr(),
+              N, H * W, C, gx.data_ptr(), dwb.data_ptr(), _lib.stream())
+    return gx, dwb[:C], dwb[C]

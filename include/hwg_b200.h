@@ -187,6 +187,7 @@ int hwg_gen_pack_input(const float* content, int64_t cs_t, int64_t cs_b, int64_t
  * a = gamma*rstd, b = beta - mean*a, so that AdaIN(x) = a*x + b. */
 int hwg_adain_coeffs(const float* stats, const float* gamma, const float* beta,
                      int64_t gb_stride_n, int N, int C, int HW, float eps, float* coef,
+                     float* save_mean_rstd /* [N,C,2] or NULL: kept for the backward */,
                      void* stream);
 
 /* BatchNorm coefficients (nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79): training
@@ -285,6 +286,33 @@ int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H, int W, int
  * from ga [N,H/2,W/2,Cout] bf16 and the fp32 image (pre-activations are recomputed). */
 int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b, const void* ga, int N, int H, int W,
                      int Cout, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Memory-bound backward passes of the generator.
+ * Half-block forward (pure_gen.py:205-214):  y = conv(+blur) + nw*z ; a = LeakyReLU(y) ;
+ * x_next = gamma*IN(a)+beta = A*a + B  with A = gamma*rstd.
+ * ---------------------------------------------------------------------- */
+
+/* pass 1: sums[n,c] = (sum_hw g, sum_hw g*ahat), ahat = (a-mean)*rstd.  g, a [N,H,W,C] bf16;
+ * save [N,C,2] = (mean, rstd).  sums [N,C,2] accumulated (caller zeroes): sums[...,0] = dbeta,
+ * sums[...,1] = dgamma. */
+int hwg_adain_bwd_reduce(const void* g, const void* a, const float* save, int N, int64_t HW, int C,
+                         float* sums, void* stream);
+/* pass 2: ga = A*(g - s0/HW - ahat*s1/HW); gy = ga * (a > 0 ? 1 : slope) -> bf16 [N,H,W,C];
+ * dch[c] = (sum gy  [= conv bias gradient when no blur follows],  sum gy*z [= noise weight gradient]),
+ * accumulated (caller zeroes).  z is the forward's noise: `noise` tensor (fp32 NHWC) or regenerated from
+ * (noise_seed, noise_subseq); row_subseq != 0 reproduces the per-output-row launches of the initial
+ * transposed conv (subsequence = noise_subseq + h, element index without h). */
+int hwg_adain_bwd_apply(const void* g, const void* a, const float* save, const float* coef,
+                        const float* sums, int N, int H, int W, int C, float slope,
+                        const float* noise, uint64_t noise_seed, uint64_t noise_subseq, int row_subseq,
+                        void* gy, float* dch, void* stream);
+
+/* Generator output backward (pure_gen.py:29,50): out = tanh(sum_c w[c]*(A*a+B)[c] + b0).
+ * g_out, out [N,1,H,W] fp32; a [N,H,W,C] bf16; coef [N,C,2] = (A,B).  Writes gx [N,H,W,C] bf16 = gradient
+ * w.r.t. the (virtual) AdaIN output; accumulates dw[c] and db0 (caller zeroes; dwb = [C+1] floats). */
+int hwg_gen_output_bwd(const float* g_out, const float* out, const void* a, const float* coef,
+                       const float* w, int N, int64_t HW, int C, void* gx, float* dwb, void* stream);
 
 #ifdef __cplusplus
 }
