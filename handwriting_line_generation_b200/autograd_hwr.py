@@ -116,8 +116,8 @@ def _w4(dw, kh, kw):
     return dw.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
 
 
-def backward_train(m, ctx, g_lp):
-    """Returns {parameter name: gradient} for every parameter of the module."""
+def backward_train(m, ctx, g_lp, want_input_grad=False):
+    """Returns ({parameter name: gradient} for every parameter of the module, image gradient or None)."""
     dg = _dgrad_packs(m)
     grads = {}
     lp = ctx["lp"]
@@ -191,7 +191,20 @@ def backward_train(m, ctx, g_lp):
     dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g)
     grads["cnn.conv0.weight"] = dw0.view(64, 1, 3, 3)
     grads["cnn.conv0.bias"] = db0
-    return grads
+    g_img = None
+    if want_input_grad:
+        # image gradient (GAN lessons): route g through pool/ReLU to conv0's output, then the 9-tap dgrad with
+        # conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] tensor-core convolution
+        gc0 = ops.hwr_stem_bwd_expand(ctx["x"], c["w0"], c["b0"], g)
+        w0 = m.cnn.conv0.weight.detach().float()                       # [64,1,3,3]
+        mats = [torch.nn.functional.pad(w0[:, 0, i, j].view(1, 64), (0, 0, 0, 15)) for i in range(3) for j in range(3)]
+        taps = [(1 - i, 1 - j) for i in range(3) for j in range(3)]
+        gi = conv.conv_fprop(gc0, conv.pack_taps(mats), taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
+        g_img = gi[..., 0].unsqueeze(1).contiguous()
+        if m.pad is not None:
+            p = m.pad.padding
+            g_img = g_img[:, :, :, p[0]:g_img.size(3) - p[1]].contiguous()
+    return grads, g_img
 
 
 class _HWRFn(torch.autograd.Function):
@@ -205,13 +218,10 @@ class _HWRFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.x_needs_grad:
-            raise NotImplementedError("gradient w.r.t. the recognizer's input image (GAN lessons) is not built yet; "
-                                      "there is deliberately no PyTorch fallback")
         with torch.no_grad():
-            grads = backward_train(ctx.module, ctx.saved, g)
+            grads, g_img = backward_train(ctx.module, ctx.saved, g, ctx.x_needs_grad)
         ctx.saved = None
-        return (None, None, None) + tuple(grads[n] for n in ctx.names)
+        return (None, None, g_img) + tuple(grads[n] for n in ctx.names)
 
 
 def hwr_apply(module, input):

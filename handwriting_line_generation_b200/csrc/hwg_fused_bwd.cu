@@ -471,6 +471,63 @@ gen_output_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
   for (int c = threadIdx.x; c <= C; c += blockDim.x) atomicAdd(&dwb[c], accs[c]);
 }
 
+// thread = (pooled pixel, 8-channel group): writes the four conv0-output gradients of its 2x2 window
+__global__ void __launch_bounds__(BW_THREADS)
+hwr_stem_bwd_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                           const uint4* __restrict__ ga, int N, int H, int W, int Cout, uint4* __restrict__ gc0) {
+  extern __shared__ float sm[];  // w [Cout*9], b [Cout]
+  float* ws = sm;
+  float* bs = sm + Cout * 9;
+  for (int i = threadIdx.x; i < Cout * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = b[i];
+  __syncthreads();
+  const int CV = Cout / 8, Hp = H / 2, Wp = W / 2;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)N * Hp * Wp * CV) return;
+  const int cv = (int)(item % CV);
+  long long pix = item / CV;
+  const int wp = (int)(pix % Wp); pix /= Wp;
+  const int hp = (int)(pix % Hp);
+  const int n = (int)(pix / Hp);
+  float patch[4][4];
+  const float* im = img + (size_t)n * H * W;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int hh = 2 * hp - 1 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ww = 2 * wp - 1 + j;
+      patch[i][j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? im[(size_t)hh * W + ww] : 0.f;
+    }
+  }
+  float gf[8], o[4][8];
+  unpack8b(ga[item], gf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float* k = ws + (cv * 8 + j) * 9;
+    float m = -CUDART_INF_F; int best = 0;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        float a = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(k[ky * 3 + kx], patch[oy + ky][ox + kx], a);
+        if (a > m) { m = a; best = oy * 2 + ox; }
+      }
+    const float gv = (m + bs[cv * 8 + j] > 0.f) ? gf[j] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q][j] = (q == best) ? gv : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int hh = 2 * hp + (q >> 1), ww = 2 * wp + (q & 1);
+    gc0[(((size_t)n * H + hh) * W + ww) * CV + cv] = pack8b(o[q]);
+  }
+}
+
 static inline unsigned bw_blocks(long long items, int per_block) {
   return (unsigned)((items + per_block - 1) / per_block);
 }
@@ -572,4 +629,15 @@ extern "C" int hwg_gen_output_bwd(const float* g_out, const float* out, const vo
   gen_output_bwd_kernel<<<grid, BW_THREADS, (size_t)(4 * C + 1) * sizeof(float), (cudaStream_t)stream>>>(
       g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, C, reinterpret_cast<uint4*>(gx), dwb);
   return check_launch("gen_output_bwd_kernel");
+}
+
+extern "C" int hwg_hwr_stem_bwd_expand(const float* img, const float* w, const float* b, const void* ga, int N,
+                                       int H, int W, int Cout, void* gc0, void* stream) {
+  HWG_REQUIRE(img && w && b && ga && gc0 && N > 0, "hwg_hwr_stem_bwd_expand: bad argument");
+  HWG_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cout % 8 == 0, "hwg_hwr_stem_bwd_expand: bad geometry");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (Cout / 8);
+  hwr_stem_bwd_expand_kernel<<<bw_blocks(total, BW_THREADS), BW_THREADS, (size_t)Cout * 10 * sizeof(float),
+                               (cudaStream_t)stream>>>(img, w, b, reinterpret_cast<const uint4*>(ga), N, H, W, Cout,
+                                                       reinterpret_cast<uint4*>(gc0));
+  return check_launch("hwr_stem_bwd_expand_kernel");
 }

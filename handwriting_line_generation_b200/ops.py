@@ -159,3 +159,13 @@ def gen_output_bwd(g_out, out, a, coef, w):
     _lib.call("hwg_gen_output_bwd", g_out.data_ptr(), out.data_ptr(), a.data_ptr(), coef.data_ptr(), w.data_ptr(),
               N, H * W, C, gx.data_ptr(), dwb.data_ptr(), _lib.stream())
     return gx, dwb[:C], dwb[C]
+
+
+def hwr_stem_bwd_expand(img, w, b, ga):
+    """ga [N,H/2,W/2,Cout] bf16 -> gradient w.r.t. conv0's output [N,H,W,Cout] bf16."""
+    N, _, H, W = img.shape
+    Cout = w.size(0)
+    gc0 = torch.empty((N, H, W, Cout), device=img.device, dtype=torch.bfloat16)
+    _lib.call("hwg_hwr_stem_bwd_expand", img.data_ptr(), w.data_ptr(), b.data_ptr(), ga.data_ptr(), N, H, W, Cout,
+              gc0.data_ptr(), _lib.stream())
+    return gc0

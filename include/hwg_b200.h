@@ -286,6 +286,12 @@ int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H, int W, int
  * from ga [N,H/2,W/2,Cout] bf16 and the fp32 image (pre-activations are recomputed). */
 int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b, const void* ga, int N, int H, int W,
                      int Cout, float* dw, float* db, void* stream);
+/* Same recomputation, but writes the gradient w.r.t. the conv0 OUTPUT, gc0 [N,H,W,Cout] bf16 (ga routed to the
+ * arg-max of each 2x2 window where it passed the ReLU, zero elsewhere).  The image gradient the GAN lessons
+ * need (trainer/hw_with_style_trainer.py:760-764: the generated line is recognised and the CTC loss flows
+ * back into the generator) is then hwg_conv_fprop(gc0) with the 9 transposed taps of conv0. */
+int hwg_hwr_stem_bwd_expand(const float* img, const float* w, const float* b, const void* ga, int N, int H,
+                            int W, int Cout, void* gc0, void* stream);
 
 /* ------------------------------------------------------------------------
  * Memory-bound backward passes of the generator.

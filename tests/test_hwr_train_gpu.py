@@ -96,5 +96,48 @@ def test_hwr_backward_without_input_grad_and_frozen_parameters():
     img = torch.from_numpy(synth.hwr_case(2, 128, 3)).cuda()
     m(img).sum().backward()
     assert m.cnn.conv0.weight.grad is None and m.cnn.conv1.weight.grad is not None
-    with pytest.raises(NotImplementedError):
-        m(img.clone().requires_grad_()).sum().backward()
+
+
+def test_hwr_input_gradient_for_gan_lessons():
+    """Gradient w.r.t. the image (the generated line in the 'gen' lessons, trainer :760-764): the stem backward
+    itself is checked on identical inputs; end to end it must be a descent direction for the fp32 oracle."""
+    import torch.nn.functional as F
+    from handwriting_line_generation_b200 import ops, conv
+    # (1) stem only, exact: conv0 + ReLU + MaxPool backward to the image
+    g0 = torch.Generator().manual_seed(3)
+    img = (torch.rand(2, 1, 64, 96, generator=g0) * 2 - 1).double().requires_grad_()
+    w = (torch.randn(64, 1, 3, 3, generator=g0) / 3).float().double()
+    b = (torch.randn(64, generator=g0) * 0.1).float().double()
+    a = F.max_pool2d(F.relu(F.conv2d(img, w, b, padding=1)), 2, 2)
+    g = torch.randn(a.shape, generator=g0).to(torch.bfloat16).double()
+    (gi_ref,) = torch.autograd.grad(a, img, g)
+    gc0 = ops.hwr_stem_bwd_expand(img.detach().float().cuda(), w.float().reshape(64, 9).contiguous().cuda(),
+                                  b.float().cuda(), g.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda())
+    mats = [F.pad(w.float()[:, 0, i, j].view(1, 64), (0, 0, 0, 15)).cuda() for i in range(3) for j in range(3)]
+    taps = [(1 - i, 1 - j) for i in range(3) for j in range(3)]
+    gi = conv.conv_fprop(gc0, conv.pack_taps(mats), taps, 64, 96, out_dtype=torch.float32)[..., 0].cpu().double()
+    assert ((gi - gi_ref[:, 0]).abs().max() / gi_ref.abs().max()).item() <= 1e-2
+    # (2) whole recognizer + CTC: cosine with the fp32 oracle and descent
+    from handwriting_line_generation_b200 import CTCLoss
+    m, sd = _hwr_module(200)
+    sd = {k: v.clone() for k, v in sd.items()}
+    m = m.cuda().train()
+    B, W, S = 2, 128, 6
+    x = synth.hwr_case(B, W, 31)
+    T = W // 4 - 6
+    tg = np.random.RandomState(5).randint(1, 80, (B, S)).astype(np.int32)
+    il, tl = np.full(B, T, np.int32), np.full(B, S, np.int32)
+    xc = torch.from_numpy(x).cuda().requires_grad_()
+    CTCLoss(m(xc), torch.from_numpy(tg).cuda(), torch.from_numpy(il), torch.from_numpy(tl)).backward()
+    xo = torch.from_numpy(x).requires_grad_()
+    lp = ohwr.hwr_forward(sd, xo, True, None)
+    lo = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    lo.backward()
+    gq, gr = xc.grad.cpu().double(), xo.grad.double()
+    cos = float((gq * gr).sum() / (gq.norm() * gr.norm()))
+    assert cos >= 0.8, cos
+    with torch.no_grad():
+        step = 0.05 * lo.item() / float((gr ** 2).sum())
+        lp2 = ohwr.hwr_forward(sd, torch.from_numpy(x) - step * gq.float(), True, None)
+        l2 = torch.nn.functional.ctc_loss(lp2, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    assert l2.item() < lo.item()
