@@ -116,10 +116,22 @@ def _w4(dw, kh, kw):
     return dw.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
 
 
-def backward_train(m, ctx, g_lp, want_input_grad=False):
-    """Returns ({parameter name: gradient} for every parameter of the module, image gradient or None)."""
+class _Needed(dict):
+    """grads[name] = lazily evaluated: the wgrad launch is skipped when the parameter's gradient is not needed
+    (frozen recognizer in the GAN lessons: the reference still computes those gradients and throws them away)."""
+
+    def __init__(self, needed):
+        super().__init__()
+        self.needed = needed
+
+    def put(self, name, fn):
+        self[name] = fn() if (self.needed is None or name in self.needed) else None
+
+
+def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
+    """Returns ({parameter name: gradient or None} for every parameter of the module, image gradient or None)."""
     dg = _dgrad_packs(m)
-    grads = {}
+    grads = _Needed(needed)
     lp = ctx["lp"]
     T, B, C = lp.shape
     Cp = ((C + 15) // 16) * 16
@@ -131,8 +143,8 @@ def backward_train(m, ctx, g_lp, want_input_grad=False):
     # ---- head: log-softmax + Conv1d(512, C, 3)
     gz, db = ops.logsoftmax_bwd(g_lp.contiguous().float(), lp, Cp)
     a10 = ctx["a10"]
-    dw = conv.conv_wgrad(a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)
-    grads["cnn1d.12.weight"] = dw[:, :C, :].permute(1, 2, 0).contiguous()
+    grads.put("cnn1d.12.weight", lambda: conv.conv_wgrad(a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)[:, :C, :]
+              .permute(1, 2, 0).contiguous())
     grads["cnn1d.12.bias"] = db
     g = dgrad(gz, "v12", 1, a10.size(2))
     # ---- dilated 1-D blocks, last to first
@@ -140,8 +152,8 @@ def backward_train(m, ctx, g_lp, want_input_grad=False):
         bn = m.cnn1d[bi]
         gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach())
         grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
-        dw = conv.conv_wgrad(a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
-        grads[f"cnn1d.{ci}.weight"] = dw.permute(1, 2, 0).contiguous()
+        grads.put(f"cnn1d.{ci}.weight", lambda: conv.conv_wgrad(a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
+                  .permute(1, 2, 0).contiguous())
         grads[f"cnn1d.{ci}.bias"] = dcb
         g = dgrad(gz, f"v{ci}", 1, a_in.size(2))
     # ---- conv6 + BN + ReLU
@@ -149,13 +161,13 @@ def backward_train(m, ctx, g_lp, want_input_grad=False):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach())
     grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
     a5 = ctx["a5"]
-    grads["cnn.conv6.weight"] = _w4(conv.conv_wgrad(a5, gz, _T3P0, 512, 512), 3, 3)
+    grads.put("cnn.conv6.weight", lambda: _w4(conv.conv_wgrad(a5, gz, _T3P0, 512, 512), 3, 3))
     grads["cnn.conv6.bias"] = dcb
     g = dgrad(gz, "w6", a5.size(1), a5.size(2))
     # ---- pool + ReLU + conv5
     gc, db = ops.relu_maxpool_bwd(g, ctx["c5"], *_POOL21)
     a4 = ctx["a4"]
-    grads["cnn.conv5.weight"] = _w4(conv.conv_wgrad(a4, gc, _T3P0, 512, 512), 3, 3)
+    grads.put("cnn.conv5.weight", lambda: _w4(conv.conv_wgrad(a4, gc, _T3P0, 512, 512), 3, 3))
     grads["cnn.conv5.bias"] = db
     g = dgrad(gc, "w5", a4.size(1), a4.size(2))
     # ---- conv4 + BN + ReLU
@@ -163,13 +175,13 @@ def backward_train(m, ctx, g_lp, want_input_grad=False):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach())
     grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
     a3 = ctx["a3"]
-    grads["cnn.conv4.weight"] = _w4(conv.conv_wgrad(a3, gz, _T3, 256, 512), 3, 3)
+    grads.put("cnn.conv4.weight", lambda: _w4(conv.conv_wgrad(a3, gz, _T3, 256, 512), 3, 3))
     grads["cnn.conv4.bias"] = dcb
     g = dgrad(gz, "w4", a3.size(1), a3.size(2))
     # ---- pool + ReLU + conv3
     gc, db = ops.relu_maxpool_bwd(g, ctx["c3"], *_POOL21)
     a2 = ctx["a2"]
-    grads["cnn.conv3.weight"] = _w4(conv.conv_wgrad(a2, gc, _T3, 256, 256), 3, 3)
+    grads.put("cnn.conv3.weight", lambda: _w4(conv.conv_wgrad(a2, gc, _T3, 256, 256), 3, 3))
     grads["cnn.conv3.bias"] = db
     g = dgrad(gc, "w3", a2.size(1), a2.size(2))
     # ---- conv2 + BN + ReLU
@@ -177,20 +189,23 @@ def backward_train(m, ctx, g_lp, want_input_grad=False):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach())
     grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
     a1 = ctx["a1"]
-    grads["cnn.conv2.weight"] = _w4(conv.conv_wgrad(a1, gz, _T3, 128, 256), 3, 3)
+    grads.put("cnn.conv2.weight", lambda: _w4(conv.conv_wgrad(a1, gz, _T3, 128, 256), 3, 3))
     grads["cnn.conv2.bias"] = dcb
     g = dgrad(gz, "w2", a1.size(1), a1.size(2))
     # ---- pool + ReLU + conv1
     gc, db = ops.relu_maxpool_bwd(g, ctx["c1"], *_POOL22)
     a0 = ctx["a0"]
-    grads["cnn.conv1.weight"] = _w4(conv.conv_wgrad(a0, gc, _T3, 64, 128), 3, 3)
+    grads.put("cnn.conv1.weight", lambda: _w4(conv.conv_wgrad(a0, gc, _T3, 64, 128), 3, 3))
     grads["cnn.conv1.bias"] = db
     g = dgrad(gc, "w1", a0.size(1), a0.size(2))
     # ---- stem
     c = m._packed()
-    dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g)
-    grads["cnn.conv0.weight"] = dw0.view(64, 1, 3, 3)
-    grads["cnn.conv0.bias"] = db0
+    if needed is None or "cnn.conv0.weight" in needed or "cnn.conv0.bias" in needed:
+        dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g)
+        grads["cnn.conv0.weight"] = dw0.view(64, 1, 3, 3)
+        grads["cnn.conv0.bias"] = db0
+    else:
+        grads["cnn.conv0.weight"] = grads["cnn.conv0.bias"] = None
     g_img = None
     if want_input_grad:
         # image gradient (GAN lessons): route g through pool/ReLU to conv0's output, then the 9-tap dgrad with
@@ -218,8 +233,9 @@ class _HWRFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        needed = {n for n, need in zip(ctx.names, ctx.needs_input_grad[3:]) if need}
         with torch.no_grad():
-            grads, g_img = backward_train(ctx.module, ctx.saved, g, ctx.x_needs_grad)
+            grads, g_img = backward_train(ctx.module, ctx.saved, g, ctx.x_needs_grad, needed)
         ctx.saved = None
         return (None, None, g_img) + tuple(grads[n] for n in ctx.names)
 

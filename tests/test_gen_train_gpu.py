@@ -90,3 +90,53 @@ def test_generator_backward_with_inkernel_noise_runs():
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
         grads.append(torch.cat([b.noise2.weight_orig.grad.flatten() for b in m.conv]).cpu().numpy())
     assert rel_l2(grads[1], grads[0]) <= 0.2
+
+
+def test_gen_lesson_chain_generator_hwr_ctc():
+    """The 'gen' lesson's recognition branch (trainer/hw_with_style_trainer.py:760-764): generated lines are read by
+    the (frozen) recognizer, the CTC loss flows back through the recognizer's input into the generator.
+    22 bf16 layers deep, so only direction is asserted: cosine with the fp32 oracle's gradient and descent."""
+    from handwriting_line_generation_b200 import CTCLoss, _lib
+    from oracle import hwr as ohwr
+    from tests.test_modules_cpu import _hwr_module
+    T, B, S = 32, 2, 5
+    g, gsd = _gen_module(100)
+    h, hsd = _hwr_module(200)
+    gsd = {k: v.clone() for k, v in gsd.items()}
+    hsd = {k: v.clone() for k, v in hsd.items()}
+    g, h = g.cuda().train(), h.cuda().train()
+    for p in h.parameters():
+        p.requires_grad_(False)                        # hwr_frozen: not optimised, no wgrad needed
+    content, style = synth.gen_case(T, B, 80, 128, 9)
+    noise = synth.gen_noise(synth.gen_noise_shapes(T, B), 10)
+    tg = np.random.RandomState(1).randint(1, 80, (B, S)).astype(np.int32)
+    Tc = 4 * T // 4 - 6
+    il, tl = np.full(B, Tc, np.int32), np.full(B, S, np.int32)
+    n0 = _lib.launch_count()
+    img = g(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), noise=[torch.from_numpy(z).cuda() for z in noise])
+    loss = CTCLoss(h(img), torch.from_numpy(tg).cuda(), torch.from_numpy(il), torch.from_numpy(tl))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert all(p.grad is None for p in h.parameters())
+    # oracle chain
+    gp = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in gsd.items()}
+    oimg = ogen.generator_forward(gp, torch.from_numpy(content), torch.from_numpy(style), [torch.from_numpy(z) for z in noise])
+    lp = ohwr.hwr_forward(hsd, oimg, True, None)
+    ol = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    ol.backward()
+    assert abs(loss.item() - ol.item()) <= 5e-2 * abs(ol.item())
+    num = den1 = den2 = 0.0
+    for n, p in g.named_parameters():
+        if n.startswith("gen.") or gp[n].grad is None:
+            continue
+        a, b = p.grad.cpu().double(), gp[n].grad.double()
+        num += float((a * b).sum()); den1 += float((a * a).sum()); den2 += float((b * b).sum())
+    cos = num / (den1 * den2) ** 0.5
+    assert cos >= 0.6, cos
+    with torch.no_grad():
+        step = 0.02 * ol.item() / den2
+        sd2 = {k: (v - step * dict(g.named_parameters())[k].grad.cpu() if k in dict(g.named_parameters()) and dict(g.named_parameters())[k].grad is not None else v)
+               for k, v in gsd.items()}
+        oimg2 = ogen.generator_forward(sd2, torch.from_numpy(content), torch.from_numpy(style), [torch.from_numpy(z) for z in noise])
+        l2 = torch.nn.functional.ctc_loss(ohwr.hwr_forward(hsd, oimg2, True, None), torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    assert l2.item() < ol.item(), (l2.item(), ol.item(), cos)
