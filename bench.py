@@ -287,6 +287,14 @@ def run_ours(args, rank, world, local_rank):
                      "issued_gflop_per_step": issued_flops / 1e9},
         "cpu_baseline": cpu,
     }
+    if world == 1:
+        try:   # training paths, measured briefly in the same run (details: bench.py --workload hwr_train)
+            import bench_hwr_train
+            del model
+            torch.cuda.empty_cache()
+            line["extra_workloads"] = bench_hwr_train.quick_train_numbers(dev)
+        except Exception as e:   # never lose the headline over the extras
+            line["extra_workloads"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -180,3 +180,73 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         "cpu_baseline": cpu}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Short device-timed measurements of the two training paths, embedded as "extra_workloads" in the default
+# bench line (N=1) so that one bench run documents inference AND training throughput.
+# ----------------------------------------------------------------------------------------------------------
+def quick_train_numbers(dev, steps=10):
+    import handwriting_line_generation_b200 as pkg
+    from oracle import synth
+    out = {}
+
+    def time_steps(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        n0 = pkg._lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (pkg._lib.launch_count() - n0) // steps
+
+    # (1) configs[0]: recognizer + CTC train step, batch 8 and 32
+    for B in (8, 32):
+        torch.manual_seed(0)
+        model = pkg.CNNOnlyHWR(HWR["C"], norm='batch').to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        T = HWR["W"] // 4 - 6
+        img = torch.from_numpy(synth.hwr_case(B, HWR["W"], 1)).to(dev)
+        tg = torch.randint(1, HWR["C"], (B, HWR["S"]), dtype=torch.int32, device=dev)
+        il = torch.full((B,), T, dtype=torch.int32, device=dev)
+        tl = torch.full((B,), HWR["S"], dtype=torch.int32, device=dev)
+
+        def step(i):
+            opt.zero_grad(set_to_none=True)
+            pkg.CTCLoss(model(img), tg, il, tl).backward()
+            opt.step()
+
+        ms, launches = time_steps(step)
+        out[f"hwr_ctc_train_step_B{B}"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
+                                          "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + Adam, 64x1024 lines"}
+        del model, opt
+    # (2) the 'gen' lesson's recognition branch: generator -> frozen recognizer -> CTC -> backward into the
+    #     generator -> Adam on the generator (trainer/hw_with_style_trainer.py:760-764), batch 16, T_s=256
+    B, Ts = 16, 256
+    torch.manual_seed(0)
+    gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True, small=False).to(dev).train()
+    hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
+    for p in hwr.parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    content, style = synth.gen_case(Ts, B, 80, 128, 3)
+    c, s = torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev)
+    T = Ts - 6
+    tg = torch.randint(1, 80, (B, 40), dtype=torch.int32, device=dev)
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), 40, dtype=torch.int32, device=dev)
+
+    def gstep(i):
+        opt.zero_grad(set_to_none=True)
+        pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl).backward()
+        opt.step()
+
+    ms, launches = time_steps(gstep)
+    out["gen_hwr_ctc_train_step_B16"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
+                                         "what": "SpacedGenerator fwd+bwd, frozen CNNOnlyHWR fwd + input-gradient bwd, CTC, "
+                                                 "Adam on the generator; 64x1024 lines (the recognition branch of the GAN 'gen' lesson)"}
+    return out

@@ -41,13 +41,13 @@ _SIGNATURES = {
     "hwg_adain_coeffs": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "hwg_adain_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
     "hwg_adain_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp,
-                                    ctypes.c_uint64, ctypes.c_uint64, c_int, c_vp, c_vp, c_vp]),
+                                    ctypes.c_uint64, ctypes.c_uint64, c_vp, c_int, c_vp, c_vp, c_vp]),
     "hwg_gen_output_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
     "hwg_bn_coeffs": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_int, c_vp, c_vp, c_vp]),
     "hwg_scale_shift_act": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_f, c_vp]),
     "hwg_blur_noise_act_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, ctypes.c_uint64,
-                                         ctypes.c_uint64, c_int, c_f, c_vp, c_vp]),
-    "hwg_gen_output": (c_int, [c_vp, c_vp, c_vp, c_f, c_int, c_i64, c_int, c_vp, c_vp]),
+                                         ctypes.c_uint64, c_vp, c_int, c_f, c_vp, c_vp]),
+    "hwg_gen_output": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
     "hwg_hwr_stem": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hwg_maxpool_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_vp]),
@@ -71,7 +71,7 @@ class ConvDesc(ctypes.Structure):
         ("tile_w", ctypes.c_int32),
         ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
         ("in_stride_h", ctypes.c_int32), ("in_stride_w", ctypes.c_int32),
-        ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64),
+        ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64), ("noise_seed_dev", ctypes.c_uint64),
     ]
 
 

@@ -62,9 +62,9 @@ def forward_train(m, content, s, gb, noise):
     T, B, ncls = content.shape
     dev = content.device
     x = ops.gen_pack_input(content.float(), s if m.append_style else None, c["cin_pad"])
-    seed = None
+    seed, seed_dev = None, None
     if noise is None:
-        seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+        seed, seed_dev = m._noise_seed()
     else:
         noise = [z.permute(0, 2, 3, 1).contiguous().float() for z in noise]
     gbs = gb.stride(0)
@@ -85,11 +85,11 @@ def forward_train(m, content, s, gb, noise):
                 conv.conv_fprop(x, e["w1"][r], e["taps1"], 1, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2,
                                 out_view=(a, Ho * Wo * C, Wo * C, C, r * Wo * C),
                                 noise_view=None if nz is None else (nz, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, stats=st)
+                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, noise_seed_dev=seed_dev, stats=st)
         elif e["kind"] == "plain":
             Ho, Wo = H, W
             a = conv.conv_fprop(x, e["w1"], TAPS3x3, Ho, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2, noise=nz,
-                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, stats=st)
+                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
         else:
             if e["kind"] == "vert_up":
                 Ho, Wo = 2 * H, W
@@ -102,7 +102,7 @@ def forward_train(m, content, s, gb, noise):
                 for py, px, taps, wp in e["w1"]:
                     conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"],
                                     out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, (py * Wo + px) * C))
-            a = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k)
+            a = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
         H, W = Ho, Wo
         coef, save = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W, save=True)
         recs.append(dict(x_in=x_in, Hin=Hin, Win=Win, a=a, coef=coef, save=save, nz=nz, subseq=16 * k, off=off))
@@ -112,7 +112,7 @@ def forward_train(m, content, s, gb, noise):
         st = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
         nz = None if noise is None else noise[k]
         a = conv.conv_fprop(x, e["w2"], TAPS3x3, H, W, bias=e["b2"], act=ACT_LRELU, slope=0.2, noise=nz,
-                            noise_w=e["nw2"], noise_seed=seed, noise_subseq=16 * k, stats=st)
+                            noise_w=e["nw2"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
         coef, save = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W, save=True)
         recs.append(dict(x_in=x, Hin=H, Win=W, a=a, coef=coef, save=save, nz=nz, subseq=16 * k, off=off))
         if bi == nblk - 1:
@@ -121,7 +121,7 @@ def forward_train(m, content, s, gb, noise):
             x = ops.scale_shift_act(a, coef, True, out=torch.empty_like(a))
         off += 2 * C
         k += 1
-    ctx = dict(recs=recs, seed=seed or 0, out=out, T=T, B=B, ncls=ncls, gb_width=gb.size(1))
+    ctx = dict(recs=recs, seed=seed or 0, seed_dev=seed_dev, out=out, T=T, B=B, ncls=ncls, gb_width=gb.size(1))
     return out, ctx
 
 
@@ -143,7 +143,7 @@ def _fused_w4(mod, w):
 
 def backward_train(m, ctx, g_out):
     """Returns (g_content [T,B,ncls], g_s [B,S], g_gb [B,sum 2C], [conv-side parameter grads in _param_list order])."""
-    recs, seed = ctx["recs"], ctx["seed"]
+    recs, seed, seed_dev = ctx["recs"], ctx["seed"], ctx["seed_dev"]
     c = m._packed()
     B, T, ncls = ctx["B"], ctx["T"], ctx["ncls"]
     dev = g_out.device
@@ -162,7 +162,7 @@ def backward_train(m, ctx, g_out):
         r1, r2 = recs[2 * bi], recs[2 * bi + 1]
         # ---------------- second half: conv2 + noise2 + lrelu + adain2
         gy, dgam, dbet, dbias2, dnw2 = ops.adain_lrelu_bwd(g, r2["a"], r2["save"], r2["coef"], 0.2, r2["nz"], seed,
-                                                           r2["subseq"])
+                                                           r2["subseq"], seed_dev=seed_dev)
         g_gb[:, r2["off"]:r2["off"] + C] = dgam
         g_gb[:, r2["off"] + C:r2["off"] + 2 * C] = dbet
         g_w2 = _w4(conv.conv_wgrad(r2["x_in"], gy, TAPS3x3, C, C), 3, 3)
@@ -171,7 +171,8 @@ def backward_train(m, ctx, g_out):
         g_nw2 = (dnw2 * sqrt(2.0 / C)).view(1, C, 1, 1)
         # ---------------- first half: conv1 (+blur) + noise1 + lrelu + adain1
         gy, dgam, dbet, dsum, dnw1 = ops.adain_lrelu_bwd(g, r1["a"], r1["save"], r1["coef"], 0.2, r1["nz"], seed,
-                                                         r1["subseq"], row_subseq=(e["kind"] == "initial"))
+                                                         r1["subseq"], row_subseq=(e["kind"] == "initial"),
+                                                         seed_dev=seed_dev)
         g_gb[:, r1["off"]:r1["off"] + C] = dgam
         g_gb[:, r1["off"] + C:r1["off"] + 2 * C] = dbet
         g_nw1 = (dnw1 * sqrt(2.0 / C)).view(1, C, 1, 1)

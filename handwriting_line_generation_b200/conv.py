@@ -38,7 +38,8 @@ def pack_conv2d_weight(weight, cin_pad=None):
 
 def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
                out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, noise_view=None,
-               noise_seed=None, noise_subseq=0, stats=None, cin=None, tile_w=0, in_stride=(1, 1)):
+               noise_seed=None, noise_subseq=0, noise_seed_dev=None, stats=None, cin=None, tile_w=0,
+               in_stride=(1, 1)):
     """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
 
     x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
@@ -87,6 +88,7 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
         if nz_ptr is None:
             assert noise_seed is not None, "noise_w without a noise tensor needs noise_seed"
             d.noise_seed, d.noise_subseq = noise_seed, noise_subseq
+            d.noise_seed_dev = 0 if noise_seed_dev is None else noise_seed_dev.data_ptr()
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout
     if stats is not None:

@@ -35,6 +35,15 @@ inline int check_launch(const char* what) {
     }                                     \
   } while (0)
 
+// Dynamic shared memory opt-in, done once per kernel (to the device maximum) so that steady-state launches make
+// no attribute calls — required for the launches to be capturable in a CUDA graph.
+int ensure_max_smem(const void* func);
+#define HWG_SMEM_OPTIN(kernel)                                               \
+  do {                                                                       \
+    int rc__ = hwg::ensure_max_smem(reinterpret_cast<const void*>(kernel));  \
+    if (rc__) return rc__;                                                   \
+  } while (0)
+
 #define HWG_CUDA(call)                                                  \
   do {                                                                  \
     cudaError_t e__ = (call);                                           \

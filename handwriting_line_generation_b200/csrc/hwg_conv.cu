@@ -56,6 +56,7 @@ struct ConvKParams {
   float* stats;
   void* y;
   unsigned long long noise_seed, noise_subseq;
+  const unsigned long long* noise_seed_dev;
 };
 
 // Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
@@ -226,7 +227,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m / p.TW, wl = m - hl * p.TW;
-    const uint2 nkey = noise_key(p.noise_seed, p.noise_subseq);
+    const uint2 nkey = noise_key(p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull), p.noise_subseq);
     int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
     int ti = 0;
     for (int t = t_begin; t < t_end; ++t, ++ti) {
@@ -565,6 +566,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.has_stats = stats != nullptr;
   p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.stats = stats; p.y = y;
   p.noise_seed = d->noise_seed; p.noise_subseq = d->noise_subseq;
+  p.noise_seed_dev = reinterpret_cast<const unsigned long long*>(d->noise_seed_dev);
 
   const CUtensorMapSwizzle swz = p.CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : (p.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -592,7 +594,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   }
   const size_t smem = (size_t)p.stages * stage_bytes + wbytes + fixed;
   ConvKernel k = pick_kernel(p);
-  HWG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HWG_SMEM_OPTIN(k);
   // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently
   k<<<grid, ctas_per_sm == 1 ? 320 : 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
   return check_launch("conv_fprop_kernel");

@@ -313,8 +313,7 @@ static int chain_launch(const float* lp, int T, int B, int C, const int32_t* tar
   dim3 grid(B, ndir);
 #define LAUNCH_CHAIN(V)                                                                      \
   do {                                                                                       \
-    HWG_CUDA(cudaFuncSetAttribute(ctc_chain_kernel<V>,                                       \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    HWG_SMEM_OPTIN(ctc_chain_kernel<V>);                                                     \
     ctc_chain_kernel<V><<<grid, NT, smem, st>>>(lp, T, B, C, targets, ts_b, ts_s, S_max,     \
                                                 in_len, tg_len, blank, nll, la, lb,          \
                                                 dir_base, TC, Cp);                           \
@@ -377,7 +376,7 @@ extern "C" int hwg_ctc_backward(const float* grad_out, const float* grad_nll_uni
   dim3 grid((T + frames - 1) / frames, B);
   size_t smem = (size_t)(2 * S_max + C + 1) * 4 + (size_t)GRAD_TT * L * 4;
   HWG_REQUIRE(smem <= 200 * 1024, "ctc backward: needs %zu B of shared memory", smem);
-  HWG_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HWG_SMEM_OPTIN(ctc_grad_kernel);
   ctc_grad_kernel<<<grid, 256, smem, st>>>(grad_out, grad_nll_unit, log_probs, T, B, C, targets,
                                            tgt_stride_b, tgt_stride_s, S_max, input_lengths,
                                            target_lengths, blank, nll, log_alpha, log_beta,
@@ -392,7 +391,7 @@ extern "C" int hwg_ctc_greedy_decode(const float* log_probs, int T, int B, int C
   HWG_REQUIRE(T > 0 && B > 0 && C > 0, "hwg_ctc_greedy_decode: bad shape");
   size_t smem = (size_t)T * 4;
   HWG_REQUIRE(smem <= 200 * 1024, "hwg_ctc_greedy_decode: T=%d too long", T);
-  HWG_CUDA(cudaFuncSetAttribute(ctc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HWG_SMEM_OPTIN(ctc_decode_kernel);
   ctc_decode_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(log_probs, T, B, C, input_lengths, blank,
                                                             raw, decoded, decoded_len);
   return check_launch("ctc_decode_kernel");

@@ -153,7 +153,8 @@ scale_shift_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const
 __global__ void __launch_bounds__(EW_THREADS)
 blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
                             const float* __restrict__ noise, const float* __restrict__ noise_w,
-                            unsigned long long seed, unsigned long long subseq, int act, float slope,
+                            unsigned long long seed, unsigned long long subseq,
+                            const unsigned long long* __restrict__ seed_dev, int act, float slope,
                             float* __restrict__ stats) {
   extern __shared__ float sacc[];  // [C][2] block-level statistics
   const int n = blockIdx.y, CV = C / 8;
@@ -170,7 +171,7 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const uint2 nkey = noise_key(seed, subseq);
+  const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
 
   for (int it = 0; it < EW_ITER; ++it) {
     const long long item = base + it * EW_THREADS + threadIdx.x;
@@ -246,7 +247,7 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
 // ---- generator output: AdaIN apply + 1x1 conv + tanh -------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS)
 gen_output_kernel(const uint4* __restrict__ x, const float* __restrict__ coef, const float* __restrict__ w,
-                  float b0, long long HW, int C, float* __restrict__ out) {
+                  const float* __restrict__ b0, long long HW, int C, float* __restrict__ out) {
   extern __shared__ float wa[];  // [C] w*a, then [1] constant
   const int n = blockIdx.y, CV = C / 8;
   if (threadIdx.x < 32) {
@@ -257,7 +258,7 @@ gen_output_kernel(const uint4* __restrict__ x, const float* __restrict__ coef, c
       cst += w[c] * b;
     }
     cst = warp_sum(cst);
-    if (threadIdx.x == 0) wa[C] = cst + b0;
+    if (threadIdx.x == 0) wa[C] = cst + b0[0];
   }
   __syncthreads();
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -419,8 +420,8 @@ extern "C" int hwg_scale_shift_act(const void* x, void* y, const float* coef, in
 
 extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, int W, int C,
                                         const float* noise, const float* noise_w, uint64_t noise_seed,
-                                        uint64_t noise_subseq, int act, float slope, float* stats,
-                                        void* stream) {
+                                        uint64_t noise_subseq, const uint64_t* noise_seed_dev, int act, float slope,
+                                        float* stats, void* stream) {
   HWG_REQUIRE(x && y && x != y && N > 0 && H > 0 && W > 0, "hwg_blur_noise_act_stats: bad argument");
   HWG_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= EW_THREADS,
               "hwg_blur_noise_act_stats: C=%d must be 8 x a power of two", C);
@@ -429,13 +430,13 @@ extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, in
   dim3 grid(blocks_for(total, EW_THREADS * EW_ITER), N);
   blur_noise_act_stats_kernel<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, noise, noise_w, noise_seed,
-      noise_subseq, act, slope, stats);
+      noise_subseq, reinterpret_cast<const unsigned long long*>(noise_seed_dev), act, slope, stats);
   return check_launch("blur_noise_act_stats_kernel");
 }
 
-extern "C" int hwg_gen_output(const void* x, const float* coef, const float* w, float b0, int N, int64_t HW,
+extern "C" int hwg_gen_output(const void* x, const float* coef, const float* w, const float* b0, int N, int64_t HW,
                               int C, float* out, void* stream) {
-  HWG_REQUIRE(x && coef && w && out && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "hwg_gen_output: bad argument");
+  HWG_REQUIRE(x && coef && w && b0 && out && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "hwg_gen_output: bad argument");
   dim3 grid(blocks_for(HW, EW_THREADS), N);
   gen_output_kernel<<<grid, EW_THREADS, (size_t)(C + 1) * sizeof(float), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), coef, w, b0, HW, C, out);

@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(BW_THREADS)
 adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a, const float* __restrict__ save,
                        const float* __restrict__ coef, const float* __restrict__ sums, int H, int W, int C,
                        float slope, const float* __restrict__ noise, unsigned long long seed,
-                       unsigned long long subseq, int row_subseq, uint4* __restrict__ gy,
-                       float* __restrict__ dch) {
+                       unsigned long long subseq, const unsigned long long* __restrict__ seed_dev, int row_subseq,
+                       uint4* __restrict__ gy, float* __restrict__ dch) {
   extern __shared__ float sacc[];  // [2][C]
   const int n = blockIdx.y, CV = C / 8;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -384,6 +384,7 @@ adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a,
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+  seed += seed_dev ? *seed_dev : 0ull;
   const uint2 nkey = noise_key(seed, subseq);
   const long long total = HW * CV;
   const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
@@ -610,14 +611,15 @@ extern "C" int hwg_adain_bwd_reduce(const void* g, const void* a, const float* s
 
 extern "C" int hwg_adain_bwd_apply(const void* g, const void* a, const float* save, const float* coef,
                                    const float* sums, int N, int H, int W, int C, float slope, const float* noise,
-                                   uint64_t noise_seed, uint64_t noise_subseq, int row_subseq, void* gy, float* dch,
-                                   void* stream) {
+                                   uint64_t noise_seed, uint64_t noise_subseq, const uint64_t* noise_seed_dev,
+                                   int row_subseq, void* gy, float* dch, void* stream) {
   HWG_REQUIRE(g && a && save && coef && sums && gy && dch && N > 0 && H > 0 && W > 0, "hwg_adain_bwd_apply: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_adain_bwd_apply: C=%d must be 8 x a power of two", C);
   dim3 grid(bw_blocks((long long)H * W * (C / 8), BW_THREADS * BW_ITER), N);
   adain_bwd_apply_kernel<<<grid, BW_THREADS, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(a), save, coef, sums, H, W, C, slope, noise,
-      noise_seed, noise_subseq, row_subseq, reinterpret_cast<uint4*>(gy), dch);
+      noise_seed, noise_subseq, reinterpret_cast<const unsigned long long*>(noise_seed_dev), row_subseq,
+      reinterpret_cast<uint4*>(gy), dch);
   return check_launch("adain_bwd_apply_kernel");
 }
 

@@ -255,7 +255,7 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
   rc = encode_nhwc(encode, &tmx, x, d->Cin, d->W, d->H, d->N, d->x_pitch, p.CBb, p.PW, p.PH, 1, 1, "x");
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  HWG_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HWG_SMEM_OPTIN(conv_wgrad_kernel);
   dim3 grid((unsigned)splits, (unsigned)units);
   conv_wgrad_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmg, tmx, p);
   return check_launch("conv_wgrad_kernel");

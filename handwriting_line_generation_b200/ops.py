@@ -57,18 +57,19 @@ def scale_shift_act(x, coef, per_sample, act=ACT_NONE, slope=0.0, out=None):
     return out
 
 
-def blur_noise_act_stats(x, noise, noise_w, stats, act=ACT_LRELU, slope=0.2, seed=0, subseq=0):
+def blur_noise_act_stats(x, noise, noise_w, stats, act=ACT_LRELU, slope=0.2, seed=0, subseq=0, seed_dev=None):
     N, H, W, C = x.shape
     y = torch.empty_like(x)
     _lib.call("hwg_blur_noise_act_stats", x.data_ptr(), y.data_ptr(), N, H, W, C, _lib.ptr(noise), _lib.ptr(noise_w),
-              seed, subseq, act, slope, _lib.ptr(stats), _lib.stream())
+              seed, subseq, _lib.ptr(seed_dev), act, slope, _lib.ptr(stats), _lib.stream())
     return y
 
 
 def gen_output(x, coef, w, b0):
+    """b0: 1-element fp32 CUDA tensor (read on the device: no host sync, CUDA-graph friendly)."""
     N, H, W, C = x.shape
     out = torch.empty((N, 1, H, W), device=x.device, dtype=torch.float32)
-    _lib.call("hwg_gen_output", x.data_ptr(), coef.data_ptr(), w.data_ptr(), float(b0), N, H * W, C, out.data_ptr(),
+    _lib.call("hwg_gen_output", x.data_ptr(), coef.data_ptr(), w.data_ptr(), b0.data_ptr(), N, H * W, C, out.data_ptr(),
               _lib.stream())
     return out
 
@@ -136,7 +137,7 @@ def hwr_stem_bwd(img, w, b, ga):
     return dw, db
 
 
-def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, row_subseq=False):
+def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, row_subseq=False, seed_dev=None):
     """Backward of x_next = AdaIN(LeakyReLU(y)), y = pre + nw*z.  g, a [N,H,W,C] bf16.
     Returns (gy bf16, dgamma [N,C], dbeta [N,C], dbias [C] = sum gy, dnoise_w [C] = sum gy*z)."""
     N, H, W, C = a.shape
@@ -146,7 +147,8 @@ def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, r
     gy = torch.empty_like(a)
     dch = torch.zeros((C, 2), device=a.device, dtype=torch.float32)
     _lib.call("hwg_adain_bwd_apply", g.data_ptr(), a.data_ptr(), save.data_ptr(), coef.data_ptr(), sums.data_ptr(),
-              N, H, W, C, slope, _lib.ptr(noise), seed, subseq, int(row_subseq), gy.data_ptr(), dch.data_ptr(),
+              N, H, W, C, slope, _lib.ptr(noise), seed, subseq, _lib.ptr(seed_dev), int(row_subseq), gy.data_ptr(),
+              dch.data_ptr(),
               _lib.stream())
     return gy, sums[:, :, 1], sums[:, :, 0], dch[:, 0], dch[:, 1]
 

@@ -198,6 +198,18 @@ class SpacedGenerator(nn.Module):
         self.gen = self.conv
         self.in_ch, self.n_class, self.style_size = in_ch, n_class, style_size
         self._cache_key, self._cache = None, None
+        # CUDA-graph mode (graphs.py): a device-side counter is added to the (captured, hence constant) host seed
+        # so that every replay draws fresh noise; off by default so that torch.manual_seed reproduces a call
+        self.register_buffer("_noise_step", torch.zeros(1, dtype=torch.int64), persistent=False)
+        self.device_noise_counter = False
+
+    def _noise_seed(self):
+        """(host seed, device counter snapshot or None) for one forward."""
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+        if not self.device_noise_counter:
+            return seed, None
+        self._noise_step += 1
+        return seed, self._noise_step.clone()
 
     # -- derived weights ------------------------------------------------------------------------
     def _packed(self):
@@ -236,7 +248,7 @@ class SpacedGenerator(nn.Module):
             c["mlp"] = [(m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
                         for m in self.style_emb if isinstance(m, nn.Linear)]
             c["w_out"] = self.out[0].effective_weight().detach().float().reshape(-1).contiguous()
-            c["b_out"] = float(self.out[0].conv.bias.detach().float().item())
+            c["b_out"] = self.out[0].conv.bias.detach().float().reshape(1).contiguous()
         self._cache_key, self._cache = key, c
         return c
 
@@ -272,9 +284,9 @@ class SpacedGenerator(nn.Module):
         dev = content.device
         s, gb = self._style_vectors(c, style)
         x = ops.gen_pack_input(content.float(), s if self.append_style else None, c["cin_pad"])
-        seed = None
+        seed, seed_dev = None, None
         if noise is None:
-            seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+            seed, seed_dev = self._noise_seed()
         else:
             noise = [z.permute(0, 2, 3, 1).contiguous().float() for z in noise]  # NHWC for the kernels
         # one zero-fill for all ten statistics buffers ([B,C,2] each)
@@ -306,11 +318,11 @@ class SpacedGenerator(nn.Module):
                     conv.conv_fprop(x, e["w1"][r], e["taps1"], 1, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2,
                                     out_view=(y, Ho * Wo * C, Wo * C, C, r * Wo * C),
                                     noise_view=None if nz is None else (nz, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, stats=st)
+                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, noise_seed_dev=seed_dev, stats=st)
             elif e["kind"] == "plain":
                 Ho, Wo = H, W
                 y = conv.conv_fprop(x, e["w1"], TAPS3x3, Ho, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2, noise=nz,
-                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, stats=st)
+                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
             else:
                 if e["kind"] == "vert_up":
                     Ho, Wo = 2 * H, W
@@ -324,7 +336,7 @@ class SpacedGenerator(nn.Module):
                     for py, px, taps, wp in e["w1"]:
                         conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"],
                                         out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, (py * Wo + px) * C))
-                y = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k)
+                y = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
             H, W = Ho, Wo
             coef = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W)
             if keep:
@@ -336,7 +348,7 @@ class SpacedGenerator(nn.Module):
             st = new_stats(C)
             nz = None if noise is None else noise[k]
             y = conv.conv_fprop(x, e["w2"], TAPS3x3, H, W, bias=e["b2"], act=ACT_LRELU, slope=0.2, noise=nz,
-                                noise_w=e["nw2"], noise_seed=seed, noise_subseq=16 * k, stats=st)
+                                noise_w=e["nw2"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
             coef = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W)
             if keep:
                 saved.append((x, y, st, coef))

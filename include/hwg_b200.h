@@ -151,6 +151,8 @@ typedef struct hwgConvDesc {
                                        (strided convolution = the input gradient of a stride-s transposed conv) */
   uint64_t noise_seed;    /* in-kernel N(0,1) noise (counter-based hash + Box-Muller) when noise == NULL and noise_w != NULL */
   uint64_t noise_subseq;  /* distinguishes launches that share a seed */
+  uint64_t noise_seed_dev; /* 0, or the DEVICE address of a uint64 that is added to noise_seed when the kernel
+                              runs: lets a captured CUDA graph draw fresh noise on every replay */
 } hwgConvDesc;
 
 /* bias [Cout] fp32 or NULL; noise_w [Cout] fp32 or NULL (no noise); noise fp32 tensor or NULL
@@ -208,13 +210,13 @@ int hwg_scale_shift_act(const void* x, void* y, const float* coef, int per_sampl
  * result.  x, y [N,H,W,C] bf16; noise fp32 NHWC or NULL (NULL + noise_w: in-kernel RNG). */
 int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, int W, int C,
                              const float* noise, const float* noise_w, uint64_t noise_seed,
-                             uint64_t noise_subseq, int act, float slope, float* stats,
-                             void* stream);
+                             uint64_t noise_subseq, const uint64_t* noise_seed_dev /* or NULL */,
+                             int act, float slope, float* stats, void* stream);
 
 /* Generator output (pure_gen.py:29,50): AdaIN apply (coef [N,C,2]) + 1x1 conv C->1
- * (weight w[C], bias b0) + tanh; x [N,H,W,C] bf16 -> out [N,1,H,W] fp32. */
-int hwg_gen_output(const void* x, const float* coef, const float* w, float b0, int N,
-                   int64_t HW, int C, float* out, void* stream);
+ * (weight w[C], bias *b0) + tanh; x [N,H,W,C] bf16 -> out [N,1,H,W] fp32. */
+int hwg_gen_output(const void* x, const float* coef, const float* w, const float* b0 /* device, 1 float */,
+                   int N, int64_t HW, int C, float* out, void* stream);
 
 /* Recognizer stem (cnn_only_hwr.py:44-46): Conv2d(1,64,3,pad 1)+ReLU+MaxPool2d(2,2)
  * in one pass.  img [N,1,H,W] fp32 -> y [N,H/2,W/2,Cout] bf16; w [Cout,9], b [Cout]. */
@@ -311,7 +313,8 @@ int hwg_adain_bwd_reduce(const void* g, const void* a, const float* save, int N,
  * transposed conv (subsequence = noise_subseq + h, element index without h). */
 int hwg_adain_bwd_apply(const void* g, const void* a, const float* save, const float* coef,
                         const float* sums, int N, int H, int W, int C, float slope,
-                        const float* noise, uint64_t noise_seed, uint64_t noise_subseq, int row_subseq,
+                        const float* noise, uint64_t noise_seed, uint64_t noise_subseq,
+                        const uint64_t* noise_seed_dev /* or NULL */, int row_subseq,
                         void* gy, float* dch, void* stream);
 
 /* Generator output backward (pure_gen.py:29,50): out = tanh(sum_c w[c]*(A*a+B)[c] + b0).
