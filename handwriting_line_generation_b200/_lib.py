@@ -72,6 +72,8 @@ class ConvDesc(ctypes.Structure):
         ("nz_stride_n", ctypes.c_int64), ("nz_stride_h", ctypes.c_int64), ("nz_stride_w", ctypes.c_int64),
         ("in_stride_h", ctypes.c_int32), ("in_stride_w", ctypes.c_int32),
         ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64), ("noise_seed_dev", ctypes.c_uint64),
+        ("fold_c", ctypes.c_int32), ("fold_w", ctypes.c_int32),
+        ("fold_stride_h", ctypes.c_int64), ("fold_stride_w", ctypes.c_int64),
     ]
 
 
@@ -84,6 +86,7 @@ class WgradDesc(ctypes.Structure):
         ("tap_dh", ctypes.c_int32 * HWG_MAX_TAPS), ("tap_dw", ctypes.c_int32 * HWG_MAX_TAPS),
         ("Hi", ctypes.c_int32), ("Wi", ctypes.c_int32), ("gy_stride_h", ctypes.c_int32),
         ("gy_stride_w", ctypes.c_int32), ("gy_off_h", ctypes.c_int32), ("gy_off_w", ctypes.c_int32),
+        ("tap_gy_h", ctypes.c_int32 * HWG_MAX_TAPS), ("tap_gy_w", ctypes.c_int32 * HWG_MAX_TAPS),
     ]
 
 

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import conv, ops
 from ._lib import ACT_LRELU, ACT_NONE
-from .pure_gen import TAPS3x3
+from .pure_gen import TAPS3x3, conv1_forward
 
 _SEL = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}  # FusedUpsample: output parity -> [(input offset, kernel index)]
 
@@ -78,31 +78,7 @@ def forward_train(m, content, s, gb, noise):
         st = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
         nz = None if noise is None else noise[k]
         x_in, Hin, Win = x, H, W
-        if e["kind"] == "initial":
-            Ho, Wo = 4, W
-            a = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-            for r in range(4):
-                conv.conv_fprop(x, e["w1"][r], e["taps1"], 1, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2,
-                                out_view=(a, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                noise_view=None if nz is None else (nz, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, noise_seed_dev=seed_dev, stats=st)
-        elif e["kind"] == "plain":
-            Ho, Wo = H, W
-            a = conv.conv_fprop(x, e["w1"], TAPS3x3, Ho, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2, noise=nz,
-                                noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
-        else:
-            if e["kind"] == "vert_up":
-                Ho, Wo = 2 * H, W
-                raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-                for par, (taps, wp) in enumerate(e["w1"]):
-                    conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"], out_view=(raw, Ho * Wo * C, 2 * Wo * C, C, par * Wo * C))
-            else:
-                Ho, Wo = 2 * H, 2 * W
-                raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-                for py, px, taps, wp in e["w1"]:
-                    conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"],
-                                    out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, (py * Wo + px) * C))
-            a = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
+        a, Ho, Wo = conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev)
         H, W = Ho, Wo
         coef, save = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W, save=True)
         recs.append(dict(x_in=x_in, Hin=Hin, Win=Win, a=a, coef=coef, save=save, nz=nz, subseq=16 * k, off=off))
@@ -229,16 +205,30 @@ def backward_train(m, ctx, g_out):
                 w4 = _fused_w4(mod, wl)                # [Cin, Cout, 4, 4]
             Cin = wl.size(0)
             dw4 = torch.empty_like(w4)
-            for py in (0, 1):
-                for px in (0, 1):
-                    taps, idx = [], []
-                    for dh, ky in _SEL[py]:
-                        for dw_, kx in _SEL[px]:
-                            taps.append((dh, dw_))
-                            idx.append((ky, kx))
-                    dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2), gy_offset=(py, px))
-                    for t, (ky, kx) in enumerate(idx):
-                        dw4[:, :, ky, kx] = dw[t].t()
+            if Cin <= 32 and C <= 32:
+                # all four parities in one launch (per-tap gy phase): gy and x are read once
+                taps, phases, idx = [], [], []
+                for py in (0, 1):
+                    for px in (0, 1):
+                        for dh, ky in _SEL[py]:
+                            for dw_, kx in _SEL[px]:
+                                taps.append((dh, dw_))
+                                phases.append((py, px))
+                                idx.append((ky, kx))
+                dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2), tap_phase=phases)
+                # taps are ordered [py][px][a][b] with ky = 2a + (1-py), kx = 2b + (1-px)  (see _SEL)
+                dw4 = dw.view(2, 2, 2, 2, C, Cin).flip(0, 1).permute(5, 4, 2, 0, 3, 1).reshape(Cin, C, 4, 4)
+            else:
+                for py in (0, 1):
+                    for px in (0, 1):
+                        taps, idx = [], []
+                        for dh, ky in _SEL[py]:
+                            for dw_, kx in _SEL[px]:
+                                taps.append((dh, dw_))
+                                idx.append((ky, kx))
+                        dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2), gy_offset=(py, px))
+                        for t, (ky, kx) in enumerate(idx):
+                            dw4[:, :, ky, kx] = dw[t].t()
             (g_w1,) = torch.autograd.grad(w4, wl, dw4)
             w4d = w4.detach()
             taps = [(ky - 1, kx - 1) for ky in range(4) for kx in range(4)]

@@ -39,7 +39,7 @@ def pack_conv2d_weight(weight, cin_pad=None):
 def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
                out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, noise_view=None,
                noise_seed=None, noise_subseq=0, noise_seed_dev=None, stats=None, cin=None, tile_w=0,
-               in_stride=(1, 1)):
+               in_stride=(1, 1), fold=None):
     """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
 
     x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
@@ -50,6 +50,9 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
               (or noise_view=(tensor, sn, sh, sw, element_offset) for a strided one); with noise_w and
               noise_seed but no tensor, N(0,1) is drawn inside the kernel (counter-based hash + Box-Muller)
     stats     optional zeroed fp32 [N,Cout,2]; receives per-(n,c) sum and sum of squares of the output
+    fold      optional (fold_c, fold_w, stride_h, stride_w): Cout = F*fold_c, channel f*fold_c+ch is channel ch of
+              the output pixel displaced by (f//fold_w)*stride_h + (f%fold_w)*stride_w elements; bias/noise_w are
+              [Cout], stats [N,fold_c,2] (see include/hwg_b200.h)
     """
     _lib.require_cuda(x, w_packed)
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
@@ -91,8 +94,10 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
             d.noise_seed_dev = 0 if noise_seed_dev is None else noise_seed_dev.data_ptr()
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cout
+    if fold is not None:
+        d.fold_c, d.fold_w, d.fold_stride_h, d.fold_stride_w = fold
     if stats is not None:
-        assert stats.dtype == torch.float32 and stats.numel() == N * Cout * 2
+        assert stats.dtype == torch.float32 and stats.numel() == N * (fold[0] if fold else Cout) * 2
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -122,7 +127,7 @@ def dgrad_pack(w_taps_f32, taps):
     return pack_taps(mats), [(-dh, -dw) for dh, dw in taps]
 
 
-def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy_offset=(0, 0)):
+def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy_offset=(0, 0), tap_phase=None):
     """dw[t][co][ci] = sum_pixels gy[n,ho,wo,co] * x[n,ho+dh_t,wo+dw_t,ci]  (fp32 [ntaps,cout,cin]).
     x [N,H,W,Cp>=cin] bf16 NHWC, gy [N,Ho,Wo,Gp>=cout] bf16 NHWC."""
     _lib.require_cuda(x, gy)
@@ -138,6 +143,9 @@ def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy
         d.Hi, d.Wi = grid
         d.gy_stride_h, d.gy_stride_w = gy_stride
         d.gy_off_h, d.gy_off_w = gy_offset
+    if tap_phase is not None:   # per-tap gy phase: all parities of an up-sampling conv in one launch (small C only)
+        for i, (ph, pw) in enumerate(tap_phase):
+            d.tap_gy_h[i], d.tap_gy_w[i] = ph, pw
     if out is None:
         out = torch.zeros((len(taps), cout, cin), device=x.device, dtype=torch.float32)
     if PROFILE is not None:

@@ -57,6 +57,11 @@ struct ConvKParams {
   void* y;
   unsigned long long noise_seed, noise_subseq;
   const unsigned long long* noise_seed_dev;
+  // channel folding: output channel c = f * fold_c + ch is channel ch of an output pixel displaced by
+  // (f / fold_w) * fold_sh + (f % fold_w) * fold_sw elements (several launches that share taps and input
+  // run as one: the four rows of the initial transposed conv, the four parities of FusedUpsample)
+  int fold_c, fold_w, stat_c;
+  long long fold_sh, fold_sw;
 };
 
 // Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
@@ -227,7 +232,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m / p.TW, wl = m - hl * p.TW;
-    const uint2 nkey = noise_key(p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull), p.noise_subseq);
+    const unsigned long long nseed = p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull);
+    const uint2 nkey0 = noise_key(nseed, p.noise_subseq);
     int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
     int ti = 0;
     for (int t = t_begin; t < t_end; ++t, ++ti) {
@@ -253,8 +259,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (stat_n >= 0) {
           const int e = et;
           for (int c = e; c < 2 * p.BN; c += 128) {
-            const int ch = stat_n0 + (c >> 1);
-            if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
+            int ch = stat_n0 + (c >> 1);
+            if (ch < p.Cout) {
+              if (p.fold_c) ch %= p.fold_c;
+              atomicAdd(&p.stats[((size_t)stat_n * p.stat_c + ch) * 2 + (c & 1)], stat_s[c]);
+            }
             stat_s[c] = 0.f;
           }
         }
@@ -308,10 +317,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           v[j] = __uint_as_float(r[j]) + bb.x; v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
           v[j + 2] = __uint_as_float(r[j + 2]) + bb.z; v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
         }
+        // folded launch: this chunk's fold and its channel offset inside the fold (fold_c % 32 == 0 whenever
+        // noise or an explicit noise tensor is used, so a chunk never straddles folds there)
+        int fold = 0, fch = n0 + c0;
+        if (p.fold_c) { fold = fch / p.fold_c; fch -= fold * p.fold_c; }
         if (noise_mode == 2) {
-          // element index in the launch's logical [N,Ho,Wo,Cout] output
+          // element index in the logical [N,Ho,Wo,C] output of this launch (of this fold: each fold draws from
+          // its own subsequence, exactly as if it had been launched separately)
           const unsigned long long e0 =
-              (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.Cout + n0 + c0;
+              (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)p.stat_c + fch;
+          const uint2 nkey = p.fold_c ? noise_key(nseed, p.noise_subseq + (unsigned)fold) : nkey0;
           const float2* w2 = reinterpret_cast<const float2*>(nw_s + n0 + c0);
           if ((e0 & 1ull) == 0) {
 #pragma unroll
@@ -328,10 +343,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], normal_one(nkey, e0 + j), v[j]);
           }
         } else if (noise_mode == 1) {
+          const long long zfold = p.fold_c ? zoff - n0 + (fold / p.fold_w) * p.fold_sh + (fold % p.fold_w) * p.fold_sw + fch
+                                           : zoff + c0;
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], p.noise[zoff + c0 + j], v[j]);
+              if (j < nc) v[j] = fmaf(nw_s[n0 + c0 + j], p.noise[zfold + j], v[j]);
           }
         }
         if (act == HWG_ACT_RELU) {
@@ -357,7 +374,25 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             }
           } else {
             __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0;
-            if ((nc & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+            if (p.fold_c) {
+              // folded channels: every 8-channel group goes to its fold's pixel (fold_c % 8 == 0)
+              __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff - n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < nc) {
+                  const int c = n0 + c0 + j, f = c / p.fold_c;
+                  __nv_bfloat16* yq = yb + (f / p.fold_w) * p.fold_sh + (f % p.fold_w) * p.fold_sw + (c - f * p.fold_c);
+                  uint4 pk;
+                  __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                  __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                  __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                  *reinterpret_cast<uint4*>(yq) = pk;
+                }
+              }
+            } else if ((nc & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 if (j < nc) {
@@ -409,8 +444,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       epi_bar_sync(grp);
       const int e = et;
       for (int c = e; c < 2 * p.BN; c += 128) {
-        const int ch = stat_n0 + (c >> 1);
-        if (ch < p.Cout) atomicAdd(&p.stats[((size_t)stat_n * p.Cout + ch) * 2 + (c & 1)], stat_s[c]);
+        int ch = stat_n0 + (c >> 1);
+        if (ch < p.Cout) {
+          if (p.fold_c) ch %= p.fold_c;
+          atomicAdd(&p.stats[((size_t)stat_n * p.stat_c + ch) * 2 + (c & 1)], stat_s[c]);
+        }
       }
     }
     tc_fence_before();
@@ -488,6 +526,14 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   HWG_REQUIRE(d->y_dtype == HWG_DT_BF16 || d->y_dtype == HWG_DT_F32, "hwg_conv_fprop: bad y_dtype");
   HWG_REQUIRE(d->act >= 0 && d->act <= HWG_ACT_LOGSOFTMAX, "hwg_conv_fprop: bad act");
   HWG_REQUIRE(d->act != HWG_ACT_LOGSOFTMAX || d->Cout <= 256, "hwg_conv_fprop: log-softmax needs Cout <= 256");
+  if (d->fold_c) {
+    HWG_REQUIRE(d->fold_c % 8 == 0 && d->Cout % d->fold_c == 0 && d->y_dtype == HWG_DT_BF16 && d->act != HWG_ACT_LOGSOFTMAX,
+                "hwg_conv_fprop: fold_c=%d needs Cout a multiple of it, 8-channel groups and a bf16 output", d->fold_c);
+    HWG_REQUIRE(noise_w == nullptr || d->fold_c % 32 == 0, "hwg_conv_fprop: noise with folding needs fold_c %% 32 == 0");
+    HWG_REQUIRE((d->y_stride_w % 8 == 0) && (d->y_stride_h % 8 == 0) && (d->y_stride_n % 8 == 0) &&
+                (d->fold_stride_h % 8 == 0) && (d->fold_stride_w % 8 == 0) && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "hwg_conv_fprop: folded output needs 16-byte aligned pixels");
+  }
   PFN_encodeTiled encode = get_encode();
   if (!encode) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return HWG_ERR_CUDA; }
 
@@ -567,6 +613,9 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.bias = bias; p.noise = noise; p.noise_w = noise_w; p.stats = stats; p.y = y;
   p.noise_seed = d->noise_seed; p.noise_subseq = d->noise_subseq;
   p.noise_seed_dev = reinterpret_cast<const unsigned long long*>(d->noise_seed_dev);
+  p.fold_c = d->fold_c; p.fold_w = d->fold_w > 0 ? d->fold_w : 1;
+  p.fold_sh = d->fold_stride_h; p.fold_sw = d->fold_stride_w;
+  p.stat_c = d->fold_c ? d->fold_c : d->Cout;
 
   const CUtensorMapSwizzle swz = p.CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : (p.CK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -150,75 +150,92 @@ scale_shift_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const
 }
 
 // ---- blur + noise + activation + statistics ---------------------------------------------------
+// Separable rolling window: a thread owns one 16-byte channel vector of one image column and walks BLUR_ROWS
+// rows downwards.  Per row it loads the three horizontal neighbours once (l + 2c + r), and combines the
+// horizontal sums of the rows above / at / below: 3(R+2)/R loads per output instead of 9, no integer
+// divisions, coalesced 16-byte accesses along (w, c).
+constexpr int BLUR_ROWS = 8;
+
+__device__ __forceinline__ void blur_hrow(const uint4* __restrict__ xn, int h, int H, long long row_items, int ci,
+                                          int CV, bool has_l, bool has_r, float (&hb)[8]) {
+  if (h < 0 || h >= H) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hb[j] = 0.f;
+    return;
+  }
+  const uint4* p = xn + (long long)h * row_items + ci;
+  float c[8], l[8], r[8];
+  unpack8(p[0], c);
+  if (has_l) unpack8(p[-CV], l);
+  if (has_r) unpack8(p[CV], r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hb[j] = 2.f * c[j] + (has_l ? l[j] : 0.f) + (has_r ? r[j] : 0.f);
+}
+
+template <bool RNG>
 __global__ void __launch_bounds__(EW_THREADS)
-blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C,
+blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C, int cv_shift,
                             const float* __restrict__ noise, const float* __restrict__ noise_w,
                             unsigned long long seed, unsigned long long subseq,
                             const unsigned long long* __restrict__ seed_dev, int act, float slope,
                             float* __restrict__ stats) {
   extern __shared__ float sacc[];  // [C][2] block-level statistics
-  const int n = blockIdx.y, CV = C / 8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const long long total = (long long)H * W * CV;
-  const long long base = (long long)blockIdx.x * EW_THREADS * EW_ITER;
-  const uint4* xn = x + (size_t)n * total;
-  uint4* yn = y + (size_t)n * total;
-  const int cv = threadIdx.x % CV;  // CV divides EW_THREADS: fixed per thread
-  float nw[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
+  const int n = blockIdx.z, CV = C / 8;
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  const long long row_items = (long long)W * CV;
+  const long long total = (long long)H * row_items;
+  const int ci = blockIdx.x * EW_THREADS + threadIdx.x;   // (w, cv) inside a row
+  const int cv = ci & (CV - 1);
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
-
-  for (int it = 0; it < EW_ITER; ++it) {
-    const long long item = base + it * EW_THREADS + threadIdx.x;
-    if (item >= total) break;
-    const long long pix = item / CV;
-    const int h = (int)(pix / W), w = (int)(pix - (long long)h * W);
-    float acc[8];
+  if (ci < row_items) {
+    const int w = ci >> cv_shift;
+    const bool has_l = w > 0, has_r = w < W - 1;
+    const uint4* xn = x + (size_t)n * total;
+    uint4* yn = y + (size_t)n * total;
+    float nw[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
+    const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
+    const int h0 = blockIdx.y * BLUR_ROWS, h1 = min(H, h0 + BLUR_ROWS);
+    float prev[8], cur[8], nxt[8];
+    blur_hrow(xn, h0 - 1, H, row_items, ci, CV, has_l, has_r, prev);
+    blur_hrow(xn, h0, H, row_items, ci, CV, has_l, has_r, cur);
+    for (int h = h0; h < h1; ++h) {
+      blur_hrow(xn, h + 1, H, row_items, ci, CV, has_l, has_r, nxt);
+      const long long item = (long long)h * row_items + ci;
+      float acc[8];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int hh = h + dy;
-      if (hh < 0 || hh >= H) continue;
+      for (int j = 0; j < 8; ++j) acc[j] = (prev[j] + 2.f * cur[j] + nxt[j]) * (1.f / 16.f);
+      if (noise_w) {
+        float z[8];
+        if (!RNG) {
+          const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
+          float4 z0 = zp[0], z1 = zp[1];
+          z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+        } else {
+          const unsigned long long e2 = ((unsigned long long)n * total + item) * 4ull;   // pair index of channel 0
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ww = w + dx;
-        if (ww < 0 || ww >= W) continue;
-        const float k = (dy == 0 ? 2.f : 1.f) * (dx == 0 ? 2.f : 1.f) * (1.f / 16.f);
-        float f[8];
-        unpack8(xn[((long long)hh * W + ww) * CV + cv], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
-      }
-    }
-    if (noise_w) {
-      float z[8];
-      if (noise) {
-        const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
-        float4 z0 = zp[0], z1 = zp[1];
-        z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
-      } else {
-        const unsigned long long e2 = ((unsigned long long)n * total + item) * 4ull;   // pair index of channel 0
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 zz = normal_pair(nkey, e2 + q);
-          z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
+          for (int q = 0; q < 4; ++q) {
+            const float2 zz = normal_pair(nkey, e2 + q);
+            z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = act_fn(acc[j], act, slope);
+        s1[j] += acc[j]; s2[j] += acc[j] * acc[j];
+        prev[j] = cur[j]; cur[j] = nxt[j];
+      }
+      yn[item] = pack8(acc);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] = act_fn(acc[j], act, slope);
-      s1[j] += acc[j]; s2[j] += acc[j] * acc[j];
-    }
-    yn[item] = pack8(acc);
   }
   if (stats) {
     // lanes congruent mod CV hold the same channels: fold them, then one shared atomic per warp
@@ -426,10 +443,14 @@ extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, in
   HWG_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= EW_THREADS,
               "hwg_blur_noise_act_stats: C=%d must be 8 x a power of two", C);
   HWG_REQUIRE(noise == nullptr || noise_w != nullptr, "hwg_blur_noise_act_stats: noise needs noise_w");
-  const long long total = (long long)H * W * (C / 8);
-  dim3 grid(blocks_for(total, EW_THREADS * EW_ITER), N);
-  blur_noise_act_stats_kernel<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, noise, noise_w, noise_seed,
+  const int CV = C / 8;
+  int cv_shift = 0;
+  while ((1 << cv_shift) < CV) ++cv_shift;
+  dim3 grid(blocks_for((long long)W * CV, EW_THREADS), (H + BLUR_ROWS - 1) / BLUR_ROWS, N);
+  HWG_REQUIRE(grid.y <= 65535 && N <= 65535, "hwg_blur_noise_act_stats: H=%d / N=%d too large", H, N);
+  auto k = (noise_w && !noise) ? blur_noise_act_stats_kernel<true> : blur_noise_act_stats_kernel<false>;
+  k<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, cv_shift, noise, noise_w, noise_seed,
       noise_subseq, reinterpret_cast<const unsigned long long*>(noise_seed_dev), act, slope, stats);
   return check_launch("blur_noise_act_stats_kernel");
 }

@@ -194,6 +194,8 @@ static int encode_nhwc(PFN_encodeTiled encode, CUtensorMap* tm, const void* base
   return HWG_OK;
 }
 
+int wgrad_small_try(const hwgWgradDesc* d, const void* x, const void* gy, float* dw, void* stream);  // hwg_wgrad_small.cu
+
 }  // namespace hwg
 
 using namespace hwg;
@@ -210,6 +212,14 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
   HWG_REQUIRE(d->ntaps >= 1 && d->ntaps <= HWG_MAX_TAPS, "hwg_conv_wgrad: ntaps=%d", d->ntaps);
   HWG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(dw) & 15) == 0, "hwg_conv_wgrad: pointers must be 16-byte aligned");
+  // small-channel layers: the HBM-bound staged-tile kernel (hwg_wgrad_small.cu)
+  {
+    const int rc = wgrad_small_try(d, x, gy, dw, stream);
+    if (rc >= 0) return rc;
+  }
+  for (int t = 0; t < d->ntaps; ++t)
+    HWG_REQUIRE(d->tap_gy_h[t] == 0 && d->tap_gy_w[t] == 0,
+                "hwg_conv_wgrad: per-tap gy phases are only supported for Cout, Cin in {16, 32}");
   PFN_encodeTiled encode = wg_get_encode();
   if (!encode) { set_error("hwg_conv_wgrad: cuTensorMapEncodeTiled unavailable"); return HWG_ERR_CUDA; }
 

@@ -165,6 +165,61 @@ def _pack_fused_up(mod):
     return out
 
 
+TAPS_UNION = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
+
+
+def _pack_fused_up_folded(mod):
+    """The four output parities of FusedUpsample as ONE launch: 9 union taps, Cout = 4 folds x C (fold = 2*py+px);
+    (tap, parity) pairs the parity does not use carry zero weights.  The operand tile of a tap is then loaded once
+    for all four parities (9 loads per tile instead of 16)."""
+    w = torch.nn.functional.pad(mod.weight * mod.multiplier, [1, 1, 1, 1])
+    w4 = (w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]) / 4  # [Cin,Cout,4,4]
+    cin, cout = w4.shape[:2]
+    sel = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}  # parity -> {input offset: kernel index}
+    mats = []
+    for dh, dw in TAPS_UNION:
+        rows = []
+        for py in (0, 1):
+            for px in (0, 1):
+                if dh in sel[py] and dw in sel[px]:
+                    rows.append(w4[:, :, sel[py][dh], sel[px][dw]].t())
+                else:
+                    rows.append(torch.zeros((cout, cin), device=w4.device, dtype=w4.dtype))
+        mats.append(torch.cat(rows, 0))
+    return conv.pack_taps(mats)
+
+
+def conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev):
+    """First convolution of a StyledConvBlock (+ Blur) + noise + LeakyReLU + statistics (pure_gen.py:205-208).
+    x [B,H,W,Cin] bf16 -> (a [B,Ho,Wo,C] bf16, Ho, Wo); shared by the inference and the training forward."""
+    C, dev = e["C"], x.device
+    if e["kind"] == "initial":
+        Ho, Wo = 4, W
+        a = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
+        # the four output rows are four channel folds of one launch (same input, same taps)
+        conv.conv_fprop(x, e["w1f"], e["taps1"], 1, Wo, bias=e["b1f"], act=ACT_LRELU, slope=0.2,
+                        out_view=(a, Ho * Wo * C, Wo * C, C, 0), fold=(C, 1, Wo * C, 0),
+                        noise_view=None if nz is None else (nz, Ho * Wo * C, Wo * C, C, 0),
+                        noise_w=e["nw1f"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
+        return a, Ho, Wo
+    if e["kind"] == "plain":
+        a = conv.conv_fprop(x, e["w1"], TAPS3x3, H, W, bias=e["b1"], act=ACT_LRELU, slope=0.2, noise=nz,
+                            noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
+        return a, H, W
+    if e["kind"] == "vert_up":
+        Ho, Wo = 2 * H, W
+        raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
+        for par, (taps, wp) in enumerate(e["w1"]):
+            conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"], out_view=(raw, Ho * Wo * C, 2 * Wo * C, C, par * Wo * C))
+    else:
+        Ho, Wo = 2 * H, 2 * W
+        raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
+        conv.conv_fprop(x, e["w1f"], TAPS_UNION, H, W, bias=e["b1f"], out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, 0),
+                        fold=(C, 2, Wo * C, C))
+    a = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
+    return a, Ho, Wo
+
+
 class SpacedGenerator(nn.Module):
     """model/pure_gen.py:12-50.  content [T,B,n_class] + style [B,style_size] -> [B,1,64,4T]."""
 
@@ -225,13 +280,17 @@ class SpacedGenerator(nn.Module):
                 e = {"kind": blk.kind, "C": blk.out_channel}
                 if blk.kind == "initial":
                     e["taps1"], e["w1"] = _pack_initial(blk.conv1.weight, cin_pad)
+                    e["w1f"] = torch.cat(e["w1"], 1).contiguous()      # [3, 4*C, cin_pad]: rows as channel folds
                     e["b1"] = blk.conv1.bias.detach().float().contiguous()
+                    e["b1f"] = e["b1"].repeat(4)
                 elif blk.kind == "vert_up":
                     e["w1"] = _pack_vert_up(blk.conv1[1].weight)
                     e["b1"] = blk.conv1[1].bias.detach().float().contiguous()
                 elif blk.kind == "fused_up":
                     e["w1"] = _pack_fused_up(blk.conv1[0])
+                    e["w1f"] = _pack_fused_up_folded(blk.conv1[0])
                     e["b1"] = blk.conv1[0].bias.detach().float().contiguous()
+                    e["b1f"] = e["b1"].repeat(4)
                 else:
                     e["w1"] = conv.pack_conv2d_weight(blk.conv1.weight)
                     e["b1"] = blk.conv1.bias.detach().float().contiguous()
@@ -239,6 +298,8 @@ class SpacedGenerator(nn.Module):
                 e["b2"] = blk.conv2.bias.detach().float().contiguous()
                 e["nw1"] = blk.noise1.effective_weight().detach().float().contiguous()
                 e["nw2"] = blk.noise2.effective_weight().detach().float().contiguous()
+                if blk.kind == "initial":
+                    e["nw1f"] = e["nw1"].repeat(4)
                 for ad in (blk.adain1, blk.adain2):
                     gb_w.append(ad.style.weight)
                     gb_b.append(ad.style.bias)
@@ -311,32 +372,7 @@ class SpacedGenerator(nn.Module):
             # ---------------- conv1 (+ blur) + noise + lrelu + stats ----------------
             st = new_stats(C)
             nz = None if noise is None else noise[k]
-            if e["kind"] == "initial":
-                Ho, Wo = 4, W
-                y = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-                for r in range(4):
-                    conv.conv_fprop(x, e["w1"][r], e["taps1"], 1, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2,
-                                    out_view=(y, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                    noise_view=None if nz is None else (nz, Ho * Wo * C, Wo * C, C, r * Wo * C),
-                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k + r, noise_seed_dev=seed_dev, stats=st)
-            elif e["kind"] == "plain":
-                Ho, Wo = H, W
-                y = conv.conv_fprop(x, e["w1"], TAPS3x3, Ho, Wo, bias=e["b1"], act=ACT_LRELU, slope=0.2, noise=nz,
-                                    noise_w=e["nw1"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
-            else:
-                if e["kind"] == "vert_up":
-                    Ho, Wo = 2 * H, W
-                    raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-                    for par, (taps, wp) in enumerate(e["w1"]):
-                        conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"],
-                                        out_view=(raw, Ho * Wo * C, 2 * Wo * C, C, par * Wo * C))
-                else:
-                    Ho, Wo = 2 * H, 2 * W
-                    raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-                    for py, px, taps, wp in e["w1"]:
-                        conv.conv_fprop(x, wp, taps, H, W, bias=e["b1"],
-                                        out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, (py * Wo + px) * C))
-                y = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
+            y, Ho, Wo = conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev)
             H, W = Ho, Wo
             coef = ops.adain_coeffs(st, gb[:, off:], gb[:, off + C:], gbs, B, C, H * W)
             if keep:

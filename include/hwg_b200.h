@@ -153,6 +153,14 @@ typedef struct hwgConvDesc {
   uint64_t noise_subseq;  /* distinguishes launches that share a seed */
   uint64_t noise_seed_dev; /* 0, or the DEVICE address of a uint64 that is added to noise_seed when the kernel
                               runs: lets a captured CUDA graph draw fresh noise on every replay */
+  /* Channel folding (0 = off): Cout = F * fold_c; output channel f*fold_c + ch is channel ch of the output pixel
+   * displaced by (f / fold_w) * fold_stride_h + (f % fold_w) * fold_stride_w elements.  Runs launches that share
+   * input and taps as one: the 4 output rows of ConvTranspose2d (4,3) (pure_gen.py:161-163) and the 4 output
+   * parities of FusedUpsample (pure_gen.py:259-279; taps = the 3x3 union, unused (tap, parity) weights zero).
+   * bias / noise_w are [Cout] (replicated per fold by the caller); stats is [N][fold_c][2]; fold f draws its
+   * in-kernel noise from subsequence noise_subseq + f. */
+  int32_t fold_c, fold_w;
+  int64_t fold_stride_h, fold_stride_w;
 } hwgConvDesc;
 
 /* bias [Cout] fp32 or NULL; noise_w [Cout] fp32 or NULL (no noise); noise fp32 tensor or NULL
@@ -251,6 +259,12 @@ typedef struct hwgWgradDesc {
    * j*gy_stride_w+gy_off_w, :] pairs with x[n, i+dh, j+dw, :].  Strides > 1 give the weight gradient of one
    * output phase of an up-sampling convolution (pure_gen.py:176-186, 259-279). */
   int32_t Hi, Wi, gy_stride_h, gy_stride_w, gy_off_h, gy_off_w;
+  /* Per-tap gy phase (added to gy_off; 0 <= phase < stride): all output phases of an up-sampling convolution in
+   * ONE launch, so that gy is read once.  Supported for Cout, Cin in {16, 32} (the staged-tile kernel
+   * wgrad_small_kernel: one TMA box of gy and one halo box of x per spatial tile, ldmatrix + mma.sync over all
+   * taps, accumulators resident in registers; HBM-bound layers). */
+  int32_t tap_gy_h[HWG_MAX_TAPS];
+  int32_t tap_gy_w[HWG_MAX_TAPS];
 } hwgWgradDesc;
 
 int hwg_conv_wgrad(const hwgWgradDesc* desc, const void* x, const void* gy, float* dw, void* stream);

@@ -112,3 +112,29 @@ def test_wgrad_of_transposed_conv_phases(Cin, Cout):
             for t, (ky, kx) in enumerate(idx):
                 got[:, :, ky, kx] = dw_[t].t()
     assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(32, 16, 10, 36), (32, 32, 9, 130), (16, 16, 33, 64)])
+def test_wgrad_all_phases_in_one_launch(Cin, Cout, H, W):
+    """Same gradient with per-tap gy phases: the four parities (16 taps) in ONE launch of the staged-tile kernel."""
+    from handwriting_line_generation_b200 import conv
+    N = 2
+    g = torch.Generator().manual_seed(Cin + Cout + W)
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).double()
+    w4 = torch.zeros(Cin, Cout, 4, 4, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose2d(x, w4, stride=2, padding=1)
+    gy = torch.randn(y.shape, generator=g).to(torch.bfloat16).double()
+    (gw_ref,) = torch.autograd.grad(y, w4, gy)
+    xc, gyc = conv.to_nhwc_bf16(x.float().cuda()), conv.to_nhwc_bf16(gy.float().cuda())
+    sel = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
+    taps, phases, idx = [], [], []
+    for py in (0, 1):
+        for px in (0, 1):
+            for dh, ky in sel[py]:
+                for dw, kx in sel[px]:
+                    taps.append((dh, dw)); phases.append((py, px)); idx.append((ky, kx))
+    dw_ = conv.conv_wgrad(xc, gyc, taps, Cin, Cout, grid=(H, W), gy_stride=(2, 2), tap_phase=phases).cpu().double()
+    got = torch.zeros_like(gw_ref)
+    for t, (ky, kx) in enumerate(idx):
+        got[:, :, ky, kx] = dw_[t].t()
+    assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)

@@ -1,0 +1,93 @@
+"""Runs a few steps of one workload (development aid; run it under `ncu --metrics gpu__time_duration.sum` for a launch
+list, or bare for an eager/graphed device time).
+
+  python tools/step_runner.py {gen_infer|hwr_train|gen_train} [--B n] [--steps k] [--graph]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import handwriting_line_generation_b200 as pkg
+from handwriting_line_generation_b200 import graphs
+from oracle import synth  # input builders only
+
+ap = argparse.ArgumentParser()
+ap.add_argument("workload")
+ap.add_argument("--B", type=int, default=16)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--graph", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+B, Ts, W = a.B, 256, 1024
+torch.manual_seed(0)
+
+if a.workload == "gen_infer":
+    gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).to(dev).eval()
+    content, style = synth.gen_case(Ts, B, 80, 128, 3)
+    ins = [torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev)]
+    mods = [gen]
+
+    def step(c, s):
+        with torch.no_grad():
+            return gen(c, s)
+elif a.workload == "hwr_train":
+    hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
+    opt = torch.optim.Adam(hwr.parameters(), lr=1e-4, capturable=a.graph)
+    T, S = W // 4 - 6, 60
+    ins = [torch.from_numpy(synth.hwr_case(B, W, 1)).to(dev),
+           torch.randint(1, 80, (B, S), dtype=torch.int32, device=dev)]
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), S, dtype=torch.int32, device=dev)
+    mods = [hwr]
+
+    def step(img, tg):
+        loss = pkg.CTCLoss(hwr(img), tg, il, tl)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=not a.graph)
+        return loss
+elif a.workload == "gen_train":
+    gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).to(dev).train()
+    hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
+    for p in hwr.parameters():
+        p.requires_grad_(False)
+    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=a.graph)
+    content, style = synth.gen_case(Ts, B, 80, 128, 3)
+    T, S = Ts - 6, 40
+    ins = [torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev),
+           torch.randint(1, 80, (B, S), dtype=torch.int32, device=dev)]
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), S, dtype=torch.int32, device=dev)
+    mods = [gen, hwr]
+
+    def step(c, s, tg):
+        loss = pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=not a.graph)
+        return loss
+else:
+    raise SystemExit("unknown workload")
+
+if a.graph:
+    fn = graphs.GraphedStep(step, ins, modules=mods, warmup=a.warmup)
+else:
+    fn = step
+    for _ in range(a.warmup):
+        fn(*ins)
+torch.cuda.synchronize()
+n0 = pkg._lib.launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    out = fn(*ins)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.steps
+print(f"{a.workload} B={B} graph={a.graph}: {ms:.3f} ms/step, {B / ms * 1e3:.1f} lines/s, "
+      f"{(pkg._lib.launch_count() - n0) // a.steps} hwg launches/step (host path)", flush=True)
