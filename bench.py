@@ -38,25 +38,32 @@ import torch  # noqa: E402
 GEN = dict(n_class=80, style_dim=128, dim=256, T=256, B=32)
 
 
-def gen_conv_flops_per_line(T, n_in=208, dim=256):
-    """Algorithmic forward conv FLOPs of SpacedGenerator per line (2*pixels*Cout*Cin*taps of the
-    reference's layers) — transposed convs counted on their input pixels."""
-    fl = 0
+def gen_conv_layers(T, n_in=208, dim=256):
+    """Algorithmic forward conv FLOPs of SpacedGenerator per line, layer by layer (2*pixels*Cout*Cin*taps of the
+    reference's layers; transposed convs counted on their input pixels), with the activation bytes a
+    layer must move at bf16 (input read once + output written once) and the kernel that serves it."""
     c = [dim, dim // 2, dim // 4, dim // 8, dim // 16]
+    L = []
     H, W = 1, T
-    fl += 2 * (H * W) * n_in * c[0] * 12          # ConvTranspose2d (4,3)
+    L.append(("b0.conv1", 2 * (H * W) * n_in * c[0] * 12, (H * W * 256 + 4 * W * c[0]) * 2, "conv_fprop_kernel"))
     H = 4
-    fl += 2 * (H * W) * c[0] * c[0] * 9           # b0.conv2
+    L.append(("b0.conv2", 2 * (H * W) * c[0] * c[0] * 9, 2 * H * W * c[0] * 2, "conv_fprop_kernel"))
     for i in (1, 2):                               # upsample(2,1) + conv3x3, conv2
+        L.append((f"b{i}.conv1", 2 * (2 * H * W) * c[i - 1] * c[i] * 9, (H * W * c[i - 1] + 2 * H * W * c[i]) * 2,
+                  "conv_fprop_kernel"))
         H *= 2
-        fl += 2 * (H * W) * c[i - 1] * c[i] * 9
-        fl += 2 * (H * W) * c[i] * c[i] * 9
+        L.append((f"b{i}.conv2", 2 * (H * W) * c[i] * c[i] * 9, 2 * H * W * c[i] * 2, "conv_fprop_kernel"))
     for i in (3, 4):                               # FusedUpsample 4x4 s2 (on input pixels), conv2
-        fl += 2 * (H * W) * c[i - 1] * c[i] * 16
+        L.append((f"b{i}.conv1", 2 * (H * W) * c[i - 1] * c[i] * 16, (H * W * c[i - 1] + 4 * H * W * c[i]) * 2,
+                  "conv_small_kernel"))
         H, W = 2 * H, 2 * W
-        fl += 2 * (H * W) * c[i] * c[i] * 9
-    fl += 2 * (H * W) * c[4]                       # 1x1 output conv
-    return fl
+        L.append((f"b{i}.conv2", 2 * (H * W) * c[i] * c[i] * 9, 2 * H * W * c[i] * 2, "conv_small_kernel"))
+    return L, 2 * (H * W) * c[4]                   # + the 1x1 output conv (fused into gen_output_kernel)
+
+
+def gen_conv_flops_per_line(T, n_in=208, dim=256):
+    L, out = gen_conv_layers(T, n_in, dim)
+    return sum(l[1] for l in L) + out
 
 
 def load_peaks():
@@ -136,7 +143,7 @@ def run_reference(args, rank):
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    sample_B = 4
+    sample_B = 16
     t0 = time.time()
     lps, times = cpu_generator_lines_per_s(sample_B, max(1, args.steps))
     sample = (f"{len(times)} timed passes of the generator forward on a {sample_B}-line slice of the batch "
@@ -158,7 +165,8 @@ def workload_config(B):
             "batch_per_gpu": B, "line_px": [64, 4 * GEN["T"]],
             "l2": "no explicit flush: the bf16 activations one step streams (~0.7 GB at B=32) exceed the 126 MB L2; "
                   "weights (4 MB) stay cached, as in production",
-            "noise": "NoiseInjection N(0,1) drawn in-kernel (counter-based hash + Box-Muller), a fresh seed every step"}
+            "noise": "NoiseInjection N(0,1) drawn in-kernel (counter-based hash + Box-Muller), a fresh seed every step",
+            "execution": "one CUDA graph per step (fixed shapes), replayed; gpu_launches = kernels inside the replayed graphs"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -194,18 +202,33 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_device(i):
-        c, s = dev_sets[i % n_sets]
+    from handwriting_line_generation_b200 import graphs
+
+    def fwd(c, s):
         with torch.no_grad():
             return model(c, s)
 
+    # one eager step counts this path's kernel launches (a graph replay makes none on the host)
+    for i in range(2):
+        fwd(*dev_sets[i])
+    torch.cuda.synchronize()
+    n0 = pkg._lib.launch_count()
+    fwd(*dev_sets[0])
+    launches_per_step = pkg._lib.launch_count() - n0
+    # the step is captured once in a CUDA graph (fixed shapes; a device-side counter re-seeds the noise every replay)
+    graphed = graphs.GraphedStep(fwd, list(dev_sets[0]), modules=[model], warmup=max(3, args.warmup))
+    in_c, in_s = graphed.static_in
+
+    def step_device(i):
+        c, s = dev_sets[i % n_sets]
+        return graphed(c, s)           # device-to-device copy into the graph's input buffers + replay
+
     def step_e2e(i):
         hc, hs = host_sets[i % n_sets]
-        c = hc.to(dev, non_blocking=True)
-        s = hs.to(dev, non_blocking=True)
-        with torch.no_grad():
-            img = model(c, s)
-        out_host[i % 2].copy_(img, non_blocking=True)
+        in_c.copy_(hc, non_blocking=True)      # H2D from pinned memory straight into the graph's inputs
+        in_s.copy_(hs, non_blocking=True)
+        graphed.graph.replay()
+        out_host[i % 2].copy_(graphed.static_out, non_blocking=True)   # D2H of the generated lines
 
     def timed(fn, steps):
         barrier()
@@ -228,30 +251,36 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    n0 = pkg._lib.launch_count()
     t0 = time.time()
     ms = timed(step_device, args.steps)
     t1 = time.time()
-    launches = pkg._lib.launch_count() - n0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
 
-    # ---- roofline of the dominant kernel: events around every conv_fprop launch of a few steps ----
+    # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream) ----
     prof = []
     hconv.PROFILE = prof
     psteps = min(args.steps, 5)
     barrier()
     for i in range(psteps):
-        step_device(i)
+        fwd(*dev_sets[i % n_sets])
     barrier()
     hconv.PROFILE = None
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof) / psteps
-    conv_launches = len(prof) // psteps
-    conv_flops = gen_conv_flops_per_line(T) * B
-    issued_flops = sum(f for _, _, f in prof) / psteps
     peaks = load_peaks()
+    layers, _ = gen_conv_layers(T)
+    kern = {}
+    for e0, e1, fl, kind, by in prof:
+        k = kern.setdefault(kind, {"ms": 0.0, "launches": 0, "issued_flop": 0.0, "bytes": 0.0})
+        k["ms"] += e0.elapsed_time(e1) / psteps
+        k["launches"] += 1 / psteps
+        k["issued_flop"] += fl / psteps
+        k["bytes"] += by / psteps
+    for kind, k in kern.items():
+        k["algorithmic_gflop_per_step"] = sum(l[1] for l in layers if l[3] == kind) * B / 1e9
+        k["algorithmic_mb_per_step"] = sum(l[2] for l in layers if l[3] == kind) * B / 1e6
 
     if rank != 0:
         if world > 1:
@@ -261,16 +290,35 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms / args.steps
     value = lines / (ms_step * 1e-3)
     e2e_value = lines / (ms_e2e / args.steps * 1e-3)
-    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1:
         torch.set_num_threads(cores)
         tb = time.time()
-        lps, times = cpu_generator_lines_per_s(4, 3)
+        lps, times = cpu_generator_lines_per_s(16, 25)
         cpu = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{len(times)} timed generator forwards on a 4-line slice (T_s={T}), torch fp32, "
+               "sample": f"{len(times)} timed generator forwards on a 16-line half of the batch (T_s={T}), torch fp32, "
                          f"{time.time() - tb:.1f}s of CPU work"}
+
+    def roof(kind):
+        k = kern[kind]
+        if kind == "conv_small_kernel":   # HBM-bound layers: activation bytes (read once + written once) / kernel time
+            ach = k["algorithmic_mb_per_step"] * 1e6 / (k["ms"] * 1e-3) / 1e9
+            r = {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                 "frac": ach / peaks["hbm"], "peak_source": f"{peaks['src']} HBM copy bandwidth",
+                 "algorithmic_mb_per_step": k["algorithmic_mb_per_step"]}
+        else:
+            ach = k["algorithmic_gflop_per_step"] * 1e9 / (k["ms"] * 1e-3) / 1e12
+            r = {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                 "frac": ach / peaks["tf_sust"],
+                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside the step)",
+                 "algorithmic_gflop_per_step": k["algorithmic_gflop_per_step"],
+                 "issued_gflop_per_step": k["issued_flop"] / 1e9}
+        r.update({"traffic": None, "launches_per_step": round(k["launches"]), "kernel_ms_per_step": k["ms"],
+                  "share_of_step": k["ms"] / ms_step})
+        return r
+
+    top = max(kern, key=lambda kk: kern[kk]["ms"])
     line = {
         "metric": "generated lines/sec", "value": value, "unit": "lines/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -279,12 +327,8 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(B * 64 * 4 * T * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_fprop_kernel", "achieved": achieved, "peak": peaks["tf_sust"],
-                     "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": None,
-                     "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside the step)",
-                     "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
-                     "share_of_step": conv_ms / ms_step, "algorithmic_gflop_per_step": conv_flops / 1e9,
-                     "issued_gflop_per_step": issued_flops / 1e9},
+        "roofline": roof(top),
+        "roofline_other_kernels": [roof(kk) for kk in kern if kk != top],
         "cpu_baseline": cpu,
     }
     if world == 1:
@@ -316,8 +360,8 @@ def main():
         import bench_hwr_train
         bench_hwr_train.main(args, rank, world, local_rank, load_peaks, ClockSampler)
     elif args.impl == "reference":
-        if args.steps > 10:
-            args.steps = 10   # bounded: each step is a 4-line slice on the CPU (~0.5 s)
+        if args.steps > 40:
+            args.steps = 40   # bounded: each step is a 16-line half batch on the CPU (~0.4 s)
         run_reference(args, rank)
     else:
         run_ours(args, rank, world, local_rank)

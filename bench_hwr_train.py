@@ -52,10 +52,10 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         if rank != 0:
             return
         torch.set_num_threads(os.cpu_count() or 1)
-        steps = min(args.steps, 5)
+        steps = min(args.steps, 30)
         t0 = time.time()
-        lps, times = cpu_lines_per_s(2, steps)
-        sample = (f"{len(times)} timed train steps on a 2-line slice of the batch, torch fp32 on "
+        lps, times = cpu_lines_per_s(4, steps)
+        sample = (f"{len(times)} timed train steps on a 4-line half of the batch, torch fp32 on "
                   f"{torch.get_num_threads()} host threads, {time.time() - t0:.1f}s")
         print(json.dumps({"impl": "reference", "metric": "train-step lines/sec", "value": lps, "unit": "lines/s",
                           "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
@@ -100,12 +100,39 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         opt.step()
         return loss
 
+    graphed = None
+    if world == 1:
+        # single GPU: the whole step (forward, CTC, backward, Adam) is one CUDA graph, replayed
+        from handwriting_line_generation_b200 import graphs
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+
+        def train_static(img, tg):
+            loss = pkg.CTCLoss(model(img), tg, il, tl)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+            return loss
+
+        n0 = pkg._lib.launch_count()
+        train(*devsets[0])
+        launches_per_step = pkg._lib.launch_count() - n0
+        opt.zero_grad(set_to_none=True)
+        graphed = graphs.GraphedStep(train_static, list(devsets[0]), modules=[model], warmup=3)
+
     def step_device(i):
+        if graphed is not None:
+            return graphed(*devsets[i % n_sets])
         return train(*devsets[i % n_sets])
 
     def step_e2e(i):
         a, b = host[i % n_sets]
-        loss = train(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
+        if graphed is not None:
+            graphed.static_in[0].copy_(a, non_blocking=True)
+            graphed.static_in[1].copy_(b, non_blocking=True)
+            graphed.graph.replay()
+            loss = graphed.static_out
+        else:
+            loss = train(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
         loss_host.copy_(loss, non_blocking=True)
 
     def barrier():
@@ -134,7 +161,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     t0 = time.time()
     ms = timed(step_device, args.steps)
     t1 = time.time()
-    launches = pkg._lib.launch_count() - n0
+    launches = (pkg._lib.launch_count() - n0) if graphed is None else launches_per_step * args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     for i in range(3):
         step_e2e(i)
@@ -144,10 +171,12 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     psteps = min(args.steps, 5)
     barrier()
     for i in range(psteps):
-        step_device(i)
+        train(*devsets[i % n_sets])      # eager: per-launch events need host-side launches
+        if graphed is not None:
+            opt.zero_grad(set_to_none=False)
     barrier()
     hconv.PROFILE = None
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in prof) / psteps
+    conv_ms = sum(r[0].elapsed_time(r[1]) for r in prof) / psteps
     peaks = load_peaks()
     if rank != 0:
         if world > 1:
@@ -161,9 +190,9 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     if world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
         tb = time.time()
-        lps, times = cpu_lines_per_s(2, 2)
+        lps, times = cpu_lines_per_s(4, 20)
         cpu = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{len(times)} timed train steps on a 2-line slice, torch fp32, {time.time() - tb:.1f}s of CPU work"}
+               "sample": f"{len(times)} timed train steps on a 4-line half of the batch, torch fp32, {time.time() - tb:.1f}s of CPU work"}
     print(json.dumps({
         "metric": "train-step lines/sec", "value": lines / (ms_step * 1e-3), "unit": "lines/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
@@ -191,38 +220,44 @@ def quick_train_numbers(dev, steps=10):
     from oracle import synth
     out = {}
 
-    def time_steps(fn):
-        for i in range(3):
-            fn(i)
-        torch.cuda.synchronize()
+    from handwriting_line_generation_b200 import graphs
+
+    def time_steps(fn, mods):
+        """fn() = one eager step with static inputs; timed as a replayed CUDA graph."""
         n0 = pkg._lib.launch_count()
+        fn()
+        launches = pkg._lib.launch_count() - n0
+        g = graphs.GraphedStep(fn, [], modules=mods, warmup=2)
+        for _ in range(2):
+            g()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            fn(i)
+            g()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps, (pkg._lib.launch_count() - n0) // steps
+        return e0.elapsed_time(e1) / steps, launches
 
     # (1) configs[0]: recognizer + CTC train step, batch 8 and 32
     for B in (8, 32):
         torch.manual_seed(0)
         model = pkg.CNNOnlyHWR(HWR["C"], norm='batch').to(dev).train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
         T = HWR["W"] // 4 - 6
         img = torch.from_numpy(synth.hwr_case(B, HWR["W"], 1)).to(dev)
         tg = torch.randint(1, HWR["C"], (B, HWR["S"]), dtype=torch.int32, device=dev)
         il = torch.full((B,), T, dtype=torch.int32, device=dev)
         tl = torch.full((B,), HWR["S"], dtype=torch.int32, device=dev)
 
-        def step(i):
-            opt.zero_grad(set_to_none=True)
+        def step():
             pkg.CTCLoss(model(img), tg, il, tl).backward()
             opt.step()
+            opt.zero_grad(set_to_none=False)
 
-        ms, launches = time_steps(step)
+        ms, launches = time_steps(step, [model])
         out[f"hwr_ctc_train_step_B{B}"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
-                                          "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + Adam, 64x1024 lines"}
+                                          "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + Adam, 64x1024 lines; one replayed CUDA graph per step"}
         del model, opt
     # (2) the 'gen' lesson's recognition branch: generator -> frozen recognizer -> CTC -> backward into the
     #     generator -> Adam on the generator (trainer/hw_with_style_trainer.py:760-764), batch 16, T_s=256
@@ -232,7 +267,7 @@ def quick_train_numbers(dev, steps=10):
     hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)
-    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=True)
     content, style = synth.gen_case(Ts, B, 80, 128, 3)
     c, s = torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev)
     T = Ts - 6
@@ -240,13 +275,13 @@ def quick_train_numbers(dev, steps=10):
     il = torch.full((B,), T, dtype=torch.int32, device=dev)
     tl = torch.full((B,), 40, dtype=torch.int32, device=dev)
 
-    def gstep(i):
-        opt.zero_grad(set_to_none=True)
+    def gstep():
         pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl).backward()
         opt.step()
+        opt.zero_grad(set_to_none=False)
 
-    ms, launches = time_steps(gstep)
+    ms, launches = time_steps(gstep, [gen, hwr])
     out["gen_hwr_ctc_train_step_B16"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
                                          "what": "SpacedGenerator fwd+bwd, frozen CNNOnlyHWR fwd + input-gradient bwd, CTC, "
-                                                 "Adam on the generator; 64x1024 lines (the recognition branch of the GAN 'gen' lesson)"}
+                                                 "Adam on the generator; 64x1024 lines (the recognition branch of the GAN 'gen' lesson); one replayed CUDA graph per step"}
     return out

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "hwg_version": (c_int, []),
     "hwg_last_error": (ctypes.c_char_p, []),
     "hwg_launch_count": (ctypes.c_uint64, []),
+    "hwg_last_conv_kernel": (c_int, []),
     "hwg_ctc_forward": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
                                 c_int, c_vp, c_vp, c_vp, c_vp]),
     "hwg_ctc_reduce_mean": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
@@ -74,6 +75,7 @@ class ConvDesc(ctypes.Structure):
         ("noise_seed", ctypes.c_uint64), ("noise_subseq", ctypes.c_uint64), ("noise_seed_dev", ctypes.c_uint64),
         ("fold_c", ctypes.c_int32), ("fold_w", ctypes.c_int32),
         ("fold_stride_h", ctypes.c_int64), ("fold_stride_w", ctypes.c_int64),
+        ("fold_taps", ctypes.c_int32), ("force_tcgen05", ctypes.c_int32),
     ]
 
 

@@ -39,7 +39,7 @@ def pack_conv2d_weight(weight, cin_pad=None):
 def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope=0.0, out=None,
                out_dtype=torch.bfloat16, out_view=None, noise=None, noise_w=None, noise_view=None,
                noise_seed=None, noise_subseq=0, noise_seed_dev=None, stats=None, cin=None, tile_w=0,
-               in_stride=(1, 1), fold=None):
+               in_stride=(1, 1), fold=None, fold_taps=0, force_tcgen05=False):
     """y[n,ho,wo,co] = epi(sum_t sum_ci x[n,ho+dh_t,wo+dw_t,ci] * w[t,co,ci]).
 
     x         [N,H,W,Cp] bf16 NHWC contiguous; `cin` (default w_packed.size(2)) channels are read
@@ -61,6 +61,10 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
     ntaps, Cout, Cin = w_packed.shape
     cin = cin or Cin
     assert cin == Cin and Cin <= Cp and ntaps == len(taps)
+    if fold is not None and not fold_taps:
+        assert Cout % fold[0] == 0
+    elif fold is not None:
+        Cout = Cout * (ntaps // fold_taps)      # w is [ntaps][fold_c][Cin]: the launch's channel count is F * fold_c
     d = _lib.ConvDesc()
     d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps = N, H, W, Cin, Cp, Cout, Ho, Wo, ntaps
     for i, (dh, dw) in enumerate(taps):
@@ -96,6 +100,8 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
         assert bias.dtype == torch.float32 and bias.numel() == Cout
     if fold is not None:
         d.fold_c, d.fold_w, d.fold_stride_h, d.fold_stride_w = fold
+        d.fold_taps = fold_taps
+    d.force_tcgen05 = int(force_tcgen05)
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.numel() == N * (fold[0] if fold else Cout) * 2
     if PROFILE is not None:
@@ -106,7 +112,10 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
               _lib.stream())
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * Cout * Cin * ntaps))
+        kind = "conv_small_kernel" if _lib.load().hwg_last_conv_kernel() == 2 else "conv_fprop_kernel"
+        by = N * H * W * Cin * 2 + N * Ho * Wo * Cout * y.element_size()    # activations read once + written once
+        flops = 2.0 * N * Ho * Wo * Cin * (w_packed.size(0) * w_packed.size(1))   # MACs actually issued
+        PROFILE.append((e0, e1, flops, kind, by))
     return out
 
 
@@ -154,5 +163,6 @@ def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy
     _lib.call("hwg_conv_wgrad", ctypes.addressof(d), x.data_ptr(), gy.data_ptr(), out.data_ptr(), _lib.stream())
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * len(taps)))
+        PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * len(taps), "conv_wgrad_kernel",
+                        (x.numel() + gy.numel()) * 2))
     return out

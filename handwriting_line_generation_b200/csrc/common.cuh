@@ -16,6 +16,7 @@ namespace hwg {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_last_conv_kernel;   // 1 = tcgen05 implicit GEMM, 2 = staged-tile mma.sync kernel
 
 inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);

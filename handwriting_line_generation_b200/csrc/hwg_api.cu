@@ -7,6 +7,7 @@
 namespace hwg {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_last_conv_kernel{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,3 +36,4 @@ int ensure_max_smem(const void* func) {
 extern "C" int hwg_version(void) { return 100; }
 extern "C" const char* hwg_last_error(void) { return hwg::g_err; }
 extern "C" uint64_t hwg_launch_count(void) { return hwg::g_launches.load(); }
+extern "C" int hwg_last_conv_kernel(void) { return hwg::g_last_conv_kernel.load(); }

@@ -507,6 +507,9 @@ static ConvKernel pick_kernel(const ConvKParams& p) {
   return conv_fprop_kernel<-1, -1, -1, -1>;
 }
 
+int conv_small_try(const hwgConvDesc* d, const void* x, const void* w, const float* bias, const float* noise,
+                   const float* noise_w, float* stats, void* y, void* stream);   // hwg_conv_small.cu
+
 }  // namespace hwg
 
 using namespace hwg;
@@ -526,6 +529,12 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   HWG_REQUIRE(d->y_dtype == HWG_DT_BF16 || d->y_dtype == HWG_DT_F32, "hwg_conv_fprop: bad y_dtype");
   HWG_REQUIRE(d->act >= 0 && d->act <= HWG_ACT_LOGSOFTMAX, "hwg_conv_fprop: bad act");
   HWG_REQUIRE(d->act != HWG_ACT_LOGSOFTMAX || d->Cout <= 256, "hwg_conv_fprop: log-softmax needs Cout <= 256");
+  if (!d->force_tcgen05) {
+    // small-channel (HBM-bound) layers: staged-tile kernel
+    const int rc = conv_small_try(d, x, w, bias, noise, noise_w, stats, y, stream);
+    if (rc >= 0) { g_last_conv_kernel.store(2); return rc; }
+  }
+  HWG_REQUIRE(d->fold_taps == 0, "hwg_conv_fprop: per-fold taps need Cin in {16,32,64} and <= 64 channels per fold");
   if (d->fold_c) {
     HWG_REQUIRE(d->fold_c % 8 == 0 && d->Cout % d->fold_c == 0 && d->y_dtype == HWG_DT_BF16 && d->act != HWG_ACT_LOGSOFTMAX,
                 "hwg_conv_fprop: fold_c=%d needs Cout a multiple of it, 8-channel groups and a bf16 output", d->fold_c);
@@ -646,5 +655,6 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   HWG_SMEM_OPTIN(k);
   // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently
   k<<<grid, ctas_per_sm == 1 ? 320 : 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
+  g_last_conv_kernel.store(1);
   return check_launch("conv_fprop_kernel");
 }

@@ -30,7 +30,8 @@ __device__ __forceinline__ float2 normal_pair(uint2 key, unsigned long long pair
   y ^= y >> 15; y *= 0x297A2D39u; y ^= y >> 16;
   const float u1 = fmaf((float)(x >> 8), 5.9604645e-8f, 2.9802322e-8f);   // (0,1): (k + 0.5) / 2^24
   const float ang = (float)(y >> 8) * 3.7450704e-7f;                       // 2*pi*k / 2^24
-  const float r = sqrtf(-1.3862944f * __log2f(u1));                        // sqrt(-2 ln u1), ln = lg2 * ln2
+  float r;                                                                 // sqrt(-2 ln u1), ln = lg2 * ln2
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862944f * __log2f(u1)));   // one MUFU op instead of the IEEE sequence
   float s, c;
   __sincosf(ang, &s, &c);
   return make_float2(r * c, r * s);

@@ -214,8 +214,9 @@ def conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev):
     else:
         Ho, Wo = 2 * H, 2 * W
         raw = torch.empty((B, Ho, Wo, C), device=dev, dtype=torch.bfloat16)
-        conv.conv_fprop(x, e["w1f"], TAPS_UNION, H, W, bias=e["b1f"], out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, 0),
-                        fold=(C, 2, Wo * C, C))
+        # the four output parities are four folds of one launch, four taps each
+        conv.conv_fprop(x, e["w1f"], e["taps1f"], H, W, bias=e["b1f"], out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, 0),
+                        fold=(C, 2, Wo * C, C), fold_taps=4)
     a = ops.blur_noise_act_stats(raw, nz, e["nw1"], st, ACT_LRELU, 0.2, seed or 0, 16 * k, seed_dev)
     return a, Ho, Wo
 
@@ -288,7 +289,8 @@ class SpacedGenerator(nn.Module):
                     e["b1"] = blk.conv1[1].bias.detach().float().contiguous()
                 elif blk.kind == "fused_up":
                     e["w1"] = _pack_fused_up(blk.conv1[0])
-                    e["w1f"] = _pack_fused_up_folded(blk.conv1[0])
+                    e["w1f"] = torch.cat([wp for _, _, _, wp in e["w1"]], 0).contiguous()   # [16, C, Cin], parity-major
+                    e["taps1f"] = [t for _, _, taps, _ in e["w1"] for t in taps]
                     e["b1"] = blk.conv1[0].bias.detach().float().contiguous()
                     e["b1f"] = e["b1"].repeat(4)
                 else:

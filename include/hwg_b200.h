@@ -161,6 +161,11 @@ typedef struct hwgConvDesc {
    * in-kernel noise from subsequence noise_subseq + f. */
   int32_t fold_c, fold_w;
   int64_t fold_stride_h, fold_stride_w;
+  /* 0: every tap feeds every fold (w is [ntaps][Cout][Cin]).  k > 0: taps [f*k, (f+1)*k) belong to fold f only and
+   * w is [ntaps][fold_c][Cin] — a stride-2 transposed convolution as one launch whose folds are the output
+   * parities (4 taps each).  k > 0 is served by the staged-tile kernel (hwg_conv_small.cu; Cin in {16,32,64}). */
+  int32_t fold_taps;
+  int32_t force_tcgen05;  /* 1: never route to the staged-tile kernel (benchmark / test switch) */
 } hwgConvDesc;
 
 /* bias [Cout] fp32 or NULL; noise_w [Cout] fp32 or NULL (no noise); noise fp32 tensor or NULL
@@ -170,6 +175,10 @@ typedef struct hwgConvDesc {
 int hwg_conv_fprop(const hwgConvDesc* desc, const void* x, const void* w, const float* bias,
                    const float* noise, const float* noise_w, float* stats, void* y,
                    void* stream);
+/* Which kernel served the most recent hwg_conv_fprop call: 1 = conv_fprop_kernel (tcgen05 implicit GEMM, the
+ * tensor-bound layers), 2 = conv_small_kernel (TMA-staged tiles + mma.sync, the HBM-bound 16-64 channel layers).
+ * For benchmarks / profiles. */
+int hwg_last_conv_kernel(void);
 
 /* ------------------------------------------------------------------------
  * Fused memory-bound passes around the convolutions.  Activations are NHWC

@@ -227,3 +227,81 @@ def test_folded_launch_rows_with_noise_tensor_and_stats():
     s1 = ref.sum((2, 3))
     s2 = (ref * ref).sum((2, 3))
     assert _rel(st[:, :, 0].cpu(), s1) <= 5e-3 and _rel(st[:, :, 1].cpu(), s2) <= 5e-3
+
+
+# ---- staged-tile kernel for the small-channel layers (hwg_conv_small.cu) ------------------------------------
+SMALL_CASES = [
+    # N, Cin, Cout, H, W
+    (2, 16, 16, 20, 150),
+    (2, 32, 32, 9, 70),
+    (1, 16, 32, 33, 64),
+    (2, 32, 16, 5, 16),
+    (1, 32, 64, 12, 40),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_small_channel_kernel_matches_torch(case):
+    """bf16-output 3x3 convolutions with Cin in {16,32}: routed to conv_small_kernel (TMA-staged halo tiles +
+    mma.sync); bias + explicit noise + LeakyReLU + statistics epilogue; also checked against the tcgen05 kernel."""
+    from handwriting_line_generation_b200 import conv, _lib
+    N, Cin, Cout, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b, nw = torch.randn(Cout, generator=g), torch.rand(Cout, generator=g)
+    nz = torch.randn(N, Cout, H, W, generator=g)
+    ref = F.leaky_relu(_ref_conv(x, w, b, (1, 1)) + nw.view(1, Cout, 1, 1) * nz, 0.2)
+    xs, ws = conv.to_nhwc_bf16(x.cuda()), conv.pack_conv2d_weight(w.cuda())
+    taps = conv.conv_taps(3, 3, 1, 1)
+    outs = []
+    for force in (False, True):
+        st = torch.zeros((N, Cout, 2), device="cuda")
+        y = conv.conv_fprop(xs, ws, taps, H, W, bias=b.cuda(), act=_lib.ACT_LRELU, slope=0.2,
+                            noise=nz.permute(0, 2, 3, 1).contiguous().cuda(), noise_w=nw.cuda(), stats=st,
+                            force_tcgen05=force)
+        got = y.float().permute(0, 3, 1, 2).cpu()
+        assert _rel(got, ref) <= 1e-2, (force, _rel(got, ref))
+        assert _rel(st[:, :, 0].cpu(), ref.sum((2, 3))) <= 5e-3 and _rel(st[:, :, 1].cpu(), (ref * ref).sum((2, 3))) <= 5e-3
+        outs.append(got)
+    assert _rel(outs[0], outs[1]) <= 1e-2
+
+
+@pytest.mark.parametrize("case", [(2, 32, 16, 12, 40), (1, 64, 32, 9, 70), (2, 64, 32, 4, 64)])
+def test_small_channel_kernel_transposed_conv_one_launch(case):
+    """FusedUpsample's conv_transpose2d(4x4, stride 2, pad 1) as one launch: 4 folds (output parities) x 4 taps."""
+    from handwriting_line_generation_b200 import conv
+    from handwriting_line_generation_b200.pure_gen import FusedUpsample, _pack_fused_up
+    N, Cin, C, H, W = case
+    torch.manual_seed(sum(case))
+    mod = FusedUpsample(Cin, C, 3, padding=1)
+    mod.bias.data.normal_()
+    x = torch.randn(N, Cin, H, W)
+    wpad = F.pad(mod.weight * mod.multiplier, [1, 1, 1, 1])
+    w4 = (wpad[:, :, 1:, 1:] + wpad[:, :, :-1, 1:] + wpad[:, :, 1:, :-1] + wpad[:, :, :-1, :-1]) / 4
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).double(), w4.to(torch.bfloat16).double(), mod.bias.double(),
+                             stride=2, padding=1).float().detach()
+    packs = _pack_fused_up(mod.cuda())
+    wf = torch.cat([wp for _, _, _, wp in packs], 0).contiguous()
+    taps = [t for _, _, tp, _ in packs for t in tp]
+    Ho, Wo = 2 * H, 2 * W
+    raw = torch.zeros((N, Ho, Wo, C), device="cuda", dtype=torch.bfloat16)
+    conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), wf, taps, H, W, bias=mod.bias.detach().float().repeat(4).cuda(),
+                    out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, 0), fold=(C, 2, Wo * C, C), fold_taps=4)
+    assert _rel(raw.float().permute(0, 3, 1, 2).cpu(), ref) <= 1e-2
+
+
+@pytest.mark.parametrize("case", [(2, 16, 32, 16, 64), (1, 32, 64, 10, 36)])
+def test_small_channel_kernel_strided_input(case):
+    """Stride-2 input access (the input gradient of the stride-2 transposed convolutions) on the staged-tile kernel."""
+    from handwriting_line_generation_b200 import conv
+    N, Cin, Cout, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).to(torch.bfloat16).double()
+    w = (torch.randn(Cout, Cin, 4, 4, generator=g) / (Cin * 16) ** 0.5).to(torch.bfloat16).double()
+    ref = F.conv2d(x, w, stride=2, padding=1).float()
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    taps = [(i - 1, j - 1) for i in range(4) for j in range(4)]
+    y = conv.conv_fprop(conv.to_nhwc_bf16(x.float().cuda()), conv.pack_conv2d_weight(w.float().cuda()), taps, Ho, Wo,
+                        in_stride=(2, 2))
+    assert _rel(y.float().permute(0, 3, 1, 2).cpu(), ref) <= 1e-2

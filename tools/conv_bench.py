@@ -15,7 +15,7 @@ SHAPES = {
     "gen_b4c2": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "noise_stats"),
     "gen_b4c2_plain": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "none"),
 }
-which = sys.argv[1:] or list(SHAPES)
+which = [a for a in sys.argv[1:] if a in SHAPES] or ([] if sys.argv[1:] else list(SHAPES))
 reps = 10
 for name in which:
     N, H, W, Cin, Cout, (kh, kw, ph, pw), epi = SHAPES[name]
@@ -44,3 +44,21 @@ for name in which:
     fl = 2.0 * N * Ho * Wo * Cout * Cin * kh * kw
     by = (x.numel() + out.numel()) * 2
     print(f"{name:16s} {us:9.1f} us  {fl / us / 1e6:8.1f} TFLOP/s  act-bytes {by / us / 1e3:8.1f} GB/s", flush=True)
+
+if "blur_b4" in sys.argv[1:]:
+    from handwriting_line_generation_b200 import ops
+    N, H, W, C = 32, 64, 1024, 16
+    x = torch.randn(N, H, W, C, device="cuda").to(torch.bfloat16)
+    nw = torch.ones(C, device="cuda")
+    st = torch.zeros(N, C, 2, device="cuda")
+    for _ in range(3):
+        ops.blur_noise_act_stats(x, None, nw, st, _lib.ACT_LRELU, 0.2, 1, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.blur_noise_act_stats(x, None, nw, st, _lib.ACT_LRELU, 0.2, 1, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    print(f"blur_b4 {us:9.1f} us  {2 * x.numel() * 2 / us / 1e3:8.1f} GB/s", flush=True)
