@@ -3,8 +3,11 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Default workload = BASELINE.json configs[1]: pure_gen generator inference, batch 32 per GPU,
-T_s=256 spaced characters -> 32 x [1,64,1024] lines per step, in-kernel noise.
+Default workload (`--workload gan_train`, bench_gan_train.py) = BASELINE.json's metric: the HWWithStyle GAN "gen"
+lesson train step on the SURVEY 8(a) rows — generator fwd+bwd, frozen recognizer fwd + input-gradient bwd, CTC
+fwd+bwd, gradient all-reduce (N>1), Adam — 16 lines of 64x1024 px per GPU.
+`--workload gen_infer` (this file) = configs[1]: pure_gen generator inference, batch 32 per GPU, T_s=256;
+`--workload hwr_train` (bench_hwr_train.py) = configs[0]: recognizer + CTC train step, batch 8 per GPU.
 A "step" is one pass of that path over one batch of synthetic input.
 
   value     lines/s with the inputs already resident in HBM (device-timed, CUDA events)
@@ -331,14 +334,6 @@ def run_ours(args, rank, world, local_rank):
         "roofline_other_kernels": [roof(kk) for kk in kern if kk != top],
         "cpu_baseline": cpu,
     }
-    if world == 1:
-        try:   # training paths, measured briefly in the same run (details: bench.py --workload hwr_train)
-            import bench_hwr_train
-            del model
-            torch.cuda.empty_cache()
-            line["extra_workloads"] = bench_hwr_train.quick_train_numbers(dev)
-        except Exception as e:   # never lose the headline over the extras
-            line["extra_workloads"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -350,13 +345,17 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gen_infer", choices=["gen_infer", "hwr_train"],
-                    help="gen_infer = BASELINE configs[1] (default); hwr_train = configs[0] recognizer+CTC train step")
+    ap.add_argument("--workload", default="gan_train", choices=["gan_train", "gen_infer", "hwr_train"],
+                    help="gan_train (default) = the GAN 'gen' lesson train step on the hot path (BASELINE metric); "
+                         "gen_infer = BASELINE configs[1]; hwr_train = configs[0] recognizer+CTC train step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "hwr_train":
+    if args.workload == "gan_train":
+        import bench_gan_train
+        bench_gan_train.main(args, rank, world, local_rank, load_peaks, ClockSampler)
+    elif args.workload == "hwr_train":
         import bench_hwr_train
         bench_hwr_train.main(args, rank, world, local_rank, load_peaks, ClockSampler)
     elif args.impl == "reference":

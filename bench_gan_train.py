@@ -1,0 +1,335 @@
+"""bench.py default workload: the HWWithStyle GAN "gen" lesson restricted to the SURVEY.md §8(a) rows — the
+one data-parallel hot path BASELINE.json:north_star names.
+
+One step (trainer/hw_with_style_trainer.py:514-530,752-764 `run_gen` with the genRecog loss, then :381-391):
+  generator forward  (SpacedGenerator, model/pure_gen.py:42-50)          synthetic spaced text + style -> 64x1024 lines
+  recognizer forward (CNNOnlyHWR, model/cnn_only_hwr.py:96-107)          frozen weights, BatchNorm in train mode
+  CTC loss           (CTCLoss, model/loss.py:28-30)                      forward + backward
+  backward           recognizer input-gradient chain (dgrad), generator dgrad + wgrad + norm/noise backward
+  gradient all-reduce over NCCL (world > 1), launched from grad-ready hooks on a side stream (dp.GradReducer)
+  Adam on the generator (lr 2e-4, betas (0.5, 0.999): configs/cf_IAM*.json:35-46)
+The discriminator and perceptual-encoder branches of the full step (BASELINE configs[2]) are not part
+of this path and are not executed.
+
+Batch 16 lines per GPU (weak scaling; 8 GPUs = BASELINE configs[3]'s global batch 128), T_s = 256 -> 64x1024 px,
+IAM charset (80 classes), 40-character targets.
+"""
+import json
+import os
+import statistics
+import time
+
+import numpy as np
+import torch
+
+GAN = dict(B=16, Ts=256, S=40, C=80, style=128, dim=256)
+HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per 64x1024 line
+HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
+
+
+def config(B, world, executed):
+    return {"workload": "HWWithStyle GAN 'gen' lesson train step on the SURVEY 8(a) rows (BASELINE configs[2]/[3] shapes): "
+                        "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
+                        "CTC loss fwd+bwd, gradient all-reduce (N>1), Adam on the generator; discriminator/perceptual "
+                        "branches (SURVEY 8 f1) not included",
+            "batch_per_gpu": B, "global_batch": B * world, "line_px": [64, 4 * GAN["Ts"]], "classes": GAN["C"],
+            "target_chars": GAN["S"], "parallelism": f"dp{world}",
+            "l2": "no explicit flush: the bf16 activations + gradients one step streams (~1.5 GB at B=16) exceed the "
+                  "126 MB L2; weights stay cached, as in production",
+            "noise": "NoiseInjection N(0,1) drawn in-kernel, re-seeded every step by a device-side counter",
+            "execution": executed}
+
+
+def gen_layers(T, n_in=208, dim=256):
+    from bench import gen_conv_layers
+    return gen_conv_layers(T, n_in, dim)
+
+
+def cpu_lines_per_s(sample_B, reps):
+    """The reference's CPU path for this step (oracle port: torch fp32 autograd through oracle/gen.py and
+    oracle/hwr.py + F.ctc_loss + Adam on the generator), all host threads."""
+    from oracle import gen as ogen, hwr as ohwr, synth
+    from handwriting_line_generation_b200 import CNNOnlyHWR, SpacedGenerator   # parameter containers only (CPU)
+    torch.manual_seed(0)
+    gmod = SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False, append_style=True,
+                           small=False)
+    trainable = {n for n, _ in gmod.named_parameters()}
+    gsd = {k: v.clone().requires_grad_(k in trainable) for k, v in gmod.state_dict().items()}
+    hsd = {k: v.clone() for k, v in CNNOnlyHWR(GAN["C"], norm='batch').state_dict().items()}
+    params = [v for v in gsd.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
+    content, style = synth.gen_case(GAN["Ts"], sample_B, GAN["C"], GAN["style"], 3)
+    c, s = torch.from_numpy(content), torch.from_numpy(style)
+    shapes = synth.gen_noise_shapes(GAN["Ts"], sample_B, GAN["dim"])
+    T = GAN["Ts"] - 6
+    tg = torch.randint(1, GAN["C"], (sample_B, GAN["S"]), dtype=torch.int32)
+    il, tl = torch.full((sample_B,), T, dtype=torch.int32), torch.full((sample_B,), GAN["S"], dtype=torch.int32)
+    times = []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        noise = [torch.randn(sh) for sh in shapes]
+        img = ogen.generator_forward(gsd, c, s, noise)
+        lp = ohwr.hwr_forward(hsd, img, True, {})
+        torch.nn.functional.ctc_loss(lp, tg, il, tl).backward()
+        opt.step()
+        if i:
+            times.append(time.perf_counter() - t0)
+    return sample_B / statistics.median(times), times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    steps = min(args.steps, 12)
+    t0 = time.time()
+    sample_B = 4
+    lps, times = cpu_lines_per_s(sample_B, steps)
+    sample = (f"{len(times)} timed train steps on a {sample_B}-line quarter of the batch, torch fp32 on "
+              f"{torch.get_num_threads()} host threads, {time.time() - t0:.1f}s")
+    print(json.dumps({"impl": "reference", "metric": "GAN train-step lines/sec", "value": lps, "unit": "lines/s",
+                      "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": config(GAN["B"], args.gpus, "oracle port on the host cores"),
+                      "cpu_baseline": {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(),
+                                       "kind": "port", "sample": sample},
+                      "e2e": {"value": lps, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+          flush=True)
+
+
+def main(args, rank, world, local_rank, load_peaks, ClockSampler):
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import conv as hconv, dp, graphs
+    from oracle import synth   # input builders only (numpy)
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, Ts, S, C = GAN["B"], GAN["Ts"], GAN["S"], GAN["C"]
+    T = Ts - 6
+    torch.manual_seed(0)       # identical initial weights on every rank
+    gen = pkg.SpacedGenerator(C, GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False, append_style=True,
+                              small=False).to(dev).train()
+    hwr = pkg.CNNOnlyHWR(C, norm='batch').to(dev).train()
+    for p in hwr.parameters():
+        p.requires_grad_(False)            # hwr_frozen: no optimizer touches it; its wgrad is skipped
+    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=True)
+    reducer = dp.GradReducer(gen.parameters()) if world > 1 else None
+    n_sets = 4
+    host = []
+    for i in range(n_sets):
+        content, style = synth.gen_case(Ts, B, C, GAN["style"], 1000 * rank + i)
+        tg = np.random.RandomState(7000 + 1000 * rank + i).randint(1, C, (B, S)).astype(np.int32)
+        host.append(tuple(torch.from_numpy(a).pin_memory() for a in (content, style, tg)))
+    devsets = [tuple(a.to(dev) for a in h) for h in host]
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), S, dtype=torch.int32, device=dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    torch.manual_seed(1234 + rank)   # per-rank noise streams
+
+    def train(c, s, tg):
+        loss = pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+            opt.step()
+            reducer.zero_grad()
+        else:
+            opt.step()
+            opt.zero_grad(set_to_none=False)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # eager steps: allocator warm-up, optimizer state, and the launch count of one step
+    for i in range(2):
+        train(*devsets[i])
+    torch.cuda.synchronize()
+    n0 = pkg._lib.launch_count()
+    train(*devsets[0])
+    launches_per_step = pkg._lib.launch_count() - n0
+    graphed, executed = None, "eager launches"
+    try:
+        if os.environ.get("HWG_BENCH_NO_GRAPH"):
+            raise RuntimeError("disabled by HWG_BENCH_NO_GRAPH")
+        graphed = graphs.GraphedStep(train, list(devsets[0]), modules=[gen, hwr], warmup=3)
+        executed = ("one CUDA graph per step (fixed shapes; forward, CTC, backward, "
+                    + ("NCCL all-reduce on a side stream, " if world > 1 else "") + "Adam), replayed")
+    except Exception as e:        # a capture failure must not lose the measurement: run the same step eagerly
+        graphed = None
+        executed = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        if graphed is not None:
+            return graphed(*devsets[i % n_sets])
+        return train(*devsets[i % n_sets])
+
+    def step_e2e(i):
+        hc, hs, ht = host[i % n_sets]
+        if graphed is not None:
+            for dst, src in zip(graphed.static_in, (hc, hs, ht)):
+                dst.copy_(src, non_blocking=True)       # H2D from pinned memory into the graph's input buffers
+            graphed.graph.replay()
+            loss = graphed.static_out
+        else:
+            loss = train(hc.to(dev, non_blocking=True), hs.to(dev, non_blocking=True), ht.to(dev, non_blocking=True))
+        loss_host.copy_(loss, non_blocking=True)        # D2H of the step's loss
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return dp.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    W = max(3, args.warmup)
+    for i in range(W):
+        step_device(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t0 = time.time()
+    ms = timed(step_device, args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    loss_value = float(loss_host)
+
+    # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream)
+    prof = []
+    hconv.PROFILE = prof
+    psteps = min(args.steps, 4)
+    barrier()
+    for i in range(psteps):
+        train(*devsets[i % n_sets])
+    barrier()
+    hconv.PROFILE = None
+    kern = {}
+    for e0, e1, fl, kind, by in prof:
+        k = kern.setdefault(kind, {"ms": 0.0, "launches": 0.0, "issued_flop": 0.0, "bytes": 0.0})
+        k["ms"] += e0.elapsed_time(e1) / psteps
+        k["launches"] += 1 / psteps
+        k["issued_flop"] += fl / psteps
+        k["bytes"] += by / psteps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    layers, _ = gen_layers(Ts)
+    ms_step = ms / args.steps
+    # algorithmic work per step by kernel: a layer's dgrad runs on the kernel that serves its fprop
+    alg = {
+        "conv_fprop_kernel": {"gflop": B * (2 * sum(l[1] for l in layers if l[3] == "conv_fprop_kernel") / 1e9
+                                            + 2 * (HWR_GF_FWD_PER_LINE - HWR_GF_STEM_PER_LINE)),
+                              "what": "fprop + dgrad of generator b0-b2 and recognizer conv1-6 + 1-D head (tcgen05)"},
+        "conv_small_kernel": {"gflop": B * 2 * sum(l[1] for l in layers if l[3] == "conv_small_kernel") / 1e9,
+                              "mb": B * 2 * sum(l[2] for l in layers if l[3] == "conv_small_kernel") / 1e6,
+                              "what": "fprop + dgrad of generator b3-b4 (16-64 channels, HBM-bound)"},
+        "conv_wgrad_kernel": {"gflop": B * sum(l[1] for l in layers) / 1e9,
+                              "what": "wgrad of all generator convolutions (tcgen05 + staged-tile kernels)"},
+    }
+
+    def roof(kind):
+        k = kern[kind]
+        a = alg.get(kind, {})
+        if kind == "conv_small_kernel":
+            ach = a["mb"] * 1e6 / (k["ms"] * 1e-3) / 1e9
+            r = {"bound": "hbm", "kernel": kind, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                 "frac": ach / peaks["hbm"], "peak_source": f"{peaks['src']} HBM copy bandwidth",
+                 "algorithmic_mb_per_step": a["mb"]}
+        else:
+            gf = a.get("gflop", k["issued_flop"] / 1e9)
+            ach = gf * 1e9 / (k["ms"] * 1e-3) / 1e12
+            r = {"bound": "tensor", "kernel": kind, "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                 "frac": ach / peaks["tf_sust"],
+                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside the step)",
+                 "algorithmic_gflop_per_step": gf, "issued_gflop_per_step": k["issued_flop"] / 1e9}
+        r.update({"covers": a.get("what"), "traffic": None, "launches_per_step": round(k["launches"]),
+                  "kernel_ms_per_step": k["ms"], "share_of_step": k["ms"] / ms_step})
+        return r
+
+    top = max(kern, key=lambda kk: kern[kk]["ms"])
+    lines = B * world
+    cpu = None
+    if world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        tb = time.time()
+        lps, times = cpu_lines_per_s(4, 6)
+        cpu = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{len(times)} timed train steps on a 4-line quarter of the batch (T_s={Ts}), torch fp32, "
+                         f"{time.time() - tb:.1f}s of CPU work"}
+    h2d = int(Ts * B * C * 4 + B * GAN["style"] * 4 + B * S * 4)
+    line = {
+        "metric": "GAN train-step lines/sec", "value": lines / (ms_step * 1e-3), "unit": "lines/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(B, world, executed),
+        "e2e": {"value": lines / (ms_e2e / args.steps * 1e-3), "unit": "lines/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,
+        "roofline": roof(top), "roofline_other_kernels": [roof(kk) for kk in kern if kk != top],
+        "cpu_baseline": cpu, "final_loss": loss_value,
+    }
+    if world == 1 and not os.environ.get("HWG_BENCH_NO_EXTRAS"):
+        try:   # the other configs, measured briefly in the same run (bench.py --workload gen_infer / hwr_train)
+            import bench_hwr_train
+            del gen, hwr, opt, graphed
+            torch.cuda.empty_cache()
+            line["extra_workloads"] = bench_hwr_train.quick_train_numbers(dev, gen_lesson=False)
+            line["extra_workloads"].update(quick_gen_infer(dev))
+        except Exception as e:   # never lose the headline over the extras
+            line["extra_workloads"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def quick_gen_infer(dev, steps=20):
+    """BASELINE configs[1] (generator inference, batch 32), device-timed graph replays."""
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import graphs
+    from oracle import synth
+    B, Ts = 32, GAN["Ts"]
+    torch.manual_seed(0)
+    gen = pkg.SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False,
+                              append_style=True, small=False).to(dev).eval()
+    content, style = synth.gen_case(Ts, B, GAN["C"], GAN["style"], 5)
+    c, s = torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev)
+
+    def fwd(c, s):
+        with torch.no_grad():
+            return gen(c, s)
+
+    g = graphs.GraphedStep(fwd, [c, s], modules=[gen], warmup=3)
+    for _ in range(3):
+        g(c, s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g(c, s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"gen_infer_B32": {"ms_per_step": ms, "lines_per_s": B / ms * 1e3,
+                              "what": "BASELINE configs[1]: SpacedGenerator inference, 32 lines of 64x1024 px, one "
+                                      "replayed CUDA graph per step (full line: bench.py --workload gen_infer)"}}

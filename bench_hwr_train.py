@@ -215,7 +215,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
 # Short device-timed measurements of the two training paths, embedded as "extra_workloads" in the default
 # bench line (N=1) so that one bench run documents inference AND training throughput.
 # ----------------------------------------------------------------------------------------------------------
-def quick_train_numbers(dev, steps=10):
+def quick_train_numbers(dev, steps=10, gen_lesson=True):
     import handwriting_line_generation_b200 as pkg
     from oracle import synth
     out = {}
@@ -259,6 +259,8 @@ def quick_train_numbers(dev, steps=10):
         out[f"hwr_ctc_train_step_B{B}"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
                                           "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + Adam, 64x1024 lines; one replayed CUDA graph per step"}
         del model, opt
+    if not gen_lesson:
+        return out
     # (2) the 'gen' lesson's recognition branch: generator -> frozen recognizer -> CTC -> backward into the
     #     generator -> Adam on the generator (trainer/hw_with_style_trainer.py:760-764), batch 16, T_s=256
     B, Ts = 16, 256

@@ -86,3 +86,102 @@ class GradBuckets:
                 else:
                     p.grad.copy_(g)
                 off += n
+
+
+class GradReducer:
+    """Gradient all-reduce overlapped with the backward pass (the reference itself is single-GPU,
+    trainer/hw_with_style_trainer.py:300-391 being the step this slots into before the optimizer).
+
+    Parameters are grouped, in reverse registration order (≈ the order the backward produces their gradients), into
+    flat fp32 buckets; every `.grad` is a view into its bucket, so there is no gather/scatter copy.  A
+    post-accumulate-grad hook counts the gradients of a bucket; when the last one lands, the bucket is pre-scaled by
+    1/world and all-reduced (sum) on a side stream ordered after the producing stream by an event, while the
+    backward keeps running on the main stream.  `finish()` makes the main stream wait for the outstanding buckets —
+    call it between `loss.backward()` and `optimizer.step()`.  All of this is stream work only (no host
+    synchronisation), so a whole step including the collectives can be captured in one CUDA graph.
+    With world_size 1 the hooks are not installed and finish() is a no-op."""
+
+    def __init__(self, params, bucket_bytes=4 << 20, group=None):
+        self.group = group
+        self.rank, self.world = world()
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []            # dicts: params, flat, views, pending, work
+        cur, size = [], 0
+        for p in reversed(self.params):
+            n = p.numel() * 4
+            if cur and size + n > bucket_bytes:
+                self._close(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += n
+        if cur:
+            self._close(cur)
+        self.cuda = bool(self.params) and self.params[0].is_cuda
+        self.comm = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
+        self._handles = []
+        if self.world > 1:
+            for bi, b in enumerate(self.buckets):
+                for p in b["params"]:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _close(self, plist):
+        dev = plist[0].device
+        flat = torch.zeros(sum(-(-p.numel() // 4) * 4 for p in plist), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for p in plist:
+            v = flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            views.append(v)
+            off += -(-p.numel() // 4) * 4          # 16-byte aligned slots
+        self.buckets.append({"params": plist, "flat": flat, "views": views, "pending": len(plist), "work": None})
+
+    def _make_hook(self, bi):
+        def hook(p):
+            b = self.buckets[bi]
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        for p, v in zip(b["params"], b["views"]):
+            if p.grad is None:
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():   # autograd installed its own tensor: move it into the bucket
+                v.copy_(p.grad)
+                p.grad = v
+        if self.comm is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                b["flat"].mul_(1.0 / self.world)
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            b["flat"].mul_(1.0 / self.world)
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """Launches the buckets that never filled (parameters without a gradient this step), then waits."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b["work"] is None:
+                self._launch(b)
+        for b in self.buckets:
+            b["work"].wait()
+            b["work"] = None
+            b["pending"] = len(b["params"])
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+    def zero_grad(self):
+        """One fill per bucket instead of one per parameter (gradients stay views into the buckets)."""
+        for b in self.buckets:
+            b["flat"].zero_()
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

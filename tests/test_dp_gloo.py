@@ -40,6 +40,21 @@ def _worker(rank, world, port, ret):
         dp.GradBuckets(model.parameters(), bucket_bytes=256).reduce()
         for p, g in zip(model.parameters(), full):
             assert torch.allclose(p.grad, g, atol=1e-6), (p.grad - g).abs().max()
+        # overlapped reducer: hooks + flat bucket views; two steps, grads zeroed in between, one parameter unused
+        torch.manual_seed(0)
+        model2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+        unused = torch.nn.Parameter(torch.ones(5))
+        red = dp.GradReducer(list(model2.parameters()) + [unused], bucket_bytes=300)
+        assert len(red.buckets) > 1
+        for _ in range(2):
+            red.zero_grad()
+            (((model2(xs) - ys) ** 2).sum() / 12 * world).backward()
+            red.finish()
+            for p, g in zip(model2.parameters(), full):
+                assert torch.allclose(p.grad, g, atol=1e-6), (p.grad - g).abs().max()
+                assert any(p.grad.data_ptr() == v.data_ptr() for b in red.buckets for v in b["views"])
+            assert unused.grad.abs().max() == 0
+        red.remove()
         ret[rank] = True
     finally:
         dist.destroy_process_group()
