@@ -186,7 +186,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             loss = graphed.static_out
         else:
             loss = train(hc.to(dev, non_blocking=True), hs.to(dev, non_blocking=True), ht.to(dev, non_blocking=True))
-        loss_host.copy_(loss, non_blocking=True)        # D2H of the step's loss
+        loss_host.copy_(loss.detach(), non_blocking=True)        # D2H of the step's loss
 
     def timed(fn, steps):
         barrier()
@@ -212,7 +212,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
-    loss_value = float(loss_host)
+    loss_value = float(loss_host.detach())
 
     # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream)
     prof = []
@@ -230,10 +230,19 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         k["launches"] += 1 / psteps
         k["issued_flop"] += fl / psteps
         k["bytes"] += by / psteps
-    if rank != 0:
+    def leave():
+        """A process group whose collectives were captured in a live CUDA graph does not tear down cleanly
+        (destroy_process_group blocked until the launcher's timeout on the first 2-GPU run): synchronise, flush, exit."""
         if world > 1:
-            dist.destroy_process_group()
-        return
+            torch.cuda.synchronize()
+            dist.barrier()
+            import sys
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        return leave()
     peaks = load_peaks()
     layers, _ = gen_layers(Ts)
     ms_step = ms / args.steps
@@ -299,8 +308,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         except Exception as e:   # never lose the headline over the extras
             line["extra_workloads"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def quick_gen_infer(dev, steps=20):

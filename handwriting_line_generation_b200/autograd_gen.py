@@ -16,11 +16,10 @@ from math import sqrt
 import torch
 import torch.nn.functional as F
 
-from . import conv, ops
+from . import conv, ops, weightmap
 from ._lib import ACT_LRELU, ACT_NONE
 from .pure_gen import TAPS3x3, conv1_forward
 
-_SEL = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}  # FusedUpsample: output parity -> [(input offset, kernel index)]
 
 
 def _vert_src(par, kh):
@@ -73,9 +72,19 @@ def forward_train(m, content, s, gb, noise):
     H, W = 1, T
     out = None
     nblk = len(c["blocks"])
+    # one zero-fill for all ten statistics accumulators ([B,C,2] each)
+    stats_all = torch.zeros(sum(2 * B * e["C"] * 2 for e in c["blocks"]), device=dev, dtype=torch.float32)
+    soff = 0
+
+    def new_stats(C):
+        nonlocal soff
+        st = stats_all[soff:soff + B * C * 2].view(B, C, 2)
+        soff += B * C * 2
+        return st
+
     for bi, e in enumerate(c["blocks"]):
         C = e["C"]
-        st = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
+        st = new_stats(C)
         nz = None if noise is None else noise[k]
         x_in, Hin, Win = x, H, W
         a, Ho, Wo = conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev)
@@ -85,7 +94,7 @@ def forward_train(m, content, s, gb, noise):
         x = ops.scale_shift_act(a, coef, True, out=torch.empty_like(a))
         off += 2 * C
         k += 1
-        st = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
+        st = new_stats(C)
         nz = None if noise is None else noise[k]
         a = conv.conv_fprop(x, e["w2"], TAPS3x3, H, W, bias=e["b2"], act=ACT_LRELU, slope=0.2, noise=nz,
                             noise_w=e["nw2"], noise_seed=seed, noise_subseq=16 * k, noise_seed_dev=seed_dev, stats=st)
@@ -102,145 +111,150 @@ def forward_train(m, content, s, gb, noise):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def _taps_f32(w4d):
-    co, ci, kh, kw = w4d.shape
-    return w4d.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+def _bwd_plan(m, c, B, gbw):
+    """Workspace layout + hwg_linear_map job table of one backward pass, built once per (module, batch).
 
+    Workspace `ws` (fp32, zero-filled by ONE memset per backward): every accumulator the backward kernels add into —
+    the per-(n,c) AdaIN sums, the per-channel bias / noise-weight sums, the blur-adjoint statistics, the output-head
+    sums and the tap-major wgrad outputs of all convolutions.  The job table then writes, in ONE launch, every
+    conv-side parameter gradient in the parameter's own layout (adjoint of the forward pack, EqualLR scales) and the
+    gradient of the AdaIN projections `g_gb`, into one flat buffer `gflat`."""
+    off = {"n": 0}
+    lay = {}
 
-def _w4(dw, kh, kw):
-    t, co, ci = dw.shape
-    return dw.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
+    def ws(name, numel):
+        lay[name] = (off["n"], numel)
+        off["n"] += -(-numel // 4) * 4           # 16-byte aligned slots
 
+    params = _param_list(m)
+    goff, n = [], 0
+    for p in params:
+        goff.append(n)
+        n += -(-p.numel() // 4) * 4
+    g_gb_off = n
+    n += B * gbw
+    t = weightmap.JobTable()
+    one = [[1.0]]
 
-def _fused_w4(mod, w):
-    wp = F.pad(w * mod.multiplier, [1, 1, 1, 1])
-    return (wp[:, :, 1:, 1:] + wp[:, :, :-1, 1:] + wp[:, :, 1:, :-1] + wp[:, :, :-1, :-1]) / 4
+    def vec(src_name, src_elem, dst_param_idx, C, scale=1.0, s_c=2):
+        t.add(4 * (lay[src_name][0] + src_elem), 4 * goff[dst_param_idx], R=1, C=C, s_r=0, s_c=s_c, d_r=0, d_c=1,
+              M=one, scale=scale)
+
+    gb_off = 0
+    for bi, (blk, e) in enumerate(zip(m.conv, c["blocks"])):
+        C = e["C"]
+        m1, m2 = e["m1"], e["m2"]
+        cip1 = e.get("m1_cip", m1.Cip)
+        for h in (1, 2):
+            ws(f"sums{bi}{h}", B * C * 2)
+            ws(f"dch{bi}{h}", C * 2)
+        ws(f"dw{bi}1", m1.Tf * m1.Co * cip1)
+        ws(f"dw{bi}2", m2.Tf * m2.Co * m2.Cip)
+        if e["kind"] in ("vert_up", "fused_up"):
+            ws(f"st{bi}", B * C * 2)
+        base = 6 * bi
+        m1.add_unpack_wgrad(t, 4 * lay[f"dw{bi}1"][0], 4 * goff[base + 0], Cip=cip1)
+        if e["kind"] in ("vert_up", "fused_up"):
+            # Blur is self-adjoint; the per-channel sums of the blurred gradient are the conv bias gradient
+            t.add(4 * lay[f"st{bi}"][0], 4 * goff[base + 1], R=1, C=C, s_r=0, s_c=2, d_r=0, d_c=1, M=None, nin=B,
+                  in_stride=2 * C)
+        else:
+            vec(f"dch{bi}1", 0, base + 1, C)
+        vec(f"dch{bi}1", 1, base + 2, C, sqrt(2.0 / C))
+        m2.add_unpack_wgrad(t, 4 * lay[f"dw{bi}2"][0], 4 * goff[base + 3])
+        vec(f"dch{bi}2", 0, base + 4, C)
+        vec(f"dch{bi}2", 1, base + 5, C, sqrt(2.0 / C))
+        for h in (1, 2):
+            # sums[n,c] = (dbeta, dgamma)  ->  g_gb[n, off + c] = dgamma, g_gb[n, off + C + c] = dbeta
+            t.add(4 * lay[f"sums{bi}{h}"][0], 4 * (g_gb_off + gb_off), R=B, C=C, s_r=2 * C, s_c=2, d_r=gbw, d_c=1,
+                  M=[[1.0, 0.0], [0.0, 1.0]], in_off=[0, 1], out_off=[C, 0])
+            gb_off += 2 * C
+    Cl = c["blocks"][-1]["C"]
+    ws("dwb", Cl + 1)
+    vec("dwb", 0, len(params) - 2, Cl, c["out_scale"], s_c=1)
+    vec("dwb", Cl, len(params) - 1, 1, 1.0, s_c=1)
+    t.finalize(params[0].device)
+    return dict(lay=lay, ws_numel=off["n"], goff=goff, g_gb_off=g_gb_off, gflat_numel=n, table=t,
+                shapes=[p.shape for p in params], numels=[p.numel() for p in params])
 
 
 def backward_train(m, ctx, g_out):
     """Returns (g_content [T,B,ncls], g_s [B,S], g_gb [B,sum 2C], [conv-side parameter grads in _param_list order])."""
     recs, seed, seed_dev = ctx["recs"], ctx["seed"], ctx["seed_dev"]
     c = m._packed()
-    B, T, ncls = ctx["B"], ctx["T"], ctx["ncls"]
+    B, T, ncls, gbw = ctx["B"], ctx["T"], ctx["ncls"], ctx["gb_width"]
     dev = g_out.device
-    g_gb = torch.zeros((B, ctx["gb_width"]), device=dev, dtype=torch.float32)
-    pgrads = []
+    plan = m._bwd_plans.get((B, gbw))
+    if plan is None:
+        plan = m._bwd_plans[(B, gbw)] = _bwd_plan(m, c, B, gbw)
+    ws = torch.zeros(plan["ws_numel"], device=dev, dtype=torch.float32)
+    gflat = torch.empty(plan["gflat_numel"], device=dev, dtype=torch.float32)
+
+    def W(name, *shape):
+        o, n = plan["lay"][name]
+        return ws[o:o + n].view(*shape)
+
     # ---- output head
     last = recs[-1]
-    g, dw_out, db0 = ops.gen_output_bwd(g_out.contiguous().float(), ctx["out"], last["a"], last["coef"], c["w_out"])
-    w_orig = m.out[0].conv.weight_orig
-    g_wout = (dw_out * sqrt(2.0 / (w_orig.size(1) * w_orig[0][0].numel()))).view_as(w_orig)
-    g_bout = db0.view(1)
+    g, _, _ = ops.gen_output_bwd(g_out.contiguous().float(), ctx["out"], last["a"], last["coef"], c["w_out"],
+                                 dwb=W("dwb", -1))
     blocks = list(m.conv)
     for bi in range(len(blocks) - 1, -1, -1):
         blk, e = blocks[bi], c["blocks"][bi]
         C = e["C"]
+        m1, m2 = e["m1"], e["m2"]
         r1, r2 = recs[2 * bi], recs[2 * bi + 1]
         # ---------------- second half: conv2 + noise2 + lrelu + adain2
-        gy, dgam, dbet, dbias2, dnw2 = ops.adain_lrelu_bwd(g, r2["a"], r2["save"], r2["coef"], 0.2, r2["nz"], seed,
-                                                           r2["subseq"], seed_dev=seed_dev)
-        g_gb[:, r2["off"]:r2["off"] + C] = dgam
-        g_gb[:, r2["off"] + C:r2["off"] + 2 * C] = dbet
-        g_w2 = _w4(conv.conv_wgrad(r2["x_in"], gy, TAPS3x3, C, C), 3, 3)
-        wd, tapsd = conv.dgrad_pack(_taps_f32(blk.conv2.weight), TAPS3x3)
-        g = conv.conv_fprop(gy, wd, tapsd, r2["Hin"], r2["Win"])
-        g_nw2 = (dnw2 * sqrt(2.0 / C)).view(1, C, 1, 1)
+        gy = ops.adain_lrelu_bwd(g, r2["a"], r2["save"], r2["coef"], 0.2, r2["nz"], seed, r2["subseq"],
+                                 seed_dev=seed_dev, sums=W(f"sums{bi}2", B, C, 2), dch=W(f"dch{bi}2", C, 2))[0]
+        conv.conv_wgrad(r2["x_in"], gy, TAPS3x3, C, C, out=W(f"dw{bi}2", 9, C, C))
+        g = conv.conv_fprop(gy, e["d2"], m2.taps_d, r2["Hin"], r2["Win"])
         # ---------------- first half: conv1 (+blur) + noise1 + lrelu + adain1
-        gy, dgam, dbet, dsum, dnw1 = ops.adain_lrelu_bwd(g, r1["a"], r1["save"], r1["coef"], 0.2, r1["nz"], seed,
-                                                         r1["subseq"], row_subseq=(e["kind"] == "initial"),
-                                                         seed_dev=seed_dev)
-        g_gb[:, r1["off"]:r1["off"] + C] = dgam
-        g_gb[:, r1["off"] + C:r1["off"] + 2 * C] = dbet
-        g_nw1 = (dnw1 * sqrt(2.0 / C)).view(1, C, 1, 1)
+        gy = ops.adain_lrelu_bwd(g, r1["a"], r1["save"], r1["coef"], 0.2, r1["nz"], seed, r1["subseq"],
+                                 row_subseq=(e["kind"] == "initial"), seed_dev=seed_dev,
+                                 sums=W(f"sums{bi}1", B, C, 2), dch=W(f"dch{bi}1", C, 2))[0]
         x_in, Hin, Win = r1["x_in"], r1["Hin"], r1["Win"]
         kind = e["kind"]
         if kind in ("vert_up", "fused_up"):
-            # Blur is self-adjoint (symmetric stencil, zero padding); its per-channel sums are the conv bias gradient
-            st = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
-            gy = ops.blur_noise_act_stats(gy, None, None, st, ACT_NONE, 0.0)
-            g_b1 = st[:, :, 0].sum(0)
-        else:
-            g_b1 = dsum
+            gy = ops.blur_noise_act_stats(gy, None, None, W(f"st{bi}", B, C, 2), ACT_NONE, 0.0)
+        Cin = m1.Ci
         if kind == "plain":
-            Cin = blk.in_channel
-            g_w1 = _w4(conv.conv_wgrad(x_in, gy, TAPS3x3, Cin, C), 3, 3)
-            wd, tapsd = conv.dgrad_pack(_taps_f32(blk.conv1.weight), TAPS3x3)
-            g = conv.conv_fprop(gy, wd, tapsd, Hin, Win)
+            conv.conv_wgrad(x_in, gy, TAPS3x3, Cin, C, out=W(f"dw{bi}1", 9, C, Cin))
+            g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win)
         elif kind == "initial":
-            w = blk.conv1.weight                      # [Cin, Cout, 4, 3]
-            Cin, cin_pad = w.size(0), c["cin_pad"]
-            g_w1 = torch.empty_like(w, dtype=torch.float32)
+            cin_pad = c["cin_pad"]
+            dw = W(f"dw{bi}1", 12, C, cin_pad)
             for r in range(4):
-                dw = conv.conv_wgrad(x_in, gy, e["taps1"], cin_pad, C, grid=(1, Win), gy_offset=(r, 0))  # [3,C,cin_pad]
-                g_w1[:, :, r, :] = dw[:, :, :Cin].permute(2, 1, 0)
-            # gradient w.r.t. the packed input: 12-tap convolution of gy [B,4,T,C] -> [B,1,T,Cin8]
-            cin8 = ((Cin + 15) // 16) * 16
-            mats = [torch.nn.functional.pad(w.detach().float()[:, :, r, kx], (0, 0, 0, cin8 - Cin))
-                    for r in range(4) for kx in range(3)]
-            taps = [(r, kx - 1) for r in range(4) for kx in range(3)]
-            g = conv.conv_fprop(gy, conv.pack_taps(mats), taps, 1, Win)
+                conv.conv_wgrad(x_in, gy, e["taps1"], cin_pad, C, grid=(1, Win), gy_offset=(r, 0), out=dw[3 * r:3 * r + 3])
+            # gradient w.r.t. the packed input: 12-tap convolution of gy [B,4,T,C] -> [B,1,T,Cin16]
+            g = conv.conv_fprop(gy, e["d1"], m1.taps_d, 1, Win)
         elif kind == "vert_up":
-            w = blk.conv1[1].weight                   # [Cout, Cin, 3, 3]
-            Cin = w.size(1)
-            g_w1 = torch.zeros_like(w, dtype=torch.float32)
-            for par, (taps, _) in enumerate(e["w1"]):
-                dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 1), gy_offset=(par, 0))
-                dhs = sorted({t[0] for t in taps})
-                for kh in range(3):
-                    j = dhs.index(_vert_src(par, kh))
-                    g_w1[:, :, kh, :] += dw[3 * j:3 * j + 3].permute(1, 2, 0)
-            wf = w.detach().float()
-            comb = {-1: [2], 0: [1, 2], 1: [0, 1], 2: [0]}   # dh -> kh of the rows that land there (r - kh + 1 = dh)
-            mats, taps = [], []
-            for dh in (-1, 0, 1, 2):
-                wk = sum(wf[:, :, kh, :] for kh in comb[dh])  # [Cout, Cin, 3]
-                for kw in range(3):
-                    taps.append((dh, 1 - kw))
-                    mats.append(wk[:, :, kw].t())
-            g = conv.conv_fprop(gy, conv.pack_taps(mats), taps, Hin, Win, in_stride=(2, 1))
+            dw = W(f"dw{bi}1", 12, C, Cin)
+            for par in (0, 1):
+                conv.conv_wgrad(x_in, gy, weightmap.vert_taps(par), Cin, C, grid=(Hin, Win), gy_stride=(2, 1),
+                                gy_offset=(par, 0), out=dw[6 * par:6 * par + 6])
+            g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win, in_stride=m1.d_in_stride)
         else:  # fused_up
-            mod = blk.conv1[0]
-            wl = mod.weight.detach().float().requires_grad_()
-            with torch.enable_grad():
-                w4 = _fused_w4(mod, wl)                # [Cin, Cout, 4, 4]
-            Cin = wl.size(0)
-            dw4 = torch.empty_like(w4)
+            dw = W(f"dw{bi}1", 16, C, Cin)
+            taps = weightmap.fused_taps()
             if Cin <= 32 and C <= 32:
                 # all four parities in one launch (per-tap gy phase): gy and x are read once
-                taps, phases, idx = [], [], []
-                for py in (0, 1):
-                    for px in (0, 1):
-                        for dh, ky in _SEL[py]:
-                            for dw_, kx in _SEL[px]:
-                                taps.append((dh, dw_))
-                                phases.append((py, px))
-                                idx.append((ky, kx))
-                dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2), tap_phase=phases)
-                # taps are ordered [py][px][a][b] with ky = 2a + (1-py), kx = 2b + (1-px)  (see _SEL)
-                dw4 = dw.view(2, 2, 2, 2, C, Cin).flip(0, 1).permute(5, 4, 2, 0, 3, 1).reshape(Cin, C, 4, 4)
+                conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
+                                tap_phase=weightmap.fused_phases(), out=dw)
             else:
-                for py in (0, 1):
-                    for px in (0, 1):
-                        taps, idx = [], []
-                        for dh, ky in _SEL[py]:
-                            for dw_, kx in _SEL[px]:
-                                taps.append((dh, dw_))
-                                idx.append((ky, kx))
-                        dw = conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2), gy_offset=(py, px))
-                        for t, (ky, kx) in enumerate(idx):
-                            dw4[:, :, ky, kx] = dw[t].t()
-            (g_w1,) = torch.autograd.grad(w4, wl, dw4)
-            w4d = w4.detach()
-            taps = [(ky - 1, kx - 1) for ky in range(4) for kx in range(4)]
-            mats = [w4d[:, :, ky, kx] for ky in range(4) for kx in range(4)]   # [out=Cin][in=Cout]
-            g = conv.conv_fprop(gy, conv.pack_taps(mats), taps, Hin, Win, in_stride=(2, 2))
-        pgrads.insert(0, [g_w1, g_b1, g_nw1, g_w2, dbias2, g_nw2])
+                for q, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                    conv.conv_wgrad(x_in, gy, taps[4 * q:4 * q + 4], Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
+                                    gy_offset=(py, px), out=dw[4 * q:4 * q + 4])
+            g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win, in_stride=m1.d_in_stride)
+    # ---- every parameter gradient + g_gb in one launch
+    plan["table"].run(src_base=ws, dst_base=gflat)
+    flat = [gflat[o:o + n].view(sh) for o, n, sh in zip(plan["goff"], plan["numels"], plan["shapes"])]
+    g_gb = gflat[plan["g_gb_off"]:plan["g_gb_off"] + B * gbw].view(B, gbw)
     # ---- packed input -> content and style
     S = m.style_size if m.append_style else 0
-    gx0 = g[:, 0].float()                                # [B, T, Cin8]
+    gx0 = g[:, 0].float()                                # [B, T, Cin16]
     g_content = gx0[:, :, :ncls].permute(1, 0, 2).contiguous()
     g_s = gx0[:, :, ncls:ncls + S].sum(1) if S else None
-    flat = [t for grp in pgrads for t in grp] + [g_wout, g_bout]
     return g_content, g_s, g_gb, flat
 
 

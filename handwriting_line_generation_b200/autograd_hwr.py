@@ -36,6 +36,10 @@ def _dgrad_packs(m):
         for ci, _, pad, dil in _CNN1D + [(12, None, 0, 1)]:
             taps = conv.conv_taps(1, 3, 0, pad, 1, dil)
             d[f"v{ci}"] = conv.dgrad_pack(_taps_f32(m.cnn1d[ci].weight.unsqueeze(2)), taps)
+        # image gradient: conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] 9-tap dgrad convolution
+        w0 = m.cnn.conv0.weight.detach().float()                       # [64,1,3,3]
+        mats = [torch.nn.functional.pad(w0[:, 0, i, j].view(1, 64), (0, 0, 0, 15)) for i in range(3) for j in range(3)]
+        d["w0"] = (conv.pack_taps(mats), [(1 - i, 1 - j) for i in range(3) for j in range(3)])
         c["dgrad"] = d
     return c["dgrad"]
 
@@ -47,7 +51,7 @@ def _bn_train(m, y, stats, bn):
     coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                bn.running_var, momentum, bn.eps, use_batch)
     if m.training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        m._bn_counters.append(bn.num_batches_tracked)     # bumped together at the end of the forward
     if not use_batch:  # eval-mode BN under autograd: (mean, rstd) from the running statistics
         save = torch.stack([bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)], 1).contiguous()
     a = ops.scale_shift_act(y, coef, False, ACT_RELU, out=torch.empty_like(y))
@@ -65,9 +69,12 @@ def forward_train(m, x):
     B = x.size(0)
     dev = x.device
     ctx = {"x": x}
+    m._bn_counters = []
+
+    arena = ops.ZeroArena(B * 2 * (256 + 6 * 512) + 64, dev)     # all BatchNorm statistics of this pass: one memset
 
     def stats_for(C):
-        return torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
+        return arena.take(B, C, 2)
 
     a0 = ops.hwr_stem(x, c["w0"], c["b0"])
     c1 = conv.conv_fprop(a0, c["w1"], _T3, a0.size(1), a0.size(2), bias=c["b1"], act=ACT_RELU)
@@ -107,6 +114,9 @@ def forward_train(m, x):
                     out_view=(out, C, 0, B * C, 0))
     ctx["a10"] = a
     ctx["lp"] = out
+    if m._bn_counters:
+        torch._foreach_add_(m._bn_counters, 1)
+    m._bn_counters = []
     return out, ctx
 
 
@@ -135,13 +145,14 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     lp = ctx["lp"]
     T, B, C = lp.shape
     Cp = ((C + 15) // 16) * 16
+    arena = ops.ZeroArena(16384, lp.device)      # every per-channel accumulator of this pass: one memset
 
     def dgrad(gz, key, H, W):
         wd, tapsd = dg[key]
         return conv.conv_fprop(gz, wd, tapsd, H, W)
 
     # ---- head: log-softmax + Conv1d(512, C, 3)
-    gz, db = ops.logsoftmax_bwd(g_lp.contiguous().float(), lp, Cp)
+    gz, db = ops.logsoftmax_bwd(g_lp.contiguous().float(), lp, Cp, arena=arena)
     a10 = ctx["a10"]
     grads.put("cnn1d.12.weight", lambda: conv.conv_wgrad(a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)[:, :C, :]
               .permute(1, 2, 0).contiguous())
@@ -150,7 +161,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- dilated 1-D blocks, last to first
     for (ci, bi, pad, dil), (a_in, z, coef, save) in zip(reversed(_CNN1D), reversed(ctx["head_in"])):
         bn = m.cnn1d[bi]
-        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach())
+        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena)
         grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
         grads.put(f"cnn1d.{ci}.weight", lambda: conv.conv_wgrad(a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
                   .permute(1, 2, 0).contiguous())
@@ -158,42 +169,42 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
         g = dgrad(gz, f"v{ci}", 1, a_in.size(2))
     # ---- conv6 + BN + ReLU
     coef, save = ctx["bn6"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach())
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach(), arena=arena)
     grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
     a5 = ctx["a5"]
     grads.put("cnn.conv6.weight", lambda: _w4(conv.conv_wgrad(a5, gz, _T3P0, 512, 512), 3, 3))
     grads["cnn.conv6.bias"] = dcb
     g = dgrad(gz, "w6", a5.size(1), a5.size(2))
     # ---- pool + ReLU + conv5
-    gc, db = ops.relu_maxpool_bwd(g, ctx["c5"], *_POOL21)
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c5"], *_POOL21, arena=arena)
     a4 = ctx["a4"]
     grads.put("cnn.conv5.weight", lambda: _w4(conv.conv_wgrad(a4, gc, _T3P0, 512, 512), 3, 3))
     grads["cnn.conv5.bias"] = db
     g = dgrad(gc, "w5", a4.size(1), a4.size(2))
     # ---- conv4 + BN + ReLU
     coef, save = ctx["bn4"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach())
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach(), arena=arena)
     grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
     a3 = ctx["a3"]
     grads.put("cnn.conv4.weight", lambda: _w4(conv.conv_wgrad(a3, gz, _T3, 256, 512), 3, 3))
     grads["cnn.conv4.bias"] = dcb
     g = dgrad(gz, "w4", a3.size(1), a3.size(2))
     # ---- pool + ReLU + conv3
-    gc, db = ops.relu_maxpool_bwd(g, ctx["c3"], *_POOL21)
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c3"], *_POOL21, arena=arena)
     a2 = ctx["a2"]
     grads.put("cnn.conv3.weight", lambda: _w4(conv.conv_wgrad(a2, gc, _T3, 256, 256), 3, 3))
     grads["cnn.conv3.bias"] = db
     g = dgrad(gc, "w3", a2.size(1), a2.size(2))
     # ---- conv2 + BN + ReLU
     coef, save = ctx["bn2"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach())
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach(), arena=arena)
     grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
     a1 = ctx["a1"]
     grads.put("cnn.conv2.weight", lambda: _w4(conv.conv_wgrad(a1, gz, _T3, 128, 256), 3, 3))
     grads["cnn.conv2.bias"] = dcb
     g = dgrad(gz, "w2", a1.size(1), a1.size(2))
     # ---- pool + ReLU + conv1
-    gc, db = ops.relu_maxpool_bwd(g, ctx["c1"], *_POOL22)
+    gc, db = ops.relu_maxpool_bwd(g, ctx["c1"], *_POOL22, arena=arena)
     a0 = ctx["a0"]
     grads.put("cnn.conv1.weight", lambda: _w4(conv.conv_wgrad(a0, gc, _T3, 64, 128), 3, 3))
     grads["cnn.conv1.bias"] = db
@@ -211,10 +222,8 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
         # image gradient (GAN lessons): route g through pool/ReLU to conv0's output, then the 9-tap dgrad with
         # conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] tensor-core convolution
         gc0 = ops.hwr_stem_bwd_expand(ctx["x"], c["w0"], c["b0"], g)
-        w0 = m.cnn.conv0.weight.detach().float()                       # [64,1,3,3]
-        mats = [torch.nn.functional.pad(w0[:, 0, i, j].view(1, 64), (0, 0, 0, 15)) for i in range(3) for j in range(3)]
-        taps = [(1 - i, 1 - j) for i in range(3) for j in range(3)]
-        gi = conv.conv_fprop(gc0, conv.pack_taps(mats), taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
+        w0d, taps = dg["w0"]
+        gi = conv.conv_fprop(gc0, w0d, taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
         g_img = gi[..., 0].unsqueeze(1).contiguous()
         if m.pad is not None:
             p = m.pad.padding

@@ -93,35 +93,59 @@ def maxpool_nhwc(x, k, s, p):
 
 
 # ---- backward passes (hwg_fused_bwd.cu) ----------------------------------------------------------------
-def logsoftmax_bwd(g, lp, Cp):
+class ZeroArena:
+    """Pre-zeroed fp32 accumulators for one pass, carved out of ONE zero-filled allocation (one memset instead of one
+    fill launch per accumulator)."""
+
+    def __init__(self, numel, device):
+        self.buf = torch.zeros(numel, device=device, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():      # sized too small by the caller: fall back to a fresh fill
+            return torch.zeros(shape, device=self.buf.device, dtype=torch.float32)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += -(-n // 4) * 4
+        return v
+
+
+def _zeros(arena, shape, device):
+    return arena.take(*shape) if arena is not None else torch.zeros(shape, device=device, dtype=torch.float32)
+
+
+def logsoftmax_bwd(g, lp, Cp, arena=None):
     """g, lp [T,B,C] fp32 -> (gz [B,1,T,Cp] bf16 NHWC, dbias [C] fp32)."""
     T, B, C = lp.shape
     gz = torch.empty((B, 1, T, Cp), device=lp.device, dtype=torch.bfloat16)
-    db = torch.zeros(C, device=lp.device, dtype=torch.float32)
+    db = _zeros(arena, (C,), lp.device)
     _lib.call("hwg_logsoftmax_bwd", g.data_ptr(), lp.data_ptr(), T, B, C, Cp, gz.data_ptr(), db.data_ptr(), _lib.stream())
     return gz, db
 
 
-def bn_bwd(g, z, coef, save, weight, relu=True):
-    """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C])."""
+def bn_bwd(g, z, coef, save, weight, relu=True, arena=None):
+    """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C]);
+    dweight/dbias are strided views of the [C,2] sums."""
     C = z.size(-1)
     rows = z.numel() // C
-    sums = torch.zeros((C, 2), device=z.device, dtype=torch.float32)
+    sums = _zeros(arena, (C, 2), z.device)
     _lib.call("hwg_bn_bwd_reduce", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), rows, C, int(relu),
               sums.data_ptr(), _lib.stream())
     gz = torch.empty_like(z)
-    dcb = torch.zeros(C, device=z.device, dtype=torch.float32)
+    dcb = _zeros(arena, (C,), z.device)
     _lib.call("hwg_bn_bwd_apply", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), weight.data_ptr(),
               sums.data_ptr(), rows, C, int(relu), gz.data_ptr(), dcb.data_ptr(), _lib.stream())
-    return gz, sums[:, 1].contiguous(), sums[:, 0].contiguous(), dcb
+    return gz, sums[:, 1], sums[:, 0], dcb
 
 
-def relu_maxpool_bwd(ga, c, k, s, p):
+def relu_maxpool_bwd(ga, c, k, s, p, arena=None):
     """ga [N,Ho,Wo,C], c [N,H,W,C] (post-ReLU, pre-pool) -> (gc [N,H,W,C] bf16, dbias [C])."""
     N, H, W, C = c.shape
     Ho, Wo = ga.size(1), ga.size(2)
     gc = torch.empty_like(c)
-    db = torch.zeros(C, device=c.device, dtype=torch.float32)
+    db = _zeros(arena, (C,), c.device)
     _lib.call("hwg_relu_maxpool_bwd", ga.data_ptr(), c.data_ptr(), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1], Ho, Wo,
               gc.data_ptr(), db.data_ptr(), _lib.stream())
     return gc, db
@@ -137,15 +161,19 @@ def hwr_stem_bwd(img, w, b, ga):
     return dw, db
 
 
-def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, row_subseq=False, seed_dev=None):
+def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, row_subseq=False, seed_dev=None,
+                    sums=None, dch=None):
     """Backward of x_next = AdaIN(LeakyReLU(y)), y = pre + nw*z.  g, a [N,H,W,C] bf16.
-    Returns (gy bf16, dgamma [N,C], dbeta [N,C], dbias [C] = sum gy, dnoise_w [C] = sum gy*z)."""
+    Returns (gy bf16, dgamma [N,C], dbeta [N,C], dbias [C] = sum gy, dnoise_w [C] = sum gy*z).
+    sums [N,C,2] / dch [C,2]: optional pre-zeroed fp32 accumulators (slices of a workspace)."""
     N, H, W, C = a.shape
-    sums = torch.zeros((N, C, 2), device=a.device, dtype=torch.float32)
+    if sums is None:
+        sums = torch.zeros((N, C, 2), device=a.device, dtype=torch.float32)
     _lib.call("hwg_adain_bwd_reduce", g.data_ptr(), a.data_ptr(), save.data_ptr(), N, H * W, C, sums.data_ptr(),
               _lib.stream())
     gy = torch.empty_like(a)
-    dch = torch.zeros((C, 2), device=a.device, dtype=torch.float32)
+    if dch is None:
+        dch = torch.zeros((C, 2), device=a.device, dtype=torch.float32)
     _lib.call("hwg_adain_bwd_apply", g.data_ptr(), a.data_ptr(), save.data_ptr(), coef.data_ptr(), sums.data_ptr(),
               N, H, W, C, slope, _lib.ptr(noise), seed, subseq, _lib.ptr(seed_dev), int(row_subseq), gy.data_ptr(),
               dch.data_ptr(),
@@ -153,11 +181,12 @@ def adain_lrelu_bwd(g, a, save, coef, slope=0.2, noise=None, seed=0, subseq=0, r
     return gy, sums[:, :, 1], sums[:, :, 0], dch[:, 0], dch[:, 1]
 
 
-def gen_output_bwd(g_out, out, a, coef, w):
-    """Returns (gx [N,H,W,C] bf16, dw [C], db0 [])."""
+def gen_output_bwd(g_out, out, a, coef, w, dwb=None):
+    """Returns (gx [N,H,W,C] bf16, dw [C], db0 []).  dwb: optional pre-zeroed fp32 [C+1] accumulator."""
     N, H, W, C = a.shape
     gx = torch.empty_like(a)
-    dwb = torch.zeros(C + 1, device=a.device, dtype=torch.float32)
+    if dwb is None:
+        dwb = torch.zeros(C + 1, device=a.device, dtype=torch.float32)
     _lib.call("hwg_gen_output_bwd", g_out.data_ptr(), out.data_ptr(), a.data_ptr(), coef.data_ptr(), w.data_ptr(),
               N, H * W, C, gx.data_ptr(), dwb.data_ptr(), _lib.stream())
     return gx, dwb[:C], dwb[C]

@@ -12,7 +12,7 @@ from math import sqrt
 import torch
 import torch.nn as nn
 
-from . import _lib, conv, ops
+from . import _lib, conv, ops, weightmap
 from ._lib import ACT_LRELU, ACT_NONE
 
 
@@ -121,74 +121,6 @@ class StyledConvBlock(nn.Module):  # pure_gen.py:140-216
 TAPS3x3 = conv.conv_taps(3, 3, 1, 1)
 
 
-def _pack_initial(w, cin_pad):
-    """ConvTranspose2d(Cin,Cout,(4,3),pad(0,1)) on H=1: out row r is a 1x3 correlation with flipped kx
-    (pure_gen.py:161-163): out[r,x] = sum_kx in[x+1-kx] W[:, :, r, kx]."""
-    taps = [(0, 1 - kx) for kx in range(3)]
-    packs = [conv.pack_taps([w[:, :, r, kx].t() for kx in range(3)], cin_pad) for r in range(4)]
-    return taps, packs
-
-
-def _pack_vert_up(w):
-    """nearest (2,1) upsample + 3x3 conv = two row-parity convolutions on the un-upsampled input with
-    the taps that hit the same source row summed (pure_gen.py:176-186)."""
-    out = []
-    for par in (0, 1):
-        rows = {}
-        for kh in range(3):
-            src = (par + kh - 1) // 2
-            rows[src] = rows[src] + w[:, :, kh, :] if src in rows else w[:, :, kh, :]
-        taps, mats = [], []
-        for dh in sorted(rows):
-            for kw in range(3):
-                taps.append((dh, kw - 1))
-                mats.append(rows[dh][:, :, kw])
-        out.append((taps, conv.pack_taps(mats)))
-    return out
-
-
-def _pack_fused_up(mod):
-    """FusedUpsample (pure_gen.py:259-279): 4x4 averaged kernel, conv_transpose2d stride 2 pad 1 =
-    four output-parity 2x2 convolutions."""
-    w = torch.nn.functional.pad(mod.weight * mod.multiplier, [1, 1, 1, 1])
-    w4 = (w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]) / 4  # [Cin,Cout,4,4]
-    sel = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}  # parity -> [(input offset, kernel index)]
-    out = []
-    for py in (0, 1):
-        for px in (0, 1):
-            taps, mats = [], []
-            for dh, ky in sel[py]:
-                for dw, kx in sel[px]:
-                    taps.append((dh, dw))
-                    mats.append(w4[:, :, ky, kx].t())
-            out.append((py, px, taps, conv.pack_taps(mats)))
-    return out
-
-
-TAPS_UNION = [(dh, dw) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]
-
-
-def _pack_fused_up_folded(mod):
-    """The four output parities of FusedUpsample as ONE launch: 9 union taps, Cout = 4 folds x C (fold = 2*py+px);
-    (tap, parity) pairs the parity does not use carry zero weights.  The operand tile of a tap is then loaded once
-    for all four parities (9 loads per tile instead of 16)."""
-    w = torch.nn.functional.pad(mod.weight * mod.multiplier, [1, 1, 1, 1])
-    w4 = (w[:, :, 1:, 1:] + w[:, :, :-1, 1:] + w[:, :, 1:, :-1] + w[:, :, :-1, :-1]) / 4  # [Cin,Cout,4,4]
-    cin, cout = w4.shape[:2]
-    sel = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}  # parity -> {input offset: kernel index}
-    mats = []
-    for dh, dw in TAPS_UNION:
-        rows = []
-        for py in (0, 1):
-            for px in (0, 1):
-                if dh in sel[py] and dw in sel[px]:
-                    rows.append(w4[:, :, sel[py][dh], sel[px][dw]].t())
-                else:
-                    rows.append(torch.zeros((cout, cin), device=w4.device, dtype=w4.dtype))
-        mats.append(torch.cat(rows, 0))
-    return conv.pack_taps(mats)
-
-
 def conv1_forward(x, e, B, H, W, st, nz, k, seed, seed_dev):
     """First convolution of a StyledConvBlock (+ Blur) + noise + LeakyReLU + statistics (pure_gen.py:205-208).
     x [B,H,W,Cin] bf16 -> (a [B,Ho,Wo,C] bf16, Ho, Wo); shared by the inference and the training forward."""
@@ -254,6 +186,7 @@ class SpacedGenerator(nn.Module):
         self.gen = self.conv
         self.in_ch, self.n_class, self.style_size = in_ch, n_class, style_size
         self._cache_key, self._cache = None, None
+        self._plan, self._plan_ptrs, self._bwd_plans = None, None, {}
         # CUDA-graph mode (graphs.py): a device-side counter is added to the (captured, hence constant) host seed
         # so that every replay draws fresh noise; off by default so that torch.manual_seed reproduces a call
         self.register_buffer("_noise_step", torch.zeros(1, dtype=torch.int64), persistent=False)
@@ -268,52 +201,104 @@ class SpacedGenerator(nn.Module):
         return seed, self._noise_step.clone()
 
     # -- derived weights ------------------------------------------------------------------------
+    def _build_plan(self):
+        """Allocates the kernel-side operand buffers once and the hwg_linear_map job table that (re)fills all of them
+        from the fp32 parameters in ONE launch (weightmap.py): tap-major bf16 forward and dgrad operands of every
+        convolution, EqualLR-scaled noise/output weights, folded biases, the concatenated AdaIN projections."""
+        dev = self.out[0].conv.weight_orig.device
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        f32 = dict(device=dev, dtype=torch.float32)
+        t = weightmap.JobTable()
+        c = {"blocks": []}
+        cin_pad = ((self.in_ch + 63) // 64) * 64
+        c["cin_pad"] = cin_pad
+        one = [[1.0]]
+
+        def vec_job(src, dst, C, scale=1.0, reps=1):
+            t.add(src, dst, R=1, C=C, s_r=0, s_c=1, d_r=0, d_c=1, M=[[1.0] * reps], out_off=[f * C for f in range(reps)],
+                  scale=scale)
+
+        n_gb = sum(2 * blk.out_channel for blk in self.conv) * 2
+        c["gb_w"] = torch.empty((n_gb, self.style_size), **f32)
+        c["gb_b"] = torch.empty(n_gb, **f32)
+        row = 0
+        for blk in self.conv:
+            C = blk.out_channel
+            e = {"kind": blk.kind, "C": C}
+            if blk.kind == "initial":
+                w, b = blk.conv1.weight, blk.conv1.bias
+                m1 = weightmap.map_initial(self.in_ch, C)
+                e["taps1"] = [(0, 1 - kx) for kx in range(3)]
+                e["w1f"] = torch.empty((3, 4 * C, cin_pad), **bf)      # output rows as channel folds
+                m1.add_pack_fwd(t, w, e["w1f"], Cip=cin_pad,
+                                out_off=[kx * 4 * C * cin_pad + r * C * cin_pad for r in range(4) for kx in range(3)])
+                e["m1_cip"] = cin_pad
+            elif blk.kind == "vert_up":
+                w, b = blk.conv1[1].weight, blk.conv1[1].bias
+                m1 = weightmap.map_vert_up(C, blk.in_channel)
+                buf = torch.empty((12, C, m1.Cip), **bf)
+                m1.add_pack_fwd(t, w, buf)
+                e["w1"] = [(weightmap.vert_taps(par), buf[6 * par:6 * par + 6]) for par in (0, 1)]
+            elif blk.kind == "fused_up":
+                w, b = blk.conv1[0].weight, blk.conv1[0].bias
+                m1 = weightmap.map_fused_up(blk.in_channel, C, blk.conv1[0].multiplier)
+                e["w1f"] = torch.empty((16, C, m1.Cip), **bf)          # output parities as channel folds
+                m1.add_pack_fwd(t, w, e["w1f"])
+                e["taps1f"] = weightmap.fused_taps()
+            else:
+                w, b = blk.conv1.weight, blk.conv1.bias
+                m1 = weightmap.map_conv3x3(C, blk.in_channel)
+                e["w1"] = torch.empty((9, C, m1.Cip), **bf)
+                m1.add_pack_fwd(t, w, e["w1"])
+            e["d1"] = torch.empty(m1.dgrad_shape(), **bf)
+            m1.add_pack_dgrad(t, w, e["d1"])
+            e["m1"], e["p_w1"], e["p_b1"] = m1, w, b
+            e["b1"] = b.detach()
+            if blk.kind in ("initial", "fused_up"):
+                e["b1f"] = torch.empty(4 * C, **f32)
+                vec_job(b, e["b1f"], C, reps=4)
+            m2 = weightmap.map_conv3x3(C, C)
+            e["w2"] = torch.empty((9, C, C), **bf)
+            e["d2"] = torch.empty(m2.dgrad_shape(), **bf)
+            m2.add_pack_fwd(t, blk.conv2.weight, e["w2"])
+            m2.add_pack_dgrad(t, blk.conv2.weight, e["d2"])
+            e["m2"] = m2
+            e["b2"] = blk.conv2.bias.detach()
+            nscale = sqrt(2.0 / C)                   # EqualLR on NoiseInjection: fan_in = C (pure_gen.py:222-226)
+            e["nw1"], e["nw2"] = torch.empty(C, **f32), torch.empty(C, **f32)
+            vec_job(blk.noise1.weight_orig, e["nw1"], C, nscale)
+            vec_job(blk.noise2.weight_orig, e["nw2"], C, nscale)
+            if blk.kind == "initial":
+                e["nw1f"] = torch.empty(4 * C, **f32)
+                vec_job(blk.noise1.weight_orig, e["nw1f"], C, nscale, reps=4)
+            for ad in (blk.adain1, blk.adain2):
+                t.add(ad.style.weight, c["gb_w"], R=2 * C, C=self.style_size, s_r=self.style_size, s_c=1,
+                      d_r=self.style_size, d_c=1, M=one, out_off=[row * self.style_size])
+                t.add(ad.style.bias, c["gb_b"], R=1, C=2 * C, s_r=0, s_c=1, d_r=0, d_c=1, M=one, out_off=[row])
+                row += 2 * C
+            c["blocks"].append(e)
+        c["mlp"] = [(m.weight.detach(), m.bias.detach()) for m in self.style_emb if isinstance(m, nn.Linear)]
+        wo = self.out[0].conv.weight_orig
+        c["out_scale"] = sqrt(2.0 / (wo.size(1) * wo[0][0].numel()))
+        c["w_out"] = torch.empty(wo.size(1), **f32)
+        vec_job(wo, c["w_out"], wo.size(1), c["out_scale"])
+        c["b_out"] = self.out[0].conv.bias.detach().reshape(1)
+        for p in self.parameters():
+            assert p.is_contiguous() and p.dtype == torch.float32, "generator parameters must be contiguous fp32"
+        t.finalize(dev)
+        return {"table": t, "c": c}
+
     def _packed(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._cache_key == key:
             return self._cache
-        with torch.no_grad():
-            c = {"blocks": []}
-            cin_pad = ((self.in_ch + 63) // 64) * 64
-            c["cin_pad"] = cin_pad
-            gb_w, gb_b = [], []
-            for blk in self.conv:
-                e = {"kind": blk.kind, "C": blk.out_channel}
-                if blk.kind == "initial":
-                    e["taps1"], e["w1"] = _pack_initial(blk.conv1.weight, cin_pad)
-                    e["w1f"] = torch.cat(e["w1"], 1).contiguous()      # [3, 4*C, cin_pad]: rows as channel folds
-                    e["b1"] = blk.conv1.bias.detach().float().contiguous()
-                    e["b1f"] = e["b1"].repeat(4)
-                elif blk.kind == "vert_up":
-                    e["w1"] = _pack_vert_up(blk.conv1[1].weight)
-                    e["b1"] = blk.conv1[1].bias.detach().float().contiguous()
-                elif blk.kind == "fused_up":
-                    e["w1"] = _pack_fused_up(blk.conv1[0])
-                    e["w1f"] = torch.cat([wp for _, _, _, wp in e["w1"]], 0).contiguous()   # [16, C, Cin], parity-major
-                    e["taps1f"] = [t for _, _, taps, _ in e["w1"] for t in taps]
-                    e["b1"] = blk.conv1[0].bias.detach().float().contiguous()
-                    e["b1f"] = e["b1"].repeat(4)
-                else:
-                    e["w1"] = conv.pack_conv2d_weight(blk.conv1.weight)
-                    e["b1"] = blk.conv1.bias.detach().float().contiguous()
-                e["w2"] = conv.pack_conv2d_weight(blk.conv2.weight)
-                e["b2"] = blk.conv2.bias.detach().float().contiguous()
-                e["nw1"] = blk.noise1.effective_weight().detach().float().contiguous()
-                e["nw2"] = blk.noise2.effective_weight().detach().float().contiguous()
-                if blk.kind == "initial":
-                    e["nw1f"] = e["nw1"].repeat(4)
-                for ad in (blk.adain1, blk.adain2):
-                    gb_w.append(ad.style.weight)
-                    gb_b.append(ad.style.bias)
-                c["blocks"].append(e)
-            c["gb_w"] = torch.cat(gb_w, 0).detach().float().contiguous()
-            c["gb_b"] = torch.cat(gb_b, 0).detach().float().contiguous()
-            c["mlp"] = [(m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
-                        for m in self.style_emb if isinstance(m, nn.Linear)]
-            c["w_out"] = self.out[0].effective_weight().detach().float().reshape(-1).contiguous()
-            c["b_out"] = self.out[0].conv.bias.detach().float().reshape(1).contiguous()
-        self._cache_key, self._cache = key, c
-        return c
+        ptrs = tuple(k[0] for k in key)
+        if self._plan is None or self._plan_ptrs != ptrs:
+            self._plan, self._plan_ptrs = self._build_plan(), ptrs
+            self._bwd_plans = {}
+        self._plan["table"].run()
+        self._cache_key, self._cache = key, self._plan["c"]
+        return self._cache
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, content, style, return_intermediate=False, noise=None):

@@ -346,6 +346,42 @@ int hwg_adain_bwd_apply(const void* g, const void* a, const float* save, const f
 int hwg_gen_output_bwd(const float* g_out, const float* out, const void* a, const float* coef,
                        const float* w, int N, int64_t HW, int C, void* gx, float* dwb, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Batched linear maps between parameter layouts and kernel layouts — one launch
+ * for every weight of a module.  Replaces, in the reference, the per-forward
+ * weight re-parameterisations done with ATen ops: the EqualLR pre-hook
+ * (pure_gen.py:222-226,239-241), FusedUpsample.forward's pad/average
+ * (pure_gen.py:259-271), and — together with their adjoints — what autograd
+ * records for them; it also produces the tap-major bf16 operands of
+ * hwg_conv_fprop (forward and dgrad) and maps hwg_conv_wgrad's tap-major fp32
+ * output back to the parameters' own layouts.
+ *
+ *   dst[out_off[o] + r*d_r + c*d_c] (+)= scale * sum_i M[i*nout + o] * src[in_off[i] + r*s_r + c*s_c]
+ *
+ * for r < R, c < C; zeros are written for R <= r < Rp or C <= c < Cp (operand
+ * padding; skipped when accumulating).  With M == NULL the job is a plain sum
+ * over nin strided inputs (in_off[i] = i*in_stride, nout = 1) — batch
+ * reductions of per-sample sums.  src is fp32; dst fp32 or bf16.
+ * Offsets/strides are in ELEMENTS of the respective dtype except src_off/dst_off
+ * (BYTES, added to the src_base/dst_base launch arguments unless the job's flags
+ * mark them as absolute device addresses).  The job table and the M tables live in device memory.
+ * ---------------------------------------------------------------------- */
+#define HWG_MAP_MAX 16
+typedef struct hwgMapJob {
+  int64_t src_off, dst_off;        /* bytes, relative to src_base / dst_base */
+  const float* M;                  /* [nin][nout] device pointer, or NULL (sum of strided inputs) */
+  int32_t nin, nout;               /* nin, nout <= HWG_MAP_MAX unless M == NULL */
+  int32_t R, C, Rp, Cp;
+  int32_t dst_bf16, accumulate;
+  float scale; int32_t flags;      /* bit 0: src_off is an absolute address; bit 1: dst_off is */
+  int64_t in_stride;               /* used when M == NULL */
+  int64_t s_r, s_c, d_r, d_c;
+  int64_t in_off[HWG_MAP_MAX], out_off[HWG_MAP_MAX];
+} hwgMapJob;
+/* max_items = max over jobs of Rp*Cp (sizes the grid). */
+int hwg_linear_map(const hwgMapJob* jobs_dev, int njobs, int64_t max_items,
+                   const void* src_base, void* dst_base, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,7 +182,8 @@ def test_many_tiles_per_cta_and_two_n_tiles():
 def test_folded_launch_fused_upsample_matches_conv_transpose():
     """FusedUpsample (pure_gen.py:259-279) as ONE launch: 9 union taps, the four output parities as channel folds."""
     from handwriting_line_generation_b200 import conv
-    from handwriting_line_generation_b200.pure_gen import FusedUpsample, _pack_fused_up_folded, TAPS_UNION
+    from handwriting_line_generation_b200.pure_gen import FusedUpsample
+    from tests.ref_pack import fused_up_folded, TAPS_UNION
     torch.manual_seed(5)
     Cin, C, N, H, W = 32, 16, 2, 12, 40
     mod = FusedUpsample(Cin, C, 3, padding=1)
@@ -194,7 +195,7 @@ def test_folded_launch_fused_upsample_matches_conv_transpose():
                              stride=2, padding=1).float()
     Ho, Wo = 2 * H, 2 * W
     raw = torch.zeros((N, Ho, Wo, C), device="cuda", dtype=torch.bfloat16)
-    conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), _pack_fused_up_folded(mod.cuda()), TAPS_UNION, H, W,
+    conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), fused_up_folded(mod.weight.detach().cuda(), mod.multiplier), TAPS_UNION, H, W,
                     bias=mod.bias.detach().float().repeat(4).cuda(), out_view=(raw, Ho * Wo * C, 2 * Wo * C, 2 * C, 0),
                     fold=(C, 2, Wo * C, C))
     got = raw.float().permute(0, 3, 1, 2).cpu()
@@ -205,7 +206,7 @@ def test_folded_launch_rows_with_noise_tensor_and_stats():
     """ConvTranspose2d (4,3) on H=1 (pure_gen.py:161-163): the four output rows as channel folds of one launch, with
     bias + explicit noise + LeakyReLU + per-(n,c) statistics accumulated over all four rows."""
     from handwriting_line_generation_b200 import conv, _lib
-    from handwriting_line_generation_b200.pure_gen import _pack_initial
+    from tests.ref_pack import initial_fwd
     torch.manual_seed(6)
     Cin, C, N, W = 64, 64, 2, 70
     wt = torch.randn(Cin, C, 4, 3) / (3 * Cin) ** 0.5
@@ -215,11 +216,11 @@ def test_folded_launch_rows_with_noise_tensor_and_stats():
     pre = F.conv_transpose2d(x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double(), b.double(),
                              padding=(0, 1)).float() + nw.view(1, C, 1, 1) * nz
     ref = F.leaky_relu(pre, 0.2)
-    taps, packs = _pack_initial(wt.cuda(), Cin)
+    taps = [(0, 1 - kx) for kx in range(3)]
     a = torch.zeros((N, 4, W, C), device="cuda", dtype=torch.bfloat16)
     st = torch.zeros((N, C, 2), device="cuda")
     nzh = nz.permute(0, 2, 3, 1).contiguous().cuda()
-    conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), torch.cat(packs, 1).contiguous(), taps, 1, W, bias=b.repeat(4).cuda(),
+    conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), initial_fwd(wt.cuda(), Cin), taps, 1, W, bias=b.repeat(4).cuda(),
                     act=_lib.ACT_LRELU, slope=0.2, out_view=(a, 4 * W * C, W * C, C, 0), fold=(C, 1, W * C, 0),
                     noise_view=(nzh, 4 * W * C, W * C, C, 0), noise_w=nw.repeat(4).cuda(), stats=st)
     got = a.float().permute(0, 3, 1, 2).cpu()
@@ -271,7 +272,8 @@ def test_small_channel_kernel_matches_torch(case):
 def test_small_channel_kernel_transposed_conv_one_launch(case):
     """FusedUpsample's conv_transpose2d(4x4, stride 2, pad 1) as one launch: 4 folds (output parities) x 4 taps."""
     from handwriting_line_generation_b200 import conv
-    from handwriting_line_generation_b200.pure_gen import FusedUpsample, _pack_fused_up
+    from handwriting_line_generation_b200.pure_gen import FusedUpsample
+    from tests.ref_pack import fused_up_fwd
     N, Cin, C, H, W = case
     torch.manual_seed(sum(case))
     mod = FusedUpsample(Cin, C, 3, padding=1)
@@ -281,9 +283,7 @@ def test_small_channel_kernel_transposed_conv_one_launch(case):
     w4 = (wpad[:, :, 1:, 1:] + wpad[:, :, :-1, 1:] + wpad[:, :, 1:, :-1] + wpad[:, :, :-1, :-1]) / 4
     ref = F.conv_transpose2d(x.to(torch.bfloat16).double(), w4.to(torch.bfloat16).double(), mod.bias.double(),
                              stride=2, padding=1).float().detach()
-    packs = _pack_fused_up(mod.cuda())
-    wf = torch.cat([wp for _, _, _, wp in packs], 0).contiguous()
-    taps = [t for _, _, tp, _ in packs for t in tp]
+    wf, taps = fused_up_fwd(mod.weight.detach().cuda(), mod.multiplier)
     Ho, Wo = 2 * H, 2 * W
     raw = torch.zeros((N, Ho, Wo, C), device="cuda", dtype=torch.bfloat16)
     conv.conv_fprop(conv.to_nhwc_bf16(x.cuda()), wf, taps, H, W, bias=mod.bias.detach().float().repeat(4).cuda(),
