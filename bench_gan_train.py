@@ -7,7 +7,7 @@ One step (trainer/hw_with_style_trainer.py:514-530,752-764 `run_gen` with the ge
   CTC loss           (CTCLoss, model/loss.py:28-30)                      forward + backward
   backward           recognizer input-gradient chain (dgrad), generator dgrad + wgrad + norm/noise backward
   gradient all-reduce over NCCL (world > 1), launched from grad-ready hooks on a side stream (dp.GradReducer)
-  Adam on the generator (lr 2e-4, betas (0.5, 0.999): configs/cf_IAM*.json:35-46)
+  clip_grad_value_(2) + Adam on the generator (lr 2e-4, betas (0.5, 0.999): configs/cf_IAM*.json:35-46, trainer :381)
 The discriminator and perceptual-encoder branches of the full step (BASELINE configs[2]) are not part
 of this path and are not executed.
 
@@ -121,8 +121,14 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     hwr = pkg.CNNOnlyHWR(C, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)            # hwr_frozen: no optimizer touches it; its wgrad is skipped
-    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=True)
-    reducer = dp.GradReducer(gen.parameters()) if world > 1 else None
+    # flat fused optimizer: parameters / gradients / moments of the generator as slices of flat buffers; the
+    # backward kernels add their gradients straight into the gradient buffer (gen._grad_sink), the all-reduce
+    # buckets are slices of it, clip_grad_value_(2) + Adam + zero_grad is one launch
+    opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
+    gen._grad_sink = opt
+    reducer = dp.GradReducer(gen.parameters(), flat=opt) if world > 1 else None
+    if reducer is not None:
+        gen._grad_ready_cb = reducer.mark_ready
     n_sets = 4
     host = []
     for i in range(n_sets):
@@ -140,11 +146,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         loss.backward()
         if reducer is not None:
             reducer.finish()
-            opt.step()
-            reducer.zero_grad()
-        else:
-            opt.step()
-            opt.zero_grad(set_to_none=False)
+        opt.step()             # clip + Adam + gradient zeroing, one launch
         return loss
 
     def barrier():

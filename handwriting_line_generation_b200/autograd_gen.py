@@ -111,7 +111,7 @@ def forward_train(m, content, s, gb, noise):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def _bwd_plan(m, c, B, gbw):
+def _bwd_plan(m, c, B, gbw, sink=None):
     """Workspace layout + hwg_linear_map job table of one backward pass, built once per (module, batch).
 
     Workspace `ws` (fp32, zero-filled by ONE memset per backward): every accumulator the backward kernels add into —
@@ -127,18 +127,23 @@ def _bwd_plan(m, c, B, gbw):
         off["n"] += -(-numel // 4) * 4           # 16-byte aligned slots
 
     params = _param_list(m)
+    acc = sink is not None         # gradients are ADDED straight into the optimizer's flat gradient buffer
     goff, n = [], 0
-    for p in params:
-        goff.append(n)
-        n += -(-p.numel() // 4) * 4
+    if not acc:
+        for p in params:
+            goff.append(n)
+            n += -(-p.numel() // 4) * 4
     g_gb_off = n
     n += B * gbw
     t = weightmap.JobTable()
     one = [[1.0]]
 
+    def dst(i):
+        return sink.grad_view(params[i]) if acc else 4 * goff[i]
+
     def vec(src_name, src_elem, dst_param_idx, C, scale=1.0, s_c=2):
-        t.add(4 * (lay[src_name][0] + src_elem), 4 * goff[dst_param_idx], R=1, C=C, s_r=0, s_c=s_c, d_r=0, d_c=1,
-              M=one, scale=scale)
+        t.add(4 * (lay[src_name][0] + src_elem), dst(dst_param_idx), R=1, C=C, s_r=0, s_c=s_c, d_r=0, d_c=1,
+              M=one, scale=scale, accumulate=acc)
 
     gb_off = 0
     for bi, (blk, e) in enumerate(zip(m.conv, c["blocks"])):
@@ -153,15 +158,15 @@ def _bwd_plan(m, c, B, gbw):
         if e["kind"] in ("vert_up", "fused_up"):
             ws(f"st{bi}", B * C * 2)
         base = 6 * bi
-        m1.add_unpack_wgrad(t, 4 * lay[f"dw{bi}1"][0], 4 * goff[base + 0], Cip=cip1)
+        m1.add_unpack_wgrad(t, 4 * lay[f"dw{bi}1"][0], dst(base + 0), Cip=cip1, accumulate=acc)
         if e["kind"] in ("vert_up", "fused_up"):
             # Blur is self-adjoint; the per-channel sums of the blurred gradient are the conv bias gradient
-            t.add(4 * lay[f"st{bi}"][0], 4 * goff[base + 1], R=1, C=C, s_r=0, s_c=2, d_r=0, d_c=1, M=None, nin=B,
-                  in_stride=2 * C)
+            t.add(4 * lay[f"st{bi}"][0], dst(base + 1), R=1, C=C, s_r=0, s_c=2, d_r=0, d_c=1, M=None, nin=B,
+                  in_stride=2 * C, accumulate=acc)
         else:
             vec(f"dch{bi}1", 0, base + 1, C)
         vec(f"dch{bi}1", 1, base + 2, C, sqrt(2.0 / C))
-        m2.add_unpack_wgrad(t, 4 * lay[f"dw{bi}2"][0], 4 * goff[base + 3])
+        m2.add_unpack_wgrad(t, 4 * lay[f"dw{bi}2"][0], dst(base + 3), accumulate=acc)
         vec(f"dch{bi}2", 0, base + 4, C)
         vec(f"dch{bi}2", 1, base + 5, C, sqrt(2.0 / C))
         for h in (1, 2):
@@ -184,9 +189,13 @@ def backward_train(m, ctx, g_out):
     c = m._packed()
     B, T, ncls, gbw = ctx["B"], ctx["T"], ctx["ncls"], ctx["gb_width"]
     dev = g_out.device
-    plan = m._bwd_plans.get((B, gbw))
+    sink = getattr(m, "_grad_sink", None)
+    if sink is not None and not all(sink.owns(p) for p in _param_list(m)):
+        sink = None
+    key = (B, gbw, id(sink))
+    plan = m._bwd_plans.get(key)
     if plan is None:
-        plan = m._bwd_plans[(B, gbw)] = _bwd_plan(m, c, B, gbw)
+        plan = m._bwd_plans[key] = _bwd_plan(m, c, B, gbw, sink)
     ws = torch.zeros(plan["ws_numel"], device=dev, dtype=torch.float32)
     gflat = torch.empty(plan["gflat_numel"], device=dev, dtype=torch.float32)
 
@@ -248,7 +257,14 @@ def backward_train(m, ctx, g_out):
             g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win, in_stride=m1.d_in_stride)
     # ---- every parameter gradient + g_gb in one launch
     plan["table"].run(src_base=ws, dst_base=gflat)
-    flat = [gflat[o:o + n].view(sh) for o, n, sh in zip(plan["goff"], plan["numels"], plan["shapes"])]
+    if sink is None:
+        flat = [gflat[o:o + n].view(sh) for o, n, sh in zip(plan["goff"], plan["numels"], plan["shapes"])]
+    else:
+        flat = [None] * len(plan["shapes"])      # already accumulated into the flat gradient buffer
+        ready = getattr(m, "_grad_ready_cb", None)
+        if ready is not None:
+            for p in _param_list(m):
+                ready(p)
     g_gb = gflat[plan["g_gb_off"]:plan["g_gb_off"] + B * gbw].view(B, gbw)
     # ---- packed input -> content and style
     S = m.style_size if m.append_style else 0
@@ -256,6 +272,95 @@ def backward_train(m, ctx, g_out):
     g_content = gx0[:, :, :ncls].permute(1, 0, 2).contiguous()
     g_s = gx0[:, :, ncls:ncls + S].sum(1) if S else None
     return g_content, g_s, g_gb, flat
+
+
+def _style_params(m):
+    ps = []
+    for mod in m.style_emb:
+        if isinstance(mod, torch.nn.Linear):
+            ps += [mod.weight, mod.bias]
+    for blk in m.conv:
+        for ad in (blk.adain1, blk.adain2):
+            ps += [ad.style.weight, ad.style.bias]
+    return ps
+
+
+def _style_scatter_table(m, c, sink):
+    """Jobs that add the gradient of the concatenated AdaIN projection ([sum 2C, S] weights | [sum 2C] biases, one
+    temporary) into the twenty separate parameters' slots of the flat gradient buffer."""
+    S, n_gb = m.style_size, c["gb_w"].size(0)
+    t = weightmap.JobTable()
+    row = 0
+    for blk in m.conv:
+        for ad in (blk.adain1, blk.adain2):
+            C2 = ad.style.weight.size(0)
+            t.add(4 * row * S, sink.grad_view(ad.style.weight), R=C2, C=S, s_r=S, s_c=1, d_r=S, d_c=1, M=[[1.0]],
+                  accumulate=True)
+            t.add(4 * (n_gb * S + row), sink.grad_view(ad.style.bias), R=1, C=C2, s_r=0, s_c=1, d_r=0, d_c=1, M=[[1.0]],
+                  accumulate=True)
+            row += C2
+    return t.finalize(c["gb_w"].device)
+
+
+class _StyleFn(torch.autograd.Function):
+    """PixelNorm'ed style -> (s, gb): the six Linear+LeakyReLU(0.2) layers and the ten AdaIN projections as one
+    concatenated Linear (pure_gen.py:31-39,57,63) on hwg_linear_f32 / hwg_linear_bwd_f32."""
+
+    @staticmethod
+    def forward(ctx, module, s0, *params):
+        c = module._packed()
+        acts = [s0.contiguous()]
+        for w, b in c["mlp"]:
+            acts.append(ops.linear(acts[-1], w, b, ACT_LRELU, 0.2))
+        gb = ops.linear(acts[-1], c["gb_w"], c["gb_b"])
+        ctx.module, ctx.acts = module, acts
+        return acts[-1], gb
+
+    @staticmethod
+    def backward(ctx, g_s, g_gb):
+        m, acts = ctx.module, ctx.acts
+        c = m._packed()
+        sink = getattr(m, "_grad_sink", None)
+        sp = _style_params(m)
+        if sink is not None and not all(sink.owns(p) for p in sp):
+            sink = None
+        s = acts[-1]
+        S, n_gb, L = m.style_size, c["gb_w"].size(0), len(c["mlp"])
+        grads = [None] * len(sp)
+        g = g_s
+        if g_gb is not None:
+            tmp = torch.empty(n_gb * S + n_gb, device=s.device, dtype=torch.float32)
+            tw, tb = tmp[:n_gb * S].view(n_gb, S), tmp[n_gb * S:]
+            gx, _, _ = ops.linear_bwd(s, None, g_gb.contiguous(), c["gb_w"], gW=tw, gb=tb)
+            g = gx if g is None else g + gx
+            if sink is not None:
+                key = ("style_scatter", id(sink))
+                t = m._bwd_plans.get(key)
+                if t is None:
+                    t = m._bwd_plans[key] = _style_scatter_table(m, c, sink)
+                t.run(src_base=tmp)
+            else:
+                row = 0
+                for i in range(2 * L, len(sp), 2):
+                    C2 = sp[i].size(0)
+                    grads[i], grads[i + 1] = tw[row:row + C2], tb[row:row + C2]
+                    row += C2
+        for li in range(L - 1, -1, -1):
+            w, _ = c["mlp"][li]
+            need_gx = li > 0 or ctx.needs_input_grad[1]
+            if sink is not None:
+                g, _, _ = ops.linear_bwd(acts[li], acts[li + 1], g.contiguous(), w, ACT_LRELU, 0.2, need_gx,
+                                         gW=sink.grad_view(sp[2 * li]), gb=sink.grad_view(sp[2 * li + 1]), accumulate=True)
+            else:
+                g, grads[2 * li], grads[2 * li + 1] = ops.linear_bwd(acts[li], acts[li + 1], g.contiguous(), w,
+                                                                     ACT_LRELU, 0.2, need_gx)
+        if sink is not None:
+            ready = getattr(m, "_grad_ready_cb", None)
+            if ready is not None:
+                for p in sp:
+                    ready(p)
+        ctx.acts = None
+        return (None, g) + tuple(grads)
 
 
 class _GenFn(torch.autograd.Function):
@@ -275,5 +380,13 @@ class _GenFn(torch.autograd.Function):
 
 
 def generator_apply(module, content, style, noise):
-    s, gb = _style_path(module, style)
+    if module.training and any(isinstance(mod, torch.nn.Dropout) for mod in module.style_emb):
+        s, gb = _style_path(module, style)       # style dropout (unused by the shipped configs): torch autograd
+    else:
+        st = style.float()
+        if st.requires_grad:                      # PixelNorm (pure_gen.py:306-311) under autograd
+            s0 = st / torch.sqrt((st * st).mean(1, keepdim=True) + 1e-8)
+        else:
+            s0 = ops.pixelnorm(st.contiguous())
+        s, gb = _StyleFn.apply(module, s0, *_style_params(module))
     return _GenFn.apply(module, noise, content, s, gb, *_param_list(module))

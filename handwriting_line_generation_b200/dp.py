@@ -101,8 +101,10 @@ class GradReducer:
     synchronisation), so a whole step including the collectives can be captured in one CUDA graph.
     With world_size 1 the hooks are not installed and finish() is a no-op."""
 
-    def __init__(self, params, bucket_bytes=4 << 20, group=None):
-        self.group = group
+    def __init__(self, params, bucket_bytes=4 << 20, group=None, flat=None):
+        """flat: an optim.FlatAdam over the same parameters (same order) — its gradient buffer is bucketed in place
+        instead of allocating new buckets."""
+        self.group, self.flat = group, flat
         self.rank, self.world = world()
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []            # dicts: params, flat, views, pending, work
@@ -118,7 +120,7 @@ class GradReducer:
             self._close(cur)
         self.cuda = bool(self.params) and self.params[0].is_cuda
         self.comm = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
-        self._handles = []
+        self._handles, self._bucket_of = [], {}
         if self.world > 1:
             for bi, b in enumerate(self.buckets):
                 for p in b["params"]:
@@ -126,13 +128,20 @@ class GradReducer:
 
     def _close(self, plist):
         dev = plist[0].device
-        flat = torch.zeros(sum(-(-p.numel() // 4) * 4 for p in plist), dtype=torch.float32, device=dev)
-        views, off = [], 0
-        for p in plist:
-            v = flat[off:off + p.numel()].view_as(p)
-            p.grad = v
-            views.append(v)
-            off += -(-p.numel() // 4) * 4          # 16-byte aligned slots
+        size = sum(-(-p.numel() // 4) * 4 for p in plist)
+        if self.flat is not None:                 # contiguous range of the optimizer's flat gradient buffer
+            lo = min(self.flat.offsets[id(p)][0] for p in plist)
+            flat = self.flat.flat_g[lo:lo + size]
+            views = [self.flat.grad_view(p) for p in plist]
+            assert all(lo <= self.flat.offsets[id(p)][0] < lo + size for p in plist), "parameter order differs from the optimizer's"
+        else:
+            flat = torch.zeros(size, dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for p in plist:
+                v = flat[off:off + p.numel()].view_as(p)
+                p.grad = v
+                views.append(v)
+                off += -(-p.numel() // 4) * 4          # 16-byte aligned slots
         self.buckets.append({"params": plist, "flat": flat, "views": views, "pending": len(plist), "work": None})
 
     def _make_hook(self, bi):
@@ -141,7 +150,17 @@ class GradReducer:
             b["pending"] -= 1
             if b["pending"] == 0:
                 self._launch(b)
+        self._bucket_of.update({id(p): bi for p in self.buckets[bi]["params"]})
         return hook
+
+    def mark_ready(self, p):
+        """For gradients written straight into the flat buffer by a backward kernel (no AccumulateGrad, so no hook):
+        the producer reports the parameter itself."""
+        if self.world > 1 and id(p) in self._bucket_of:
+            b = self.buckets[self._bucket_of[id(p)]]
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                self._launch(b)
 
     def _launch(self, b):
         for p, v in zip(b["params"], b["views"]):

@@ -14,6 +14,21 @@ def linear(x, W, b, act=ACT_NONE, slope=0.0):
     return out
 
 
+def linear_bwd(x, y, gy, W, act=ACT_NONE, slope=0.0, need_gx=True, gW=None, gb=None, accumulate=False):
+    """Backward of y = act(x W^T + b) (fp32).  Returns (gx or None, gW, gb); gW/gb may be caller-provided buffers
+    (with accumulate=True they are added to — e.g. views of a flat gradient buffer)."""
+    B, K = x.shape
+    O = W.size(0)
+    gx = torch.empty((B, K), device=x.device, dtype=torch.float32) if need_gx else None
+    if gW is None:
+        gW = torch.empty((O, K), device=x.device, dtype=torch.float32)
+        gb = torch.empty(O, device=x.device, dtype=torch.float32)
+        accumulate = False
+    _lib.call("hwg_linear_bwd_f32", x.data_ptr(), _lib.ptr(y), gy.data_ptr(), W.data_ptr(), B, K, O, act, slope,
+              _lib.ptr(gx), gW.data_ptr(), gb.data_ptr(), int(accumulate), _lib.stream())
+    return gx, gW, gb
+
+
 def pixelnorm(x):
     out = torch.empty_like(x)
     _lib.call("hwg_pixelnorm_f32", x.data_ptr(), out.data_ptr(), x.size(0), x.size(1), _lib.stream())

@@ -382,6 +382,30 @@ typedef struct hwgMapJob {
 int hwg_linear_map(const hwgMapJob* jobs_dev, int njobs, int64_t max_items,
                    const void* src_base, void* dst_base, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Flat fused optimizer step — replaces clip_grad_value_ + torch.optim.Adam.step
+ * + zero_grad of the reference trainer (trainer/hw_with_style_trainer.py:381-391,
+ * base/base_trainer.py:95-100; Adam lr 2e-4, betas (0.5, 0.999), weight_decay 0)
+ * for an optimizer group stored as ONE flat fp32 buffer (n elements, multiple
+ * of 4, 16-byte aligned): p, g, exp_avg m, exp_avg_sq v.
+ *   g' = clamp(g*grad_scale, +-clip_value) (clip_value <= 0: no clipping)
+ *   m = lerp(m, g', 1-beta1); v = beta2*v + (1-beta2)*g'^2
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ * t = ++step_dev[0] (device-resident float counter, so a captured launch advances
+ * on every CUDA-graph replay).  zero_grad != 0 clears g on the way out. */
+int hwg_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float clip_value, float grad_scale, float* step_dev,
+                  int zero_grad, void* stream);
+
+/* Backward of y = act(x W^T + b), fp32, act in {none, LeakyReLU(slope)} — the style MLP (pure_gen.py:31-39) and the
+ * concatenated AdaIN projections (pure_gen.py:57,63); replaces autograd's addmm/leaky_relu backward kernels.
+ * x [B,K], y [B,O] (post-activation; only read for LeakyReLU), gy [B,O], W [O,K].
+ * gx [B,K] or NULL (written); gW [O,K] or NULL, gb [O] or NULL (written, or added to when accumulate != 0 — e.g.
+ * straight into the flat gradient buffer of hwg_adam_flat). */
+int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const float* W, int B, int K,
+                       int O, int act, float slope, float* gx, float* gW, float* gb, int accumulate,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,8 @@ elif a.workload == "gen_train":
     hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)
-    opt = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), capturable=a.graph)
+    opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
+    gen._grad_sink = opt
     content, style = synth.gen_case(Ts, B, 80, 128, 3)
     T, S = Ts - 6, 40
     ins = [torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev),
@@ -69,7 +70,6 @@ elif a.workload == "gen_train":
         loss = pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl)
         loss.backward()
         opt.step()
-        opt.zero_grad(set_to_none=not a.graph)
         return loss
 else:
     raise SystemExit("unknown workload")
