@@ -52,7 +52,8 @@ _SIGNATURES = {
     "hwg_hwr_stem": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hwg_adam_flat": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, c_vp, c_int, c_vp]),
     "hwg_linear_bwd_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp, c_int, c_vp]),
-    "hwg_linear_map": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "hwg_linear_map": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "hwg_map_items_per_block": (c_int, []),
     "hwg_maxpool_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_vp]),
 }

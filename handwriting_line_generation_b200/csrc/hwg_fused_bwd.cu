@@ -227,6 +227,123 @@ relu_maxpool_bwd_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ 
   if (dbias) channel_reduce<1>(acc, cv, CV, C, sacc, dbias, 1);
 }
 
+// ---- ReLU + MaxPool backward, window-centric specialisations -----------------------------------------------
+// The two poolings of CNNOnlyHWR (cnn_only_hwr.py:44-56): MODE 0 = MaxPool2d(2,2) (disjoint windows) and
+// MODE 1 = MaxPool2d((2,2),(2,1),(0,1)) (windows overlap by one column; padding is -inf).  A thread owns one 8-channel
+// vector of a row pair (rows 2ho, 2ho+1) — MODE 0: columns 2wo, 2wo+1 (one window, four outputs); MODE 1: column w
+// (windows wo = w and w+1, two outputs) — so every activation is read once per window that contains it by the thread
+// that needs it, with no per-pixel division chains or data-dependent loops.  First maximum in row-major scan order
+// wins, as in ATen's max_pool2d_with_indices.
+template <int MODE>
+__global__ void __launch_bounds__(BW_THREADS)
+relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ c, int N, int H, int W, int C,
+                            int Ho, int Wo, uint4* __restrict__ gc, float* __restrict__ dbias) {
+  extern __shared__ float sacc[];  // [1][C]
+  const int CV = C / 8;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  const int HP = (H + 1) / 2;                               // row pairs (the last one may be half)
+  const int WP = MODE == 0 ? (W + 1) / 2 : W;               // column groups
+  const long long total = (long long)N * HP * WP * CV;
+  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  for (int it = 0; it < BW_ITER; ++it) {
+    const long long item = base + it * BW_THREADS + threadIdx.x;
+    if (item >= total) break;
+    long long q = item / CV;
+    const int wg = (int)(q % WP); q /= WP;
+    const int hp = (int)(q % HP);
+    const int n = (int)(q / HP);
+    const int h0 = 2 * hp, h1 = h0 + 1;
+    const bool row1 = h1 < H;
+    const bool win_h = hp < Ho;                              // a pooling window covers this row pair
+    const uint4* cn = c + (long long)n * H * W * CV;
+    uint4* gn = gc + (long long)n * H * W * CV;
+    const uint4* gan = ga + (long long)n * Ho * Wo * CV;
+    if (MODE == 0) {
+      const int w0 = 2 * wg, w1 = w0 + 1;
+      const bool col1 = w1 < W;
+      const bool win = win_h && wg < Wo && row1 && col1;     // floor mode: partial windows do not exist
+      float v[4][8], o[4][8], g[8];
+      unpack8b(cn[((long long)h0 * W + w0) * CV + cv], v[0]);
+      if (col1) unpack8b(cn[((long long)h0 * W + w1) * CV + cv], v[1]);
+      if (row1) unpack8b(cn[((long long)h1 * W + w0) * CV + cv], v[2]);
+      if (row1 && col1) unpack8b(cn[((long long)h1 * W + w1) * CV + cv], v[3]);
+      if (win) unpack8b(gan[((long long)hp * Wo + wg) * CV + cv], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[0][j] = o[1][j] = o[2][j] = o[3][j] = 0.f;
+        if (win) {
+          int best = 0;
+          float m = v[0][j];
+          if (v[1][j] > m) { m = v[1][j]; best = 1; }
+          if (v[2][j] > m) { m = v[2][j]; best = 2; }
+          if (v[3][j] > m) { m = v[3][j]; best = 3; }
+          const float gr = m > 0.f ? g[j] : 0.f;             // ReLU mask (c is the post-ReLU activation)
+          o[0][j] = best == 0 ? gr : 0.f; o[1][j] = best == 1 ? gr : 0.f;
+          o[2][j] = best == 2 ? gr : 0.f; o[3][j] = best == 3 ? gr : 0.f;
+          acc[0][j] += gr;
+        }
+      }
+      gn[((long long)h0 * W + w0) * CV + cv] = pack8b(o[0]);
+      if (col1) gn[((long long)h0 * W + w1) * CV + cv] = pack8b(o[1]);
+      if (row1) gn[((long long)h1 * W + w0) * CV + cv] = pack8b(o[2]);
+      if (row1 && col1) gn[((long long)h1 * W + w1) * CV + cv] = pack8b(o[3]);
+    } else {
+      const int w = wg;
+      // columns w-1, w, w+1 of both rows; outside the image = padding = -inf (never a maximum)
+      float v[2][3][8], o[2][8], gl[8], gr8[8];
+      const float NEG = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int ww = w - 1 + d, hh = h0 + r;
+          if (ww >= 0 && ww < W && hh < H) unpack8b(cn[((long long)hh * W + ww) * CV + cv], v[r][d]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[r][d][j] = NEG;
+          }
+        }
+      const bool win = win_h && row1;
+      if (win) {
+        unpack8b(gan[((long long)hp * Wo + w) * CV + cv], gl);         // window wo = w   : columns w-1, w
+        unpack8b(gan[((long long)hp * Wo + w + 1) * CV + cv], gr8);    // window wo = w+1 : columns w, w+1
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[0][j] = o[1][j] = 0.f;
+        if (win) {
+          // window wo = w, scan order (r0,w-1) (r0,w) (r1,w-1) (r1,w): positions 1 and 3 are ours
+          int best = 0;
+          float m = v[0][0][j];
+          if (v[0][1][j] > m) { m = v[0][1][j]; best = 1; }
+          if (v[1][0][j] > m) { m = v[1][0][j]; best = 2; }
+          if (v[1][1][j] > m) { m = v[1][1][j]; best = 3; }
+          if (best == 1) o[0][j] += gl[j];
+          if (best == 3) o[1][j] += gl[j];
+          // window wo = w+1, scan order (r0,w) (r0,w+1) (r1,w) (r1,w+1): positions 0 and 2 are ours
+          best = 0; m = v[0][1][j];
+          if (v[0][2][j] > m) { m = v[0][2][j]; best = 1; }
+          if (v[1][1][j] > m) { m = v[1][1][j]; best = 2; }
+          if (v[1][2][j] > m) { m = v[1][2][j]; best = 3; }
+          if (best == 0) o[0][j] += gr8[j];
+          if (best == 2) o[1][j] += gr8[j];
+          o[0][j] = v[0][1][j] > 0.f ? o[0][j] : 0.f;        // ReLU mask
+          o[1][j] = v[1][1][j] > 0.f ? o[1][j] : 0.f;
+          acc[0][j] += o[0][j] + o[1][j];
+        }
+      }
+      gn[((long long)h0 * W + w) * CV + cv] = pack8b(o[0]);
+      if (row1) gn[((long long)h1 * W + w) * CV + cv] = pack8b(o[1]);
+    }
+  }
+  if (dbias) channel_reduce<1>(acc, cv, CV, C, sacc, dbias, 1);
+}
+
 // ---- stem backward ---------------------------------------------------------------------------------
 // thread = (pooled pixel, 8-channel group); block-level reduction of dw[c][9], db[c] in shared memory
 __global__ void __launch_bounds__(BW_THREADS)
@@ -581,6 +698,15 @@ extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H,
   HWG_REQUIRE(cv_ok(C), "hwg_relu_maxpool_bwd: C=%d must be 8 x a power of two", C);
   HWG_REQUIRE(Ho == (H + 2 * ph - kh) / sh + 1 && Wo == (W + 2 * pw - kw) / sw + 1,
               "hwg_relu_maxpool_bwd: Ho/Wo do not match the pooling geometry");
+  if (kh == 2 && kw == 2 && sh == 2 && ph == 0 && ((sw == 2 && pw == 0) || (sw == 1 && pw == 1)) && cv_ok(C)) {
+    const int mode = sw == 2 ? 0 : 1;
+    const long long items = (long long)N * ((H + 1) / 2) * (mode == 0 ? (W + 1) / 2 : W) * (C / 8);
+    auto kern = mode == 0 ? relu_maxpool_bwd_win_kernel<0> : relu_maxpool_bwd_win_kernel<1>;
+    kern<<<bw_blocks(items, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(ga), reinterpret_cast<const uint4*>(c), N, H, W, C, Ho, Wo,
+        reinterpret_cast<uint4*>(gc), dbias);
+    return check_launch("relu_maxpool_bwd_win_kernel");
+  }
   const long long total = (long long)N * H * W * (C / 8);
   relu_maxpool_bwd_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float),
                             (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(ga),

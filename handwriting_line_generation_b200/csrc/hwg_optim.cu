@@ -56,17 +56,21 @@ extern "C" int hwg_adam_flat(float* p, float* g, float* m, float* v, int64_t n, 
 
 // ---- backward of the small fp32 dense layers of the style path (style MLP pure_gen.py:31-39, AdaIN projections
 // pure_gen.py:57,63): y = act(x W^T + b).  One launch: blocks [0,O) produce row o of g_W and g_b[o] (threads over k,
-// loop over the batch), blocks [O, O+B) produce row b of g_x (threads over k, loop over o; W read along k).
+// loop over the batch); blocks [O, O+B) produce row b of g_x: LB_PARTS groups of threads each reduce a slice of the
+// O outputs for every k (W read along k, coalesced), combined through shared memory.
 namespace hwg {
-__global__ void __launch_bounds__(128) linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                         const float* __restrict__ gy, const float* __restrict__ W,
-                                                         int B, int K, int O, int act, float slope,
-                                                         float* __restrict__ gx, float* __restrict__ gW,
-                                                         float* __restrict__ gb, int accumulate) {
-  extern __shared__ float gp[];   // g_pre for this block's row: [B] (weight blocks) or [O] (input blocks)
+constexpr int LB_THREADS = 512, LB_OSLICE = 128;
+
+__global__ void __launch_bounds__(LB_THREADS) linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                const float* __restrict__ gy, const float* __restrict__ W,
+                                                                int B, int K, int O, int act, float slope,
+                                                                float* __restrict__ gx, float* __restrict__ gW,
+                                                                float* __restrict__ gb, int accumulate) {
+  extern __shared__ float sm[];   // g_pre of this block's row: [max(B,O)], then the partial sums [parts][K]
   const int blk = blockIdx.x;
   if (blk < O) {
     const int o = blk;
+    float* gp = sm;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
       float g = gy[(size_t)b * O + o];
       if (act == HWG_ACT_LRELU) g *= (y[(size_t)b * O + o] > 0.f) ? 1.f : slope;
@@ -86,17 +90,39 @@ __global__ void __launch_bounds__(128) linear_bwd_kernel(const float* __restrict
       gb[o] = accumulate ? gb[o] + acc : acc;
     }
   } else if (gx) {
-    const int b = blk - O;
-    for (int o = threadIdx.x; o < O; o += blockDim.x) {
-      float g = gy[(size_t)b * O + o];
-      if (act == HWG_ACT_LRELU) g *= (y[(size_t)b * O + o] > 0.f) ? 1.f : slope;
+    // block = (batch row b, slice of LB_OSLICE outputs): partial g_x[b, :] over the slice, added atomically
+    // (g_x is zeroed by the caller) — O = 1984 for the concatenated AdaIN projections would otherwise be one
+    // long serial loop on a handful of blocks
+    const int nsl = (O + LB_OSLICE - 1) / LB_OSLICE;
+    const int b = (blk - O) / nsl, o0 = ((blk - O) % nsl) * LB_OSLICE;
+    const int on = min(LB_OSLICE, O - o0);
+    float* gp = sm;
+    const int nmax = B > O ? B : O;
+    float* part = sm + nmax;
+    for (int o = threadIdx.x; o < on; o += blockDim.x) {
+      float g = gy[(size_t)b * O + o0 + o];
+      if (act == HWG_ACT_LRELU) g *= (y[(size_t)b * O + o0 + o] > 0.f) ? 1.f : slope;
       gp[o] = g;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int kw = K < (int)blockDim.x ? K : (int)blockDim.x;   // threads along k
+    const int parts = blockDim.x / kw;                            // groups along o
+    const int k0 = threadIdx.x % kw, pr = threadIdx.x / kw;
+    for (int kb = 0; kb < K; kb += kw) {
+      const int k = kb + k0;
       float acc = 0.f;
-      for (int o = 0; o < O; ++o) acc = fmaf(gp[o], W[(size_t)o * K + k], acc);
-      gx[(size_t)b * K + k] = acc;      // g_x is always written (never accumulated)
+      if (pr < parts && k < K) {
+#pragma unroll 4
+        for (int o = pr; o < on; o += parts) acc = fmaf(gp[o], W[(size_t)(o0 + o) * K + k], acc);
+      }
+      if (pr < parts) part[pr * kw + k0] = acc;
+      __syncthreads();
+      if (pr == 0 && k < K) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += part[q * kw + k0];
+        atomicAdd(&gx[(size_t)b * K + k], t);
+      }
+      __syncthreads();
     }
   }
 }
@@ -109,7 +135,9 @@ extern "C" int hwg_linear_bwd_f32(const float* x, const float* y, const float* g
   HWG_REQUIRE(act == 0 || (act == HWG_ACT_LRELU && y), "hwg_linear_bwd_f32: activation must be none or LeakyReLU (needs y)");
   const int nmax = B > O ? B : O;
   HWG_REQUIRE(nmax <= 8192, "hwg_linear_bwd_f32: B and O must be <= 8192");
-  hwg::linear_bwd_kernel<<<O + (gx ? B : 0), 128, (size_t)nmax * sizeof(float), (cudaStream_t)stream>>>(
+  const size_t smem = (size_t)(nmax + hwg::LB_THREADS) * sizeof(float);
+  const int nsl = (O + hwg::LB_OSLICE - 1) / hwg::LB_OSLICE;
+  hwg::linear_bwd_kernel<<<O + (gx ? B * nsl : 0), hwg::LB_THREADS, smem, (cudaStream_t)stream>>>(
       x, y, gy, W, B, K, O, act, slope, gx, gW, gb, accumulate);
   return hwg::check_launch("linear_bwd_kernel");
 }

@@ -19,7 +19,7 @@ def linear_bwd(x, y, gy, W, act=ACT_NONE, slope=0.0, need_gx=True, gW=None, gb=N
     (with accumulate=True they are added to — e.g. views of a flat gradient buffer)."""
     B, K = x.shape
     O = W.size(0)
-    gx = torch.empty((B, K), device=x.device, dtype=torch.float32) if need_gx else None
+    gx = torch.zeros((B, K), device=x.device, dtype=torch.float32) if need_gx else None    # the kernel adds slices
     if gW is None:
         gW = torch.empty((O, K), device=x.device, dtype=torch.float32)
         gb = torch.empty(O, device=x.device, dtype=torch.float32)

@@ -68,8 +68,9 @@ class JobTable:
         mflat = torch.from_numpy(np.concatenate(ms) if ms else np.zeros(1, np.float32)).to(device)
         arr = (MapJob * len(self.jobs))()
         moff = 0
-        self.max_items = 1
-        for a, j in zip(arr, self.jobs):
+        per_block = _lib.load().hwg_map_items_per_block()
+        tab = []
+        for ji, (a, j) in enumerate(zip(arr, self.jobs)):
             a.flags = 0
             for bit, key in enumerate(("src", "dst")):
                 v = j[key]
@@ -90,14 +91,15 @@ class JobTable:
                 a.in_off[i] = v
             for i, v in enumerate(j["out_off"]):
                 a.out_off[i] = v
-            self.max_items = max(self.max_items, j["Rp"] * j["Cp"])
+            tab += [(ji, b) for b in range(-(-(j["Rp"] * j["Cp"]) // per_block))]
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self._tab = torch.tensor(tab, dtype=torch.int32).reshape(-1, 2).to(device)
         self._dev, self._keep = raw, [mflat]
         return self
 
     def run(self, src_base=None, dst_base=None):
         assert self._dev is not None, "JobTable.finalize() first"
-        _lib.call("hwg_linear_map", self._dev.data_ptr(), len(self.jobs), self.max_items,
+        _lib.call("hwg_linear_map", self._dev.data_ptr(), self._tab.data_ptr(), self._tab.size(0),
                   _lib.ptr(src_base), _lib.ptr(dst_base), _lib.stream())
 
 

@@ -378,8 +378,10 @@ typedef struct hwgMapJob {
   int64_t s_r, s_c, d_r, d_c;
   int64_t in_off[HWG_MAP_MAX], out_off[HWG_MAP_MAX];
 } hwgMapJob;
-/* max_items = max over jobs of Rp*Cp (sizes the grid). */
-int hwg_linear_map(const hwgMapJob* jobs_dev, int njobs, int64_t max_items,
+/* block_tab_dev: nblocks pairs (job index, block index within the job) of int32 in device memory; one block covers
+ * hwg_map_items_per_block() consecutive (r, c) items of its job, so a job needs ceil(Rp*Cp / that) blocks. */
+int hwg_map_items_per_block(void);
+int hwg_linear_map(const hwgMapJob* jobs_dev, const int32_t* block_tab_dev, int nblocks,
                    const void* src_base, void* dst_base, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -400,7 +402,7 @@ int hwg_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, f
 /* Backward of y = act(x W^T + b), fp32, act in {none, LeakyReLU(slope)} — the style MLP (pure_gen.py:31-39) and the
  * concatenated AdaIN projections (pure_gen.py:57,63); replaces autograd's addmm/leaky_relu backward kernels.
  * x [B,K], y [B,O] (post-activation; only read for LeakyReLU), gy [B,O], W [O,K].
- * gx [B,K] or NULL (written); gW [O,K] or NULL, gb [O] or NULL (written, or added to when accumulate != 0 — e.g.
+ * gx [B,K] or NULL (ADDED to: the caller zeroes it); gW [O,K] or NULL, gb [O] or NULL (written, or added to when accumulate != 0 — e.g.
  * straight into the flat gradient buffer of hwg_adam_flat). */
 int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const float* W, int B, int K,
                        int O, int act, float slope, float* gx, float* gW, float* gb, int accumulate,

@@ -60,7 +60,7 @@ def test_bn_relu_bwd(N, C, H, W):
 
 
 @pytest.mark.parametrize("geom", [((2, 2), (2, 2), (0, 0)), ((2, 2), (2, 1), (0, 1))])
-@pytest.mark.parametrize("N,C,H,W", [(2, 128, 32, 64), (3, 256, 16, 65), (2, 512, 6, 31)])
+@pytest.mark.parametrize("N,C,H,W", [(2, 128, 32, 64), (3, 256, 16, 65), (2, 512, 6, 31), (1, 64, 7, 9)])
 def test_relu_maxpool_bwd(geom, N, C, H, W):
     from handwriting_line_generation_b200 import ops
     k, s, p = geom
@@ -83,6 +83,17 @@ def test_relu_maxpool_bwd_ties_first_max_wins():
     g = torch.arange(1, 5, dtype=torch.float64).view(1, 1, 2, 2).expand(1, 64, 2, 2).contiguous()
     (ref,) = torch.autograd.grad(a, c, g)
     gc, _ = ops.relu_maxpool_bwd(_nhwc(g), _nhwc(c.detach()), (2, 2), (2, 2), (0, 0))
+    assert torch.equal(gc.float().permute(0, 3, 1, 2).cpu().double(), ref)
+
+
+def test_relu_maxpool_bwd_ties_overlapping_windows():
+    from handwriting_line_generation_b200 import ops
+    # MaxPool2d((2,2),(2,1),(0,1)) on a constant positive map: every window's first in-image element takes the gradient
+    c = torch.ones(1, 64, 4, 5, dtype=torch.float64, requires_grad=True)
+    a = F.max_pool2d(c, (2, 2), (2, 1), (0, 1))
+    g = torch.arange(1, a.numel() // 64 + 1, dtype=torch.float64).view(1, 1, a.size(2), a.size(3)).expand(1, 64, -1, -1).contiguous()
+    (ref,) = torch.autograd.grad(a, c, g)
+    gc, _ = ops.relu_maxpool_bwd(_nhwc(g), _nhwc(c.detach()), (2, 2), (2, 1), (0, 1))
     assert torch.equal(gc.float().permute(0, 3, 1, 2).cpu().double(), ref)
 
 

@@ -56,9 +56,12 @@ def test_linear_bwd_matches_autograd(act):
 
 def test_generator_gradients_direct_to_flat_buffer_equal_autograd_path():
     """Same weights, inputs and noise: gradients accumulated by the backward kernels straight into FlatAdam's
-    buffer (module._grad_sink) == the gradients the autograd.Functions return."""
+    buffer (module._grad_sink) == the gradients the autograd.Functions return.  The statistics are summed with fp32
+    atomics, so two runs of the SAME path differ at the bf16 noise floor (a few rounding flips cascade through ten
+    layers); that floor is measured here (two autograd-path runs) and the flat-buffer path must sit within 3x of it."""
     import handwriting_line_generation_b200 as pkg
     from oracle import synth
+    from tests.test_modules_gpu import rel_l2
     torch.manual_seed(2)
     T, B = 24, 2
     gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).cuda().train()
@@ -67,22 +70,30 @@ def test_generator_gradients_direct_to_flat_buffer_equal_autograd_path():
     s = torch.from_numpy(style).cuda().requires_grad_()
     noise = [torch.randn(sh, device="cuda") for sh in synth.gen_noise_shapes(T, B, 256)]
     w = torch.randn(B, 1, 64, 4 * T, device="cuda")
-    (gen(c, s, noise=noise) * w).sum().backward()
-    ref = {n: p.grad.clone() for n, p in gen.named_parameters()}
-    ref_c, ref_s = c.grad.clone(), s.grad.clone()
-    for p in gen.parameters():
-        p.grad = None
-    c.grad = s.grad = None
+
+    def run():
+        for p in gen.parameters():
+            if getattr(gen, "_grad_sink", None) is None:
+                p.grad = None
+        c.grad = s.grad = None
+        (gen(c, s, noise=noise) * w).sum().backward()
+        torch.cuda.synchronize()
+        g = {n: p.grad.detach().cpu().numpy().copy() for n, p in gen.named_parameters()}
+        g["<content>"], g["<style>"] = c.grad.cpu().numpy().copy(), s.grad.cpu().numpy().copy()
+        return g
+
+    ref, ref2 = run(), run()
     opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999))
     gen._grad_sink = opt
-    (gen(c, s, noise=noise) * w).sum().backward()
-    torch.cuda.synchronize()
+    got = run()
     for n, p in gen.named_parameters():
         assert p.grad.data_ptr() == opt.grad_view(p).data_ptr(), n
-        d = (p.grad - ref[n]).abs().max()
-        assert d <= 2e-3 * ref[n].abs().max() + 1e-6, (n, float(d), float(ref[n].abs().max()))
-    assert torch.allclose(c.grad, ref_c, rtol=1e-3, atol=1e-5) and torch.allclose(s.grad, ref_s, rtol=1e-3, atol=1e-4)
-    # a second backward accumulates
+    for n in ref:
+        floor = rel_l2(ref2[n], ref[n])
+        assert rel_l2(got[n], ref[n]) <= 3 * floor + 2e-3, (n, rel_l2(got[n], ref[n]), floor)
+    # a second backward accumulates into the same buffer
+    n0 = "out.0.conv.weight_orig"
+    before = dict(gen.named_parameters())[n0].grad.clone()
     (gen(c, s, noise=noise) * w).sum().backward()
-    n0, p0 = next(iter(gen.named_parameters()))
-    assert (p0.grad - 2 * ref[n0]).abs().max() <= 4e-3 * ref[n0].abs().max() + 1e-6
+    after = dict(gen.named_parameters())[n0].grad
+    assert rel_l2((after - before).cpu().numpy(), ref[n0]) <= 2e-2
