@@ -30,6 +30,7 @@
 #include <math_constants.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hwg {
 using namespace sm100;
@@ -557,6 +558,10 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   if (cout16 <= 256) p.BN = cout16;
   else if (cout16 % 256 == 0) p.BN = 256;
   else p.BN = 128;
+  if (const char* ov = getenv("HWG_CONV_BN")) {      // development override (tools/conv_bench.py): force the N tile
+    const int bn = atoi(ov);
+    if ((bn == 64 || bn == 128 || bn == 256) && bn <= cout16 && d->act != HWG_ACT_LOGSOFTMAX) p.BN = bn;
+  }
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
   // output tile TW x TH = 128 pixels
   int TW = d->tile_w;

@@ -1,6 +1,7 @@
 // HBM-bound fused passes around the convolutions (sm_100a): every kernel moves 16-byte
 // vectors of 8 bf16 channels, NHWC, and touches each activation once.
 #include "common.cuh"
+#include "stream.cuh"
 #include "noise_rng.cuh"
 #include <math_constants.h>
 
@@ -129,16 +130,25 @@ scale_shift_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) cs[i] = cf[i];
   __syncthreads();
   const long long total = HW * CV;
-  const long long base = (long long)blockIdx.x * EW_THREADS * EW_ITER;
   const uint4* xn = x + (size_t)n * total;
   uint4* yn = y + (size_t)n * total;
+  constexpr int U = 4;   // independent 16-byte loads issued before any is consumed (bytes in flight per thread)
+  for (long long chunk = blockIdx.x; chunk * (EW_THREADS * EW_ITER) < total; chunk += gridDim.x)   // persistent blocks
+  for (int it0 = 0; it0 < EW_ITER; it0 += U) {
+    const long long base = chunk * (EW_THREADS * EW_ITER) + threadIdx.x;
+    uint4 v[U];
 #pragma unroll
-  for (int it = 0; it < EW_ITER; ++it) {
-    const long long item = base + it * EW_THREADS + threadIdx.x;
-    if (item < total) {
+    for (int u = 0; u < U; ++u) {
+      const long long item = base + (long long)(it0 + u) * EW_THREADS;
+      if (item < total) v[u] = xn[item];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long item = base + (long long)(it0 + u) * EW_THREADS;
+      if (item >= total) continue;
       const int cv = (int)(item % CV);
       float f[8];
-      unpack8(xn[item], f);
+      unpack8(v[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 ab = *reinterpret_cast<const float2*>(&cs[2 * (cv * 8 + j)]);
@@ -147,6 +157,32 @@ scale_shift_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const
       yn[item] = pack8(f);
     }
   }
+}
+
+// Bulk-staged variant (stream.cuh) for channel counts 8 x 2^k: the TMA engine streams x through a shared-memory ring,
+// the per-channel (a, b) pairs sit in shared memory as two planes (conflict-free: lanes read consecutive words).
+__global__ void __launch_bounds__(ST_THREADS)
+scale_shift_act_stream_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ coef,
+                              int per_sample, long long HW, int C, int act, float slope) {
+  extern __shared__ unsigned char smraw[];
+  unsigned char* ring = smraw + ((128u - (sm100::smem_u32(smraw) & 127u)) & 127u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)ST_STAGES * ST_CHUNK * 16);
+  float* cst = reinterpret_cast<float*>(bars + ST_BAR_SLOTS);     // a [C], b [C]; 16-byte aligned
+  const int n = blockIdx.y, CV = C / 8;
+  const float* cf = coef + (per_sample ? (size_t)n * C * 2 : 0);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { cst[c] = cf[2 * c]; cst[C + c] = cf[2 * c + 1]; }
+  const float* kc = cst + (threadIdx.x % CV) * 8;
+  const long long total = HW * CV;
+  uint4* yn = y + (size_t)n * total;
+  const uint4* const src[1] = {x + (size_t)n * total};
+  stream_chunks<1>(src, total, blockIdx.x, gridDim.x, ring, bars, [&](long long item, const uint4 (&v)[1]) {
+    float f[8], a[8], b[8];
+    unpack8(v[0], f);
+    ld8s(kc, a); ld8s(kc + C, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act_fn(fmaf(a[j], f[j], b[j]), act, slope);
+    yn[item] = pack8(f);
+  });
 }
 
 // ---- blur + noise + activation + statistics ---------------------------------------------------
@@ -429,7 +465,18 @@ extern "C" int hwg_scale_shift_act(const void* x, void* y, const float* coef, in
                                    int64_t HW, int C, int act, float slope, void* stream) {
   HWG_REQUIRE(x && y && coef && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "hwg_scale_shift_act: bad argument");
   const long long total = HW * (C / 8);
-  dim3 grid(blocks_for(total, EW_THREADS * EW_ITER), N);
+  if (pow2(C / 8) && C / 8 <= ST_THREADS) {
+    // in-place (x == y) is fine: a block only ever writes items of chunks it has already pulled into its ring
+    const long long need = blocks_for(total, ST_CHUNK), cap = (148LL * 3 + N - 1) / N;
+    dim3 grid((unsigned)(need < cap ? need : cap), N);
+    HWG_SMEM_OPTIN(scale_shift_act_stream_kernel);
+    scale_shift_act_stream_kernel<<<grid, ST_THREADS, stream_smem_bytes(1) + ST_BAR_SLOTS * 8 + (size_t)2 * C * sizeof(float),
+                                    (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+                                                            reinterpret_cast<uint4*>(y), coef, per_sample, HW, C, act, slope);
+    return check_launch("scale_shift_act_stream_kernel");
+  }
+  const long long need = blocks_for(total, EW_THREADS * EW_ITER), cap = (148LL * 8 + N - 1) / N;   // persistent
+  dim3 grid((unsigned)(need < cap ? need : cap), N);
   scale_shift_act_kernel<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), coef, per_sample, HW, C, act, slope);
   return check_launch("scale_shift_act_kernel");

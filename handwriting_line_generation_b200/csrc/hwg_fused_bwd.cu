@@ -2,6 +2,7 @@
 // 8 channels per thread, per-channel reductions folded warp -> shared -> one global atomic per block.
 #include "common.cuh"
 #include "noise_rng.cuh"
+#include "stream.cuh"
 #include <math_constants.h>
 
 namespace hwg {
@@ -24,12 +25,29 @@ __device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
 
 constexpr int BW_THREADS = 256;
 constexpr int BW_ITER = 8;
+constexpr int BW_U = 4;   // items whose loads are issued back to back before any is consumed (bytes in flight)
+
+// The streaming kernels below keep their per-channel constants in SHARED memory ([k][C] floats, read as two
+// float4 per use) instead of 40-60 registers per thread: at ~100 registers only two 256-thread blocks fit an SM and
+// a one-load-at-a-time loop leaves ~16 KB in flight per SM (measured 1.3-2.8 TB/s); with the constants in shared
+// memory and BW_U independent 16-byte loads per tensor issued up front the same kernels keep >= 64 KB in flight.
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 
 // Per-channel reduction of K x 8 per-thread partial sums.  The thread's channel vector `cv` is fixed
 // (CV divides BW_THREADS).  sacc: [K][C] shared floats (zeroed by the caller, followed by a barrier).
+// Threads that share a channel vector within a warp are folded with shuffles (CV < 32); the per-warp partials are
+// then combined through a shared scratch tile with plain stores and a strided sum (no shared-memory atomics: with
+// 256 threads adding 16 values each into <= 1024 addresses those were ~45 % of the kernel time, stall_short_sb),
+// and every block issues ONE global atomic per (k, channel).
 template <int K>
-__device__ __forceinline__ void channel_reduce(float (&acc)[K][8], int cv, int CV, int C, float* sacc,
-                                               float* gout, int gstride) {
+__device__ __forceinline__ void channel_reduce_in(float (&acc)[K][8], int cv, int CV, int C, float* red,
+                                                  float* gout, int gstride) {
+  constexpr int RW = K * 8 * 32 + 4;                        // floats per warp row of `red`
   if (CV < 32) {
     for (int off = 16; off >= CV; off >>= 1) {
 #pragma unroll
@@ -38,18 +56,41 @@ __device__ __forceinline__ void channel_reduce(float (&acc)[K][8], int cv, int C
         for (int j = 0; j < 8; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], off);
     }
   }
-  const int lane = threadIdx.x & 31;
-  if (CV >= 32 || lane < CV) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slots = CV < 32 ? CV : 32;                      // distinct channel vectors held by one warp
+  if (lane < slots) {
+    float4* dst = reinterpret_cast<float4*>(&red[warp * RW + lane * (K * 8)]);
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[k * C + cv * 8 + j], acc[k][j]);
+    for (int k = 0; k < K; ++k) {
+      dst[2 * k] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      dst[2 * k + 1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
   }
   __syncthreads();
+  // warp w, lane l holds channel vector (w*32 + l) % CV  (CV >= 32)  or  l % CV  (CV < 32)
+  const int nwarps = BW_THREADS / 32;
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
     const int k = i / C, c = i - k * C;
-    atomicAdd(&gout[c * gstride + k], sacc[i]);
+    const int v = c >> 3, j = c & 7;                        // channel vector, element
+    float t = 0.f;
+    if (CV >= 32) {
+      const int wstep = CV / 32;                            // warps w0, w0 + wstep, ... hold vector v
+      for (int w = v / 32; w < nwarps; w += wstep) t += red[w * RW + (v & 31) * (K * 8) + k * 8 + j];
+    } else {
+      for (int w = 0; w < nwarps; ++w) t += red[w * RW + v * (K * 8) + k * 8 + j];
+    }
+    atomicAdd(&gout[c * gstride + k], t);
   }
+}
+template <int K>
+constexpr int channel_reduce_scratch_floats() { return (BW_THREADS / 32) * (K * 8 * 32 + 4); }
+
+// with a static scratch tile (kernels that have no shared-memory ring to reuse)
+template <int K>
+__device__ __forceinline__ void channel_reduce(float (&acc)[K][8], int cv, int CV, int C, float* /*unused*/,
+                                               float* gout, int gstride) {
+  __shared__ __align__(16) float red[channel_reduce_scratch_floats<K>()];
+  channel_reduce_in<K>(acc, cv, CV, C, red, gout, gstride);
 }
 
 // ---- log-softmax backward ---------------------------------------------------------------------
@@ -83,82 +124,106 @@ logsoftmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp,
 }
 
 // ---- BatchNorm (+ReLU) backward ----------------------------------------------------------------
-__global__ void __launch_bounds__(BW_THREADS)
+// Shared memory of the bulk-staged kernels: [ring | mbarriers | per-channel constants]; the ring doubles as the
+// scratch tile of the final per-channel reduction.
+struct StreamSmem {
+  unsigned char* ring; uint64_t* bars; float* cst;
+};
+template <int NS>
+__device__ __forceinline__ StreamSmem stream_smem(unsigned char* raw) {
+  StreamSmem m;
+  m.ring = raw + ((128u - (sm100::smem_u32(raw) & 127u)) & 127u);
+  m.bars = reinterpret_cast<uint64_t*>(m.ring + (size_t)ST_STAGES * NS * ST_CHUNK * 16);
+  m.cst = reinterpret_cast<float*>(m.bars + ST_BAR_SLOTS);   // 16-byte aligned (ld.shared.v4)
+  return m;
+}
+static size_t stream_kernel_smem(int nstream, int const_floats) {
+  return stream_smem_bytes(nstream) + ST_BAR_SLOTS * 8 + (size_t)const_floats * sizeof(float);
+}
+static_assert(BW_THREADS == ST_THREADS, "channel_reduce assumes the streaming block size");
+static_assert((size_t)ST_STAGES * ST_CHUNK * 16 >= sizeof(float) * (BW_THREADS / 32) * (2 * 8 * 32 + 4),
+              "ring too small to double as the reduction scratch");
+
+__global__ void __launch_bounds__(ST_THREADS)
 bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
                      const float* __restrict__ save, long long rows, int C, int relu, float* __restrict__ sums) {
-  extern __shared__ float sacc[];  // [2][C]
+  extern __shared__ unsigned char smraw[];
+  const StreamSmem sm = stream_smem<2>(smraw);      // constants a, b, mean, rstd [4][C]
   const int CV = C / 8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int cv = threadIdx.x % CV;
-  float a[8], b[8], mean[8], rstd[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    a[j] = coef[2 * c]; b[j] = coef[2 * c + 1]; mean[j] = save[2 * c]; rstd[j] = save[2 * c + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sm.cst[c] = coef[2 * c]; sm.cst[C + c] = coef[2 * c + 1];
+    sm.cst[2 * C + c] = save[2 * c]; sm.cst[3 * C + c] = save[2 * c + 1];
   }
+  const int cv = threadIdx.x % CV;
+  const float* kc = sm.cst + cv * 8;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
-  const long long total = rows * CV;
-  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
-  for (int it = 0; it < BW_ITER; ++it) {
-    const long long item = base + it * BW_THREADS + threadIdx.x;
-    if (item >= total) break;
+  const uint4* const src[2] = {g, z};
+  stream_chunks<2>(src, rows * CV, blockIdx.x, gridDim.x, sm.ring, sm.bars, [&](long long, const uint4 (&v)[2]) {
     float gf[8], zf[8];
-    unpack8b(g[item], gf);
-    unpack8b(z[item], zf);
+    unpack8b(v[0], gf);
+    unpack8b(v[1], zf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gy = (!relu || fmaf(a[j], zf[j], b[j]) > 0.f) ? gf[j] : 0.f;
-      acc[0][j] += gy;
-      acc[1][j] += gy * (zf[j] - mean[j]) * rstd[j];
+    for (int hf = 0; hf < 2; ++hf) {
+      float a[4], b[4], mean[4], rstd[4];
+      ld4s(kc + 4 * hf, a); ld4s(kc + C + 4 * hf, b); ld4s(kc + 2 * C + 4 * hf, mean); ld4s(kc + 3 * C + 4 * hf, rstd);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * hf + jj;
+        const float gy = (!relu || fmaf(a[jj], zf[j], b[jj]) > 0.f) ? gf[j] : 0.f;
+        acc[0][j] += gy;
+        acc[1][j] += gy * (zf[j] - mean[jj]) * rstd[jj];
+      }
     }
-  }
-  channel_reduce<2>(acc, cv, CV, C, sacc, sums, 2);
+  });
+  channel_reduce_in<2>(acc, cv, CV, C, reinterpret_cast<float*>(sm.ring), sums, 2);
 }
 
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(ST_THREADS)
 bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
                     const float* __restrict__ save, const float* __restrict__ weight,
                     const float* __restrict__ sums, long long rows, int C, int relu, uint4* __restrict__ gz,
                     float* __restrict__ dconv_bias) {
-  extern __shared__ float sacc[];  // [1][C]
+  extern __shared__ unsigned char smraw[];
+  const StreamSmem sm = stream_smem<2>(smraw);      // constants a, b, sc, P, Q [5][C]
   const int CV = C / 8;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int cv = threadIdx.x % CV;
   const float invM = 1.f / (float)rows;
-  float a[8], b[8], mean[8], rstd[8], k0[8], k1[8], sc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    a[j] = coef[2 * c]; b[j] = coef[2 * c + 1]; mean[j] = save[2 * c]; rstd[j] = save[2 * c + 1];
-    sc[j] = (weight ? weight[c] : 1.f) * rstd[j];
-    k0[j] = sums[2 * c] * invM;       // mean of gy
-    k1[j] = sums[2 * c + 1] * invM;   // mean of gy*xhat
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // gz = sc*(gy - k0 - xhat*k1), xhat = (z - mean)*rstd   ==   sc*gy + P*z + Q
+    const float mean = save[2 * c], rstd = save[2 * c + 1];
+    const float sc = (weight ? weight[c] : 1.f) * rstd;
+    const float k0 = sums[2 * c] * invM, k1 = sums[2 * c + 1] * invM;
+    sm.cst[c] = coef[2 * c]; sm.cst[C + c] = coef[2 * c + 1]; sm.cst[2 * C + c] = sc;
+    sm.cst[3 * C + c] = -sc * k1 * rstd;
+    sm.cst[4 * C + c] = sc * (k1 * rstd * mean - k0);
   }
+  const int cv = threadIdx.x % CV;
+  const float* kc = sm.cst + cv * 8;
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
-  const long long total = rows * CV;
-  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
-  for (int it = 0; it < BW_ITER; ++it) {
-    const long long item = base + it * BW_THREADS + threadIdx.x;
-    if (item >= total) break;
+  const uint4* const src[2] = {g, z};
+  stream_chunks<2>(src, rows * CV, blockIdx.x, gridDim.x, sm.ring, sm.bars, [&](long long item, const uint4 (&v)[2]) {
     float gf[8], zf[8], o[8];
-    unpack8b(g[item], gf);
-    unpack8b(z[item], zf);
+    unpack8b(v[0], gf);
+    unpack8b(v[1], zf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gy = (!relu || fmaf(a[j], zf[j], b[j]) > 0.f) ? gf[j] : 0.f;
-      const float xh = (zf[j] - mean[j]) * rstd[j];
-      o[j] = sc[j] * (gy - k0[j] - xh * k1[j]);
-      acc[0][j] += o[j];
+    for (int hf = 0; hf < 2; ++hf) {
+      float a[4], b[4], sc[4], P[4], Q[4];
+      ld4s(kc + 4 * hf, a); ld4s(kc + C + 4 * hf, b); ld4s(kc + 2 * C + 4 * hf, sc);
+      ld4s(kc + 3 * C + 4 * hf, P); ld4s(kc + 4 * C + 4 * hf, Q);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * hf + jj;
+        const float gy = (!relu || fmaf(a[jj], zf[j], b[jj]) > 0.f) ? gf[j] : 0.f;
+        o[j] = fmaf(sc[jj], gy, fmaf(P[jj], zf[j], Q[jj]));
+        acc[0][j] += o[j];
+      }
     }
     gz[item] = pack8b(o);
-  }
-  if (dconv_bias) channel_reduce<1>(acc, cv, CV, C, sacc, dconv_bias, 1);
+  });
+  if (dconv_bias) channel_reduce_in<1>(acc, cv, CV, C, reinterpret_cast<float*>(sm.ring), dconv_bias, 1);
 }
 
 // ---- ReLU + MaxPool backward (gather) ------------------------------------------------------------
@@ -249,7 +314,8 @@ relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restric
   const int HP = (H + 1) / 2;                               // row pairs (the last one may be half)
   const int WP = MODE == 0 ? (W + 1) / 2 : W;               // column groups
   const long long total = (long long)N * HP * WP * CV;
-  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
+  for (long long chunk = blockIdx.x; chunk * (BW_THREADS * BW_ITER) < total; chunk += gridDim.x) {   // persistent blocks
+  const long long base = chunk * (BW_THREADS * BW_ITER);
   for (int it = 0; it < BW_ITER; ++it) {
     const long long item = base + it * BW_THREADS + threadIdx.x;
     if (item >= total) break;
@@ -340,6 +406,7 @@ relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restric
       gn[((long long)h0 * W + w) * CV + cv] = pack8b(o[0]);
       if (row1) gn[((long long)h1 * W + w) * CV + cv] = pack8b(o[1]);
     }
+  }
   }
   if (dbias) channel_reduce<1>(acc, cv, CV, C, sacc, dbias, 1);
 }
@@ -441,79 +508,70 @@ hwr_stem_bwd_kernel(const float* __restrict__ img, const float* __restrict__ w, 
 
 
 // ---- generator: AdaIN + LeakyReLU (+ noise weight) backward ------------------------------------------
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(ST_THREADS)
 adain_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a, const float* __restrict__ save,
                         long long HW, int C, float* __restrict__ sums) {
-  extern __shared__ float sacc[];  // [2][C]
+  extern __shared__ unsigned char smraw[];
+  const StreamSmem sm = stream_smem<2>(smraw);      // constants mean, rstd [2][C]
   const int n = blockIdx.y, CV = C / 8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int cv = threadIdx.x % CV;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const size_t i = ((size_t)n * C + cv * 8 + j) * 2;
-    mean[j] = save[i]; rstd[j] = save[i + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sm.cst[c] = save[((size_t)n * C + c) * 2]; sm.cst[C + c] = save[((size_t)n * C + c) * 2 + 1];
   }
+  const int cv = threadIdx.x % CV;
+  const float* kc = sm.cst + cv * 8;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   const long long total = HW * CV;
-  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
-  const uint4* gn = g + (size_t)n * total;
-  const uint4* an = a + (size_t)n * total;
-  for (int it = 0; it < BW_ITER; ++it) {
-    const long long item = base + it * BW_THREADS + threadIdx.x;
-    if (item >= total) break;
-    float gf[8], af[8];
-    unpack8b(gn[item], gf);
-    unpack8b(an[item], af);
+  const uint4* const src[2] = {g + (size_t)n * total, a + (size_t)n * total};
+  stream_chunks<2>(src, total, blockIdx.x, gridDim.x, sm.ring, sm.bars, [&](long long, const uint4 (&v)[2]) {
+    float gf[8], af[8], mean[8], rstd[8];
+    unpack8b(v[0], gf);
+    unpack8b(v[1], af);
+    ld8s(kc, mean); ld8s(kc + C, rstd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[0][j] += gf[j];
       acc[1][j] += gf[j] * (af[j] - mean[j]) * rstd[j];
     }
-  }
-  channel_reduce<2>(acc, cv, CV, C, sacc, sums + (size_t)n * C * 2, 2);
+  });
+  channel_reduce_in<2>(acc, cv, CV, C, reinterpret_cast<float*>(sm.ring), sums + (size_t)n * C * 2, 2);
 }
 
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(ST_THREADS)
 adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a, const float* __restrict__ save,
                        const float* __restrict__ coef, const float* __restrict__ sums, int H, int W, int C,
                        float slope, const float* __restrict__ noise, unsigned long long seed,
                        unsigned long long subseq, const unsigned long long* __restrict__ seed_dev, int row_subseq,
                        uint4* __restrict__ gy, float* __restrict__ dch) {
-  extern __shared__ float sacc[];  // [2][C]
+  extern __shared__ unsigned char smraw[];
+  const StreamSmem sm = stream_smem<2>(smraw);      // constants A, P, Q [3][C]
   const int n = blockIdx.y, CV = C / 8;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int cv = threadIdx.x % CV;
   const long long HW = (long long)H * W;
   const float inv = 1.f / (float)HW;
-  float mean[8], rstd[8], A[8], k0[8], k1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const size_t i = ((size_t)n * C + cv * 8 + j) * 2;
-    mean[j] = save[i]; rstd[j] = save[i + 1];
-    A[j] = coef[i];
-    k0[j] = sums[i] * inv; k1[j] = sums[i + 1] * inv;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // ga = A*(g - k0 - ahat*k1), ahat = (a - mean)*rstd   ==   A*g + P*a + Q
+    const size_t i = ((size_t)n * C + c) * 2;
+    const float mean = save[i], rstd = save[i + 1], A = coef[i];
+    const float k0 = sums[i] * inv, k1 = sums[i + 1] * inv;
+    sm.cst[c] = A;
+    sm.cst[C + c] = -A * k1 * rstd;
+    sm.cst[2 * C + c] = A * (k1 * rstd * mean - k0);
   }
+  const int cv = threadIdx.x % CV;
+  const float* kc = sm.cst + cv * 8;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
   seed += seed_dev ? *seed_dev : 0ull;
   const uint2 nkey = noise_key(seed, subseq);
   const long long total = HW * CV;
-  const long long base = (long long)blockIdx.x * BW_THREADS * BW_ITER;
-  const uint4* gn = g + (size_t)n * total;
-  const uint4* an = a + (size_t)n * total;
   uint4* yn = gy + (size_t)n * total;
-  for (int it = 0; it < BW_ITER; ++it) {
-    const long long item = base + it * BW_THREADS + threadIdx.x;
-    if (item >= total) break;
-    float gf[8], af[8], o[8], z[8];
-    unpack8b(gn[item], gf);
-    unpack8b(an[item], af);
+  const uint4* const src[2] = {g + (size_t)n * total, a + (size_t)n * total};
+  stream_chunks<2>(src, total, blockIdx.x, gridDim.x, sm.ring, sm.bars, [&](long long item, const uint4 (&v)[2]) {
+    float gf[8], af[8], o[8], z[8], A[8], P[8], Q[8];
+    unpack8b(v[0], gf);
+    unpack8b(v[1], af);
     if (noise) {
       const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
       const float4 z0 = zp[0], z1 = zp[1];
@@ -535,17 +593,17 @@ adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a,
         z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
       }
     }
+    ld8s(kc, A); ld8s(kc + C, P); ld8s(kc + 2 * C, Q);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float ah = (af[j] - mean[j]) * rstd[j];
-      const float ga = A[j] * (gf[j] - k0[j] - ah * k1[j]);
+      const float ga = fmaf(A[j], gf[j], fmaf(P[j], af[j], Q[j]));
       o[j] = af[j] > 0.f ? ga : ga * slope;
       acc[0][j] += o[j];
       acc[1][j] = fmaf(o[j], z[j], acc[1][j]);
     }
     yn[item] = pack8b(o);
-  }
-  channel_reduce<2>(acc, cv, CV, C, sacc, dch, 2);
+  });
+  channel_reduce_in<2>(acc, cv, CV, C, reinterpret_cast<float*>(sm.ring), dch, 2);
 }
 
 // ---- generator output backward ----------------------------------------------------------------------
@@ -649,6 +707,14 @@ hwr_stem_bwd_expand_kernel(const float* __restrict__ img, const float* __restric
 static inline unsigned bw_blocks(long long items, int per_block) {
   return (unsigned)((items + per_block - 1) / per_block);
 }
+// persistent streaming kernels: at most `per_sm` blocks per SM (148 SMs), each looping over chunks, so that the
+// per-block prologue (constants -> shared memory) and epilogue (shared -> global atomics) are paid ~600 times per
+// launch instead of once per 64 KB of input
+static inline unsigned bw_blocks_persistent(long long items, int per_block, int split = 1, int per_sm = 2) {
+  const long long need = (items + per_block - 1) / per_block;
+  const long long cap = (148LL * per_sm + split - 1) / split;
+  return (unsigned)(need < cap ? need : cap);
+}
 static inline bool cv_ok(int C) {
   const int cv = C / 8;
   return C % 8 == 0 && cv > 0 && (cv & (cv - 1)) == 0 && cv <= BW_THREADS;
@@ -672,7 +738,8 @@ extern "C" int hwg_bn_bwd_reduce(const void* g, const void* z, const float* coef
   HWG_REQUIRE(g && z && coef && save && sums && rows > 0, "hwg_bn_bwd_reduce: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_bn_bwd_reduce: C=%d must be 8 x a power of two", C);
   const long long total = rows * (C / 8);
-  bn_bwd_reduce_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)2 * C * sizeof(float),
+  HWG_SMEM_OPTIN(bn_bwd_reduce_kernel);
+  bn_bwd_reduce_kernel<<<bw_blocks_persistent(total, ST_CHUNK, 1, 3), ST_THREADS, stream_kernel_smem(2, 4 * C),
                          (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z),
                                                  coef, save, rows, C, relu, sums);
   return check_launch("bn_bwd_reduce_kernel");
@@ -684,7 +751,8 @@ extern "C" int hwg_bn_bwd_apply(const void* g, const void* z, const float* coef,
   HWG_REQUIRE(g && z && coef && save && sums && gz && rows > 0, "hwg_bn_bwd_apply: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_bn_bwd_apply: C=%d must be 8 x a power of two", C);
   const long long total = rows * (C / 8);
-  bn_bwd_apply_kernel<<<bw_blocks(total, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float),
+  HWG_SMEM_OPTIN(bn_bwd_apply_kernel);
+  bn_bwd_apply_kernel<<<bw_blocks_persistent(total, ST_CHUNK, 1, 3), ST_THREADS, stream_kernel_smem(2, 5 * C),
                         (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z),
                                                 coef, save, weight, sums, rows, C, relu,
                                                 reinterpret_cast<uint4*>(gz), dconv_bias);
@@ -702,7 +770,7 @@ extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H,
     const int mode = sw == 2 ? 0 : 1;
     const long long items = (long long)N * ((H + 1) / 2) * (mode == 0 ? (W + 1) / 2 : W) * (C / 8);
     auto kern = mode == 0 ? relu_maxpool_bwd_win_kernel<0> : relu_maxpool_bwd_win_kernel<1>;
-    kern<<<bw_blocks(items, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+    kern<<<bw_blocks_persistent(items, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(ga), reinterpret_cast<const uint4*>(c), N, H, W, C, Ho, Wo,
         reinterpret_cast<uint4*>(gc), dbias);
     return check_launch("relu_maxpool_bwd_win_kernel");
@@ -729,8 +797,9 @@ extern "C" int hwg_adain_bwd_reduce(const void* g, const void* a, const float* s
                                     float* sums, void* stream) {
   HWG_REQUIRE(g && a && save && sums && N > 0 && HW > 0, "hwg_adain_bwd_reduce: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_adain_bwd_reduce: C=%d must be 8 x a power of two", C);
-  dim3 grid(bw_blocks(HW * (C / 8), BW_THREADS * BW_ITER), N);
-  adain_bwd_reduce_kernel<<<grid, BW_THREADS, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  dim3 grid(bw_blocks_persistent(HW * (C / 8), ST_CHUNK, N, 3), N);
+  HWG_SMEM_OPTIN(adain_bwd_reduce_kernel);
+  adain_bwd_reduce_kernel<<<grid, ST_THREADS, stream_kernel_smem(2, 2 * C), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(a), save, HW, C, sums);
   return check_launch("adain_bwd_reduce_kernel");
 }
@@ -741,8 +810,9 @@ extern "C" int hwg_adain_bwd_apply(const void* g, const void* a, const float* sa
                                    int row_subseq, void* gy, float* dch, void* stream) {
   HWG_REQUIRE(g && a && save && coef && sums && gy && dch && N > 0 && H > 0 && W > 0, "hwg_adain_bwd_apply: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_adain_bwd_apply: C=%d must be 8 x a power of two", C);
-  dim3 grid(bw_blocks((long long)H * W * (C / 8), BW_THREADS * BW_ITER), N);
-  adain_bwd_apply_kernel<<<grid, BW_THREADS, (size_t)2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  dim3 grid(bw_blocks_persistent((long long)H * W * (C / 8), ST_CHUNK, N, 3), N);
+  HWG_SMEM_OPTIN(adain_bwd_apply_kernel);
+  adain_bwd_apply_kernel<<<grid, ST_THREADS, stream_kernel_smem(2, 3 * C), (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(a), save, coef, sums, H, W, C, slope, noise,
       noise_seed, noise_subseq, reinterpret_cast<const unsigned long long*>(noise_seed_dev), row_subseq,
       reinterpret_cast<uint4*>(gy), dch);

@@ -55,45 +55,64 @@ def test_linear_bwd_matches_autograd(act):
 
 
 def test_generator_gradients_direct_to_flat_buffer_equal_autograd_path():
-    """Same weights, inputs and noise: gradients accumulated by the backward kernels straight into FlatAdam's
-    buffer (module._grad_sink) == the gradients the autograd.Functions return.  The statistics are summed with fp32
-    atomics, so two runs of the SAME path differ at the bf16 noise floor (a few rounding flips cascade through ten
-    layers); that floor is measured here (two autograd-path runs) and the flat-buffer path must sit within 3x of it."""
+    """The backward kernels can add their gradients straight into FlatAdam's buffer (module._grad_sink) instead of
+    returning them to autograd.  Both modes are run on the SAME saved forward state (one forward_train context), so
+    the only differences left are fp32 atomics orders inside the backward kernels (a few bf16 rounding flips in the
+    propagated gradient): every tensor must agree to 2e-2 rel-L2, the style path (no bf16 anywhere) to 1e-4."""
     import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import autograd_gen as ag, ops
     from oracle import synth
     from tests.test_modules_gpu import rel_l2
     torch.manual_seed(2)
     T, B = 24, 2
     gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).cuda().train()
     content, style = synth.gen_case(T, B, 80, 128, 4, dense=True)
-    c = torch.from_numpy(content).cuda().requires_grad_()
-    s = torch.from_numpy(style).cuda().requires_grad_()
+    c, st = torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda()
     noise = [torch.randn(sh, device="cuda") for sh in synth.gen_noise_shapes(T, B, 256)]
-    w = torch.randn(B, 1, 64, 4 * T, device="cuda")
-
-    def run():
-        for p in gen.parameters():
-            if getattr(gen, "_grad_sink", None) is None:
-                p.grad = None
-        c.grad = s.grad = None
-        (gen(c, s, noise=noise) * w).sum().backward()
-        torch.cuda.synchronize()
-        g = {n: p.grad.detach().cpu().numpy().copy() for n, p in gen.named_parameters()}
-        g["<content>"], g["<style>"] = c.grad.cpu().numpy().copy(), s.grad.cpu().numpy().copy()
-        return g
-
-    ref, ref2 = run(), run()
+    g_out = torch.randn(B, 1, 64, 4 * T, device="cuda")
+    plist, splist = ag._param_list(gen), ag._style_params(gen)
+    with torch.no_grad():
+        s0 = ops.pixelnorm(st)
+        s_, gb = ag._style_path(gen, st)
+        out, ctx = ag.forward_train(gen, c, s_, gb, noise)
+        g_content, g_s, g_gb, flat = ag.backward_train(gen, ctx, g_out)
+        ref = [t.clone() for t in flat]
+        ref_c, ref_s, ref_gb = g_content.clone(), g_s.clone(), g_gb.clone()
+    # style path reference through torch autograd
+    s0r = s0.clone().requires_grad_()
+    s2, gb2 = ag._StyleFn.apply(gen, s0r, *splist)
+    torch.autograd.backward([s2, gb2], [ref_s, ref_gb])
+    ref_style = [p.grad.clone() for p in splist]
+    ref_s0 = s0r.grad.clone()
+    for p in gen.parameters():
+        p.grad = None
+    # ---- flat-buffer mode
     opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999))
     gen._grad_sink = opt
-    got = run()
-    for n, p in gen.named_parameters():
-        assert p.grad.data_ptr() == opt.grad_view(p).data_ptr(), n
-    for n in ref:
-        floor = rel_l2(ref2[n], ref[n])
-        assert rel_l2(got[n], ref[n]) <= 3 * floor + 2e-3, (n, rel_l2(got[n], ref[n]), floor)
-    # a second backward accumulates into the same buffer
-    n0 = "out.0.conv.weight_orig"
-    before = dict(gen.named_parameters())[n0].grad.clone()
-    (gen(c, s, noise=noise) * w).sum().backward()
-    after = dict(gen.named_parameters())[n0].grad
-    assert rel_l2((after - before).cpu().numpy(), ref[n0]) <= 2e-2
+    with torch.no_grad():
+        g_content, g_s, g_gb, flat = ag.backward_train(gen, ctx, g_out)
+    assert all(t is None for t in flat)
+    torch.cuda.synchronize()
+    for p, r in zip(plist, ref):
+        assert rel_l2(opt.grad_view(p).cpu().numpy(), r.cpu().numpy()) <= 2e-2, tuple(p.shape)
+    assert rel_l2(g_content.cpu().numpy(), ref_c.cpu().numpy()) <= 2e-2
+    assert rel_l2(g_gb.cpu().numpy(), ref_gb.cpu().numpy()) <= 2e-2
+    s0r = s0.clone().requires_grad_()
+    s2, gb2 = ag._StyleFn.apply(gen, s0r, *splist)
+    torch.autograd.backward([s2, gb2], [ref_s, ref_gb])
+    torch.cuda.synchronize()
+    for p, r in zip(splist, ref_style):
+        assert p.grad.data_ptr() == opt.grad_view(p).data_ptr()
+        assert rel_l2(p.grad.cpu().numpy(), r.cpu().numpy()) <= 1e-4, tuple(p.shape)
+    assert rel_l2(s0r.grad.cpu().numpy(), ref_s0.cpu().numpy()) <= 1e-4
+    # a second backward accumulates
+    before = opt.grad_view(plist[-2]).clone()
+    with torch.no_grad():
+        ag.backward_train(gen, ctx, g_out)
+    assert rel_l2((opt.grad_view(plist[-2]) - before).cpu().numpy(), ref[-2].cpu().numpy()) <= 2e-2
+    # the public path end to end: gradients land in the flat buffer, optimizer step consumes and clears it
+    w0 = plist[0].detach().clone()
+    (gen(c, st, noise=noise) * g_out).sum().backward()
+    assert all(p.grad.data_ptr() == opt.grad_view(p).data_ptr() for p in gen.parameters())
+    opt.step()
+    assert float(opt.flat_g.abs().max()) == 0.0 and float((plist[0] - w0).abs().max()) > 0

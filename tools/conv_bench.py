@@ -14,6 +14,17 @@ SHAPES = {
     "gen_b3c2": (32, 32, 512, 32, 32, (3, 3, 1, 1), "noise_stats"),
     "gen_b4c2": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "noise_stats"),
     "gen_b4c2_plain": (32, 64, 1024, 16, 16, (3, 3, 1, 1), "none"),
+    # train-step shapes at 16 lines per GPU
+    "t_hwr_1d": (16, 1, 256, 512, 512, (1, 3, 0, 0), "stats"),
+    "t_hwr_conv6": (16, 3, 256, 512, 512, (3, 3, 0, 0), "stats"),
+    "t_hwr_conv5": (16, 8, 257, 512, 512, (3, 3, 0, 0), "relu"),
+    "t_hwr_conv4": (16, 8, 257, 256, 512, (3, 3, 1, 1), "stats"),
+    "t_hwr_conv2": (16, 16, 256, 128, 256, (3, 3, 1, 1), "stats"),
+    "t_hwr_conv1": (16, 32, 512, 64, 128, (3, 3, 1, 1), "relu"),
+    "t_gen_b0c2": (16, 4, 256, 256, 256, (3, 3, 1, 1), "noise_stats"),
+    "t_gen_b0c2_dgrad": (16, 4, 256, 256, 256, (3, 3, 1, 1), "none"),
+    "t_gen_b1c2": (16, 8, 256, 128, 128, (3, 3, 1, 1), "noise_stats"),
+    "t_gen_b2c2": (16, 16, 256, 64, 64, (3, 3, 1, 1), "noise_stats"),
 }
 which = [a for a in sys.argv[1:] if a in SHAPES] or ([] if sys.argv[1:] else list(SHAPES))
 reps = 10
@@ -27,6 +38,8 @@ for name in which:
     kw_ = dict(bias=b)
     if epi == "relu":
         kw_.update(act=_lib.ACT_RELU)
+    elif epi == "stats":
+        kw_.update(stats=torch.zeros(N, Cout, 2, device="cuda"))
     elif epi == "noise_stats":
         kw_.update(act=_lib.ACT_LRELU, slope=0.2, noise_w=torch.ones(Cout, device="cuda"), noise_seed=1,
                    stats=torch.zeros(N, Cout, 2, device="cuda"))
