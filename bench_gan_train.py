@@ -260,6 +260,17 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
                               "what": "wgrad of all generator convolutions (tcgen05 + staged-tile kernels)"},
     }
 
+    # DRAM traffic per step by kernel from the committed ncu pass over one steady-state step (same command, B=16)
+    traffic = {}
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_gan_train_r01.json")
+    if os.path.exists(tp) and B == 16:
+        names = {"conv_fprop_kernel": ("conv_fprop_kernel",), "conv_small_kernel": ("conv_small_kernel",),
+                 "conv_wgrad_kernel": ("conv_wgrad_kernel", "wgrad_small_kernel")}
+        for kind, prefixes in names.items():
+            tot = sum((v["dram_read_mb"] + v["dram_write_mb"]) * 1e6 for n, v in json.load(open(tp))["kernels"].items()
+                      if n.startswith(prefixes))
+            traffic[kind] = int(tot)
+
     def roof(kind):
         k = kern[kind]
         a = alg.get(kind, {})
@@ -275,7 +286,9 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
                  "frac": ach / peaks["tf_sust"],
                  "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside the step)",
                  "algorithmic_gflop_per_step": gf, "issued_gflop_per_step": k["issued_flop"] / 1e9}
-        r.update({"covers": a.get("what"), "traffic": None, "launches_per_step": round(k["launches"]),
+        r.update({"covers": a.get("what"), "traffic": traffic.get(kind), "traffic_unit": "bytes per step (all launches "
+                  "of this kernel; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic_gan_train_r01.json)",
+                  "launches_per_step": round(k["launches"]),
                   "kernel_ms_per_step": k["ms"], "share_of_step": k["ms"] / ms_step})
         return r
 

@@ -13,6 +13,7 @@
 //   warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warps 2-5 = epilogue that adds the
 //   fp32 accumulator into dw with red.global.add.v4.f32.
 #include "common.cuh"
+#include <stdlib.h>
 #include "sm100.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -253,7 +254,12 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
   p.dw = dw;
   // split the pixel range so that the grid covers the SMs ~2x
   const int units = d->ntaps * p.co_tiles * p.ci_tiles;
-  int splits = (2 * 148 + units - 1) / units;
+  int cta_target = 2 * 148;
+  if (const char* ov = getenv("HWG_WGRAD_CTAS")) {   // development override (tools/step_runner.py sweeps)
+    const int v = atoi(ov);
+    if (v > 0) cta_target = v;
+  }
+  int splits = (cta_target + units - 1) / units;
   if (splits > p.total_chunks) splits = p.total_chunks;
   if (splits < 1) splits = 1;
   p.chunks_per_split = (p.total_chunks + splits - 1) / splits;

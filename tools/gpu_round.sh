@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
-tail -5 gpurun_out/pytest_gpu.log
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 800 -c 420 --csv --log-file gpurun_out/launches_gan_train.csv \
-  python tools/step_runner.py gen_train --B 16 --steps 3 --warmup 4 > gpurun_out/step_runner_ncu.log 2>&1
-tail -2 gpurun_out/step_runner_ncu.log
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench exit $?"
+tail -c 300 gpurun_out/bench_default.err
+python bench.py --impl reference --steps 6 --warmup 1 > gpurun_out/bench_reference.json 2>/dev/null; echo "ref exit $?"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
