@@ -35,6 +35,7 @@ _SIGNATURES = {
     "hwg_relu_maxpool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_hwr_stem_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_hwr_stem_bwd_image": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hwg_hwr_stem_bwd_expand": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hwg_linear_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_vp]),
     "hwg_pixelnorm_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),

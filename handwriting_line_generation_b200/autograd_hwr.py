@@ -221,10 +221,13 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     if want_input_grad:
         # image gradient (GAN lessons): route g through pool/ReLU to conv0's output, then the 9-tap dgrad with
         # conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] tensor-core convolution
-        gc0 = ops.hwr_stem_bwd_expand(ctx["x"], c["w0"], c["b0"], g)
-        w0d, taps = dg["w0"]
-        gi = conv.conv_fprop(gc0, w0d, taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
-        g_img = gi[..., 0].unsqueeze(1).contiguous()
+        if c["w0"].size(0) == 64 and ctx["x"].size(2) % 2 == 0 and ctx["x"].size(3) % 2 == 0:
+            g_img = ops.hwr_stem_bwd_image(ctx["x"], c["w0"], c["b0"], g)       # one fused pass
+        else:
+            gc0 = ops.hwr_stem_bwd_expand(ctx["x"], c["w0"], c["b0"], g)
+            w0d, taps = dg["w0"]
+            gi = conv.conv_fprop(gc0, w0d, taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
+            g_img = gi[..., 0].unsqueeze(1).contiguous()
         if m.pad is not None:
             p = m.pad.padding
             g_img = g_img[:, :, :, p[0]:g_img.size(3) - p[1]].contiguous()

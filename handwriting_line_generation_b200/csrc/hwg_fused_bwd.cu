@@ -704,6 +704,110 @@ hwr_stem_bwd_expand_kernel(const float* __restrict__ img, const float* __restric
   }
 }
 
+// ---- stem: image gradient in one pass ------------------------------------------------------------------
+// d loss / d image for conv0 (1->Cout, 3x3, pad 1) + ReLU + MaxPool 2x2 (cnn_only_hwr.py:44-46), needed by the GAN
+// lessons (the recognizer reads generated lines).  Replaces hwr_stem_bwd_expand (which materialises the
+// [N,H,W,Cout] bf16 gradient of conv0's output: 134 MB at 16 lines) + a 9-tap tensor-core dgrad with one output
+// channel + a channel-0 slice copy.  A thread owns (pooled pixel, 8 channels): it recomputes the four conv0 outputs of
+// its window, finds the first maximum (ATen's rule), and scatters gy * w[c][ky][kx] of the winner into a private
+// 4x4 image patch (the window plus its one-pixel ring); the eight channel groups of a pooled pixel are folded with a
+// 14-shuffle recursive halving, accumulated into a shared-memory image tile (8 pooled rows x 32 pooled columns per
+// block) and flushed with one fp32 global atomic per image pixel of the tile.
+constexpr int SB_PR = 8, SB_PC = 32;          // pooled rows / columns per block
+__global__ void __launch_bounds__(256)
+hwr_stem_bwd_image_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                          const uint4* __restrict__ ga, int N, int H, int W, float* __restrict__ gimg) {
+  constexpr int COUT = 64, CV = 8;
+  constexpr int TR = 2 * SB_PR + 2, TC = 2 * SB_PC + 2;
+  __shared__ float ws[COUT * 9], bs[COUT];
+  __shared__ float tile[TR * TC];
+  for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = b[i];
+  for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  const int Hp = H / 2, Wp = W / 2;
+  const int n = blockIdx.z, hp0 = blockIdx.y * SB_PR, wp0 = blockIdx.x * SB_PC;
+  const int cv = threadIdx.x & 7, px = threadIdx.x >> 3;
+  const int wp = wp0 + px;
+  const float* im = img + (size_t)n * H * W;
+  for (int r = 0; r < SB_PR; ++r) {
+    const int hp = hp0 + r;
+    if (hp >= Hp) break;                                  // uniform over the block
+    float gp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gp[i] = 0.f;
+    if (wp < Wp) {
+      float patch[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int hh = 2 * hp - 1 + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ww = 2 * wp - 1 + j;
+          patch[i][j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? im[(size_t)hh * W + ww] : 0.f;
+        }
+      }
+      float gf[8];
+      unpack8b(ga[(((size_t)n * Hp + hp) * Wp + wp) * CV + cv], gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* k = ws + (cv * 8 + j) * 9;
+        float kk[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) kk[t] = k[t];
+        float m = -CUDART_INF_F; int best = 0;
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) {
+            float a = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) a = fmaf(kk[ky * 3 + kx], patch[oy + ky][ox + kx], a);
+            if (a > m) { m = a; best = oy * 2 + ox; }
+          }
+        const float gv = (m + bs[cv * 8 + j] > 0.f) ? gf[j] : 0.f;
+        // conv0 output pixel (oy, ox) of the window reads patch[oy+ky][ox+kx]: its gradient lands there
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float gq = (q == best) ? gv : 0.f;
+          const int oy = q >> 1, ox = q & 1;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) gp[(oy + ky) * 4 + ox + kx] = fmaf(gq, kk[ky * 3 + kx], gp[(oy + ky) * 4 + ox + kx]);
+        }
+      }
+    }
+    // fold the 8 channel groups (lanes cv = 0..7 of the same pooled pixel): afterwards lane cv holds entries 2cv, 2cv+1
+#pragma unroll
+    for (int half = 8; half >= 2; half >>= 1) {
+      const bool upper = (cv & (half >> 1)) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = upper ? gp[i] : gp[i + half];
+        const float keep = upper ? gp[i + half] : gp[i];
+        gp[i] = keep + __shfl_xor_sync(0xffffffffu, send, half >> 1);
+      }
+    }
+    if (wp < Wp) {
+      const int e0 = 2 * cv, pi = e0 >> 2, pj = e0 & 3;   // patch row / first column of this lane's two entries
+      float* t = &tile[(2 * r + pi) * TC + 2 * px + pj];
+      atomicAdd(t, gp[0]);
+      atomicAdd(t + 1, gp[1]);
+    }
+  }
+  __syncthreads();
+  float* gn = gimg + (size_t)n * H * W;
+  for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
+    const int tr = i / TC, tc = i - tr * TC;
+    const int hh = 2 * hp0 - 1 + tr, ww = 2 * wp0 - 1 + tc;
+    const float v = tile[i];
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W && v != 0.f) atomicAdd(&gn[(size_t)hh * W + ww], v);
+  }
+}
+
 static inline unsigned bw_blocks(long long items, int per_block) {
   return (unsigned)((items + per_block - 1) / per_block);
 }
@@ -827,6 +931,17 @@ extern "C" int hwg_gen_output_bwd(const float* g_out, const float* out, const vo
   gen_output_bwd_kernel<<<grid, BW_THREADS, (size_t)(4 * C + 1) * sizeof(float), (cudaStream_t)stream>>>(
       g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, C, reinterpret_cast<uint4*>(gx), dwb);
   return check_launch("gen_output_bwd_kernel");
+}
+
+extern "C" int hwg_hwr_stem_bwd_image(const float* img, const float* w, const float* b, const void* ga, int N, int H,
+                                      int W, int Cout, float* gimg, void* stream) {
+  HWG_REQUIRE(img && w && b && ga && gimg && N > 0, "hwg_hwr_stem_bwd_image: bad argument");
+  HWG_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cout == 64, "hwg_hwr_stem_bwd_image: needs even H, W and Cout == 64");
+  HWG_REQUIRE(N <= 65535, "hwg_hwr_stem_bwd_image: N too large");
+  dim3 grid((W / 2 + SB_PC - 1) / SB_PC, (H / 2 + SB_PR - 1) / SB_PR, N);
+  hwr_stem_bwd_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, w, b, reinterpret_cast<const uint4*>(ga), N, H,
+                                                                   W, gimg);
+  return check_launch("hwr_stem_bwd_image_kernel");
 }
 
 extern "C" int hwg_hwr_stem_bwd_expand(const float* img, const float* w, const float* b, const void* ga, int N,

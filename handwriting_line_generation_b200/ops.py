@@ -207,6 +207,15 @@ def gen_output_bwd(g_out, out, a, coef, w, dwb=None):
     return gx, dwb[:C], dwb[C]
 
 
+def hwr_stem_bwd_image(img, w, b, ga):
+    """ga [N,H/2,W/2,64] bf16 -> gradient w.r.t. the image [N,1,H,W] fp32 (conv0 + ReLU + MaxPool backward, fused)."""
+    N, _, H, W = img.shape
+    g = torch.zeros((N, 1, H, W), device=img.device, dtype=torch.float32)
+    _lib.call("hwg_hwr_stem_bwd_image", img.data_ptr(), w.data_ptr(), b.data_ptr(), ga.data_ptr(), N, H, W, w.size(0),
+              g.data_ptr(), _lib.stream())
+    return g
+
+
 def hwr_stem_bwd_expand(img, w, b, ga):
     """ga [N,H/2,W/2,Cout] bf16 -> gradient w.r.t. conv0's output [N,H,W,Cout] bf16."""
     N, _, H, W = img.shape

@@ -311,6 +311,14 @@ int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H, int W, int
  * from ga [N,H/2,W/2,Cout] bf16 and the fp32 image (pre-activations are recomputed). */
 int hwg_hwr_stem_bwd(const float* img, const float* w, const float* b, const void* ga, int N, int H, int W,
                      int Cout, float* dw, float* db, void* stream);
+/* d loss / d image of the stem in ONE pass (the GAN lessons back-propagate through the recognizer's input,
+ * trainer/hw_with_style_trainer.py:752-764): conv0 1->64 3x3 pad 1 + ReLU + MaxPool 2x2 (cnn_only_hwr.py:44-46).
+ * img [N,1,H,W] fp32, w [64,9], b [64] fp32, ga [N,H/2,W/2,64] bf16 = gradient w.r.t. the pooled output.
+ * gimg [N,1,H,W] fp32 is ADDED to (caller zeroes).  Equivalent to hwg_hwr_stem_bwd_expand followed by the
+ * 9-tap transposed convolution with conv0's weights, without materialising the [N,H,W,64] gradient. */
+int hwg_hwr_stem_bwd_image(const float* img, const float* w, const float* b, const void* ga, int N, int H,
+                           int W, int Cout, float* gimg, void* stream);
+
 /* Same recomputation, but writes the gradient w.r.t. the conv0 OUTPUT, gc0 [N,H,W,Cout] bf16 (ga routed to the
  * arg-max of each 2x2 window where it passed the ReLU, zero elsewhere).  The image gradient the GAN lessons
  * need (trainer/hw_with_style_trainer.py:760-764: the generated line is recognised and the CTC loss flows

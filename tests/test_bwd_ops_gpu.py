@@ -113,3 +113,21 @@ def test_stem_fwd_bwd(N, H, W):
     dw, db = ops.hwr_stem_bwd(img.float().cuda(), wc, bc, _nhwc(g))
     assert _rel(dw.view(64, 1, 3, 3).cpu(), gw_ref) <= 2e-3
     assert _rel(db.cpu(), gb_ref) <= 2e-3
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 128), (1, 64, 200), (3, 16, 72)])
+def test_stem_image_gradient_fused(N, H, W):
+    """hwg_hwr_stem_bwd_image == autograd of MaxPool(ReLU(conv0(img))) w.r.t. the image, and == the two-step path
+    (expand + 9-tap transposed convolution) it replaces."""
+    from handwriting_line_generation_b200 import ops
+    g0 = torch.Generator().manual_seed(W + N)
+    img = (torch.rand(N, 1, H, W, generator=g0) * 2 - 1).double().requires_grad_()
+    w = (torch.randn(64, 1, 3, 3, generator=g0) / 3).float().double()
+    b = (torch.randn(64, generator=g0) * 0.1).float().double()
+    a = F.max_pool2d(F.relu(F.conv2d(img, w, b, padding=1)), 2, 2)
+    g = _bf(torch.randn(a.shape, generator=g0))
+    (ref,) = torch.autograd.grad(a, img, g.double())
+    wc, bc = w.float().reshape(64, 9).contiguous().cuda(), b.float().cuda()
+    got = ops.hwr_stem_bwd_image(img.detach().float().cuda(), wc, bc, _nhwc(g))
+    assert got.shape == (N, 1, H, W)
+    assert _rel(got.cpu().double(), ref) <= 2e-3
