@@ -9,7 +9,7 @@ between them (log-softmax, BatchNorm+ReLU, ReLU+MaxPool, stem) emit the bias gra
 """
 import torch
 
-from . import conv, ops
+from . import conv, ops, weightmap
 from ._lib import ACT_LOGSOFTMAX, ACT_NONE, ACT_RELU
 
 _T3 = conv.conv_taps(3, 3, 1, 1)
@@ -19,29 +19,19 @@ _POOL22 = ((2, 2), (2, 2), (0, 0))
 _POOL21 = ((2, 2), (2, 1), (0, 1))
 
 
-def _taps_f32(weight4d):
-    """[Cout,Cin,kh,kw] -> fp32 tap matrices [kh*kw, Cout, Cin]."""
-    co, ci, kh, kw = weight4d.shape
-    return weight4d.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
-
-
 def _dgrad_packs(m):
-    """Transposed tap matrices for every tensor-core convolution (cached with the forward packs)."""
-    c = m._packed()
-    if "dgrad" not in c:
-        d = {}
-        for i in range(1, 7):
-            taps = _T3 if i <= 4 else _T3P0
-            d[f"w{i}"] = conv.dgrad_pack(_taps_f32(getattr(m.cnn, f"conv{i}").weight), taps)
-        for ci, _, pad, dil in _CNN1D + [(12, None, 0, 1)]:
-            taps = conv.conv_taps(1, 3, 0, pad, 1, dil)
-            d[f"v{ci}"] = conv.dgrad_pack(_taps_f32(m.cnn1d[ci].weight.unsqueeze(2)), taps)
-        # image gradient: conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] 9-tap dgrad convolution
+    """Transposed tap operands of every tensor-core convolution (filled by the module's hwg_linear_map table), plus
+    the 9-tap operand of the two-step image-gradient path (only built when that path is used)."""
+    return m._packed()["dgrad"]
+
+
+def _w0_dgrad(m, c):
+    if "w0" not in c["dgrad"]:
+        # conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] 9-tap dgrad convolution
         w0 = m.cnn.conv0.weight.detach().float()                       # [64,1,3,3]
         mats = [torch.nn.functional.pad(w0[:, 0, i, j].view(1, 64), (0, 0, 0, 15)) for i in range(3) for j in range(3)]
-        d["w0"] = (conv.pack_taps(mats), [(1 - i, 1 - j) for i in range(3) for j in range(3)])
-        c["dgrad"] = d
-    return c["dgrad"]
+        c["dgrad"]["w0"] = (conv.pack_taps(mats), [(1 - i, 1 - j) for i in range(3) for j in range(3)])
+    return c["dgrad"]["w0"]
 
 
 def _bn_train(m, y, stats, bn):
@@ -126,26 +116,98 @@ def _w4(dw, kh, kw):
     return dw.view(kh, kw, co, ci).permute(2, 3, 0, 1).contiguous()
 
 
-class _Needed(dict):
-    """grads[name] = lazily evaluated: the wgrad launch is skipped when the parameter's gradient is not needed
-    (frozen recognizer in the GAN lessons: the reference still computes those gradients and throws them away)."""
+class _Grads(dict):
+    """Collects the parameter gradients of one backward pass.
 
-    def __init__(self, needed):
+    Every accumulator (per-channel sums, tap-major wgrad outputs) is a slice of ONE zero-filled arena.  Small vectors
+    are stored as views; convolution weights are registered with their ConvMap and turned into the parameter layout
+    by one hwg_linear_map launch at the end (`finish`).  With a flat optimizer attached (module._grad_sink) every
+    gradient is ADDED straight into its flat buffer by that launch and nothing is returned to autograd.
+    wgrad launches of parameters whose gradient is not needed are skipped (frozen recognizer in the GAN lessons:
+    the reference computes those gradients and throws them away)."""
+
+    def __init__(self, m, needed, arena):
         super().__init__()
-        self.needed = needed
+        self.m, self.needed, self.arena = m, needed, arena
+        self.conv = []        # (name, ConvMap, dW view)
 
-    def put(self, name, fn):
-        self[name] = fn() if (self.needed is None or name in self.needed) else None
+    def want(self, name):
+        return self.needed is None or name in self.needed
+
+    def wgrad(self, name, key, x, gy, taps, cin, cout):
+        if not self.want(name):
+            self[name] = None
+            return
+        cm = self.m._packed()["maps"][key]
+        dw = self.arena.take(cm.Tf, cout, cm.Cip)
+        conv.conv_wgrad(x, gy, taps, cin, cout, out=dw)
+        self.conv.append((name, cm, dw, cout))
+        self[name] = None     # filled by finish()
+
+    def finish(self, params):
+        """params: {name: parameter}.  Returns {name: gradient or None}."""
+        m, base = self.m, self.arena.buf
+        sink = getattr(m, "_grad_sink", None)
+        if sink is not None and not all(sink.owns(p) for p in params.values()):
+            sink = None
+        vecs = [(n, v) for n, v in self.items() if v is not None and self.want(n)] if sink is not None else []
+        if not self.conv and not vecs:
+            return self
+        def off(t):
+            assert t.untyped_storage().data_ptr() == base.untyped_storage().data_ptr(), "accumulator outside the arena"
+            return 4 * (t.storage_offset() - base.storage_offset())
+
+        sig = (id(sink), tuple((n, off(dw), co) for n, _, dw, co in self.conv),
+               tuple((n, off(v), v.stride()) for n, v in vecs))
+        plan = m._bwd_plans.get("hwr_unpack")
+        if plan is None or plan["sig"] != sig:
+            t = weightmap.JobTable()
+            goff, n_el = {}, 0
+            for name, cm, dw, co_rows in self.conv:
+                if sink is not None:
+                    dst = sink.grad_view(params[name])
+                else:
+                    goff[name] = n_el
+                    dst = 4 * n_el
+                    n_el += -(-params[name].numel() // 4) * 4
+                cm.add_unpack_wgrad(t, off(dw), dst, accumulate=sink is not None, co_rows=co_rows)
+            for name, v in vecs:
+                assert v.dim() == 1
+                t.add(off(v), sink.grad_view(params[name]), R=1, C=v.numel(), s_r=0, s_c=v.stride(0), d_r=0, d_c=1,
+                      M=[[1.0]], accumulate=True)
+            t.finalize(base.device)
+            plan = m._bwd_plans["hwr_unpack"] = dict(sig=sig, table=t, goff=goff, numel=n_el)
+        gflat = None if sink is not None else torch.empty(max(plan["numel"], 4), device=base.device, dtype=torch.float32)
+        plan["table"].run(src_base=base, dst_base=gflat)
+        if sink is not None:
+            for n in list(self):
+                self[n] = None                         # already accumulated into the flat gradient buffer
+            ready = getattr(m, "_grad_ready_cb", None)
+            if ready is not None:
+                for p in params.values():
+                    ready(p)
+        else:
+            for name, _, _, _ in self.conv:
+                o = plan["goff"][name]
+                self[name] = gflat[o:o + params[name].numel()].view_as(params[name])
+        return self
 
 
 def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     """Returns ({parameter name: gradient or None} for every parameter of the module, image gradient or None)."""
-    dg = _dgrad_packs(m)
-    grads = _Needed(needed)
+    c = m._packed()
+    dg = c["dgrad"]
     lp = ctx["lp"]
     T, B, C = lp.shape
     Cp = ((C + 15) // 16) * 16
-    arena = ops.ZeroArena(16384, lp.device)      # every per-channel accumulator of this pass: one memset
+    params = dict(m.named_parameters())
+    # one zero-filled arena: every per-channel accumulator of this pass and the tap-major wgrad outputs
+    wnames = {"w%d" % i: "cnn.conv%d.weight" % i for i in range(1, 7)}
+    wnames.update({"v%d" % ci: "cnn1d.%d.weight" % ci for ci in (0, 3, 6, 9, 12)})
+    dw_floats = sum(cm.Tf * (-(-cm.Co // 16) * 16) * cm.Cip + 4 for key, cm in c["maps"].items()
+                    if needed is None or wnames[key] in needed)
+    arena = ops.ZeroArena(dw_floats + 32768, lp.device)
+    grads = _Grads(m, needed, arena)
 
     def dgrad(gz, key, H, W):
         wd, tapsd = dg[key]
@@ -154,8 +216,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- head: log-softmax + Conv1d(512, C, 3)
     gz, db = ops.logsoftmax_bwd(g_lp.contiguous().float(), lp, Cp, arena=arena)
     a10 = ctx["a10"]
-    grads.put("cnn1d.12.weight", lambda: conv.conv_wgrad(a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)[:, :C, :]
-              .permute(1, 2, 0).contiguous())
+    grads.wgrad("cnn1d.12.weight", "v12", a10, gz, conv.conv_taps(1, 3, 0, 0), 512, Cp)
     grads["cnn1d.12.bias"] = db
     g = dgrad(gz, "v12", 1, a10.size(2))
     # ---- dilated 1-D blocks, last to first
@@ -163,8 +224,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
         bn = m.cnn1d[bi]
         gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena)
         grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
-        grads.put(f"cnn1d.{ci}.weight", lambda: conv.conv_wgrad(a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
-                  .permute(1, 2, 0).contiguous())
+        grads.wgrad(f"cnn1d.{ci}.weight", f"v{ci}", a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
         grads[f"cnn1d.{ci}.bias"] = dcb
         g = dgrad(gz, f"v{ci}", 1, a_in.size(2))
     # ---- conv6 + BN + ReLU
@@ -172,13 +232,13 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach(), arena=arena)
     grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
     a5 = ctx["a5"]
-    grads.put("cnn.conv6.weight", lambda: _w4(conv.conv_wgrad(a5, gz, _T3P0, 512, 512), 3, 3))
+    grads.wgrad("cnn.conv6.weight", "w6", a5, gz, _T3P0, 512, 512)
     grads["cnn.conv6.bias"] = dcb
     g = dgrad(gz, "w6", a5.size(1), a5.size(2))
     # ---- pool + ReLU + conv5
     gc, db = ops.relu_maxpool_bwd(g, ctx["c5"], *_POOL21, arena=arena)
     a4 = ctx["a4"]
-    grads.put("cnn.conv5.weight", lambda: _w4(conv.conv_wgrad(a4, gc, _T3P0, 512, 512), 3, 3))
+    grads.wgrad("cnn.conv5.weight", "w5", a4, gc, _T3P0, 512, 512)
     grads["cnn.conv5.bias"] = db
     g = dgrad(gc, "w5", a4.size(1), a4.size(2))
     # ---- conv4 + BN + ReLU
@@ -186,13 +246,13 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach(), arena=arena)
     grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
     a3 = ctx["a3"]
-    grads.put("cnn.conv4.weight", lambda: _w4(conv.conv_wgrad(a3, gz, _T3, 256, 512), 3, 3))
+    grads.wgrad("cnn.conv4.weight", "w4", a3, gz, _T3, 256, 512)
     grads["cnn.conv4.bias"] = dcb
     g = dgrad(gz, "w4", a3.size(1), a3.size(2))
     # ---- pool + ReLU + conv3
     gc, db = ops.relu_maxpool_bwd(g, ctx["c3"], *_POOL21, arena=arena)
     a2 = ctx["a2"]
-    grads.put("cnn.conv3.weight", lambda: _w4(conv.conv_wgrad(a2, gc, _T3, 256, 256), 3, 3))
+    grads.wgrad("cnn.conv3.weight", "w3", a2, gc, _T3, 256, 256)
     grads["cnn.conv3.bias"] = db
     g = dgrad(gc, "w3", a2.size(1), a2.size(2))
     # ---- conv2 + BN + ReLU
@@ -200,32 +260,33 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach(), arena=arena)
     grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
     a1 = ctx["a1"]
-    grads.put("cnn.conv2.weight", lambda: _w4(conv.conv_wgrad(a1, gz, _T3, 128, 256), 3, 3))
+    grads.wgrad("cnn.conv2.weight", "w2", a1, gz, _T3, 128, 256)
     grads["cnn.conv2.bias"] = dcb
     g = dgrad(gz, "w2", a1.size(1), a1.size(2))
     # ---- pool + ReLU + conv1
     gc, db = ops.relu_maxpool_bwd(g, ctx["c1"], *_POOL22, arena=arena)
     a0 = ctx["a0"]
-    grads.put("cnn.conv1.weight", lambda: _w4(conv.conv_wgrad(a0, gc, _T3, 64, 128), 3, 3))
+    grads.wgrad("cnn.conv1.weight", "w1", a0, gc, _T3, 64, 128)
     grads["cnn.conv1.bias"] = db
     g = dgrad(gc, "w1", a0.size(1), a0.size(2))
     # ---- stem
-    c = m._packed()
     if needed is None or "cnn.conv0.weight" in needed or "cnn.conv0.bias" in needed:
-        dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g)
-        grads["cnn.conv0.weight"] = dw0.view(64, 1, 3, 3)
+        dw0, db0 = ops.hwr_stem_bwd(ctx["x"], c["w0"], c["b0"], g, arena=arena)
+        grads["cnn.conv0.weight"] = dw0.view(-1)
         grads["cnn.conv0.bias"] = db0
     else:
         grads["cnn.conv0.weight"] = grads["cnn.conv0.bias"] = None
+    grads.finish(params)
+    if grads.get("cnn.conv0.weight") is not None:
+        grads["cnn.conv0.weight"] = grads["cnn.conv0.weight"].view(64, 1, 3, 3)
     g_img = None
     if want_input_grad:
-        # image gradient (GAN lessons): route g through pool/ReLU to conv0's output, then the 9-tap dgrad with
-        # conv0's weights as a [Cout=1 (padded to 16)] x [Cin=64] tensor-core convolution
+        # image gradient (GAN lessons): conv0 + ReLU + MaxPool backward to the image
         if c["w0"].size(0) == 64 and ctx["x"].size(2) % 2 == 0 and ctx["x"].size(3) % 2 == 0:
             g_img = ops.hwr_stem_bwd_image(ctx["x"], c["w0"], c["b0"], g)       # one fused pass
         else:
             gc0 = ops.hwr_stem_bwd_expand(ctx["x"], c["w0"], c["b0"], g)
-            w0d, taps = dg["w0"]
+            w0d, taps = _w0_dgrad(m, c)
             gi = conv.conv_fprop(gc0, w0d, taps, gc0.size(1), gc0.size(2), out_dtype=torch.float32)
             g_img = gi[..., 0].unsqueeze(1).contiguous()
         if m.pad is not None:

@@ -10,7 +10,7 @@ containers; their forward is never called.
 import torch
 import torch.nn as nn
 
-from . import _lib, conv, ops
+from . import _lib, conv, ops, weightmap
 from ._lib import ACT_LOGSOFTMAX, ACT_NONE, ACT_RELU
 
 _PADS = [1, 1, 1, 1, 1, 0, 0]
@@ -68,6 +68,7 @@ class CNNOnlyHWR(nn.Module):
         self.saved_features = None
         self._save = False
         self._cache_key, self._cache = None, None
+        self._plan, self._plan_ptrs, self._bwd_plans = None, None, {}
 
     def setup_save_features(self):
         """cnn_only_hwr.py:109-117 hooks cnn[15] (conv5, whose in-place ReLU has run by the time anyone
@@ -76,24 +77,47 @@ class CNNOnlyHWR(nn.Module):
         self.saved_features = [None]
 
     # -- derived weights --------------------------------------------------------------------------
+    def conv_layers(self):
+        """(key, parameter module, tap list) of every tensor-core convolution, in forward order."""
+        t3, t3p0 = conv.conv_taps(3, 3, 1, 1), conv.conv_taps(3, 3, 0, 0)
+        out = [(f"w{i}", getattr(self.cnn, f"conv{i}"), t3 if i <= 4 else t3p0) for i in range(1, 7)]
+        for ci, _, pad, dil in _CNN1D + [(12, None, 0, 1)]:
+            out.append((f"v{ci}", self.cnn1d[ci], conv.conv_taps(1, 3, 0, pad, 1, dil)))
+        return out
+
+    def _build_plan(self):
+        """Persistent kernel-side operand buffers + ONE hwg_linear_map job table that (re)fills them from the fp32
+        parameters (weightmap.py): tap-major bf16 forward and dgrad operands of the eleven tensor-core convolutions."""
+        dev = self.cnn.conv0.weight.device
+        t = weightmap.JobTable()
+        c = {"maps": {}, "dgrad": {}}
+        for key, mod, taps in self.conv_layers():
+            w = mod.weight
+            assert w.is_contiguous() and w.dtype == torch.float32
+            m = weightmap.map_conv_taps(w.size(0), w.size(1), taps)
+            c[key] = torch.empty((m.Tf, m.Co, m.Cip), device=dev, dtype=torch.bfloat16)
+            d = torch.empty(m.dgrad_shape(), device=dev, dtype=torch.bfloat16)
+            m.add_pack_fwd(t, w, c[key])
+            m.add_pack_dgrad(t, w, d)
+            c["maps"][key] = m
+            c["dgrad"][key] = (d, m.taps_d)
+            c[("b" if key[0] == "w" else "c") + key[1:]] = mod.bias.detach()
+        c["w0"] = self.cnn.conv0.weight.detach().reshape(64, 9)        # stem: fp32, read directly (a view)
+        c["b0"] = self.cnn.conv0.bias.detach()
+        t.finalize(dev)
+        return {"table": t, "c": c}
+
     def _packed(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._cache_key == key:
             return self._cache
-        with torch.no_grad():
-            c = {}
-            c["w0"] = self.cnn.conv0.weight.detach().float().reshape(64, 9).contiguous()
-            c["b0"] = self.cnn.conv0.bias.detach().float().contiguous()
-            for i in range(1, 7):
-                m = getattr(self.cnn, f"conv{i}")
-                c[f"w{i}"] = conv.pack_conv2d_weight(m.weight)
-                c[f"b{i}"] = m.bias.detach().float().contiguous()
-            for ci, _, _, _ in _CNN1D + [(12, None, 0, 1)]:
-                m = self.cnn1d[ci]
-                c[f"v{ci}"] = conv.pack_conv2d_weight(m.weight.unsqueeze(2))  # [Cout,Cin,1,3]
-                c[f"c{ci}"] = m.bias.detach().float().contiguous()
-        self._cache_key, self._cache = key, c
-        return c
+        ptrs = tuple(k[0] for k in key)
+        if self._plan is None or self._plan_ptrs != ptrs:
+            self._plan, self._plan_ptrs = self._build_plan(), ptrs
+            self._bwd_plans = {}
+        self._plan["table"].run()
+        self._cache_key, self._cache = key, self._plan["c"]
+        return self._cache
 
     def _bn(self, y, stats, bn):
         """BatchNorm (+ReLU) on an NHWC bf16 activation whose per-(n,c) sums came from the conv epilogue."""

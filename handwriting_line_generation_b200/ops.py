@@ -166,11 +166,11 @@ def relu_maxpool_bwd(ga, c, k, s, p, arena=None):
     return gc, db
 
 
-def hwr_stem_bwd(img, w, b, ga):
+def hwr_stem_bwd(img, w, b, ga, arena=None):
     N, _, H, W = img.shape
     Cout = w.size(0)
-    dw = torch.zeros((Cout, 9), device=img.device, dtype=torch.float32)
-    db = torch.zeros(Cout, device=img.device, dtype=torch.float32)
+    dw = _zeros(arena, (Cout, 9), img.device)
+    db = _zeros(arena, (Cout,), img.device)
     _lib.call("hwg_hwr_stem_bwd", img.data_ptr(), w.data_ptr(), b.data_ptr(), ga.data_ptr(), N, H, W, Cout, dw.data_ptr(),
               db.data_ptr(), _lib.stream())
     return dw, db

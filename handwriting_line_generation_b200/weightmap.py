@@ -132,11 +132,13 @@ class ConvMap:
     def dgrad_shape(self):
         return (self.Td, -(-self.Ci // 16) * 16, self.Cop)
 
-    def add_unpack_wgrad(self, table, dw_src, g_dst, Cip=None, accumulate=False):
-        """dw_src fp32 [Tf][Co][Cip] (hwg_conv_wgrad layout) -> g_dst in the parameter's layout."""
+    def add_unpack_wgrad(self, table, dw_src, g_dst, Cip=None, accumulate=False, co_rows=None):
+        """dw_src fp32 [Tf][co_rows][Cip] (hwg_conv_wgrad layout; co_rows >= Co when the launch padded the output
+        channels) -> g_dst in the parameter's layout."""
         Cip = Cip or self.Cip
+        co_rows = co_rows or self.Co
         table.add(dw_src, g_dst, R=self.Co, C=self.Ci, s_r=Cip, s_c=1, d_r=self.s_co, d_c=self.s_ci,
-                  M=self.Af.T.copy(), in_off=[t * self.Co * Cip for t in range(self.Tf)],
+                  M=self.Af.T.copy(), in_off=[t * co_rows * Cip for t in range(self.Tf)],
                   out_off=list(range(self.K)), accumulate=accumulate)
 
 
@@ -147,6 +149,13 @@ TAPS3x3 = [(i - 1, j - 1) for i in range(3) for j in range(3)]
 def map_conv3x3(Co, Ci):
     """nn.Conv2d 3x3 pad 1 (pure_gen.py:197): taps in row-major kernel order; dgrad = transposed matrices, negated taps."""
     return ConvMap(Co, Ci, 9, False, np.eye(9), np.eye(9), [(-dh, -dw) for dh, dw in TAPS3x3])
+
+
+def map_conv_taps(Co, Ci, taps):
+    """Stride-1 nn.Conv2d / nn.Conv1d with K = len(taps) kernel positions (cnn_only_hwr.py:31,78-90): identity maps;
+    dgrad = transposed matrices with negated taps."""
+    K = len(taps)
+    return ConvMap(Co, Ci, K, False, np.eye(K), np.eye(K), [(-dh, -dw) for dh, dw in taps])
 
 
 def map_initial(Ci, Co):

@@ -116,3 +116,40 @@ def test_generator_gradients_direct_to_flat_buffer_equal_autograd_path():
     assert all(p.grad.data_ptr() == opt.grad_view(p).data_ptr() for p in gen.parameters())
     opt.step()
     assert float(opt.flat_g.abs().max()) == 0.0 and float((plist[0] - w0).abs().max()) > 0
+
+
+def test_recognizer_gradients_direct_to_flat_buffer_equal_autograd_path():
+    """CNNOnlyHWR backward on ONE saved forward state: gradients returned to autograd (job table -> fresh flat tensor)
+    vs added straight into FlatAdam's buffer (module._grad_sink)."""
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import autograd_hwr as ah
+    from oracle import synth
+    from tests.test_modules_gpu import rel_l2
+    torch.manual_seed(4)
+    B, W, C = 2, 256, 78                               # 78 classes: the head's wgrad runs on 80 padded channels
+    hwr = pkg.CNNOnlyHWR(C, norm='batch').cuda().train()
+    x = torch.from_numpy(synth.hwr_case(B, W, 5)).cuda()
+    with torch.no_grad():
+        lp, ctx = ah.forward_train(hwr, x)
+        g_lp = torch.randn_like(lp)
+        ref, g_img = ah.backward_train(hwr, ctx, g_lp, want_input_grad=True)
+        ref = {n: v.clone() for n, v in ref.items()}
+    assert set(ref) == {n for n, _ in hwr.named_parameters()} and all(v is not None for v in ref.values())
+    for n, p in hwr.named_parameters():
+        assert ref[n].shape == p.shape, n
+    opt = pkg.FlatAdam(hwr.parameters(), lr=1e-4)
+    hwr._grad_sink = opt
+    with torch.no_grad():
+        got, g_img2 = ah.backward_train(hwr, ctx, g_lp, want_input_grad=True)
+    assert all(v is None for v in got.values())
+    torch.cuda.synchronize()
+    for n, p in hwr.named_parameters():
+        assert rel_l2(opt.grad_view(p).cpu().numpy(), ref[n].cpu().numpy()) <= 2e-2, n
+    assert rel_l2(g_img2.cpu().numpy(), g_img.cpu().numpy()) <= 2e-2
+    # frozen recognizer: no wgrad launches, no gradients, image gradient only
+    for p in hwr.parameters():
+        p.requires_grad_(False)
+    hwr._grad_sink = None
+    xg = x.clone().requires_grad_()
+    hwr(xg).backward(g_lp)
+    assert xg.grad is not None and all(p.grad is None or p.grad.data_ptr() == opt.grad_view(p).data_ptr() for p in hwr.parameters())

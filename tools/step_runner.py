@@ -37,7 +37,8 @@ if a.workload == "gen_infer":
             return gen(c, s)
 elif a.workload == "hwr_train":
     hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
-    opt = torch.optim.Adam(hwr.parameters(), lr=1e-4, capturable=a.graph)
+    opt = pkg.FlatAdam(hwr.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    hwr._grad_sink = opt
     T, S = W // 4 - 6, 60
     ins = [torch.from_numpy(synth.hwr_case(B, W, 1)).to(dev),
            torch.randint(1, 80, (B, S), dtype=torch.int32, device=dev)]
@@ -49,7 +50,6 @@ elif a.workload == "hwr_train":
         loss = pkg.CTCLoss(hwr(img), tg, il, tl)
         loss.backward()
         opt.step()
-        opt.zero_grad(set_to_none=not a.graph)
         return loss
 elif a.workload == "gen_train":
     gen = pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True).to(dev).train()
