@@ -77,8 +77,12 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = pkg.CNNOnlyHWR(HWR["C"], norm='batch').to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    buckets = dp.GradBuckets(model.parameters()) if world > 1 else None
+    # flat fused optimizer; the backward adds gradients straight into its buffer, the all-reduce buckets are slices of it
+    opt = pkg.FlatAdam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    model._grad_sink = opt
+    reducer = dp.GradReducer(model.parameters(), bucket_bytes=16 << 20, flat=opt) if world > 1 else None
+    if reducer is not None:
+        model._grad_ready_cb = reducer.mark_ready
     T = HWR["W"] // 4 - 6
     n_sets = 4
     host = []
@@ -92,32 +96,26 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def train(img, tg):
-        opt.zero_grad(set_to_none=True)
         loss = pkg.CTCLoss(model(img), tg, il, tl)
         loss.backward()
-        if buckets is not None:
-            buckets.reduce()
+        if reducer is not None:
+            reducer.finish()
         opt.step()
         return loss
 
+    from handwriting_line_generation_b200 import graphs
+    for i in range(2):
+        train(*devsets[i])
+    torch.cuda.synchronize()
+    n0 = pkg._lib.launch_count()
+    train(*devsets[0])
+    launches_per_step = pkg._lib.launch_count() - n0
     graphed = None
-    if world == 1:
-        # single GPU: the whole step (forward, CTC, backward, Adam) is one CUDA graph, replayed
-        from handwriting_line_generation_b200 import graphs
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
-
-        def train_static(img, tg):
-            loss = pkg.CTCLoss(model(img), tg, il, tl)
-            loss.backward()
-            opt.step()
-            opt.zero_grad(set_to_none=False)
-            return loss
-
-        n0 = pkg._lib.launch_count()
-        train(*devsets[0])
-        launches_per_step = pkg._lib.launch_count() - n0
-        opt.zero_grad(set_to_none=True)
-        graphed = graphs.GraphedStep(train_static, list(devsets[0]), modules=[model], warmup=3)
+    try:   # the whole step (forward, CTC, backward, all-reduce, optimizer) as one CUDA graph, replayed
+        graphed = graphs.GraphedStep(train, list(devsets[0]), modules=[model], warmup=3)
+    except Exception:
+        graphed = None
+        torch.cuda.synchronize()
 
     def step_device(i):
         if graphed is not None:
@@ -133,7 +131,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             loss = graphed.static_out
         else:
             loss = train(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
-        loss_host.copy_(loss, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -172,16 +170,20 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     barrier()
     for i in range(psteps):
         train(*devsets[i % n_sets])      # eager: per-launch events need host-side launches
-        if graphed is not None:
-            opt.zero_grad(set_to_none=False)
     barrier()
     hconv.PROFILE = None
     conv_ms = sum(r[0].elapsed_time(r[1]) for r in prof) / psteps
     peaks = load_peaks()
+    def leave():
+        if world > 1:      # see bench_gan_train.leave(): collectives captured in a live graph block the teardown
+            torch.cuda.synchronize()
+            dist.barrier()
+            import sys
+            sys.stdout.flush()
+            os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return leave()
     lines = B * world
     ms_step = ms / args.steps
     conv_flops = 3 * GF_FWD_PER_LINE * 1e9 * B
@@ -207,8 +209,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
                      "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
                      "algorithmic_gflop_per_step": conv_flops / 1e9},
         "cpu_baseline": cpu}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -243,7 +244,8 @@ def quick_train_numbers(dev, steps=10, gen_lesson=True):
     for B in (8, 32):
         torch.manual_seed(0)
         model = pkg.CNNOnlyHWR(HWR["C"], norm='batch').to(dev).train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+        opt = pkg.FlatAdam(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+        model._grad_sink = opt
         T = HWR["W"] // 4 - 6
         img = torch.from_numpy(synth.hwr_case(B, HWR["W"], 1)).to(dev)
         tg = torch.randint(1, HWR["C"], (B, HWR["S"]), dtype=torch.int32, device=dev)
@@ -253,11 +255,10 @@ def quick_train_numbers(dev, steps=10, gen_lesson=True):
         def step():
             pkg.CTCLoss(model(img), tg, il, tl).backward()
             opt.step()
-            opt.zero_grad(set_to_none=False)
 
         ms, launches = time_steps(step, [model])
         out[f"hwr_ctc_train_step_B{B}"] = {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "hwg_launches_per_step": launches,
-                                          "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + Adam, 64x1024 lines; one replayed CUDA graph per step"}
+                                          "what": "CNNOnlyHWR fwd + CTC + bwd (dgrad+wgrad) + flat fused Adam, 64x1024 lines; one replayed CUDA graph per step"}
         del model, opt
     if not gen_lesson:
         return out
