@@ -27,7 +27,7 @@ HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per
 HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
 
 
-def config(B, world, executed):
+def config(B, world, executed, sync_bn=False):
     return {"workload": "HWWithStyle GAN 'gen' lesson train step on the SURVEY 8(a) rows (BASELINE configs[2]/[3] shapes): "
                         "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
                         "CTC loss fwd+bwd, gradient all-reduce (N>1), Adam on the generator; discriminator/perceptual "
@@ -37,6 +37,8 @@ def config(B, world, executed):
             "l2": "no explicit flush: the bf16 activations + gradients one step streams (~1.5 GB at B=16) exceed the "
                   "126 MB L2; weights stay cached, as in production",
             "noise": "NoiseInjection N(0,1) drawn in-kernel, re-seeded every step by a device-side counter",
+            "batchnorm": ("recognizer BatchNorm statistics all-reduced over the ranks (global batch, 14 small NCCL "
+                          "all-reduces per step)" if sync_bn else "recognizer BatchNorm statistics per rank"),
             "execution": executed}
 
 
@@ -121,6 +123,9 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     hwr = pkg.CNNOnlyHWR(C, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)            # hwr_frozen: no optimizer touches it; its wgrad is skipped
+    sync_bn = world > 1 and bool(os.environ.get("HWG_BENCH_SYNC_BN"))   # opt-in (SyncBN over the ranks)
+    if sync_bn:
+        hwr.sync_bn_group = dist.group.WORLD   # train-mode BatchNorm over the global batch, as in the single-process reference
     # flat fused optimizer: parameters / gradients / moments of the generator as slices of flat buffers; the
     # backward kernels add their gradients straight into the gradient buffer (gen._grad_sink), the all-reduce
     # buckets are slices of it, clip_grad_value_(2) + Adam + zero_grad is one launch
@@ -306,7 +311,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     line = {
         "metric": "GAN train-step lines/sec", "value": lines / (ms_step * 1e-3), "unit": "lines/s", "n_gpus": world,
         "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(B, world, executed),
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(B, world, executed, sync_bn),
         "e2e": {"value": lines / (ms_e2e / args.steps * 1e-3), "unit": "lines/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,

@@ -31,7 +31,7 @@ _SIGNATURES = {
     "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_logsoftmax_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_bn_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
-    "hwg_bn_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_bn_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_relu_maxpool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_hwr_stem_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
@@ -117,11 +117,19 @@ def load():
     return _lib
 
 
+_DEBUG_SYNC = bool(os.environ.get("HWG_DEBUG_SYNC"))   # development aid: synchronise after every launch, name the faulting one
+
+
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.hwg_last_error().decode()}")
+    if _DEBUG_SYNC:
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError as e:
+            raise RuntimeError(f"{name}: device fault after this launch: {e}") from None
 
 
 def launch_count():

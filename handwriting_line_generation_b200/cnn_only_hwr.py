@@ -69,6 +69,10 @@ class CNNOnlyHWR(nn.Module):
         self._save = False
         self._cache_key, self._cache = None, None
         self._plan, self._plan_ptrs, self._bwd_plans = None, None, {}
+        # data parallelism: set to a torch.distributed group to normalise train-mode BatchNorm with the statistics of
+        # the JOINT batch of its ranks (the reference is single-process, so its batch statistics span the whole
+        # batch); None = per-rank statistics (what DistributedDataParallel does by default)
+        self.sync_bn_group = None
 
     def setup_save_features(self):
         """cnn_only_hwr.py:109-117 hooks cnn[15] (conv5, whose in-place ReLU has run by the time anyone
@@ -124,10 +128,14 @@ class CNNOnlyHWR(nn.Module):
         N, H, W, C = y.shape
         use_batch = self.training or not bn.track_running_stats
         momentum = 0.1 if bn.momentum is None else bn.momentum
-        coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(),
-                                   bn.running_mean if (self.training or not use_batch) else None,
-                                   bn.running_var if (self.training or not use_batch) else None,
-                                   momentum, bn.eps, use_batch)
+        if use_batch and self.training and self.sync_bn_group is not None:
+            coef, save = ops.bn_coeffs_synced(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                                              bn.running_var, momentum, bn.eps, self.sync_bn_group)
+        else:
+            coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(),
+                                       bn.running_mean if (self.training or not use_batch) else None,
+                                       bn.running_var if (self.training or not use_batch) else None,
+                                       momentum, bn.eps, use_batch)
         if self.training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         return ops.scale_shift_act(y, coef, False, ACT_RELU), save

@@ -183,12 +183,12 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, c
 __global__ void __launch_bounds__(ST_THREADS)
 bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
                     const float* __restrict__ save, const float* __restrict__ weight,
-                    const float* __restrict__ sums, long long rows, int C, int relu, uint4* __restrict__ gz,
-                    float* __restrict__ dconv_bias) {
+                    const float* __restrict__ sums, long long rows, long long norm_rows, int C, int relu,
+                    uint4* __restrict__ gz, float* __restrict__ dconv_bias) {
   extern __shared__ unsigned char smraw[];
   const StreamSmem sm = stream_smem<2>(smraw);      // constants a, b, sc, P, Q [5][C]
   const int CV = C / 8;
-  const float invM = 1.f / (float)rows;
+  const float invM = 1.f / (float)norm_rows;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     // gz = sc*(gy - k0 - xhat*k1), xhat = (z - mean)*rstd   ==   sc*gy + P*z + Q
     const float mean = save[2 * c], rstd = save[2 * c + 1];
@@ -850,16 +850,16 @@ extern "C" int hwg_bn_bwd_reduce(const void* g, const void* z, const float* coef
 }
 
 extern "C" int hwg_bn_bwd_apply(const void* g, const void* z, const float* coef, const float* save,
-                                const float* weight, const float* sums, int64_t rows, int C, int relu, void* gz,
-                                float* dconv_bias, void* stream) {
+                                const float* weight, const float* sums, int64_t rows, int64_t norm_rows, int C,
+                                int relu, void* gz, float* dconv_bias, void* stream) {
   HWG_REQUIRE(g && z && coef && save && sums && gz && rows > 0, "hwg_bn_bwd_apply: bad argument");
   HWG_REQUIRE(cv_ok(C), "hwg_bn_bwd_apply: C=%d must be 8 x a power of two", C);
   const long long total = rows * (C / 8);
   HWG_SMEM_OPTIN(bn_bwd_apply_kernel);
   bn_bwd_apply_kernel<<<bw_blocks_persistent(total, ST_CHUNK, 1, 3), ST_THREADS, stream_kernel_smem(2, 5 * C),
                         (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z),
-                                                coef, save, weight, sums, rows, C, relu,
-                                                reinterpret_cast<uint4*>(gz), dconv_bias);
+                                                coef, save, weight, sums, rows, norm_rows > 0 ? norm_rows : rows, C,
+                                                relu, reinterpret_cast<uint4*>(gz), dconv_bias);
   return check_launch("bn_bwd_apply_kernel");
 }
 

@@ -140,19 +140,38 @@ def logsoftmax_bwd(g, lp, Cp, arena=None):
     return gz, db
 
 
-def bn_bwd(g, z, coef, save, weight, relu=True, arena=None):
+def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None):
     """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C]);
-    dweight/dbias are strided views of the [C,2] sums."""
+    dweight/dbias are strided views of the [C,2] sums.
+    sync_group: a torch.distributed group whose ranks normalised with JOINT batch statistics in the forward (SyncBN):
+    the (sum gy, sum gy*xhat) pair that enters the input gradient is then all-reduced and divided by the global row
+    count; the parameter gradients stay the local sums (the gradient all-reduce averages those)."""
     C = z.size(-1)
     rows = z.numel() // C
     sums = _zeros(arena, (C, 2), z.device)
     _lib.call("hwg_bn_bwd_reduce", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), rows, C, int(relu),
               sums.data_ptr(), _lib.stream())
+    gsums, grows = sums, rows
+    if sync_group is not None:
+        import torch.distributed as dist
+        gsums = sums.clone()
+        dist.all_reduce(gsums, group=sync_group)
+        grows = rows * dist.get_world_size(sync_group)
     gz = torch.empty_like(z)
     dcb = _zeros(arena, (C,), z.device)
     _lib.call("hwg_bn_bwd_apply", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), weight.data_ptr(),
-              sums.data_ptr(), rows, C, int(relu), gz.data_ptr(), dcb.data_ptr(), _lib.stream())
+              gsums.data_ptr(), rows, grows, C, int(relu), gz.data_ptr(), dcb.data_ptr(), _lib.stream())
     return gz, sums[:, 1], sums[:, 0], dcb
+
+
+def bn_coeffs_synced(stats, N, C, count_per_n, weight, bias, running_mean, running_var, momentum, eps, group):
+    """bn_coeffs over the JOINT batch of a process group (SyncBN; SURVEY 8e coupling 1): the per-(n,c) sums are folded
+    over the local lines, all-reduced ([C,2] floats), and normalised by the global element count."""
+    import torch.distributed as dist
+    tot = stats.view(N, C, 2).sum(0, keepdim=True).contiguous()
+    dist.all_reduce(tot, group=group)
+    return bn_coeffs(tot, 1, C, count_per_n * N * dist.get_world_size(group), weight, bias, running_mean, running_var,
+                     momentum, eps, True)
 
 
 def relu_maxpool_bwd(ga, c, k, s, p, arena=None):

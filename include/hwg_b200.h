@@ -296,10 +296,12 @@ int hwg_logsoftmax_bwd(const float* g, const float* lp, int T, int B, int C, int
 int hwg_bn_bwd_reduce(const void* g, const void* z, const float* coef, const float* save, int64_t rows,
                       int C, int relu, float* sums, void* stream);
 /* pass 2: gz = weight*rstd*(gy - sums0/M - xhat*sums1/M) -> bf16 [rows,C]; dweight = sums1, dbias = sums0
- * are read by the host from `sums`; dconv_bias [C] fp32 accumulates sum gz (caller zeroes). */
+ * are read by the host from `sums`; dconv_bias [C] fp32 accumulates sum gz (caller zeroes).
+ * M = norm_rows if > 0, else rows: with statistics synchronised over a process group (SyncBN) `sums` holds the
+ * all-reduced pair and norm_rows the global row count, while `rows` stays the local extent of g / z / gz. */
 int hwg_bn_bwd_apply(const void* g, const void* z, const float* coef, const float* save, const float* weight,
-                     const float* sums, int64_t rows, int C, int relu, void* gz, float* dconv_bias,
-                     void* stream);
+                     const float* sums, int64_t rows, int64_t norm_rows, int C, int relu, void* gz,
+                     float* dconv_bias, void* stream);
 
 /* ReLU + MaxPool2d backward in gather form (no atomics): gc[n,h,w,:] = (c>0) * sum over the pooling
  * windows that contain (h,w) and whose first maximum is (h,w) of ga[window].  c [N,H,W,C] is the

@@ -50,7 +50,7 @@ if want("bn_bwd"):
     timed("bn_bwd_reduce 512ch", lambda i: _lib.call("hwg_bn_bwd_reduce", g[i].data_ptr(), z[i].data_ptr(), coef.data_ptr(),
           save.data_ptr(), N * H * W, C, 1, sums.data_ptr(), _lib.stream()), NS, 2 * nb)
     timed("bn_bwd_apply 512ch", lambda i: _lib.call("hwg_bn_bwd_apply", g[i].data_ptr(), z[i].data_ptr(), coef.data_ptr(),
-          save.data_ptr(), wgt.data_ptr(), sums.data_ptr(), N * H * W, C, 1, gz.data_ptr(), dcb.data_ptr(), _lib.stream()), NS, 3 * nb)
+          save.data_ptr(), wgt.data_ptr(), sums.data_ptr(), N * H * W, 0, C, 1, gz.data_ptr(), dcb.data_ptr(), _lib.stream()), NS, 3 * nb)
 if want("adain_bwd"):
     for (N, H, W, C) in ((16, 64, 1024, 16), (16, 8, 256, 128)):
         a = [bf(N, H, W, C) for _ in range(NS)]
