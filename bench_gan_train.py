@@ -17,6 +17,7 @@ IAM charset (80 classes), 40-character targets.
 import json
 import os
 import statistics
+import sys
 import time
 
 import numpy as np
@@ -27,7 +28,10 @@ HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per
 HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
 
 
-def config(B, world, executed, sync_bn=False):
+DEFAULT_SYNC_BN = "peer"
+
+
+def config(B, world, executed, sync_bn="off"):
     return {"workload": "HWWithStyle GAN 'gen' lesson train step on the SURVEY 8(a) rows (BASELINE configs[2]/[3] shapes): "
                         "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
                         "CTC loss fwd+bwd, gradient all-reduce (N>1), Adam on the generator; discriminator/perceptual "
@@ -37,8 +41,10 @@ def config(B, world, executed, sync_bn=False):
             "l2": "no explicit flush: the bf16 activations + gradients one step streams (~1.5 GB at B=16) exceed the "
                   "126 MB L2; weights stay cached, as in production",
             "noise": "NoiseInjection N(0,1) drawn in-kernel, re-seeded every step by a device-side counter",
-            "batchnorm": ("recognizer BatchNorm statistics all-reduced over the ranks (global batch, 14 small NCCL "
-                          "all-reduces per step)" if sync_bn else "recognizer BatchNorm statistics per rank"),
+            "batchnorm": {"peer": "recognizer BatchNorm statistics over the global batch: summed over the ranks inside "
+                                  "the coefficient kernels through NVLink peer memory (14 in-kernel exchanges per step)",
+                          "nccl": "recognizer BatchNorm statistics over the global batch: 14 small NCCL all-reduces per step",
+                          "off": "recognizer BatchNorm statistics per rank"}[sync_bn],
             "execution": executed}
 
 
@@ -123,9 +129,24 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     hwr = pkg.CNNOnlyHWR(C, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)            # hwr_frozen: no optimizer touches it; its wgrad is skipped
-    sync_bn = world > 1 and bool(os.environ.get("HWG_BENCH_SYNC_BN"))   # opt-in (SyncBN over the ranks)
-    if sync_bn:
-        hwr.sync_bn_group = dist.group.WORLD   # train-mode BatchNorm over the global batch, as in the single-process reference
+    # train-mode BatchNorm over the GLOBAL batch, as in the single-process reference: "peer" = in-kernel exchange over
+    # NVLink peer memory (dp.PeerExchange), "nccl" = one NCCL all-reduce per layer and direction, "off" = per-rank
+    sync_bn = os.environ.get("HWG_BENCH_SYNC_BN", DEFAULT_SYNC_BN) if world > 1 else "off"
+    if sync_bn == "peer":
+        try:
+            hwr.sync_bn_group = dp.PeerExchange(dist.group.WORLD)
+        except Exception as e:   # noqa: BLE001 - peer mapping refused on this box: same semantics through NCCL
+            sys.stderr.write(f"[bench] PeerExchange unavailable ({e!r}); SyncBN through NCCL\n")
+            sync_bn = "nccl"
+        # every rank must take the same route
+        route = torch.tensor([1.0 if sync_bn == "peer" else 0.0], device=dev)
+        dist.all_reduce(route, op=dist.ReduceOp.MIN)
+        if route.item() == 0:
+            sync_bn = "nccl"
+    if sync_bn == "nccl":
+        hwr.sync_bn_group = dist.group.WORLD
+    elif sync_bn not in ("off", "peer"):
+        raise ValueError(f"HWG_BENCH_SYNC_BN={sync_bn!r}: expected peer, nccl or off")
     # flat fused optimizer: parameters / gradients / moments of the generator as slices of flat buffers; the
     # backward kernels add their gradients straight into the gradient buffer (gen._grad_sink), the all-reduce
     # buckets are slices of it, clip_grad_value_(2) + Adam + zero_grad is one launch

@@ -30,6 +30,11 @@ _SIGNATURES = {
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_logsoftmax_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_peer_mailbox_bytes": (c_i64, [c_int, c_int]),
+    "hwg_peer_enable_access": (c_int, [c_int]),
+    "hwg_bn_coeffs_peer": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp,
+                                   c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_peer_allreduce_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_bn_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "hwg_bn_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_relu_maxpool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -40,7 +40,7 @@ def _bn_train(m, y, stats, bn):
     use_batch = m.training or not bn.track_running_stats
     if use_batch and m.sync_bn_group is not None:
         coef, save = ops.bn_coeffs_synced(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                          bn.running_var, momentum, bn.eps, m.sync_bn_group)
+                                          bn.running_var, momentum, bn.eps, m.sync_bn_group, key=("f", id(bn)))
     else:
         coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                    bn.running_var, momentum, bn.eps, use_batch)
@@ -227,14 +227,15 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- dilated 1-D blocks, last to first
     for (ci, bi, pad, dil), (a_in, z, coef, save) in zip(reversed(_CNN1D), reversed(ctx["head_in"])):
         bn = m.cnn1d[bi]
-        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena, sync_group=sync)
+        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena, sync_group=sync, sync_key=("b", id(bn)))
         grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
         grads.wgrad(f"cnn1d.{ci}.weight", f"v{ci}", a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
         grads[f"cnn1d.{ci}.bias"] = dcb
         g = dgrad(gz, f"v{ci}", 1, a_in.size(2))
     # ---- conv6 + BN + ReLU
     coef, save = ctx["bn6"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach(), arena=arena, sync_group=sync)
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach(), arena=arena, sync_group=sync,
+                                     sync_key=("b", id(m.cnn.batchnorm6)))
     grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
     a5 = ctx["a5"]
     grads.wgrad("cnn.conv6.weight", "w6", a5, gz, _T3P0, 512, 512)
@@ -248,7 +249,8 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     g = dgrad(gc, "w5", a4.size(1), a4.size(2))
     # ---- conv4 + BN + ReLU
     coef, save = ctx["bn4"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach(), arena=arena, sync_group=sync)
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach(), arena=arena, sync_group=sync,
+                                     sync_key=("b", id(m.cnn.batchnorm4)))
     grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
     a3 = ctx["a3"]
     grads.wgrad("cnn.conv4.weight", "w4", a3, gz, _T3, 256, 512)
@@ -262,7 +264,8 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     g = dgrad(gc, "w3", a2.size(1), a2.size(2))
     # ---- conv2 + BN + ReLU
     coef, save = ctx["bn2"]
-    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach(), arena=arena, sync_group=sync)
+    gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach(), arena=arena, sync_group=sync,
+                                     sync_key=("b", id(m.cnn.batchnorm2)))
     grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
     a1 = ctx["a1"]
     grads.wgrad("cnn.conv2.weight", "w2", a1, gz, _T3, 128, 256)

@@ -69,8 +69,9 @@ class CNNOnlyHWR(nn.Module):
         self._save = False
         self._cache_key, self._cache = None, None
         self._plan, self._plan_ptrs, self._bwd_plans = None, None, {}
-        # data parallelism: set to a torch.distributed group to normalise train-mode BatchNorm with the statistics of
-        # the JOINT batch of its ranks (the reference is single-process, so its batch statistics span the whole
+        # data parallelism: set to a dp.PeerExchange (in-kernel exchange over NVLink peer memory) or a
+        # torch.distributed group (NCCL all-reduce per layer) to normalise train-mode BatchNorm with the statistics of
+        # the JOINT batch of the ranks (the reference is single-process, so its batch statistics span the whole
         # batch); None = per-rank statistics (what DistributedDataParallel does by default)
         self.sync_bn_group = None
 
@@ -130,7 +131,7 @@ class CNNOnlyHWR(nn.Module):
         momentum = 0.1 if bn.momentum is None else bn.momentum
         if use_batch and self.training and self.sync_bn_group is not None:
             coef, save = ops.bn_coeffs_synced(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                              bn.running_var, momentum, bn.eps, self.sync_bn_group)
+                                              bn.running_var, momentum, bn.eps, self.sync_bn_group, key=("f", id(bn)))
         else:
             coef, save = ops.bn_coeffs(stats, N, C, H * W, bn.weight.detach(), bn.bias.detach(),
                                        bn.running_mean if (self.training or not use_batch) else None,

@@ -204,3 +204,97 @@ class GradReducer:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+class PeerExchange:
+    """Peer-mapped mailboxes for the in-kernel exchanges of include/hwg_b200.h ("Peer-memory exchange"): SyncBN
+    statistics of the data-parallel recognizer summed over the ranks inside `hwg_bn_coeffs_peer` /
+    `hwg_peer_allreduce_f32` (NVLink stores with the flag in the payload) instead of one NCCL all-reduce + stream
+    fork/join per BatchNorm layer.  Set `CNNOnlyHWR.sync_bn_group = PeerExchange(group)`.
+
+    Every rank allocates a zero-filled mailbox and maps the mailboxes of all ranks of `group` (one node) into its own
+    address space: torch symmetric memory (CUDA VMM handles) when available, else CUDA IPC handles exchanged with
+    `all_gather_object`.  PyTorch owns the memory; the library only receives the device table of base addresses.
+    A slot is handed out per call-site key in first-use order — every rank must run the same exchanges in the same
+    order (they do: same model, same step)."""
+    SLOTS = 64
+
+    def __init__(self, group=None, device=None):
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = _lib.load().hwg_peer_mailbox_bytes(self.world, self.SLOTS)
+        if nbytes <= 0:
+            raise RuntimeError(f"PeerExchange: world size {self.world} not supported")
+        self._keep = []
+        try:
+            ptrs, self.mapping = self._map_symmetric(nbytes), "symmetric_memory"
+        except Exception as e:                       # noqa: BLE001 - any failure of the VMM path: fall back to CUDA IPC
+            self._symm_error = repr(e)
+            ptrs, self.mapping = self._map_ipc(nbytes, _lib), "cuda_ipc"
+        self.table = torch.tensor([int(p) for p in ptrs], dtype=torch.int64, device=self.device)
+        self.epochs = torch.zeros(self.SLOTS, dtype=torch.int32, device=self.device)
+        self.fault = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._slots = {}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)               # every mailbox is zeroed and mapped before anyone writes
+
+    def _map_symmetric(self, nbytes):
+        import torch.distributed._symmetric_memory as symm_mem
+        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+        if enable is not None:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                enable(self.group.group_name)
+        buf = symm_mem.empty(nbytes // 4, dtype=torch.int32, device=self.device)
+        buf.zero_()
+        torch.cuda.synchronize(self.device)
+        hdl = symm_mem.rendezvous(buf, group=self.group)
+        ptrs = list(hdl.buffer_ptrs)
+        if len(ptrs) != self.world or int(ptrs[self.rank]) != buf.data_ptr():
+            raise RuntimeError("symmetric memory rendezvous returned an unexpected pointer table")
+        self._keep += [buf, hdl]
+        return ptrs
+
+    def _map_ipc(self, nbytes, _lib):
+        from torch.multiprocessing.reductions import reduce_tensor
+        buf = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        fn, args = reduce_tensor(buf)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (fn, args), group=self.group)
+        views = [buf if r == self.rank else g[0](*g[1]) for r, g in enumerate(gathered)]
+        with torch.cuda.device(self.device):
+            for v in views:
+                if v.device != self.device:
+                    _lib.call("hwg_peer_enable_access", v.device.index)
+        self._keep += views
+        return [v.data_ptr() for v in views]
+
+    def slot(self, key):
+        s = self._slots.get(key)
+        if s is None:
+            s = self._slots[key] = len(self._slots)
+            if s >= self.SLOTS:
+                raise RuntimeError(f"PeerExchange: more than {self.SLOTS} exchange sites")
+        return s
+
+    def args(self, key):
+        """(peer_mailboxes, world, rank, slot, slots, epochs, fault) as the C-ABI takes them."""
+        return (self.table.data_ptr(), self.world, self.rank, self.slot(key), self.SLOTS, self.epochs.data_ptr(),
+                self.fault.data_ptr())
+
+    def allreduce_(self, t, key):
+        """In-place sum over the ranks of a small contiguous fp32 tensor (<= 1024 values), one launch on the current
+        stream."""
+        from . import _lib
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        _lib.call("hwg_peer_allreduce_f32", t.data_ptr(), t.data_ptr(), t.numel(), *self.args(key), _lib.stream())
+        return t
+
+    def check(self):
+        """Host-side check (synchronises): raises if an exchange timed out waiting for a peer."""
+        if int(self.fault.item()) != 0:
+            raise RuntimeError("PeerExchange: a peer did not answer an in-kernel exchange within the time-out")

@@ -140,11 +140,16 @@ def logsoftmax_bwd(g, lp, Cp, arena=None):
     return gz, db
 
 
-def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None):
+def _is_peer(sync):
+    return hasattr(sync, "allreduce_")          # dp.PeerExchange (in-kernel NVLink exchange) vs a torch process group
+
+
+def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None, sync_key=None):
     """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C]);
     dweight/dbias are strided views of the [C,2] sums.
-    sync_group: a torch.distributed group whose ranks normalised with JOINT batch statistics in the forward (SyncBN):
-    the (sum gy, sum gy*xhat) pair that enters the input gradient is then all-reduced and divided by the global row
+    sync_group: what the forward normalised JOINT batch statistics with (SyncBN) — a dp.PeerExchange (one
+    hwg_peer_allreduce_f32 launch, slot `sync_key`) or a torch.distributed group (NCCL all-reduce): the
+    (sum gy, sum gy*xhat) pair that enters the input gradient is summed over the ranks and divided by the global row
     count; the parameter gradients stay the local sums (the gradient all-reduce averages those)."""
     C = z.size(-1)
     rows = z.numel() // C
@@ -153,10 +158,16 @@ def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None):
               sums.data_ptr(), _lib.stream())
     gsums, grows = sums, rows
     if sync_group is not None:
-        import torch.distributed as dist
-        gsums = sums.clone()
-        dist.all_reduce(gsums, group=sync_group)
-        grows = rows * dist.get_world_size(sync_group)
+        gsums = torch.empty_like(sums)
+        if _is_peer(sync_group):
+            _lib.call("hwg_peer_allreduce_f32", sums.data_ptr(), gsums.data_ptr(), 2 * C, *sync_group.args(sync_key),
+                      _lib.stream())
+            grows = rows * sync_group.world
+        else:
+            import torch.distributed as dist
+            gsums.copy_(sums)
+            dist.all_reduce(gsums, group=sync_group)
+            grows = rows * dist.get_world_size(sync_group)
     gz = torch.empty_like(z)
     dcb = _zeros(arena, (C,), z.device)
     _lib.call("hwg_bn_bwd_apply", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), weight.data_ptr(),
@@ -164,9 +175,19 @@ def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None):
     return gz, sums[:, 1], sums[:, 0], dcb
 
 
-def bn_coeffs_synced(stats, N, C, count_per_n, weight, bias, running_mean, running_var, momentum, eps, group):
-    """bn_coeffs over the JOINT batch of a process group (SyncBN; SURVEY 8e coupling 1): the per-(n,c) sums are folded
-    over the local lines, all-reduced ([C,2] floats), and normalised by the global element count."""
+def bn_coeffs_synced(stats, N, C, count_per_n, weight, bias, running_mean, running_var, momentum, eps, group, key=None):
+    """bn_coeffs over the JOINT batch of the ranks (SyncBN; SURVEY 8e coupling 1), equal shards per rank.
+    group = dp.PeerExchange: ONE launch folds the local per-(n,c) sums, adds them over the ranks through peer memory
+    and writes coefficients / running statistics (hwg_bn_coeffs_peer).  group = torch.distributed group: fold,
+    NCCL all-reduce of [C,2] floats, hwg_bn_coeffs with the global element count."""
+    if _is_peer(group):
+        dev = weight.device
+        coef = torch.empty((C, 2), device=dev, dtype=torch.float32)
+        save = torch.empty((C, 2), device=dev, dtype=torch.float32)
+        _lib.call("hwg_bn_coeffs_peer", stats.data_ptr(), N, C, count_per_n * N * group.world, _lib.ptr(weight),
+                  _lib.ptr(bias), _lib.ptr(running_mean), _lib.ptr(running_var), momentum, eps, coef.data_ptr(),
+                  save.data_ptr(), *group.args(key), _lib.stream())
+        return coef, save
     import torch.distributed as dist
     tot = stats.view(N, C, 2).sum(0, keepdim=True).contiguous()
     dist.all_reduce(tot, group=group)

@@ -418,6 +418,39 @@ int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const fl
                        int O, int act, float slope, float* gx, float* gW, float* gb, int accumulate,
                        void* stream);
 
+/* ------------------------------------------------------------------------
+ * Peer-memory exchange for data-parallel BatchNorm (coupling 1).
+ * The reference is single-process: nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79
+ * normalise with the statistics of the WHOLE batch.  With the batch sharded
+ * over one process per GPU the per-channel sums are added over the ranks inside
+ * the consuming kernel, through mailboxes in peer-mapped HBM (NVLink stores with
+ * flags in the payload) — no NCCL launch, no stream fork/join, graph-capturable.
+ *
+ * The caller (dp.PeerExchange) owns all memory: a zero-filled mailbox of
+ * hwg_peer_mailbox_bytes(world, slots) on every rank, mapped into every other
+ * rank's address space (torch symmetric memory or CUDA IPC); peer_mailboxes is a
+ * DEVICE array [world] of those base addresses as seen from this process;
+ * epochs is a zero-filled device uint32 [slots]; fault a device int that a rank
+ * sets (instead of hanging) when a peer has not answered within 10 s.
+ * A slot identifies one call site; all ranks must use the same slot for the same
+ * exchange and launch their exchanges in the same order. */
+#define HWG_PEER_MAX_WORLD 16
+#define HWG_PEER_SLOT_VALUES 1024 /* fp32 values one exchange can carry */
+int64_t hwg_peer_mailbox_bytes(int world, int slots);
+/* cudaDeviceEnablePeerAccess(current -> peer_device), tolerant of "already enabled" (CUDA-IPC mapping only). */
+int hwg_peer_enable_access(int peer_device);
+/* hwg_bn_coeffs (training mode) over the joint batch: folds the local [N,C,2] sums over n, adds them over the
+ * ranks, then coefficients / saved (mean, rstd) / running statistics from global_count = elements per channel
+ * over ALL ranks.  C <= 512.  One launch. */
+int hwg_bn_coeffs_peer(const float* stats, int N, int C, int64_t global_count, const float* weight,
+                       const float* bias, float* running_mean, float* running_var, float momentum, float eps,
+                       float* coef, float* save_mean_rstd, const uint64_t* peer_mailboxes, int world, int rank,
+                       int slot, int slots, uint32_t* epochs, int* fault, void* stream);
+/* out[i] = sum over ranks of in[i], n <= HWG_PEER_SLOT_VALUES fp32 values, identical bits on every rank
+ * (in == out allowed).  Used between hwg_bn_bwd_reduce and hwg_bn_bwd_apply. */
+int hwg_peer_allreduce_f32(const float* in, float* out, int n, const uint64_t* peer_mailboxes, int world,
+                           int rank, int slot, int slots, uint32_t* epochs, int* fault, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
