@@ -8,5 +8,7 @@ from .ctc import CTCLoss, ctc_greedy_decode, naive_decode  # noqa: F401
 from .pure_gen import SpacedGenerator  # noqa: F401
 from .cnn_only_hwr import CNNOnlyHWR  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
+from .discriminator_ap import DiscriminatorAP  # noqa: F401
 
-__all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam"]
+__all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam",
+           "DiscriminatorAP"]

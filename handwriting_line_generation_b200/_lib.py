@@ -30,6 +30,15 @@ _SIGNATURES = {
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_logsoftmax_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_shift_expand": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "hwg_shift_collapse": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "hwg_gn_coeffs": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_f, c_vp, c_vp, c_vp]),
+    "hwg_avgpool_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "hwg_act_bwd": (c_int, [c_vp, c_vp, c_vp, c_f, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "hwg_norm_bwd_reduce": (c_int, [c_vp, c_vp, c_vp, c_f, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "hwg_gn_bwd_coeffs": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_norm_bwd_apply": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "hwg_spectral_norm": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "hwg_peer_mailbox_bytes": (c_i64, [c_int, c_int]),
     "hwg_peer_enable_access": (c_int, [c_int]),
     "hwg_bn_coeffs_peer": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp,

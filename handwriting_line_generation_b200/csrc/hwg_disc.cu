@@ -1,0 +1,412 @@
+// Memory-bound passes of the discriminator (reference model/discriminator_ap.py:68-161) around the tensor-core
+// convolutions: the 7-wide shift expansion that turns the 1-channel 7x7 input convolution into a 7-tap, 16-channel
+// implicit GEMM (and its adjoint back to the image), GroupNorm coefficients and backward, AvgPool2d, and the fused
+// backward of [Dropout2d ->] LeakyReLU [-> AvgPool2d].  NHWC bf16, 16-byte vectors of 8 channels, fp32 arithmetic.
+// Every kernel's roofline is HBM: activation bytes read + written once per pass.
+#include "common.cuh"
+
+namespace hwg {
+namespace {
+
+constexpr int DT = 256;      // threads per block
+constexpr int SHIFT_C = 16;  // channels of the expanded image (kw <= 16)
+
+__device__ __forceinline__ void unpack8d(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __bfloat1622float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8d(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+inline unsigned grid_for(long long items, int per_block, long long cap = 148LL * 16) {
+  long long b = (items + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+// ---- image -> [N,H,W,16] bf16, channel j = image[h, w + j - pad] (zero outside), j < kw ----------------------
+__global__ void __launch_bounds__(DT)
+shift_expand_kernel(const float* __restrict__ img, uint4* __restrict__ out, long long pixels, int W, int kw, int pad) {
+  for (long long p = (long long)blockIdx.x * DT + threadIdx.x; p < pixels; p += (long long)gridDim.x * DT) {
+    const int w = (int)(p % W);
+    const float* row = img + (p - w);
+    float f[SHIFT_C];
+#pragma unroll
+    for (int j = 0; j < SHIFT_C; ++j) {
+      const int x = w + j - pad;
+      f[j] = (j < kw && x >= 0 && x < W) ? __ldg(row + x) : 0.f;
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+    out[2 * p] = pack8d(lo);
+    out[2 * p + 1] = pack8d(hi);
+  }
+}
+
+// ---- adjoint: dimg[h, x] (+)= sum_j g[h, x - j + pad, j] --------------------------------------------------------
+__global__ void __launch_bounds__(DT)
+shift_collapse_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ dimg, long long pixels, int W, int kw,
+                      int pad, int accumulate) {
+  for (long long p = (long long)blockIdx.x * DT + threadIdx.x; p < pixels; p += (long long)gridDim.x * DT) {
+    const int x = (int)(p % W);
+    const __nv_bfloat16* row = g + (p - x) * SHIFT_C;
+    float acc = 0.f;
+    for (int j = 0; j < kw; ++j) {
+      const int w = x - j + pad;
+      if (w >= 0 && w < W) acc += __bfloat162float(row[(long long)w * SHIFT_C + j]);
+    }
+    dimg[p] = accumulate ? dimg[p] + acc : acc;
+  }
+}
+
+// ---- GroupNorm coefficients from per-(n,c) sums ---------------------------------------------------------------
+// coef[n,c] = (a, b): GroupNorm(z) = a*z + b;  save[n,c] = (mean, rstd) of c's group
+__global__ void gn_coeffs_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int C, int cg, float count, float eps,
+                                 float* __restrict__ coef, float* __restrict__ save) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cg) * cg;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < cg; ++k) {
+      s1 += stats[((size_t)n * C + g0 + k) * 2];
+      s2 += stats[((size_t)n * C + g0 + k) * 2 + 1];
+    }
+    const float mean = s1 / count;
+    const float var = fmaxf(s2 / count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = (gamma ? gamma[c] : 1.f) * rstd;
+    coef[((size_t)n * C + c) * 2] = a;
+    coef[((size_t)n * C + c) * 2 + 1] = (beta ? beta[c] : 0.f) - mean * a;
+    if (save) { save[((size_t)n * C + c) * 2] = mean; save[((size_t)n * C + c) * 2 + 1] = rstd; }
+  }
+}
+
+// ---- AvgPool2d(kh,kw) (stride = kernel, floor) ----------------------------------------------------------------
+__global__ void __launch_bounds__(DT)
+avgpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV, int kh, int kw, int Ho,
+               int Wo) {
+  const long long total = (long long)N * Ho * Wo * CV;
+  const float inv = 1.f / (float)(kh * kw);
+  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho), n = (int)(p / Ho);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) {
+        float f[8];
+        unpack8d(x[(((long long)n * H + ho * kh + a) * W + wo * kw + b) * CV + cv], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= inv;
+    y[i] = pack8d(acc);
+  }
+}
+
+// ---- backward of  y = LeakyReLU(scale[n,c] * conv) [-> AvgPool(kh,kw)] ------------------------------------------
+// gz[n,h,w,c] = scale[n,c] * (y > 0 ? 1 : slope) * g[n, h/kh, w/kw, c] / (kh*kw)   (0 where the pool's floor cut)
+__global__ void __launch_bounds__(DT)
+act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y, const float* __restrict__ scale, float slope,
+               int N, int H, int W, int CV, int kh, int kw, int Ho, int Wo, uint4* __restrict__ gz) {
+  const long long total = (long long)N * H * W * CV;
+  const float inv = 1.f / (float)(kh * kw);
+  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H), n = (int)(p / H);
+    const int ho = h / kh, wo = w / kw;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ho < Ho && wo < Wo) {
+      float gv[8], yv[8];
+      unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
+      unpack8d(y[i], yv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float s = scale ? scale[(size_t)n * CV * 8 + cv * 8 + k] : 1.f;
+        o[k] = gv[k] * inv * s * (yv[k] > 0.f ? 1.f : slope);
+      }
+    }
+    gz[i] = pack8d(o);
+  }
+}
+
+// ---- backward of  a = LeakyReLU(coef_a*z + coef_b) [-> AvgPool(kh,kw)]  with per-(n,c) coefficients, pass 1 ------
+// sums[n,c] += (sum gy', sum gy'*z),  gy' = g[n,h/kh,w/kw,c]/(kh*kw) * (coef_a*z + coef_b > 0 ? 1 : slope)
+template <int CV>
+__global__ void __launch_bounds__(DT)
+norm_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
+                       float slope, int H, int W, int kh, int kw, int Ho, int Wo, float* __restrict__ sums) {
+  constexpr int LANES = DT / CV;                   // pixels in flight per block
+  __shared__ float red[LANES][CV * 8 * 2 + 1];
+  const int n = blockIdx.y, cv = threadIdx.x % CV, lane = threadIdx.x / CV;
+  const int C = CV * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a[k] = coef[((size_t)n * C + cv * 8 + k) * 2];
+    b[k] = coef[((size_t)n * C + cv * 8 + k) * 2 + 1];
+  }
+  float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float inv = 1.f / (float)(kh * kw);
+  const long long HW = (long long)H * W;
+  for (long long p = (long long)blockIdx.x * LANES + lane; p < HW; p += (long long)gridDim.x * LANES) {
+    const int h = (int)(p / W), w = (int)(p % W);
+    const int ho = h / kh, wo = w / kw;
+    if (ho >= Ho || wo >= Wo) continue;
+    float gv[8], zv[8];
+    unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
+    unpack8d(z[((long long)n * HW + p) * CV + cv], zv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gy = gv[k] * inv * (fmaf(a[k], zv[k], b[k]) > 0.f ? 1.f : slope);
+      s0[k] += gy;
+      s1[k] = fmaf(gy, zv[k], s1[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[lane][(cv * 8 + k) * 2] = s0[k];
+    red[lane][(cv * 8 + k) * 2 + 1] = s1[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += DT) {
+    float t = 0.f;
+#pragma unroll 4
+    for (int l = 0; l < LANES; ++l) t += red[l][i];
+    atomicAdd(sums + (size_t)n * C * 2 + i, t);
+  }
+}
+
+// ---- GroupNorm backward coefficients: per-(n,c) (sc, P, Q) with  gz = sc*gy' + P*z + Q --------------------------
+// group G of c (cg channels, M = cg*HW elements), r = rstd, mu = mean:
+//   T_c = r*(S1_c - mu*S0_c) = sum gy'*xhat;  A = sum_G gamma*S0 / M;  B = sum_G gamma*T / M
+//   sc = r*gamma_c;  P = -r*r*B;  Q = -r*A + r*r*mu*B;   dgamma_c += T_c, dbeta_c += S0_c
+__global__ void gn_bwd_coeffs_kernel(const float* __restrict__ sums, const float* __restrict__ save,
+                                     const float* __restrict__ gamma, int C, int cg, float count,
+                                     float* __restrict__ spq, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cg) * cg;
+    const float mu = save[((size_t)n * C + c) * 2], r = save[((size_t)n * C + c) * 2 + 1];
+    float A = 0.f, B = 0.f;
+    for (int k = 0; k < cg; ++k) {
+      const float S0 = sums[((size_t)n * C + g0 + k) * 2], S1 = sums[((size_t)n * C + g0 + k) * 2 + 1];
+      const float gm = gamma ? gamma[g0 + k] : 1.f;
+      A += gm * S0;
+      B += gm * r * (S1 - mu * S0);
+    }
+    A /= count;
+    B /= count;
+    spq[((size_t)n * C + c) * 3] = r * (gamma ? gamma[c] : 1.f);
+    spq[((size_t)n * C + c) * 3 + 1] = -r * r * B;
+    spq[((size_t)n * C + c) * 3 + 2] = -r * A + r * r * mu * B;
+    const float S0 = sums[((size_t)n * C + c) * 2], S1 = sums[((size_t)n * C + c) * 2 + 1];
+    if (dgamma) atomicAdd(dgamma + c, r * (S1 - mu * S0));
+    if (dbeta) atomicAdd(dbeta + c, S0);
+  }
+}
+
+// ---- pass 2: gz = sc*gy' + P*z + Q ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DT)
+norm_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
+                      const float* __restrict__ spq, float slope, int H, int W, int CV, int kh, int kw, int Ho, int Wo,
+                      uint4* __restrict__ gz) {
+  extern __shared__ float cs[];                    // [C][5]: a, b, sc, P, Q
+  const int n = blockIdx.y, C = CV * 8;
+  for (int c = threadIdx.x; c < C; c += DT) {
+    cs[c * 5] = coef[((size_t)n * C + c) * 2];
+    cs[c * 5 + 1] = coef[((size_t)n * C + c) * 2 + 1];
+    cs[c * 5 + 2] = spq[((size_t)n * C + c) * 3];
+    cs[c * 5 + 3] = spq[((size_t)n * C + c) * 3 + 1];
+    cs[c * 5 + 4] = spq[((size_t)n * C + c) * 3 + 2];
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)(kh * kw);
+  const long long total = (long long)H * W * CV;
+  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
+    const int cv = (int)(i % CV);
+    const long long p = i / CV;
+    const int h = (int)(p / W), w = (int)(p % W);
+    const int ho = h / kh, wo = w / kw;
+    float zv[8], gv[8], o[8];
+    unpack8d(z[(long long)n * total + i], zv);
+    const bool in = ho < Ho && wo < Wo;
+    if (in) unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float* c5 = cs + (cv * 8 + k) * 5;
+      const float gy = in ? gv[k] * inv * (fmaf(c5[0], zv[k], c5[1]) > 0.f ? 1.f : slope) : 0.f;
+      o[k] = fmaf(c5[2], gy, fmaf(c5[3], zv[k], c5[4]));
+    }
+    gz[(long long)n * total + i] = pack8d(o);
+  }
+}
+
+// ---- SpectralNorm (discriminator_ap.py:19-32): one power iteration per layer, all layers in one launch ---------
+// block = layer: v = normalize(W^T u); u = normalize(W v); inv_sigma = 1 / (u . W v); u, v updated in place
+struct SnJob { const float* w; float* u; float* v; int h, wd; };
+__global__ void __launch_bounds__(DT) spectral_norm_kernel(const SnJob* __restrict__ jobs, float* __restrict__ inv_sigma) {
+  const SnJob j = jobs[blockIdx.x];
+  __shared__ float red[DT / 32];
+  __shared__ float bc;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < DT / 32 ? red[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) bc = t;
+    }
+    __syncthreads();
+    const float r = bc;
+    __syncthreads();
+    return r;
+  };
+  // v = W^T u  (column sums: thread per column, rows sequential -> coalesced across threads)
+  float nv = 0.f;
+  for (int c = threadIdx.x; c < j.wd; c += DT) {
+    float acc = 0.f;
+    for (int r = 0; r < j.h; ++r) acc = fmaf(j.w[(size_t)r * j.wd + c], j.u[r], acc);
+    j.v[c] = acc;
+    nv = fmaf(acc, acc, nv);
+  }
+  const float vn = sqrtf(block_sum(nv)) + 1e-12f;
+  for (int c = threadIdx.x; c < j.wd; c += DT) j.v[c] /= vn;
+  __syncthreads();
+  // u = W v  (warp per row)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float nu = 0.f;
+  for (int r = warp; r < j.h; r += DT / 32) {
+    float acc = 0.f;
+    for (int c = lane; c < j.wd; c += 32) acc = fmaf(j.w[(size_t)r * j.wd + c], j.v[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) { j.u[r] = acc; nu = fmaf(acc, acc, nu); }      // un-normalised W v for now
+  }
+  const float wv2 = block_sum(nu);                                 // |W v|^2
+  const float un = sqrtf(wv2) + 1e-12f;
+  // sigma = u . (W v) with u = Wv/un  ->  |Wv|^2 / un
+  for (int r = threadIdx.x; r < j.h; r += DT) j.u[r] /= un;
+  if (threadIdx.x == 0) inv_sigma[blockIdx.x] = un / wv2;
+}
+
+bool cv_supported(int C) { return C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
+
+}  // namespace
+}  // namespace hwg
+
+using namespace hwg;
+
+extern "C" int hwg_shift_expand(const float* img, void* out, int N, int H, int W, int kw, int pad, void* stream) {
+  HWG_REQUIRE(img && out && N > 0 && H > 0 && W > 0 && kw >= 1 && kw <= SHIFT_C && pad >= 0, "hwg_shift_expand: bad argument");
+  const long long pixels = (long long)N * H * W;
+  shift_expand_kernel<<<grid_for(pixels, DT), DT, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<uint4*>(out), pixels, W,
+                                                                            kw, pad);
+  return check_launch("shift_expand_kernel");
+}
+
+extern "C" int hwg_shift_collapse(const void* g, float* dimg, int N, int H, int W, int kw, int pad, int accumulate,
+                                  void* stream) {
+  HWG_REQUIRE(g && dimg && N > 0 && H > 0 && W > 0 && kw >= 1 && kw <= SHIFT_C && pad >= 0, "hwg_shift_collapse: bad argument");
+  const long long pixels = (long long)N * H * W;
+  shift_collapse_kernel<<<grid_for(pixels, DT), DT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g),
+                                                                              dimg, pixels, W, kw, pad, accumulate);
+  return check_launch("shift_collapse_kernel");
+}
+
+extern "C" int hwg_gn_coeffs(const float* stats, const float* gamma, const float* beta, int N, int C, int groups,
+                             int64_t HW, float eps, float* coef, float* save_mean_rstd, void* stream) {
+  HWG_REQUIRE(stats && coef && N > 0 && C > 0 && groups > 0 && C % groups == 0 && HW > 0, "hwg_gn_coeffs: bad argument");
+  const int cg = C / groups;
+  gn_coeffs_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(stats, gamma, beta, C, cg, (float)((double)cg * (double)HW), eps,
+                                                        coef, save_mean_rstd);
+  return check_launch("gn_coeffs_kernel");
+}
+
+extern "C" int hwg_avgpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh, int kw, void* stream) {
+  HWG_REQUIRE(x && y && N > 0 && C > 0 && C % 8 == 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "hwg_avgpool_nhwc: bad argument");
+  const int Ho = H / kh, Wo = W / kw;
+  avgpool_kernel<<<grid_for((long long)N * Ho * Wo * (C / 8), DT), DT, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), N, H, W, C / 8, kh, kw, Ho, Wo);
+  return check_launch("avgpool_kernel");
+}
+
+extern "C" int hwg_act_bwd(const void* g, const void* y, const float* scale, float slope, int N, int H, int W, int C,
+                           int kh, int kw, void* gz, void* stream) {
+  HWG_REQUIRE(g && y && gz && N > 0 && C > 0 && C % 8 == 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "hwg_act_bwd: bad argument");
+  act_bwd_kernel<<<grid_for((long long)N * H * W * (C / 8), DT), DT, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(y), scale, slope, N, H, W, C / 8, kh, kw, H / kh,
+      W / kw, reinterpret_cast<uint4*>(gz));
+  return check_launch("act_bwd_kernel");
+}
+
+extern "C" int hwg_norm_bwd_reduce(const void* g, const void* z, const float* coef, float slope, int N, int H, int W,
+                                   int C, int kh, int kw, float* sums, void* stream) {
+  HWG_REQUIRE(g && z && coef && sums && N > 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "hwg_norm_bwd_reduce: bad argument");
+  HWG_REQUIRE(cv_supported(C), "hwg_norm_bwd_reduce: C=%d not in {16,32,64,128,256}", C);
+  const long long HW = (long long)H * W;
+  const int CV = C / 8, lanes = DT / CV;
+  long long bx = (HW + lanes - 1) / lanes, cap = (148LL * 8 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, N);
+  const uint4* gp = reinterpret_cast<const uint4*>(g);
+  const uint4* zp = reinterpret_cast<const uint4*>(z);
+  const int Ho = H / kh, Wo = W / kw;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (CV) {
+    case 2: norm_bwd_reduce_kernel<2><<<grid, DT, 0, s>>>(gp, zp, coef, slope, H, W, kh, kw, Ho, Wo, sums); break;
+    case 4: norm_bwd_reduce_kernel<4><<<grid, DT, 0, s>>>(gp, zp, coef, slope, H, W, kh, kw, Ho, Wo, sums); break;
+    case 8: norm_bwd_reduce_kernel<8><<<grid, DT, 0, s>>>(gp, zp, coef, slope, H, W, kh, kw, Ho, Wo, sums); break;
+    case 16: norm_bwd_reduce_kernel<16><<<grid, DT, 0, s>>>(gp, zp, coef, slope, H, W, kh, kw, Ho, Wo, sums); break;
+    default: norm_bwd_reduce_kernel<32><<<grid, DT, 0, s>>>(gp, zp, coef, slope, H, W, kh, kw, Ho, Wo, sums); break;
+  }
+  return check_launch("norm_bwd_reduce_kernel");
+}
+
+extern "C" int hwg_gn_bwd_coeffs(const float* sums, const float* save_mean_rstd, const float* gamma, int N, int C,
+                                 int groups, int64_t HW, float* spq, float* dgamma, float* dbeta, void* stream) {
+  HWG_REQUIRE(sums && save_mean_rstd && spq && N > 0 && C > 0 && groups > 0 && C % groups == 0 && HW > 0,
+              "hwg_gn_bwd_coeffs: bad argument");
+  const int cg = C / groups;
+  gn_bwd_coeffs_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(sums, save_mean_rstd, gamma, C, cg,
+                                                            (float)((double)cg * (double)HW), spq, dgamma, dbeta);
+  return check_launch("gn_bwd_coeffs_kernel");
+}
+
+extern "C" int hwg_norm_bwd_apply(const void* g, const void* z, const float* coef, const float* spq, float slope, int N,
+                                  int H, int W, int C, int kh, int kw, void* gz, void* stream) {
+  HWG_REQUIRE(g && z && coef && spq && gz && N > 0 && C > 0 && C % 8 == 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw,
+              "hwg_norm_bwd_apply: bad argument");
+  HWG_REQUIRE(C <= 1024, "hwg_norm_bwd_apply: C=%d too large", C);
+  const long long total = (long long)H * W * (C / 8);
+  long long bx = (total + DT - 1) / DT, cap = (148LL * 16 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, N);
+  norm_bwd_apply_kernel<<<grid, DT, (size_t)C * 5 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z), coef, spq, slope, H, W, C / 8, kh, kw, H / kh,
+      W / kw, reinterpret_cast<uint4*>(gz));
+  return check_launch("norm_bwd_apply_kernel");
+}
+
+extern "C" int hwg_spectral_norm(const void* jobs_dev, int njobs, float* inv_sigma, void* stream) {
+  HWG_REQUIRE(jobs_dev && inv_sigma && njobs > 0, "hwg_spectral_norm: bad argument");
+  spectral_norm_kernel<<<njobs, DT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const SnJob*>(jobs_dev), inv_sigma);
+  return check_launch("spectral_norm_kernel");
+}

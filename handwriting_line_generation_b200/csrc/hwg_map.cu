@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(MAP_THREADS) linear_map_kernel(const hwgMapJob
   }
   __syncthreads();
   const int nin = j.nin, nout = j.nout;
+  const float jscale = j.scale * (j.scale_dev ? *j.scale_dev : 1.f);
   if (j.M != nullptr)
     for (int i = threadIdx.x; i < nin * nout; i += blockDim.x) Ms[i] = j.M[i];
   __syncthreads();
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(MAP_THREADS) linear_map_kernel(const hwgMapJob
       float acc = 0.f;
       if (!pad)
         for (int i = 0; i < nin; ++i) acc += src[(long long)i * j.in_stride];
-      acc *= j.scale;
+      acc *= jscale;
       const long long o = j.out_off[0] + drc;
       if (j.dst_bf16) reinterpret_cast<__nv_bfloat16*>(dstb)[o] = __float2bfloat16(acc);
       else if (j.accumulate) { if (!pad) reinterpret_cast<float*>(dstb)[o] += acc; }
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(MAP_THREADS) linear_map_kernel(const hwgMapJob
 #pragma unroll
       for (int i = 0; i < HWG_MAP_MAX; ++i)
         if (i < nin) acc = fmaf(Ms[i * nout + o], v[i], acc);
-      acc *= j.scale;
+      acc *= jscale;
       const long long oi = j.out_off[o] + drc;
       if (j.dst_bf16) reinterpret_cast<__nv_bfloat16*>(dstb)[oi] = __float2bfloat16(acc);
       else if (j.accumulate) { if (!pad) reinterpret_cast<float*>(dstb)[oi] += acc; }

@@ -30,6 +30,7 @@ class MapJob(ctypes.Structure):
         ("in_stride", ctypes.c_int64),
         ("s_r", ctypes.c_int64), ("s_c", ctypes.c_int64), ("d_r", ctypes.c_int64), ("d_c", ctypes.c_int64),
         ("in_off", ctypes.c_int64 * MAP_MAX), ("out_off", ctypes.c_int64 * MAP_MAX),
+        ("scale_dev", ctypes.c_void_p),
     ]
 
 
@@ -45,7 +46,7 @@ class JobTable:
         self._keep = []
 
     def add(self, src, dst, *, R, C, s_r, s_c, d_r, d_c, M=None, in_off=None, out_off=None, nin=None, in_stride=0,
-            Rp=None, Cp=None, dst_bf16=False, accumulate=False, scale=1.0):
+            Rp=None, Cp=None, dst_bf16=False, accumulate=False, scale=1.0, scale_dev=None):
         if M is not None:
             M = np.ascontiguousarray(M, dtype=np.float32)
             nin, nout = M.shape
@@ -59,7 +60,7 @@ class JobTable:
         out_off = [0] if out_off is None else list(out_off)
         assert len(out_off) == nout
         self.jobs.append(dict(src=src, dst=dst, M=M, nin=nin, nout=nout, R=R, C=C, Rp=Rp or R, Cp=Cp or C,
-                              dst_bf16=bool(dst_bf16), accumulate=bool(accumulate), scale=float(scale),
+                              dst_bf16=bool(dst_bf16), accumulate=bool(accumulate), scale=float(scale), scale_dev=scale_dev,
                               in_stride=in_stride, s_r=s_r, s_c=s_c, d_r=d_r, d_c=d_c, in_off=in_off, out_off=out_off))
         self._dev = None
 
@@ -86,6 +87,7 @@ class JobTable:
                 a.M = None
             a.nin, a.nout, a.R, a.C, a.Rp, a.Cp = j["nin"], j["nout"], j["R"], j["C"], j["Rp"], j["Cp"]
             a.dst_bf16, a.accumulate, a.scale, a.in_stride = int(j["dst_bf16"]), int(j["accumulate"]), j["scale"], j["in_stride"]
+            a.scale_dev = None if j.get("scale_dev") is None else j["scale_dev"].data_ptr()
             a.s_r, a.s_c, a.d_r, a.d_c = j["s_r"], j["s_c"], j["d_r"], j["d_c"]
             for i, v in enumerate(j["in_off"]):
                 a.in_off[i] = v
@@ -116,18 +118,20 @@ class ConvMap:
         self.Cip, self.Cop = -(-Ci // 16) * 16, -(-Co // 16) * 16
 
     # -- jobs ---------------------------------------------------------------------------------------------
-    def add_pack_fwd(self, table, w, dst, out_off=None, Cip=None):
-        """dst bf16 [Tf][Co][Cip] unless out_off (element offsets per tap) says otherwise."""
+    def add_pack_fwd(self, table, w, dst, out_off=None, Cip=None, scale_dev=None, Cop=None):
+        """dst bf16 [Tf][Co][Cip] unless out_off (element offsets per tap) says otherwise; Cop > Co zero-pads the
+        output-channel rows ([Tf][Cop][Cip]); scale_dev: 1-element device tensor multiplied in at run time."""
         Cip = Cip or self.Cip
-        out_off = [t * self.Co * Cip for t in range(self.Tf)] if out_off is None else out_off
-        table.add(w, dst, R=self.Co, C=self.Ci, Cp=Cip, s_r=self.s_co, s_c=self.s_ci, d_r=Cip, d_c=1, M=self.Af,
-                  out_off=out_off, dst_bf16=True)
+        rows = Cop or self.Co
+        out_off = [t * rows * Cip for t in range(self.Tf)] if out_off is None else out_off
+        table.add(w, dst, R=self.Co, C=self.Ci, Rp=rows, Cp=Cip, s_r=self.s_co, s_c=self.s_ci, d_r=Cip, d_c=1, M=self.Af,
+                  out_off=out_off, dst_bf16=True, scale_dev=scale_dev)
 
-    def add_pack_dgrad(self, table, w, dst):
+    def add_pack_dgrad(self, table, w, dst, scale_dev=None):
         """dst bf16 [Td][Cip16][Cop]: the transposed tap matrices."""
         Rp = -(-self.Ci // 16) * 16
         table.add(w, dst, R=self.Ci, C=self.Co, Rp=Rp, Cp=self.Cop, s_r=self.s_ci, s_c=self.s_co, d_r=self.Cop, d_c=1,
-                  M=self.Ad, out_off=[t * Rp * self.Cop for t in range(self.Td)], dst_bf16=True)
+                  M=self.Ad, out_off=[t * Rp * self.Cop for t in range(self.Td)], dst_bf16=True, scale_dev=scale_dev)
 
     def dgrad_shape(self):
         return (self.Td, -(-self.Ci // 16) * 16, self.Cop)

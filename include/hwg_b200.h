@@ -387,6 +387,7 @@ typedef struct hwgMapJob {
   int64_t in_stride;               /* used when M == NULL */
   int64_t s_r, s_c, d_r, d_c;
   int64_t in_off[HWG_MAP_MAX], out_off[HWG_MAP_MAX];
+  const float* scale_dev;          /* optional device scalar multiplied into `scale` at run time (spectral norm 1/sigma) */
 } hwgMapJob;
 /* block_tab_dev: nblocks pairs (job index, block index within the job) of int32 in device memory; one block covers
  * hwg_map_items_per_block() consecutive (r, c) items of its job, so a job needs ceil(Rp*Cp / that) blocks. */
@@ -417,6 +418,45 @@ int hwg_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, f
 int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const float* W, int B, int K,
                        int O, int act, float slope, float* gx, float* gW, float* gb, int accumulate,
                        void* stream);
+
+/* ------------------------------------------------------------------------
+ * Discriminator (reference model/discriminator_ap.py:68-161):
+ * memory-bound passes around the tensor-core convolutions.  NHWC bf16, C % 8 == 0.
+ * ---------------------------------------------------------------------- */
+/* in_conv (nn.Conv2d(1, dim, 7, padding=(0,3)), :75) as an implicit GEMM: out[n,h,w,j] = img[n,0,h,w+j-pad]
+ * (zero outside the row) for j < kw, 0 for kw <= j < 16 -> bf16 [N,H,W,16]; the 7x7 convolution is then the 7-tap
+ * (dy, 0) hwg_conv_fprop over these 16 channels.  hwg_shift_collapse is the adjoint (image gradient from the
+ * dgrad of that convolution): dimg[n,0,h,x] (+)= sum_j g[n,h,x-j+pad,j]. */
+int hwg_shift_expand(const float* img, void* out, int N, int H, int W, int kw, int pad, void* stream);
+int hwg_shift_collapse(const void* g, float* dimg, int N, int H, int W, int kw, int pad, int accumulate,
+                       void* stream);
+/* nn.GroupNorm(groups, C) (:76,101) from the per-(n,c) sums of the conv epilogue: coef[n,c] = (a, b) with
+ * GroupNorm(z) = a*z + b (apply with hwg_scale_shift_act, per_sample=1, LeakyReLU(0.1));
+ * save[n,c] = (mean, rstd) of c's group (biased variance, eps). */
+int hwg_gn_coeffs(const float* stats, const float* gamma, const float* beta, int N, int C, int groups,
+                  int64_t HW, float eps, float* coef, float* save_mean_rstd, void* stream);
+/* nn.AvgPool2d((kh,kw)) (stride = kernel, floor): [N,H,W,C] -> [N,H/kh,W/kw,C]. */
+int hwg_avgpool_nhwc(const void* x, void* y, int N, int H, int W, int C, int kh, int kw, void* stream);
+/* Backward of y = LeakyReLU(scale[n,c]*conv) [-> AvgPool2d(kh,kw)] (Dropout2d channel scale, :89-90 etc.):
+ * gz[n,h,w,c] = scale[n,c] * (y > 0 ? 1 : slope) * g[n,h/kh,w/kw,c] / (kh*kw); y is the stored post-activation
+ * tensor [N,H,W,C], g [N,H/kh,W/kw,C]; scale [N,C] fp32 or NULL (= 1). */
+int hwg_act_bwd(const void* g, const void* y, const float* scale, float slope, int N, int H, int W, int C, int kh,
+                int kw, void* gz, void* stream);
+/* Backward of a = LeakyReLU(GroupNorm(z)) [-> AvgPool2d(kh,kw)], three launches:
+ *   hwg_norm_bwd_reduce: sums[n,c] += (sum gy', sum gy'*z), gy' = g/(kh*kw) * (a*z+b > 0 ? 1 : slope)   (sums zeroed by the caller)
+ *   hwg_gn_bwd_coeffs  : spq[n,c] = (sc, P, Q) from the group sums; dgamma[c] += sum gy'*xhat, dbeta[c] += sum gy' (or NULL)
+ *   hwg_norm_bwd_apply : gz = sc*gy' + P*z + Q  */
+int hwg_norm_bwd_reduce(const void* g, const void* z, const float* coef, float slope, int N, int H, int W, int C,
+                        int kh, int kw, float* sums, void* stream);
+int hwg_gn_bwd_coeffs(const float* sums, const float* save_mean_rstd, const float* gamma, int N, int C, int groups,
+                      int64_t HW, float* spq, float* dgamma, float* dbeta, void* stream);
+int hwg_norm_bwd_apply(const void* g, const void* z, const float* coef, const float* spq, float slope, int N, int H,
+                       int W, int C, int kh, int kw, void* gz, void* stream);
+/* SpectralNorm._update_u_v (:19-32), all wrapped layers in one launch (one block per layer): v = normalize(W^T u),
+ * u = normalize(W v) written back in place, inv_sigma[layer] = 1 / (u . W v).  jobs_dev: device array of
+ * { const float* w [h][wd]; float* u [h]; float* v [wd]; int32 h, wd } (32 bytes each).  The packed bf16
+ * operands are then W * inv_sigma (hwgMapJob.scale_dev). */
+int hwg_spectral_norm(const void* jobs_dev, int njobs, float* inv_sigma, void* stream);
 
 /* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).

@@ -173,6 +173,65 @@ def make_hwr():
     np.savez_compressed(os.path.join(GOLD, "hwr.npz"), **out)
 
 
+# name -> (B, W, weight seed, input seed, training)
+DISC_CASES = {
+    "train_w128": (2, 128, 300, 301, True),
+    "train_w264": (3, 264, 300, 302, True),    # 264 -> 132 -> 66 -> 33 -> 16 -> 8: AvgPool floors, odd tile widths
+    "eval_w128": (2, 128, 300, 303, False),
+}
+
+
+def make_disc():
+    """Outputs, generator-loss input gradient and updated spectral-norm vectors of the unmodified reference
+    DiscriminatorAP (IAM GAN config: dim 64, 'use low', med on).  Dropout2d keep-masks are injected by patching
+    torch.nn.functional.dropout2d (what nn.Dropout2d.forward calls)."""
+    ref_shim.install()
+    from model.discriminator_ap import DiscriminatorAP
+    import torch.nn.functional as F
+    from . import disc as odisc
+    out = {}
+    for name, (B, W, wseed, iseed, training) in DISC_CASES.items():
+        torch.manual_seed(wseed)
+        m = DiscriminatorAP(64, use_low=True, use_med=True)
+        sd = synth.perturb_disc(m.state_dict(), wseed + 1)
+        m.train(training)
+        out[f"{name}/weights_digest"] = weights_digest(sd)
+        out["state_dict_keys"] = keys_fixture(sd)
+        masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(B, iseed + 7).items()}
+        order = iter(odisc.DROPOUT_ORDER)
+        orig = F.dropout2d
+
+        def fake_dropout2d(x, p=0.5, training=True, inplace=False):
+            if not training:
+                return x
+            site = next(order)
+            assert abs(p - odisc.DROPOUT_P[site]) < 1e-9 and x.size(1) == masks[site].size(1), (site, p, x.shape)
+            return x * (masks[site] / (1.0 - p))[:, :, None, None]
+
+        F.dropout2d = fake_dropout2d
+        try:
+            img = torch.from_numpy(synth.hwr_case(B, W, iseed)).requires_grad_()
+            preds = m(img)
+            # the generator's adversarial loss, trainer/hw_with_style_trainer.py:810-821
+            loss = 0
+            for gp in preds:
+                loss = loss - gp.mean()
+            loss = loss / len(preds)
+            loss.backward()
+        finally:
+            F.dropout2d = orig
+        for i, pr in enumerate(preds):
+            out[f"{name}/pred{i}"] = pr.detach().numpy()
+        out[f"{name}/loss"] = np.float32(loss.item())
+        dig, samp = digest(img.grad.numpy())
+        out[f"{name}/grad_digest"], out[f"{name}/grad_sample"] = dig, samp
+        sd2 = m.state_dict()
+        for k in ("convs1.0.module.weight_u", "convs3.4.module.weight_v", "convs4.14.module.weight_u"):
+            out[f"{name}/{k}"] = sd2[k].numpy()
+        print(f"disc/{name}: B={B} W={W} train={training} -> {[tuple(p.shape) for p in preds]} loss {loss.item():.5f}")
+    np.savez_compressed(os.path.join(GOLD, "disc.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -182,6 +241,8 @@ def main(argv):
         globals()["make_hwr"]()
     if what in ("gen", "all") and "make_gen" in globals():
         globals()["make_gen"]()
+    if what in ("disc", "all"):
+        make_disc()
 
 
 if __name__ == "__main__":

@@ -88,3 +88,25 @@ def state_dict_from_seed(make_module, seed):
         elif k.endswith("conv1.0.bias") or k.endswith("out.0.conv.bias"):
             v.copy_(torch.randn(v.shape, generator=g) * 0.1)
     return m, sd
+
+
+DISC_SITES = (("convs1.3", 0.05, 2), ("convs3.4", 0.05, 4), ("convs4.0", 0.025, 2), ("convs4.4", 0.025, 4),
+              ("convs4.7", 0.025, 4), ("convs4.11", 0.025, 4))   # Dropout2d site, p, channels / dim
+
+
+def disc_masks(B, seed, dim=64, p_scale=4.0):
+    """Keep-masks [B,C] of the discriminator's Dropout2d layers (model/discriminator_ap.py:89,105,116-127).
+    p_scale inflates the drop probability of the MASK DRAW (not the 1/(1-p) rescale) so that small batches really
+    contain dropped channels."""
+    r = np.random.RandomState(seed)
+    return {site: (r.rand(B, c * dim) >= p * p_scale).astype(np.float32) for site, p, c in DISC_SITES}
+
+
+def perturb_disc(sd, seed):
+    """GroupNorm affine parameters away from (1, 0), in place, so that parity is not vacuous."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    for k in ("in_conv.1", "convs3.1"):
+        sd[k + ".weight"].copy_(torch.rand(sd[k + ".weight"].shape, generator=g) * 0.5 + 0.75)
+        sd[k + ".bias"].copy_(torch.randn(sd[k + ".bias"].shape, generator=g) * 0.1)
+    return sd
