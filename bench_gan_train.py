@@ -26,16 +26,25 @@ import torch
 GAN = dict(B=16, Ts=256, S=40, C=80, style=128, dim=256)
 HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per 64x1024 line
 HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
+DISC_GF_FWD_PER_LINE = 11.295     # SURVEY.md §8d / Appendix D, DiscriminatorAP forward conv GFLOP per 64x1024 line
+W_CTC, W_GEN = 1e-4, 1.0          # loss_weights genRecog / generator of the IAM GAN config (config json :58-61)
+
+
+def use_disc():
+    return not os.environ.get("HWG_BENCH_NO_DISC")
 
 
 DEFAULT_SYNC_BN = "peer"
 
 
 def config(B, world, executed, sync_bn="off"):
-    return {"workload": "HWWithStyle GAN 'gen' lesson train step on the SURVEY 8(a) rows (BASELINE configs[2]/[3] shapes): "
+    disc = ("frozen discriminator_ap fwd (train mode: spectral-norm power iteration, Dropout2d) + input-gradient bwd "
+            "for the adversarial loss -mean(D(fake)), " if use_disc() else "")
+    return {"workload": "HWWithStyle GAN 'gen' lesson train step (BASELINE configs[2]/[3] shapes): "
                         "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
-                        "CTC loss fwd+bwd, gradient all-reduce (N>1), Adam on the generator; discriminator/perceptual "
-                        "branches (SURVEY 8 f1) not included",
+                        "CTC loss fwd+bwd, " + disc + "gradient all-reduce (N>1), clip + Adam on the generator; "
+                        + ("the perceptual (Encoder2) branch of SURVEY 8 f1 is not included" if use_disc() else
+                           "discriminator/perceptual branches (SURVEY 8 f1) not included"),
             "batch_per_gpu": B, "global_batch": B * world, "line_px": [64, 4 * GAN["Ts"]], "classes": GAN["C"],
             "target_chars": GAN["S"], "parallelism": f"dp{world}",
             "l2": "no explicit flush: the bf16 activations + gradients one step streams (~1.5 GB at B=16) exceed the "
@@ -56,14 +65,15 @@ def gen_layers(T, n_in=208, dim=256):
 def cpu_lines_per_s(sample_B, reps):
     """The reference's CPU path for this step (oracle port: torch fp32 autograd through oracle/gen.py and
     oracle/hwr.py + F.ctc_loss + Adam on the generator), all host threads."""
-    from oracle import gen as ogen, hwr as ohwr, synth
-    from handwriting_line_generation_b200 import CNNOnlyHWR, SpacedGenerator   # parameter containers only (CPU)
+    from oracle import disc as odisc, gen as ogen, hwr as ohwr, synth
+    from handwriting_line_generation_b200 import CNNOnlyHWR, DiscriminatorAP, SpacedGenerator   # parameter containers only (CPU)
     torch.manual_seed(0)
     gmod = SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False, append_style=True,
                            small=False)
     trainable = {n for n, _ in gmod.named_parameters()}
     gsd = {k: v.clone().requires_grad_(k in trainable) for k, v in gmod.state_dict().items()}
     hsd = {k: v.clone() for k, v in CNNOnlyHWR(GAN["C"], norm='batch').state_dict().items()}
+    dsd = {k: v.clone() for k, v in DiscriminatorAP(64, use_low=True, use_med=True).state_dict().items()} if use_disc() else None
     params = [v for v in gsd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
     content, style = synth.gen_case(GAN["Ts"], sample_B, GAN["C"], GAN["style"], 3)
@@ -79,7 +89,13 @@ def cpu_lines_per_s(sample_B, reps):
         noise = [torch.randn(sh) for sh in shapes]
         img = ogen.generator_forward(gsd, c, s, noise)
         lp = ohwr.hwr_forward(hsd, img, True, {})
-        torch.nn.functional.ctc_loss(lp, tg, il, tl).backward()
+        loss = W_CTC * torch.nn.functional.ctc_loss(lp, tg, il, tl)
+        if dsd is not None:
+            masks = {site: (torch.rand(sample_B, cm * 64) >= p).float() for site, p, cm in synth.DISC_SITES}
+            upd = {}
+            loss = loss + W_GEN * odisc.gen_loss(odisc.disc_forward(dsd, img, masks, training=True, update=upd))
+            dsd.update(upd)                      # the spectral-norm vectors advance on every forward
+        loss.backward()
         opt.step()
         if i:
             times.append(time.perf_counter() - t0)
@@ -129,6 +145,11 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     hwr = pkg.CNNOnlyHWR(C, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)            # hwr_frozen: no optimizer touches it; its wgrad is skipped
+    disc = None
+    if use_disc():
+        disc = pkg.DiscriminatorAP(64, use_low=True, use_med=True).to(dev).train()   # IAM GAN config: dim 64, "use low"
+        for p in disc.parameters():
+            p.requires_grad_(False)        # 'gen' lesson: the discriminator only scores; its optimizer is not stepped
     # train-mode BatchNorm over the GLOBAL batch, as in the single-process reference: "peer" = in-kernel exchange over
     # NVLink peer memory (dp.PeerExchange), "nccl" = one NCCL all-reduce per layer and direction, "off" = per-rank
     sync_bn = os.environ.get("HWG_BENCH_SYNC_BN", DEFAULT_SYNC_BN) if world > 1 else "off"
@@ -168,7 +189,11 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     torch.manual_seed(1234 + rank)   # per-rank noise streams
 
     def train(c, s, tg):
-        loss = pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl)
+        img = gen(c, s)
+        loss = W_CTC * pkg.CTCLoss(hwr(img), tg, il, tl)
+        if disc is not None:               # generator's adversarial loss, trainer/hw_with_style_trainer.py:810-821
+            preds = disc(img)
+            loss = loss - (W_GEN / len(preds)) * sum(p.mean() for p in preds)
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -277,8 +302,10 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     # algorithmic work per step by kernel: a layer's dgrad runs on the kernel that serves its fprop
     alg = {
         "conv_fprop_kernel": {"gflop": B * (2 * sum(l[1] for l in layers if l[3] == "conv_fprop_kernel") / 1e9
-                                            + 2 * (HWR_GF_FWD_PER_LINE - HWR_GF_STEM_PER_LINE)),
-                              "what": "fprop + dgrad of generator b0-b2 and recognizer conv1-6 + 1-D head (tcgen05)"},
+                                            + 2 * (HWR_GF_FWD_PER_LINE - HWR_GF_STEM_PER_LINE)
+                                            + (2 * DISC_GF_FWD_PER_LINE if disc is not None else 0.0)),
+                              "what": "fprop + dgrad of generator b0-b2, recognizer conv1-6 + 1-D head"
+                                      + (" and every discriminator convolution" if disc is not None else "") + " (tcgen05)"},
         "conv_small_kernel": {"gflop": B * 2 * sum(l[1] for l in layers if l[3] == "conv_small_kernel") / 1e9,
                               "mb": B * 2 * sum(l[2] for l in layers if l[3] == "conv_small_kernel") / 1e6,
                               "what": "fprop + dgrad of generator b3-b4 (16-64 channels, HBM-bound)"},
@@ -342,7 +369,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     if world == 1 and not os.environ.get("HWG_BENCH_NO_EXTRAS"):
         try:   # the other configs, measured briefly in the same run (bench.py --workload gen_infer / hwr_train)
             import bench_hwr_train
-            del gen, hwr, opt, graphed
+            del gen, hwr, disc, opt, graphed
             torch.cuda.empty_cache()
             line["extra_workloads"] = bench_hwr_train.quick_train_numbers(dev, gen_lesson=False)
             line["extra_workloads"].update(quick_gen_infer(dev))

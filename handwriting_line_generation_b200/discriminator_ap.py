@@ -66,6 +66,19 @@ _T13 = conv.conv_taps(1, 3, 0, 1)
 _DROP_P = {"convs1.3": 0.05, "convs3.4": 0.05, "convs4.0": 0.025, "convs4.4": 0.025, "convs4.7": 0.025, "convs4.11": 0.025}
 
 
+def _tile_w(taps, Ho, Wo):
+    """Output-tile width of a launch on a TALL activation (0 = the kernel's own choice).  A 128 x 1 pixel tile re-reads
+    every input row once per vertical tap from HBM (the 121 MB activations of in_conv / convs1 do not stay in L2: ncu
+    showed 348 MB read for a 121 MB operand); 32 x 4 (3 row taps: 1.5x) and 16 x 8 (7 row taps: 1.75x) tiles keep the
+    vertical halo inside the tile."""
+    rows = len({dh for dh, _ in taps})
+    if rows >= 7 and Ho >= 8 and Wo >= 16:
+        return 16
+    if rows >= 3 and Ho >= 4 and Wo >= 32:
+        return 32
+    return 0
+
+
 class DiscriminatorAP(nn.Module):
     def __init__(self, dim=64, use_low=False, use_med=True, small=False):
         super().__init__()
@@ -102,6 +115,8 @@ class DiscriminatorAP(nn.Module):
                 nn.LeakyReLU(leak, True),
                 SpectralNorm(nn.Conv2d(4 * dim, 1, 1, stride=1, padding=(0, 0))))
         self._plan, self._plan_ptrs = None, None
+        self._site_channels = {site: m.bias.numel() for site, m, _, _ in self.conv_layers() if site in _DROP_P}
+        self._drop_const = None
         self._generation = 0           # forwards so far: a backward must use the operands its own forward packed
         self.dropout_masks = None      # tests: dict site -> [B,C] 0/1 keep-mask instead of drawing one
 
@@ -161,40 +176,52 @@ class DiscriminatorAP(nn.Module):
             b = m.bias.detach()
             if b.numel() % 16:                                       # 1-channel heads run as 16-channel launches
                 bp = torch.zeros(-(-b.numel() // 16) * 16, device=dev, dtype=torch.float32)
+                t.add(b, bp, R=1, C=b.numel(), s_r=0, s_c=1, d_r=0, d_c=1, M=np.eye(1))   # refreshed with the weights
                 c["bias"][site] = (bp, b)
             else:
                 c["bias"][site] = (b, None)
         t.finalize(dev)
-        return {"table": t, "c": c, "inv_sigma": inv_sigma, "sn_jobs": torch.from_numpy(jobs).to(dev), "n_sn": len(sn)}
+        return {"table": t, "c": c, "inv_sigma": inv_sigma, "sn_jobs": torch.from_numpy(jobs).to(dev), "n_sn": len(sn),
+                "sn_max": (int(max(j[3] & 0xffffffff for j in jobs)), int(max(j[3] >> 32 for j in jobs))),
+                "sn_norms": torch.zeros(2 * len(sn), device=dev, dtype=torch.float32)}
 
     def _prepare(self):
         """Per forward (the reference updates u, v and re-derives weight = w_bar / sigma on EVERY forward, :62-64):
-        one hwg_spectral_norm launch + one hwg_linear_map launch."""
+        hwg_spectral_norm (three small launches for all layers) + one hwg_linear_map launch."""
         ptrs = tuple(p.data_ptr() for p in self.parameters())
         if self._plan is None or self._plan_ptrs != ptrs:
             self._plan, self._plan_ptrs = self._build_plan(), ptrs
         p = self._plan
         self._generation += 1
-        _lib.call("hwg_spectral_norm", p["sn_jobs"].data_ptr(), p["n_sn"], p["inv_sigma"].data_ptr(), _lib.stream())
+        _lib.call("hwg_spectral_norm", p["sn_jobs"].data_ptr(), p["n_sn"], p["sn_max"][0], p["sn_max"][1],
+                  p["sn_norms"].data_ptr(), p["inv_sigma"].data_ptr(), _lib.stream())
         p["table"].run()
-        for bp, b in p["c"]["bias"].values():
-            if b is not None:
-                bp[:b.numel()].copy_(b)
         return p["c"]
 
-    def _drop_scale(self, site, B, C, dev):
-        """Dropout2d (:89 etc., inplace, training only): per-(sample, channel) keep-mask / (1-p) as [B,C,2] scale-shift
-        coefficients (a, 0); None in eval mode."""
+    def _drop_all(self, B, dev):
+        """Dropout2d (:89 etc., inplace, training only) of ALL sites in a handful of launches: per-(sample, channel)
+        keep-mask / (1-p) as scale-shift coefficients [B,C,2] = (scale, 0) for the fused LeakyReLU pass and as the
+        scale [B,C] the backward reads.  Returns {site: (coef, scale)}; {} in eval mode."""
         if not self.training:
-            return None
-        p = _DROP_P[site]
+            return {}
+        sites = [(s, p, self._site_channels[s]) for s, p in _DROP_P.items() if s in self._site_channels]
+        key = (B, str(dev))
+        if getattr(self, "_drop_const", None) is None or self._drop_const[0] != key:
+            p_flat = torch.cat([torch.full((B * C,), p, dtype=torch.float32) for _, p, C in sites]).to(dev)
+            self._drop_const = (key, p_flat, 1.0 / (1.0 - p_flat))
+        _, p_flat, inv_flat = self._drop_const
         if self.dropout_masks is not None:
-            keep = self.dropout_masks[site].to(dev).float()
+            keep = torch.cat([self.dropout_masks[s].to(dev).float().reshape(-1) for s, _, _ in sites])
+            scale = keep * inv_flat
         else:
-            keep = (torch.rand((B, C), device=dev) >= p).float()
-        coef = torch.zeros((B, C, 2), device=dev, dtype=torch.float32)
-        coef[:, :, 0] = keep / (1.0 - p)
-        return coef
+            scale = (torch.rand(p_flat.numel(), device=dev) >= p_flat).float().mul_(inv_flat)
+        coef = torch.zeros((p_flat.numel(), 2), device=dev, dtype=torch.float32)
+        coef[:, 0] = scale
+        out, off = {}, 0
+        for s, _, C in sites:
+            out[s] = (coef[off:off + B * C].view(B, C, 2), scale[off:off + B * C].view(B, C))
+            off += B * C
+        return out
 
     # -- forward ----------------------------------------------------------------------------------------------------
     def forward(self, x, return_features=False):
@@ -218,10 +245,11 @@ class DiscriminatorAP(nn.Module):
         dev = x.device
         dim = self.dim
         ctx = {"shape": (B, H, W)}
+        drops = self._drop_all(B, dev)
 
         def cv(a, site, taps, Ho, Wo, act=ACT_NONE, stats=None, out_dtype=torch.bfloat16):
             return conv.conv_fprop(a, c[site], taps, Ho, Wo, bias=c["bias"][site][0], act=act, slope=LEAK, stats=stats,
-                                   out_dtype=out_dtype)
+                                   out_dtype=out_dtype, tile_w=_tile_w(taps, Ho, Wo))
 
         def gn_lrelu(z, st, gn, tag):
             N, Hh, Ww, C = z.shape
@@ -237,14 +265,13 @@ class DiscriminatorAP(nn.Module):
         def conv_drop_lrelu(a, site, taps, Ho, Wo):
             """SN conv -> Dropout2d -> LeakyReLU: the channel scale rides on the activation pass (training), or the
             activation on the conv epilogue (eval)."""
-            C = c[site].size(1)
-            sc = self._drop_scale(site, B, C, dev)
-            if sc is None:
+            coef, scale = drops.get(site, (None, None))
+            if coef is None:
                 y = cv(a, site, taps, Ho, Wo, act=ACT_LRELU)
             else:
-                y = ops.scale_shift_act(cv(a, site, taps, Ho, Wo), sc, True, ACT_LRELU, LEAK)
+                y = ops.scale_shift_act(cv(a, site, taps, Ho, Wo), coef, True, ACT_LRELU, LEAK)
             if keep:
-                ctx[site] = (a, y, None if sc is None else sc[:, :, 0].contiguous())
+                ctx[site] = (a, y, scale)
             return y
 
         def pool(a, kh, kw):
@@ -308,7 +335,7 @@ class DiscriminatorAP(nn.Module):
 
         def dgrad(g, site, Ho, Wo):
             wd, taps = dg[site]
-            return conv.conv_fprop(g, wd, taps, Ho, Wo)
+            return conv.conv_fprop(g, wd, taps, Ho, Wo, tile_w=_tile_w(taps, Ho, Wo))
 
         def head_grad(g, like_w):
             """[B, Wp] fp32 prediction gradient -> [B,1,Wp,16] bf16 (channel 0 carries it)."""

@@ -452,11 +452,13 @@ int hwg_gn_bwd_coeffs(const float* sums, const float* save_mean_rstd, const floa
                       int64_t HW, float* spq, float* dgamma, float* dbeta, void* stream);
 int hwg_norm_bwd_apply(const void* g, const void* z, const float* coef, const float* spq, float slope, int N, int H,
                        int W, int C, int kh, int kw, void* gz, void* stream);
-/* SpectralNorm._update_u_v (:19-32), all wrapped layers in one launch (one block per layer): v = normalize(W^T u),
- * u = normalize(W v) written back in place, inv_sigma[layer] = 1 / (u . W v).  jobs_dev: device array of
- * { const float* w [h][wd]; float* u [h]; float* v [wd]; int32 h, wd } (32 bytes each).  The packed bf16
- * operands are then W * inv_sigma (hwgMapJob.scale_dev). */
-int hwg_spectral_norm(const void* jobs_dev, int njobs, float* inv_sigma, void* stream);
+/* SpectralNorm._update_u_v (:19-32) for all wrapped layers at once (three small launches over (layer, chunk)
+ * grids): v = normalize(W^T u), u = normalize(W v) written back in place, inv_sigma[layer] = 1 / (u . W v).
+ * jobs_dev: device array of { const float* w [h][wd]; float* u [h]; float* v [wd]; int32 h, wd } (32 bytes each);
+ * max_h / max_wd: largest h / wd over the jobs; norms_scratch: 2*njobs floats, zeroed once by the caller (the last
+ * launch leaves them zero).  The packed bf16 operands are then W * inv_sigma (hwgMapJob.scale_dev). */
+int hwg_spectral_norm(const void* jobs_dev, int njobs, int max_h, int max_wd, float* norms_scratch,
+                      float* inv_sigma, void* stream);
 
 /* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).

@@ -56,6 +56,11 @@ elif a.workload == "gen_train":
     hwr = pkg.CNNOnlyHWR(80, norm='batch').to(dev).train()
     for p in hwr.parameters():
         p.requires_grad_(False)
+    disc = None
+    if not os.environ.get("HWG_BENCH_NO_DISC"):
+        disc = pkg.DiscriminatorAP(64, use_low=True, use_med=True).to(dev).train()
+        for p in disc.parameters():
+            p.requires_grad_(False)
     opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
     gen._grad_sink = opt
     content, style = synth.gen_case(Ts, B, 80, 128, 3)
@@ -67,7 +72,11 @@ elif a.workload == "gen_train":
     mods = [gen, hwr]
 
     def step(c, s, tg):
-        loss = pkg.CTCLoss(hwr(gen(c, s)), tg, il, tl)
+        img = gen(c, s)
+        loss = 1e-4 * pkg.CTCLoss(hwr(img), tg, il, tl)
+        if disc is not None:
+            preds = disc(img)
+            loss = loss - (1.0 / len(preds)) * sum(p.mean() for p in preds)
         loss.backward()
         opt.step()
         return loss
