@@ -326,6 +326,61 @@ __global__ void __launch_bounds__(DT) sn_finish_kernel(const SnJob* __restrict__
   }
 }
 
+// ---- per-channel sum of an NHWC bf16 tensor (bias gradients of the discriminator's convolutions) ------------------
+template <int CV>
+__global__ void __launch_bounds__(DT)
+channel_sum_kernel(const uint4* __restrict__ x, long long rows, float* __restrict__ out) {
+  constexpr int LANES = DT / CV;
+  __shared__ float red[LANES][CV * 8 + 1];
+  const int cv = threadIdx.x % CV, lane = threadIdx.x / CV;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r = (long long)blockIdx.x * LANES + lane; r < rows; r += (long long)gridDim.x * LANES) {
+    float f[8];
+    unpack8d(x[r * CV + cv], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += f[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[lane][cv * 8 + k] = s[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 8; i += DT) {
+    float t = 0.f;
+#pragma unroll 4
+    for (int l = 0; l < LANES; ++l) t += red[l][i];
+    atomicAdd(out + i, t);
+  }
+}
+
+// ---- SpectralNorm backward: W_eff = W / sigma, sigma = u^T W v with u, v constants (discriminator_ap.py:30-32) ---
+// given dW1 = (dL/dW_eff) / sigma (the unpacked wgrad, already scaled):  dW = dW1 - (<dW1, W> / sigma) * u v^T
+struct SnGradJob { const float* w; float* gw; const float* u; const float* v; int h, wd; };
+__global__ void __launch_bounds__(DT) sn_grad_dot_kernel(const SnGradJob* __restrict__ jobs, float* __restrict__ dots) {
+  const SnGradJob j = jobs[blockIdx.y];
+  const long long n = (long long)j.h * j.wd;
+  __shared__ float red[DT / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < n; i += (long long)gridDim.x * DT)
+    acc = fmaf(j.gw[i], j.w[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < DT / 32; ++i) t += red[i];
+    if (t != 0.f) atomicAdd(dots + blockIdx.y, t);
+  }
+}
+__global__ void __launch_bounds__(DT) sn_grad_apply_kernel(const SnGradJob* __restrict__ jobs, const float* __restrict__ dots,
+                                                           const float* __restrict__ inv_sigma) {
+  const SnGradJob j = jobs[blockIdx.y];
+  const long long n = (long long)j.h * j.wd;
+  const float k = dots[blockIdx.y] * inv_sigma[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < n; i += (long long)gridDim.x * DT) {
+    const int r = (int)(i / j.wd), c = (int)(i % j.wd);
+    j.gw[i] -= k * j.u[r] * j.v[c];
+  }
+}
+
 bool cv_supported(int C) { return C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
 
 }  // namespace
@@ -435,4 +490,35 @@ extern "C" int hwg_spectral_norm(const void* jobs_dev, int njobs, int max_h, int
   if (int rc = check_launch("sn_wv_kernel")) return rc;
   sn_finish_kernel<<<njobs, DT, 0, s>>>(jobs, norms_scratch, inv_sigma);
   return check_launch("sn_finish_kernel");
+}
+
+extern "C" int hwg_channel_sum(const void* x, int64_t rows, int C, float* out, void* stream) {
+  HWG_REQUIRE(x && out && rows > 0, "hwg_channel_sum: bad argument");
+  HWG_REQUIRE(cv_supported(C), "hwg_channel_sum: C=%d not in {16,32,64,128,256}", C);
+  const int CV = C / 8, lanes = DT / CV;
+  long long bx = (rows + lanes - 1) / lanes;
+  if (bx > 148LL * 8) bx = 148LL * 8;
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (CV) {
+    case 2: channel_sum_kernel<2><<<(unsigned)bx, DT, 0, s>>>(xp, rows, out); break;
+    case 4: channel_sum_kernel<4><<<(unsigned)bx, DT, 0, s>>>(xp, rows, out); break;
+    case 8: channel_sum_kernel<8><<<(unsigned)bx, DT, 0, s>>>(xp, rows, out); break;
+    case 16: channel_sum_kernel<16><<<(unsigned)bx, DT, 0, s>>>(xp, rows, out); break;
+    default: channel_sum_kernel<32><<<(unsigned)bx, DT, 0, s>>>(xp, rows, out); break;
+  }
+  return check_launch("channel_sum_kernel");
+}
+
+extern "C" int hwg_spectral_norm_bwd(const void* jobs_dev, int njobs, int64_t max_elems, const float* inv_sigma,
+                                     float* dots_scratch, void* stream) {
+  HWG_REQUIRE(jobs_dev && inv_sigma && dots_scratch && njobs > 0 && max_elems > 0, "hwg_spectral_norm_bwd: bad argument");
+  const SnGradJob* jobs = reinterpret_cast<const SnGradJob*>(jobs_dev);
+  long long bx = (max_elems + DT * 8 - 1) / (DT * 8);
+  if (bx > 64) bx = 64;
+  cudaStream_t s = (cudaStream_t)stream;
+  sn_grad_dot_kernel<<<dim3((unsigned)bx, njobs), DT, 0, s>>>(jobs, dots_scratch);
+  if (int rc = check_launch("sn_grad_dot_kernel")) return rc;
+  sn_grad_apply_kernel<<<dim3((unsigned)bx, njobs), DT, 0, s>>>(jobs, dots_scratch, inv_sigma);
+  return check_launch("sn_grad_apply_kernel");
 }

@@ -228,13 +228,10 @@ class DiscriminatorAP(nn.Module):
         _lib.require_cuda(x)
         if return_features:
             raise NotImplementedError("return_features=True is not used by the training step")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "DiscriminatorAP: gradients with respect to the discriminator's weights (the 'disc' lesson) are not "
-                "built yet; freeze the parameters (requires_grad_(False)) for the generator's adversarial loss")
-        if torch.is_grad_enabled() and x.requires_grad:
-            outs = _DiscFn.apply(self, x)
-            return list(outs)
+        if torch.is_grad_enabled():
+            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            if named or x.requires_grad:
+                return list(_DiscFn.apply(self, tuple(n for n, _ in named), x, *[p for _, p in named]))
         outs, _ = self._forward_impl(x, keep=False)
         return outs
 
@@ -282,6 +279,8 @@ class DiscriminatorAP(nn.Module):
 
         x7 = torch.empty((B, H, W, 16), device=dev, dtype=torch.bfloat16)
         _lib.call("hwg_shift_expand", x.data_ptr(), x7.data_ptr(), B, H, W, 7, 3, _lib.stream())
+        if keep:
+            ctx["x7"] = x7
         st = torch.zeros((B, dim, 2), device=dev, dtype=torch.float32)
         z0 = cv(x7, "in_conv.0", [(dy, 0) for dy in range(7)], H - 6, W, stats=st)
         a = gn_lrelu(z0, st, self.in_conv[1], "gn0")                                  # [B,58,W,64]
@@ -324,14 +323,106 @@ class DiscriminatorAP(nn.Module):
             ctx["out_shapes"] = [tuple(o.shape) for o in outs]
         return outs, ctx
 
-    # -- backward to the image -----------------------------------------------------------------------------------
-    def _backward_input(self, ctx, grads):
+    # -- backward ---------------------------------------------------------------------------------------------------
+    def _wgrad_plan(self, dev):
+        """Arena layout of one backward's accumulators (tap-major wgrad outputs, bias / GroupNorm sums, spectral-norm
+        dots), the persistent flat buffer the parameter gradients are unpacked into, ONE hwg_linear_map table for the
+        unpack (scaled by 1/sigma for the spectral-normalised layers) and the hwg_spectral_norm_bwd job table."""
+        plan = self._plan.get("wgrad")
+        if plan is not None:
+            return plan
+        layers = self.conv_layers()
+        params = dict(self.named_parameters())
+        inv_sigma, sn_sites = self._plan["inv_sigma"], [s for s, _, _, sp in layers if sp]
+        off, slots = 0, {}
+
+        def take(name, n):
+            nonlocal off
+            slots[name] = (off, n)
+            off += -(-n // 4) * 4
+
+        goff, gn_el = {}, 0
+
+        def gslot(pname):
+            nonlocal gn_el
+            goff[pname] = gn_el
+            gn_el += -(-params[pname].numel() // 4) * 4
+
+        meta = {}
+        for site, m, taps, spectral in layers:
+            wname = site + (".module.weight_bar" if spectral else ".weight")
+            bname = site + (".module.bias" if spectral else ".bias")
+            co, ci = m.bias.numel(), (16 if site == "in_conv.0" else params[wname].size(1))
+            cop = -(-co // 16) * 16
+            take(("w", site), len(taps) * cop * ci)
+            take(("b", site), cop)
+            gslot(wname)
+            gslot(bname)
+            meta[site] = (wname, bname, co, cop, ci, taps, spectral)
+        for gname in ("in_conv.1", "convs3.1"):
+            C = params[gname + ".weight"].numel()
+            take(("gamma", gname), C)
+            take(("beta", gname), C)
+            gslot(gname + ".weight")
+            gslot(gname + ".bias")
+        take("dots", len(sn_sites))
+        gflat = torch.zeros(gn_el, device=dev, dtype=torch.float32)
+        t = weightmap.JobTable()
+        sn_jobs = np.zeros((len(sn_sites), 5), np.int64)
+        for site, (wname, bname, co, cop, ci, taps, spectral) in meta.items():
+            gw = gflat[goff[wname]:goff[wname] + params[wname].numel()]
+            src = 4 * slots[("w", site)][0]
+            if site == "in_conv.0":
+                for dy in range(7):           # dw [7][64][16] -> gW[co, 0, dy, dx]
+                    t.add(src + 4 * dy * cop * 16, gw[dy * 7:], R=co, C=7, s_r=16, s_c=1, d_r=49, d_c=1, M=np.eye(1))
+            else:
+                scale = inv_sigma[sn_sites.index(site):sn_sites.index(site) + 1] if spectral else None
+                weightmap.map_conv_taps(co, ci, taps).add_unpack_wgrad(t, src, gw, co_rows=cop, scale_dev=scale)
+            t.add(4 * slots[("b", site)][0], gflat[goff[bname]:goff[bname] + co], R=1, C=co, s_r=0, s_c=1, d_r=0, d_c=1,
+                  M=np.eye(1))
+            if spectral:
+                i = sn_sites.index(site)
+                mod = dict((s_, m_) for s_, m_, _, _ in layers)[site]
+                w = mod.weight_bar
+                sn_jobs[i] = (w.data_ptr(), gw.data_ptr(), mod.weight_u.data_ptr(), mod.weight_v.data_ptr(),
+                              w.size(0) | (w[0].numel() << 32))
+        for gname in ("in_conv.1", "convs3.1"):
+            for kind, suffix in (("gamma", ".weight"), ("beta", ".bias")):
+                C = params[gname + suffix].numel()
+                t.add(4 * slots[(kind, gname)][0], gflat[goff[gname + suffix]:goff[gname + suffix] + C], R=1, C=C, s_r=0,
+                      s_c=1, d_r=0, d_c=1, M=np.eye(1))
+        t.finalize(dev)
+        plan = self._plan["wgrad"] = dict(
+            slots=slots, arena_floats=off, meta=meta, gflat=gflat, goff=goff, table=t,
+            sn_jobs=torch.from_numpy(sn_jobs).to(dev), n_sn=len(sn_sites),
+            sn_max=int(max((j[4] & 0xffffffff) * (j[4] >> 32) for j in sn_jobs)))
+        return plan
+
+    def _backward(self, ctx, grads, want_input, names):
+        """grads: prediction gradients.  Returns (image gradient or None, {parameter name: gradient} for `names`)."""
         B, H, W = ctx["shape"]
         if ctx["generation"] != self._generation:
             raise RuntimeError("DiscriminatorAP: backward after another forward of the same module — the spectral-norm "
                                "operands of this graph have been re-packed (run backward before the next forward)")
         dg = ctx["dgrad"]
         dev = ctx["mL"].device
+        want_w = bool(names)
+        if want_w:
+            wp = self._wgrad_plan(dev)
+            arena = torch.zeros(wp["arena_floats"], device=dev, dtype=torch.float32)      # one memset
+
+            def slot(key):
+                o, n = wp["slots"][key]
+                return arena[o:o + n]
+
+        def collect(site, x_in, gz):
+            """Weight and bias gradient of one convolution from its input and its output gradient."""
+            if not want_w:
+                return
+            wname, bname, co, cop, ci, taps, _ = wp["meta"][site]
+            conv.conv_wgrad(x_in, gz, taps, ci, cop, out=slot(("w", site)).view(len(taps), cop, ci))
+            _lib.call("hwg_channel_sum", gz.data_ptr(), gz.numel() // gz.size(-1), gz.size(-1),
+                      slot(("b", site)).data_ptr(), _lib.stream())
 
         def dgrad(g, site, Ho, Wo):
             wd, taps = dg[site]
@@ -351,7 +442,7 @@ class DiscriminatorAP(nn.Module):
                       gz.data_ptr(), _lib.stream())
             return gz, a_in
 
-        def gn_bwd(g, tag, gn, kh, kw):
+        def gn_bwd(g, tag, gn, kh, kw, gname):
             z, coef, save = ctx[tag]
             N, Hh, Ww, C = z.shape
             sums = torch.zeros((N, C, 2), device=dev, dtype=torch.float32)
@@ -361,7 +452,8 @@ class DiscriminatorAP(nn.Module):
             _lib.call("hwg_norm_bwd_reduce", g.data_ptr(), z.data_ptr(), coef.data_ptr(), LEAK, N, Hh, Ww, C, kh, kw,
                       sums.data_ptr(), s)
             _lib.call("hwg_gn_bwd_coeffs", sums.data_ptr(), save.data_ptr(), gn.weight.data_ptr(), N, C, gn.num_groups,
-                      Hh * Ww, spq.data_ptr(), None, None, s)
+                      Hh * Ww, spq.data_ptr(), slot(("gamma", gname)).data_ptr() if want_w else None,
+                      slot(("beta", gname)).data_ptr() if want_w else None, s)
             _lib.call("hwg_norm_bwd_apply", g.data_ptr(), z.data_ptr(), coef.data_ptr(), spq.data_ptr(), LEAK, N, Hh, Ww,
                       C, kh, kw, gz.data_ptr(), s)
             return gz
@@ -370,43 +462,73 @@ class DiscriminatorAP(nn.Module):
         g_mL = None
         gi = 0
         if self.use_med:
-            g_mL = dgrad(head_grad(grads[gi], mL.size(2)), "finalMed.0", mL.size(1), mL.size(2))
+            g16 = head_grad(grads[gi], mL.size(2))
+            collect("finalMed.0", mL, g16)
+            g_mL = dgrad(g16, "finalMed.0", mL.size(1), mL.size(2))
             gi += 1
         if self.use_low:
             a = ctx["low_in"]
-            g = dgrad(head_grad(grads[gi], a.size(2)), "convs4.14", 1, a.size(2))
+            g16 = head_grad(grads[gi], a.size(2))
+            collect("convs4.14", a, g16)
+            g = dgrad(g16, "convs4.14", 1, a.size(2))
             gz, a_in = act_bwd(g, "convs4.11")
+            collect("convs4.11", a_in, gz)
             g = dgrad(gz, "convs4.11", 1, a_in.size(2))                    # gradient of the pooled tensor
             gz, a_in = act_bwd(g, "convs4.7", 1, 2)
+            collect("convs4.7", a_in, gz)
             g = dgrad(gz, "convs4.7", 1, a_in.size(2))
             gz, a_in = act_bwd(g, "convs4.4")
+            collect("convs4.4", a_in, gz)
             g = dgrad(gz, "convs4.4", 1, a_in.size(2))                     # pooled again
             gz, a_in = act_bwd(g, "convs4.0", 1, 2)
+            collect("convs4.0", a_in, gz)
             g_low = dgrad(gz, "convs4.0", mL.size(1), mL.size(2))
             g_mL = g_low if g_mL is None else g_mL.add_(g_low)
         gz, a_in = act_bwd(g_mL, "convs3.4")
+        collect("convs3.4", a_in, gz)
         g = dgrad(gz, "convs3.4", a_in.size(1), a_in.size(2))              # [B,5,W/8,128], gradient of pool(a4)
-        gz = gn_bwd(g, "gn4", self.convs3[1], 2, 2)
+        gz = gn_bwd(g, "gn4", self.convs3[1], 2, 2, "convs3.1")
         a_in = ctx["convs3.0"]
+        collect("convs3.0", a_in, gz)
         g = dgrad(gz, "convs3.0", a_in.size(1), a_in.size(2))              # [B,12,W/4,128], gradient of pool(y3)
         gz, a_in = act_bwd(g, "convs2.0", 2, 2)
+        collect("convs2.0", a_in, gz)
         g = dgrad(gz, "convs2.0", a_in.size(1), a_in.size(2))
         gz, a_in = act_bwd(g, "convs1.3")
+        collect("convs1.3", a_in, gz)
         g = dgrad(gz, "convs1.3", a_in.size(1), a_in.size(2))              # [B,28,W/2,64], gradient of pool(y1)
         gz, a_in = act_bwd(g, "convs1.0", 2, 2)
+        collect("convs1.0", a_in, gz)
         g = dgrad(gz, "convs1.0", a_in.size(1), a_in.size(2))              # [B,58,W,64]
-        gz = gn_bwd(g, "gn0", self.in_conv[1], 1, 1)
-        g7 = dgrad(gz, "in_conv.0", H, W)                                  # [B,64,W,16]
-        dimg = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
-        _lib.call("hwg_shift_collapse", g7.data_ptr(), dimg.data_ptr(), B, H, W, 7, 3, 0, _lib.stream())
-        return dimg
+        gz = gn_bwd(g, "gn0", self.in_conv[1], 1, 1, "in_conv.1")
+        collect("in_conv.0", ctx["x7"], gz)
+        dimg = None
+        if want_input:
+            g7 = dgrad(gz, "in_conv.0", H, W)                              # [B,64,W,16]
+            dimg = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+            _lib.call("hwg_shift_collapse", g7.data_ptr(), dimg.data_ptr(), B, H, W, 7, 3, 0, _lib.stream())
+        pgrads = {}
+        if want_w:
+            # every parameter gradient in its own layout by ONE launch (spectral layers scaled by 1/sigma), then the
+            # rank-one spectral-norm term for all layers
+            wp["table"].run(src_base=arena)
+            _lib.call("hwg_spectral_norm_bwd", wp["sn_jobs"].data_ptr(), wp["n_sn"], wp["sn_max"],
+                      self._plan["inv_sigma"].data_ptr(), slot("dots").data_ptr(), _lib.stream())
+            params = dict(self.named_parameters())
+            gout = wp["gflat"].clone()      # autograd may adopt a returned gradient as .grad: never hand out the workspace
+            for n in names:
+                o = wp["goff"][n]
+                pgrads[n] = gout[o:o + params[n].numel()].view_as(params[n])
+        return dimg, pgrads
 
 
 class _DiscFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, m, x):
-        outs, saved = m._forward_impl(x, keep=True)
-        ctx.m, ctx.saved = m, saved
+    def forward(ctx, m, names, x, *params):
+        with torch.no_grad():
+            outs, saved = m._forward_impl(x, keep=True)
+        ctx.m, ctx.names, ctx.saved = m, names, saved
+        ctx.x_needs_grad = x.requires_grad
         return tuple(outs)
 
     @staticmethod
@@ -414,4 +536,7 @@ class _DiscFn(torch.autograd.Function):
         dev = ctx.saved["mL"].device
         grads = [torch.zeros(shp, device=dev) if g is None else g.contiguous().float()
                  for g, shp in zip(grads, ctx.saved["out_shapes"])]
-        return None, ctx.m._backward_input(ctx.saved, grads)
+        with torch.no_grad():
+            dimg, pg = ctx.m._backward(ctx.saved, grads, ctx.x_needs_grad, ctx.names)
+        ctx.saved = None
+        return (None, None, dimg) + tuple(pg[n] for n in ctx.names)

@@ -136,14 +136,14 @@ class ConvMap:
     def dgrad_shape(self):
         return (self.Td, -(-self.Ci // 16) * 16, self.Cop)
 
-    def add_unpack_wgrad(self, table, dw_src, g_dst, Cip=None, accumulate=False, co_rows=None):
+    def add_unpack_wgrad(self, table, dw_src, g_dst, Cip=None, accumulate=False, co_rows=None, scale_dev=None):
         """dw_src fp32 [Tf][co_rows][Cip] (hwg_conv_wgrad layout; co_rows >= Co when the launch padded the output
         channels) -> g_dst in the parameter's layout."""
         Cip = Cip or self.Cip
         co_rows = co_rows or self.Co
         table.add(dw_src, g_dst, R=self.Co, C=self.Ci, s_r=Cip, s_c=1, d_r=self.s_co, d_c=self.s_ci,
                   M=self.Af.T.copy(), in_off=[t * co_rows * Cip for t in range(self.Tf)],
-                  out_off=list(range(self.K)), accumulate=accumulate)
+                  out_off=list(range(self.K)), accumulate=accumulate, scale_dev=scale_dev)
 
 
 # ---- the generator's convolution flavours (model/pure_gen.py) -------------------------------------------------

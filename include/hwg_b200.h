@@ -459,6 +459,16 @@ int hwg_norm_bwd_apply(const void* g, const void* z, const float* coef, const fl
  * launch leaves them zero).  The packed bf16 operands are then W * inv_sigma (hwgMapJob.scale_dev). */
 int hwg_spectral_norm(const void* jobs_dev, int njobs, int max_h, int max_wd, float* norms_scratch,
                       float* inv_sigma, void* stream);
+/* out[c] += sum over rows of x[row, c] (x bf16 [rows, C] NHWC): bias gradients of the discriminator's convolutions
+ * (autograd's sum over (n, h, w) of the output gradient).  out is zeroed by the caller. */
+int hwg_channel_sum(const void* x, int64_t rows, int C, float* out, void* stream);
+/* Backward of SpectralNorm (:30-32: weight = w_bar / sigma, sigma = u . (W v), u and v constants) for all wrapped
+ * layers (two launches): given gw = (dL/dweight) / sigma in the parameter layout (the unpacked wgrad, already scaled
+ * by inv_sigma), in place  gw -= (<gw, w_bar> * inv_sigma[layer]) * u v^T.
+ * jobs_dev: device array of { const float* w_bar; float* gw; const float* u; const float* v; int32 h, wd } (40 bytes);
+ * max_elems = largest h*wd; dots_scratch: njobs floats, zeroed by the caller. */
+int hwg_spectral_norm_bwd(const void* jobs_dev, int njobs, int64_t max_elems, const float* inv_sigma,
+                          float* dots_scratch, void* stream);
 
 /* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).

@@ -181,6 +181,10 @@ DISC_CASES = {
 }
 
 
+# 'disc' lesson: hinge loss on real || fake rows, gradients of every trainable parameter.  name -> (B, W, wseed, iseed)
+DISC_LESSON_CASES = {"hinge_w128": (4, 128, 300, 304), "hinge_w200": (2, 200, 300, 305)}
+
+
 def make_disc():
     """Outputs, generator-loss input gradient and updated spectral-norm vectors of the unmodified reference
     DiscriminatorAP (IAM GAN config: dim 64, 'use low', med on).  Dropout2d keep-masks are injected by patching
@@ -229,6 +233,38 @@ def make_disc():
         for k in ("convs1.0.module.weight_u", "convs3.4.module.weight_v", "convs4.14.module.weight_u"):
             out[f"{name}/{k}"] = sd2[k].numpy()
         print(f"disc/{name}: B={B} W={W} train={training} -> {[tuple(p.shape) for p in preds]} loss {loss.item():.5f}")
+    for name, (B, W, wseed, iseed) in DISC_LESSON_CASES.items():
+        torch.manual_seed(wseed)
+        m = DiscriminatorAP(64, use_low=True, use_med=True)
+        synth.perturb_disc(m.state_dict(), wseed + 1)
+        m.train()
+        masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(B, iseed + 7).items()}
+        order = iter(odisc.DROPOUT_ORDER)
+        orig = F.dropout2d
+
+        def fake_dropout2d(x, p=0.5, training=True, inplace=False):
+            site = next(order)
+            return x * (masks[site] / (1.0 - p))[:, :, None, None]
+
+        F.dropout2d = fake_dropout2d
+        try:
+            preds = m(torch.from_numpy(synth.hwr_case(B, W, iseed)))
+            # trainer/hw_with_style_trainer.py:797-804 (real rows first, then fake)
+            loss = 0
+            for pr in preds:
+                loss = loss + F.relu(1.0 - pr[:B // 2]).mean() + F.relu(1.0 + pr[B // 2:]).mean()
+            loss = loss / len(preds)
+            loss.backward()
+        finally:
+            F.dropout2d = orig
+        out[f"{name}/loss"] = np.float32(loss.item())
+        names = [n for n, p in m.named_parameters() if p.requires_grad]
+        out[f"{name}/param_names"] = np.array(names)
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                dig, samp = digest(p.grad.numpy())
+                out[f"{name}/grad/{n}/digest"], out[f"{name}/grad/{n}/sample"] = dig, samp
+        print(f"disc/{name}: B={B} W={W} hinge loss {loss.item():.5f}, {len(names)} parameter gradients")
     np.savez_compressed(os.path.join(GOLD, "disc.npz"), **out)
 
 

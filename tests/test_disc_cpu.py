@@ -52,7 +52,33 @@ def test_disc_oracle_matches_reference_golden(name, golden_dir):
         assert np.abs(update[k].numpy() - gold[f"{name}/{k}"]).max() <= 1e-5
 
 
-def test_disc_module_refuses_cpu_and_weight_grads():
+def test_disc_module_refuses_cpu_tensors():
     m, _ = disc_module(1)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 64, 64))
+
+
+def lesson_oracle_grads(sd, B, W, iseed, emulate_bf16=False):
+    """Hinge-loss ('disc' lesson) gradients of every trainable parameter through the oracle."""
+    masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(B, iseed + 7).items()}
+    leaf = {k: v.clone().requires_grad_(not k.endswith(("weight_u", "weight_v"))) for k, v in sd.items()}
+    preds = odisc.disc_forward(leaf, torch.from_numpy(synth.hwr_case(B, W, iseed)), masks, training=True,
+                               emulate_bf16=emulate_bf16)
+    loss = odisc.hinge_loss(preds, B // 2)
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in leaf.items() if v.requires_grad}
+
+
+@pytest.mark.parametrize("name", ["hinge_w128", "hinge_w200"])
+def test_disc_oracle_parameter_gradients_match_reference_golden(name, golden_dir):
+    from oracle.make_golden import DISC_LESSON_CASES
+    gold = np.load(f"{golden_dir}/disc.npz")
+    B, W, wseed, iseed = DISC_LESSON_CASES[name]
+    _, sd = disc_module(wseed)
+    loss, grads = lesson_oracle_grads(sd, B, W, iseed)
+    assert abs(loss - float(gold[f"{name}/loss"])) <= FP32_REL * abs(float(gold[f"{name}/loss"]))
+    assert sorted(grads) == sorted(gold[f"{name}/param_names"].tolist())
+    for n, g in grads.items():
+        dig = gold[f"{name}/grad/{n}/digest"]
+        _, samp = digest(g.numpy())
+        assert np.abs(samp - gold[f"{name}/grad/{n}/sample"]).max() <= FP32_REL * dig[3] + 1e-9, n

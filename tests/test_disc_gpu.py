@@ -211,7 +211,7 @@ def test_discriminator_matches_reference_golden(name, golden_dir):
     assert e <= 1.3 * e_emul + 2e-2 and cos >= 0.95, (e, e_emul, cos)
 
 
-def test_discriminator_eval_no_grad_and_weight_grad_refusal():
+def test_discriminator_eval_no_grad():
     m, sd = _module(11, False)
     x = torch.from_numpy(synth.hwr_case(2, 96, 5)).cuda()
     with torch.no_grad():
@@ -219,6 +219,80 @@ def test_discriminator_eval_no_grad_and_weight_grad_refusal():
     ref = odisc.disc_forward(sd, torch.from_numpy(synth.hwr_case(2, 96, 5)), None, training=False)
     for p, r in zip(preds, ref):
         assert _rel_l2(p.cpu(), r) <= 2e-2
-    m.in_conv[0].weight.requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        m(x)
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 64), (37, 16), (513, 256)])
+def test_channel_sum(rows, C):
+    from handwriting_line_generation_b200 import _lib
+    x = torch.randn(rows, C, generator=torch.Generator().manual_seed(rows)).to(torch.bfloat16).cuda()
+    out = torch.zeros(C, device="cuda")
+    _lib.call("hwg_channel_sum", x.data_ptr(), rows, C, out.data_ptr(), _lib.stream())
+    assert _rel(out.cpu(), x.double().cpu().sum(0)) <= 1e-5
+
+
+def test_spectral_norm_backward_matches_autograd():
+    from handwriting_line_generation_b200 import _lib
+    g0 = torch.Generator().manual_seed(3)
+    shapes = [(64, 576), (1, 2304), (256, 1152)]
+    jobs = np.zeros((len(shapes), 5), np.int64)
+    keep, refs = [], []
+    inv = torch.empty(len(shapes))
+    for i, (h, wd) in enumerate(shapes):
+        w = torch.randn(h, wd, generator=g0, dtype=torch.float64).requires_grad_()
+        u = F.normalize(torch.randn(h, generator=g0, dtype=torch.float64), dim=0)
+        v = F.normalize(torch.randn(wd, generator=g0, dtype=torch.float64), dim=0)
+        G = torch.randn(h, wd, generator=g0, dtype=torch.float64)
+        sigma = u.dot(w.mv(v))
+        ((w / sigma) * G).sum().backward()
+        refs.append(w.grad)
+        inv[i] = 1.0 / sigma.item()
+        wd_, gw, ud, vd = w.detach().float().cuda(), (G / sigma.item()).float().cuda(), u.float().cuda(), v.float().cuda()
+        keep.append((wd_, gw, ud, vd))
+        jobs[i] = (wd_.data_ptr(), gw.data_ptr(), ud.data_ptr(), vd.data_ptr(), h | (wd << 32))
+    jd, invd = torch.from_numpy(jobs).cuda(), inv.cuda()
+    dots = torch.zeros(len(shapes), device="cuda")
+    _lib.call("hwg_spectral_norm_bwd", jd.data_ptr(), len(shapes), max(h * w for h, w in shapes), invd.data_ptr(),
+              dots.data_ptr(), _lib.stream())
+    for (_, gw, _, _), ref in zip(keep, refs):
+        assert _rel(gw.cpu(), ref) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["hinge_w128", "hinge_w200"])
+def test_discriminator_lesson_parameter_gradients(name, golden_dir):
+    """'disc' lesson: hinge loss on real || fake rows, gradient of every trainable parameter against the oracle (itself
+    pinned to the reference's gradients on CPU); bf16 pipeline bound as in DESIGN §5."""
+    from oracle.make_golden import DISC_LESSON_CASES
+    from tests.test_disc_cpu import lesson_oracle_grads
+    gold = np.load(f"{golden_dir}/disc.npz")
+    B, W, wseed, iseed = DISC_LESSON_CASES[name]
+    from handwriting_line_generation_b200 import DiscriminatorAP
+    torch.manual_seed(wseed)
+    m = DiscriminatorAP(64, use_low=True, use_med=True)
+    sd = {k: v.clone() for k, v in synth.perturb_disc(m.state_dict(), wseed + 1).items()}
+    m = m.cuda().train()
+    m.dropout_masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(B, iseed + 7).items()}
+    preds = m(torch.from_numpy(synth.hwr_case(B, W, iseed)).cuda())
+    loss = odisc.hinge_loss(preds, B // 2)
+    loss.backward()
+    assert abs(loss.item() - float(gold[f"{name}/loss"])) <= 2e-2 * abs(float(gold[f"{name}/loss"]))
+    _, ref = lesson_oracle_grads(sd, B, W, iseed)
+    _, emu = lesson_oracle_grads(sd, B, W, iseed, emulate_bf16=True)
+    got = {n: p.grad for n, p in m.named_parameters() if p.requires_grad}
+    assert sorted(got) == sorted(ref)
+    worst = {}
+    for n in ref:
+        assert got[n] is not None and got[n].shape == ref[n].shape, n
+        if ref[n].abs().max() < 1e-7:      # e.g. the bias of a head when every hinge term is active: +1/n and -1/n cancel
+            assert got[n].abs().max() <= 1e-4, n
+            continue
+        e, e_emu = _rel_l2(got[n].cpu(), ref[n]), _rel_l2(emu[n], ref[n])
+        cos = F.cosine_similarity(got[n].cpu().double().flatten(), ref[n].double().flatten(), dim=0).item()
+        worst[n] = (e, e_emu, cos)
+        assert e <= 1.3 * e_emu + 2e-2 and cos >= 0.95, (n, e, e_emu, cos)
+    # a second backward through a fresh forward must not alias the first gradients (the unpack workspace is reused)
+    g_first = {n: g.clone() for n, g in got.items()}
+    for p in m.parameters():
+        p.grad = None
+    odisc.hinge_loss(m(torch.from_numpy(synth.hwr_case(B, W, iseed)).cuda()), B // 2).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
+    assert all(torch.equal(got[n], g_first[n]) for n in g_first)
