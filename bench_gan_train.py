@@ -373,6 +373,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             torch.cuda.empty_cache()
             line["extra_workloads"] = bench_hwr_train.quick_train_numbers(dev, gen_lesson=False)
             line["extra_workloads"].update(quick_gen_infer(dev))
+            line["extra_workloads"].update(quick_disc_lesson(dev))
         except Exception as e:   # never lose the headline over the extras
             line["extra_workloads"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
@@ -409,3 +410,46 @@ def quick_gen_infer(dev, steps=20):
     return {"gen_infer_B32": {"ms_per_step": ms, "lines_per_s": B / ms * 1e3,
                               "what": "BASELINE configs[1]: SpacedGenerator inference, 32 lines of 64x1024 px, one "
                                       "replayed CUDA graph per step (full line: bench.py --workload gen_infer)"}}
+
+
+def quick_disc_lesson(dev, steps=20):
+    """The 'disc' lesson of the GAN cycle (trainer/hw_with_style_trainer.py:785-804): generator forward without
+    gradients, DiscriminatorAP on real || fake rows (2 x 16 lines), hinge loss, backward to all discriminator
+    weights (tcgen05 wgrad, spectral-norm backward), clip + Adam on the discriminator; one replayed CUDA graph."""
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import graphs
+    from oracle import synth
+    B, Ts = GAN["B"], GAN["Ts"]
+    torch.manual_seed(0)
+    gen = pkg.SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False,
+                              append_style=True, small=False).to(dev).eval()
+    disc = pkg.DiscriminatorAP(64, use_low=True, use_med=True).to(dev).train()
+    opt = pkg.FlatAdam([p for p in disc.parameters() if p.requires_grad], lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
+    content, style = synth.gen_case(Ts, B, GAN["C"], GAN["style"], 5)
+    c, s = torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev)
+    real = torch.from_numpy(synth.hwr_case(B, 4 * Ts, 11)).to(dev)
+
+    def step(c, s, real):
+        with torch.no_grad():
+            fake = gen(c, s)
+        preds = disc(torch.cat((real, fake), 0))
+        loss = sum(torch.relu(1.0 - p[:B]).mean() + torch.relu(1.0 + p[B:]).mean() for p in preds) / len(preds)
+        loss.backward()
+        opt.step()
+        return loss
+
+    g = graphs.GraphedStep(step, [c, s, real], modules=[gen], warmup=3)
+    for _ in range(3):
+        g(c, s, real)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g(c, s, real)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"disc_lesson_B16": {"ms_per_step": ms, "lines_per_s": B / ms * 1e3, "loss": float(g.static_out),
+                                "what": "GAN 'disc' lesson: generator forward (no grad) + DiscriminatorAP fwd+bwd on "
+                                        "16 real + 16 generated lines, hinge loss, Adam on the discriminator; lines/s "
+                                        "counts the 16 lines of the batch; one replayed CUDA graph"}}

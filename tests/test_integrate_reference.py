@@ -31,15 +31,15 @@ def test_hwwithstyle_builds_with_the_drop_ins_and_matches_the_reference_state_di
     try:
         hws = importlib.import_module("model.hw_with_style")
         mloss = importlib.import_module("model.loss")
-        orig = (hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss)
+        orig = (hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss, hws.DiscriminatorAP)
         ref_model = _build()
-        from handwriting_line_generation_b200 import CNNOnlyHWR, CTCLoss, SpacedGenerator, integrate
+        from handwriting_line_generation_b200 import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator, integrate
         swapped = integrate.install()
         try:
             assert ("model.hw_with_style", "SpacedGenerator") in swapped and ("model.loss", "CTCLoss") in swapped
             ours = _build()
         finally:
-            hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss = orig
+            hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss, hws.DiscriminatorAP = orig
     finally:
         os.chdir(cwd)
         sys.path[:] = saved_path                   # leave the interpreter as we found it for the other tests
@@ -48,11 +48,12 @@ def test_hwwithstyle_builds_with_the_drop_ins_and_matches_the_reference_state_di
         else:
             sys.modules.pop("datasets", None)
     assert isinstance(ours.generator, SpacedGenerator) and isinstance(ours.hwr, CNNOnlyHWR)
+    assert isinstance(ours.discriminator, DiscriminatorAP) and ours.discriminator.use_low and ours.discriminator.use_med
     assert mloss.CTCLoss is orig[2] and CTCLoss is not orig[2]
     a, b = ref_model.state_dict(), ours.state_dict()
     # our modules add no persistent state; the reference's blur buffers etc. keep their names
     assert set(a) == set(b), (sorted(set(a) ^ set(b))[:10])
     for k in a:
         assert a[k].shape == b[k].shape, k
-        if k.startswith(("generator.", "hwr.")) and a[k].is_floating_point():
+        if k.startswith(("generator.", "hwr.", "discriminator.")) and a[k].is_floating_point():
             assert torch.equal(a[k], b[k]), k           # same seed, same construction order -> same init
