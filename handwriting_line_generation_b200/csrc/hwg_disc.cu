@@ -268,13 +268,14 @@ norm_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, 
 struct SnJob { const float* w; float* u; float* v; int h, wd; };
 constexpr int SN_ROWS = 8;                         // rows (warps) per block in the W v pass
 
+constexpr int SN_COLS = 32, SN_RG = DT / SN_COLS;   // a block owns 32 columns; 8 row groups split the rows of a column
 __global__ void __launch_bounds__(DT) sn_wtu_kernel(const SnJob* __restrict__ jobs, float* __restrict__ norms) {
   const SnJob j = jobs[blockIdx.y];
-  if ((int)blockIdx.x * DT >= j.wd) return;
+  if ((int)blockIdx.x * SN_COLS >= j.wd) return;
   __shared__ float us[1024];
-  __shared__ float red[DT / 32];
-  float part = 0.f;
-  const int c = blockIdx.x * DT + threadIdx.x;
+  __shared__ float part[SN_RG][SN_COLS + 1];
+  const int cx = threadIdx.x % SN_COLS, rg = threadIdx.x / SN_COLS;
+  const int c = blockIdx.x * SN_COLS + cx;
   float acc = 0.f;
   for (int r0 = 0; r0 < j.h; r0 += 1024) {
     const int nr = min(1024, j.h - r0);
@@ -284,17 +285,19 @@ __global__ void __launch_bounds__(DT) sn_wtu_kernel(const SnJob* __restrict__ jo
     if (c < j.wd) {
       const float* wc = j.w + (size_t)r0 * j.wd + c;
 #pragma unroll 8
-      for (int r = 0; r < nr; ++r) acc = fmaf(__ldg(wc + (size_t)r * j.wd), us[r], acc);
+      for (int r = rg; r < nr; r += SN_RG) acc = fmaf(__ldg(wc + (size_t)r * j.wd), us[r], acc);
     }
   }
-  if (c < j.wd) { j.v[c] = acc; part = acc * acc; }
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  part[rg][cx] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (rg == 0) {                                   // warp 0: one lane per column
     float t = 0.f;
-    for (int i = 0; i < DT / 32; ++i) t += red[i];
-    atomicAdd(norms + 2 * blockIdx.y, t);
+#pragma unroll
+    for (int g = 0; g < SN_RG; ++g) t += part[g][cx];
+    float sq = 0.f;
+    if (c < j.wd) { j.v[c] = t; sq = t * t; }
+    sq = warp_sum(sq);
+    if (cx == 0) atomicAdd(norms + 2 * blockIdx.y, sq);
   }
 }
 
@@ -484,7 +487,7 @@ extern "C" int hwg_spectral_norm(const void* jobs_dev, int njobs, int max_h, int
   HWG_REQUIRE(jobs_dev && inv_sigma && norms_scratch && njobs > 0 && max_h > 0 && max_wd > 0, "hwg_spectral_norm: bad argument");
   const SnJob* jobs = reinterpret_cast<const SnJob*>(jobs_dev);
   cudaStream_t s = (cudaStream_t)stream;
-  sn_wtu_kernel<<<dim3((max_wd + DT - 1) / DT, njobs), DT, 0, s>>>(jobs, norms_scratch);
+  sn_wtu_kernel<<<dim3((max_wd + SN_COLS - 1) / SN_COLS, njobs), DT, 0, s>>>(jobs, norms_scratch);
   if (int rc = check_launch("sn_wtu_kernel")) return rc;
   sn_wv_kernel<<<dim3((max_h + SN_ROWS - 1) / SN_ROWS, njobs), SN_ROWS * 32, 0, s>>>(jobs, norms_scratch);
   if (int rc = check_launch("sn_wv_kernel")) return rc;
