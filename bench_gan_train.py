@@ -188,12 +188,32 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
     torch.manual_seed(1234 + rank)   # per-rank noise streams
 
+    # the two critics of the generated image are independent until their image gradients meet: the discriminator
+    # branch runs on a side stream next to recognizer + CTC (autograd replays each branch's backward on the stream of
+    # its forward), so the small-grid launches of both — 1-D head, CTC chain, the discriminator's low-resolution
+    # layers — share the GPU; captured as two parallel branches of the step's graph
+    overlap = disc is not None and not os.environ.get("HWG_BENCH_NO_OVERLAP")
+    side = torch.cuda.Stream() if overlap else None
+    branch = {"parallel": overlap}         # the per-kernel roofline pass below times the launches one stream at a time
+
+    def adversarial(img):                  # generator's adversarial loss, trainer/hw_with_style_trainer.py:810-821
+        preds = disc(img)
+        return -(W_GEN / len(preds)) * sum(p.mean() for p in preds)
+
     def train(c, s, tg):
         img = gen(c, s)
+        par = branch["parallel"]
+        if par:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                adv = adversarial(img)
         loss = W_CTC * pkg.CTCLoss(hwr(img), tg, il, tl)
-        if disc is not None:               # generator's adversarial loss, trainer/hw_with_style_trainer.py:810-821
-            preds = disc(img)
-            loss = loss - (W_GEN / len(preds)) * sum(p.mean() for p in preds)
+        if par:
+            main.wait_stream(side)
+            loss = loss + adv
+        elif disc is not None:
+            loss = loss + adversarial(img)
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -219,6 +239,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             raise RuntimeError("disabled by HWG_BENCH_NO_GRAPH")
         graphed = graphs.GraphedStep(train, list(devsets[0]), modules=[gen, hwr], warmup=3)
         executed = ("one CUDA graph per step (fixed shapes; forward, CTC, backward, "
+                    + ("discriminator branch on a parallel stream, " if overlap else "")
                     + ("NCCL all-reduce on a side stream, " if world > 1 else "") + "Adam), replayed")
     except Exception as e:        # a capture failure must not lose the measurement: run the same step eagerly
         graphed = None
@@ -269,6 +290,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
 
     # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream)
     prof = []
+    branch["parallel"] = False
     hconv.PROFILE = prof
     psteps = min(args.steps, 4)
     barrier()
