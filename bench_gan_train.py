@@ -291,6 +291,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream)
     prof = []
     branch["parallel"] = False
+    gen.parallel_wgrad = False             # ... and with the generator's wgrad launches back on the main stream
     hconv.PROFILE = prof
     psteps = min(args.steps, 4)
     barrier()

@@ -203,6 +203,27 @@ def backward_train(m, ctx, g_out):
         o, n = plan["lay"][name]
         return ws[o:o + n].view(*shape)
 
+    # The weight gradients feed nothing but the unpack launch at the end, while the input-gradient chain
+    # (AdaIN backward -> dgrad -> next layer) is serial: the wgrad launches go to a side stream and run next to the
+    # chain.  Each one is ordered after the kernel that produced its gy (wait_stream) and the chain's tensors it reads
+    # are kept alive until the streams join, so the caching allocator cannot hand them out again early.  All of it is
+    # stream work, so a captured step holds the two branches.
+    main = torch.cuda.current_stream()
+    side = None
+    if getattr(m, "parallel_wgrad", True):
+        side = getattr(m, "_wgrad_stream", None)
+        if side is None or side.device != dev:
+            side = m._wgrad_stream = torch.cuda.Stream(device=dev)
+    keep = []
+
+    def wgrad(x_in, gy, *a, **k):
+        if side is None:
+            return conv.conv_wgrad(x_in, gy, *a, **k)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            conv.conv_wgrad(x_in, gy, *a, **k)
+        keep.append(gy)
+
     # ---- output head
     last = recs[-1]
     g, _, _ = ops.gen_output_bwd(g_out.contiguous().float(), ctx["out"], last["a"], last["coef"], c["w_out"],
@@ -216,7 +237,7 @@ def backward_train(m, ctx, g_out):
         # ---------------- second half: conv2 + noise2 + lrelu + adain2
         gy = ops.adain_lrelu_bwd(g, r2["a"], r2["save"], r2["coef"], 0.2, r2["nz"], seed, r2["subseq"],
                                  seed_dev=seed_dev, sums=W(f"sums{bi}2", B, C, 2), dch=W(f"dch{bi}2", C, 2))[0]
-        conv.conv_wgrad(r2["x_in"], gy, TAPS3x3, C, C, out=W(f"dw{bi}2", 9, C, C))
+        wgrad(r2["x_in"], gy, TAPS3x3, C, C, out=W(f"dw{bi}2", 9, C, C))
         g = conv.conv_fprop(gy, e["d2"], m2.taps_d, r2["Hin"], r2["Win"])
         # ---------------- first half: conv1 (+blur) + noise1 + lrelu + adain1
         gy = ops.adain_lrelu_bwd(g, r1["a"], r1["save"], r1["coef"], 0.2, r1["nz"], seed, r1["subseq"],
@@ -228,19 +249,19 @@ def backward_train(m, ctx, g_out):
             gy = ops.blur_noise_act_stats(gy, None, None, W(f"st{bi}", B, C, 2), ACT_NONE, 0.0)
         Cin = m1.Ci
         if kind == "plain":
-            conv.conv_wgrad(x_in, gy, TAPS3x3, Cin, C, out=W(f"dw{bi}1", 9, C, Cin))
+            wgrad(x_in, gy, TAPS3x3, Cin, C, out=W(f"dw{bi}1", 9, C, Cin))
             g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win)
         elif kind == "initial":
             cin_pad = c["cin_pad"]
             dw = W(f"dw{bi}1", 12, C, cin_pad)
             for r in range(4):
-                conv.conv_wgrad(x_in, gy, e["taps1"], cin_pad, C, grid=(1, Win), gy_offset=(r, 0), out=dw[3 * r:3 * r + 3])
+                wgrad(x_in, gy, e["taps1"], cin_pad, C, grid=(1, Win), gy_offset=(r, 0), out=dw[3 * r:3 * r + 3])
             # gradient w.r.t. the packed input: 12-tap convolution of gy [B,4,T,C] -> [B,1,T,Cin16]
             g = conv.conv_fprop(gy, e["d1"], m1.taps_d, 1, Win)
         elif kind == "vert_up":
             dw = W(f"dw{bi}1", 12, C, Cin)
             for par in (0, 1):
-                conv.conv_wgrad(x_in, gy, weightmap.vert_taps(par), Cin, C, grid=(Hin, Win), gy_stride=(2, 1),
+                wgrad(x_in, gy, weightmap.vert_taps(par), Cin, C, grid=(Hin, Win), gy_stride=(2, 1),
                                 gy_offset=(par, 0), out=dw[6 * par:6 * par + 6])
             g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win, in_stride=m1.d_in_stride)
         else:  # fused_up
@@ -248,14 +269,17 @@ def backward_train(m, ctx, g_out):
             taps = weightmap.fused_taps()
             if Cin <= 32 and C <= 32:
                 # all four parities in one launch (per-tap gy phase): gy and x are read once
-                conv.conv_wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
+                wgrad(x_in, gy, taps, Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
                                 tap_phase=weightmap.fused_phases(), out=dw)
             else:
                 for q, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
-                    conv.conv_wgrad(x_in, gy, taps[4 * q:4 * q + 4], Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
+                    wgrad(x_in, gy, taps[4 * q:4 * q + 4], Cin, C, grid=(Hin, Win), gy_stride=(2, 2),
                                     gy_offset=(py, px), out=dw[4 * q:4 * q + 4])
             g = conv.conv_fprop(gy, e["d1"], m1.taps_d, Hin, Win, in_stride=m1.d_in_stride)
     # ---- every parameter gradient + g_gb in one launch
+    if side is not None:
+        main.wait_stream(side)
+    keep.clear()
     plan["table"].run(src_base=ws, dst_base=gflat)
     if sink is None:
         flat = [gflat[o:o + n].view(sh) for o, n, sh in zip(plan["goff"], plan["numels"], plan["shapes"])]
