@@ -5,33 +5,39 @@ import torch
 
 
 def _flat(t):
-    assert t.is_contiguous()
-    return t.view(-1)
+    """(flat view of the tensor's whole storage, element offset of t in it): jobs address memory as data_ptr + explicit
+    strides, so t may be any view (e.g. one kernel row of a weight)."""
+    t = t.detach()
+    n = t.untyped_storage().nbytes() // t.element_size()
+    return torch.as_strided(t, (n,), (1,), 0), t.storage_offset()
 
 
 def run_jobs_cpu(table, src_base=None, dst_base=None):
     """Applies every job of a weightmap.JobTable to CPU tensors (in place on the dst tensors)."""
     for j in table.jobs:
         if isinstance(j["src"], torch.Tensor):
-            src, so = _flat(j["src"]).float().numpy(), 0
+            src, so = _flat(j["src"])
+            src = src.float().numpy()
         else:
-            src, so = _flat(src_base).float().numpy(), j["src"] // 4
+            src, so = _flat(src_base)
+            src, so = src.float().numpy(), so + j["src"] // 4
         if isinstance(j["dst"], torch.Tensor):
-            dst_t, do = _flat(j["dst"]), 0
+            dst_t, do = _flat(j["dst"])
         else:
-            dst_t = _flat(dst_base)
-            do = j["dst"] // dst_t.element_size()
+            dst_t, do = _flat(dst_base)
+            do += j["dst"] // dst_t.element_size()
         out = dst_t.float().numpy().copy()
+        scale = np.float32(j["scale"]) * (np.float32(1.0) if j.get("scale_dev") is None else np.float32(j["scale_dev"].item()))
         rows, cols = np.arange(j["Rp"])[:, None], np.arange(j["Cp"])[None, :]
         pad = (rows >= j["R"]) | (cols >= j["C"])
         sb = np.where(pad, 0, so + rows * j["s_r"] + cols * j["s_c"])
         db = do + rows * j["d_r"] + cols * j["d_c"]
         if j["M"] is None:
             acc = sum(src[sb + i * j["in_stride"]] for i in range(j["nin"]))
-            vals = [np.where(pad, 0.0, j["scale"] * acc)]
+            vals = [np.where(pad, 0.0, scale * acc)]
         else:
             v = np.stack([np.where(pad, 0.0, src[np.where(pad, 0, sb + o)]) for o in j["in_off"]], -1)   # [Rp,Cp,nin]
-            res = (v.astype(np.float32) @ j["M"]) * np.float32(j["scale"])
+            res = (v.astype(np.float32) @ j["M"]) * scale
             vals = [res[..., o] for o in range(j["nout"])]
         for o, val in zip(j["out_off"], vals):
             if j["accumulate"]:

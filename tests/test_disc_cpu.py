@@ -82,3 +82,66 @@ def test_disc_oracle_parameter_gradients_match_reference_golden(name, golden_dir
         dig = gold[f"{name}/grad/{n}/digest"]
         _, samp = digest(g.numpy())
         assert np.abs(samp - gold[f"{name}/grad/{n}/sample"]).max() <= FP32_REL * dig[3] + 1e-9, n
+
+
+def test_disc_job_tables_match_torch_relayouts():
+    """The discriminator's two hwg_linear_map tables, interpreted on the CPU (tests/ref_map.py): (1) every forward /
+    dgrad operand equals the torch re-layout of weight_bar * (1/sigma) (hwgMapJob.scale_dev), incl. the 7-tap x
+    16-channel operand of in_conv and the 16-row padding of the one-channel heads; (2) the wgrad unpack is the adjoint
+    of the forward pack scaled by 1/sigma, biases and GroupNorm sums land in their parameters' slots."""
+    from handwriting_line_generation_b200 import conv
+    from tests import ref_map
+    m, sd = disc_module(5)
+    plan = m._build_plan()
+    g = torch.Generator().manual_seed(1)
+    plan["inv_sigma"].copy_(torch.rand(plan["n_sn"], generator=g) + 0.5)
+    ref_map.run_jobs_cpu(plan["table"])
+    c = plan["c"]
+    k = 0
+    for site, mod, taps, spectral in m.conv_layers():
+        w = (mod.weight_bar if spectral else mod.weight).detach()
+        scale = plan["inv_sigma"][k] if spectral else torch.tensor(1.0)
+        k += int(spectral)
+        co, ci = w.size(0), w.size(1)
+        if site == "in_conv.0":
+            ref_f = torch.zeros(7, co, 16)
+            ref_f[:, :, :7] = w[:, 0].permute(1, 0, 2)                       # [dy][co][dx]
+            ref_d = ref_f.permute(0, 2, 1)
+            got_d = c["dgrad"][site][0].float()
+        else:
+            ref_f = conv.pack_conv2d_weight(w * scale).float()              # [taps][co][ci]
+            ref_d = ref_f.permute(0, 2, 1)
+            got_d = c["dgrad"][site][0].float()[:, :ci, :co]
+            assert c["dgrad"][site][1] == [(-dh, -dw) for dh, dw in taps]
+        got_f = c[site].float()
+        assert (got_f[:, :co] - ref_f.to(torch.bfloat16).float()).abs().max() <= 8e-3 * ref_f.abs().max(), site
+        assert got_f[:, co:].abs().max() == 0 if got_f.size(1) > co else True
+        assert (got_d[:, :, :co] - ref_d.to(torch.bfloat16).float()).abs().max() <= 8e-3 * ref_f.abs().max(), site
+        bp, b = c["bias"][site]
+        assert torch.equal(bp[:b.numel()] if b is not None else bp, mod.bias.detach())
+    # ---- unpack
+    m._plan = plan
+    wp = m._wgrad_plan(torch.device("cpu"))
+    arena = torch.randn(wp["arena_floats"], generator=g)
+    ref_map.run_jobs_cpu(wp["table"], src_base=arena)
+    params = dict(m.named_parameters())
+    k = 0
+    for site, (wname, bname, co, cop, ci, taps, spectral) in wp["meta"].items():
+        scale = float(plan["inv_sigma"][k]) if spectral else 1.0
+        k += int(spectral)
+        o, n = wp["slots"][("w", site)]
+        dw = arena[o:o + n].view(len(taps), cop, ci)
+        got = wp["gflat"][wp["goff"][wname]:wp["goff"][wname] + params[wname].numel()].view_as(params[wname])
+        if site == "in_conv.0":
+            ref = dw[:, :co, :7].permute(1, 0, 2).reshape(co, 1, 7, 7)
+        else:
+            kh, kw = params[wname].shape[2:]
+            ref = (dw[:, :co] * scale).view(kh, kw, co, ci).permute(2, 3, 0, 1)
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6), site
+        ob, _ = wp["slots"][("b", site)]
+        assert torch.equal(wp["gflat"][wp["goff"][bname]:wp["goff"][bname] + co], arena[ob:ob + co]), site
+    for gname in ("in_conv.1", "convs3.1"):
+        for kind, suffix in (("gamma", ".weight"), ("beta", ".bias")):
+            o, n = wp["slots"][(kind, gname)]
+            go = wp["goff"][gname + suffix]
+            assert torch.equal(wp["gflat"][go:go + n], arena[o:o + n])
