@@ -13,11 +13,17 @@ forward runs on libhwg_b200:
   Dropout2d as a per-(sample, channel) scale fused with the LeakyReLU pass;
 * backward to the INPUT image (what the generator's adversarial loss needs, trainer/hw_with_style_trainer.py:810-821):
   dgrad on the tensor cores, `hwg_act_bwd` (Dropout2d + LeakyReLU + AvgPool2d backward in one pass), the three-launch
-  GroupNorm backward, `hwg_shift_collapse`.
+  GroupNorm backward, `hwg_shift_collapse`;
+* backward to the discriminator's own weights (the 'disc' lesson, trainer :785-804) when its parameters require
+  gradients: `hwg_conv_wgrad` per layer into one zero-filled arena, `hwg_channel_sum` for the biases, GroupNorm
+  gamma/beta sums from `hwg_gn_bwd_coeffs`, ONE `hwg_linear_map` launch that unpacks everything into the parameters'
+  layouts (spectral layers scaled by 1/sigma) and `hwg_spectral_norm_bwd` for the rank-one term of
+  weight = w_bar / sigma(w_bar).
 
-Gradients with respect to the discriminator's own weights (the 'disc' lesson) are not built yet: the module raises if
-asked for them, it never falls back to PyTorch."""
-import ctypes
+u / v are updated in place on every forward, as the reference does, and the packed operands are shared between forward
+and backward: the backward of a forward must run before the next forward of the same module (it raises otherwise).
+There is no PyTorch fallback."""
+
 
 import numpy as np
 import torch
