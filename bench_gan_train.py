@@ -42,7 +42,9 @@ def config(B, world, executed, sync_bn="off"):
             "for the adversarial loss -mean(D(fake)), " if use_disc() else "")
     return {"workload": "HWWithStyle GAN 'gen' lesson train step (BASELINE configs[2]/[3] shapes): "
                         "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
-                        "CTC loss fwd+bwd, " + disc + "gradient all-reduce (N>1), clip + Adam on the generator; "
+                        "CTC loss fwd+bwd, " + disc + "ONE backward over the weighted sum of the two losses (the reference's per-loss gradient "
+                        "balancing, trainer :300-377 / SURVEY 8 f2, which runs a backward per loss, is not built), "
+                        "gradient all-reduce (N>1), clip + Adam on the generator; "
                         + ("the perceptual (Encoder2) branch of SURVEY 8 f1 is not included" if use_disc() else
                            "discriminator/perceptual branches (SURVEY 8 f1) not included"),
             "batch_per_gpu": B, "global_batch": B * world, "line_px": [64, 4 * GAN["Ts"]], "classes": GAN["C"],
