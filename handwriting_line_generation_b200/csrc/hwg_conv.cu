@@ -592,7 +592,11 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
   // Small layers: keep every weight tile resident (one load per CTA) and put several (tap, chunk) operand
   // tiles behind one mbarrier round trip, so the single-thread producer / MMA loops are not the bottleneck.
-  p.wstat = (p.n_tiles == 1 && (size_t)kiters * p.b_bytes <= 40 * 1024) ? 1 : 0;
+  // development override (next experiment): HWG_CONV_WSTAT_KB raises the residency limit, e.g. 80 makes
+  // the 64->64 3x3 layers (72 KB of weights: discriminator convs1.0, generator block 2) weight-stationary
+  static const int wstat_kb = [] { const char* e = getenv("HWG_CONV_WSTAT_KB"); const int v = e ? atoi(e) : 0;
+                                   return (v >= 8 && v <= 160) ? v : 40; }();
+  p.wstat = (p.n_tiles == 1 && (size_t)kiters * p.b_bytes <= (size_t)wstat_kb * 1024) ? 1 : 0;
   p.unit_bytes = p.a_bytes + (p.wstat ? 0 : p.b_bytes);
   p.gsize = (24 * 1024) / p.unit_bytes;
   if (p.gsize < 1) p.gsize = 1;
