@@ -289,6 +289,12 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     loss_value = float(loss_host.detach())
+    peer_fault = None
+    try:                                   # an in-kernel exchange that timed out sets a flag instead of hanging
+        if hasattr(hwr.sync_bn_group, "fault"):
+            peer_fault = int(hwr.sync_bn_group.fault.item())
+    except Exception:                      # noqa: BLE001 - reporting only
+        peer_fault = None
 
     # ---- rooflines: CUDA events around every convolution launch of a few eager steps (same kernels, same stream)
     prof = []
@@ -391,6 +397,8 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         "roofline": roof(top), "roofline_other_kernels": [roof(kk) for kk in kern if kk != top],
         "cpu_baseline": cpu, "final_loss": loss_value,
     }
+    if peer_fault is not None:
+        line["config"]["peer_exchange_timeouts"] = peer_fault      # 0 = every in-kernel exchange completed
     if world == 1 and not os.environ.get("HWG_BENCH_NO_EXTRAS"):
         try:   # the other configs, measured briefly in the same run (bench.py --workload gen_infer / hwr_train)
             import bench_hwr_train
