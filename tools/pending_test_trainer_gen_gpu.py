@@ -1,5 +1,5 @@
 """PENDING (written when the round's GPU budget was spent, never run on a GPU): move to tests/test_trainer_gen_gpu.py after one
-green run on a B200 — `python -m pytest tools/pending_test_trainer_gen_gpu.py -q` works from the repo root.
+green run on a B200 (the one attempt ended in a fixture error before reaching the GPU, since fixed) — `python -m pytest tools/pending_test_trainer_gen_gpu.py -q` works from the repo root.
 
 GPU: the CUDA 'gen' lesson against the UNMODIFIED reference TRAINER (tests/golden/trainer_gen.npz, see
 tests/test_trainer_gen_cpu.py): same weights (seeded construction), the content / style / labels the trainer fed,
@@ -36,8 +36,10 @@ def _set_cosine(grads, gold, setname):
     return num / (d1 * d2) ** 0.5
 
 
-def test_cuda_gen_lesson_against_the_reference_trainer(golden_dir):
+def test_cuda_gen_lesson_against_the_reference_trainer():
+    import os
     import handwriting_line_generation_b200 as pkg
+    golden_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     gold = np.load(f"{golden_dir}/trainer_gen.npz")
     gsd, hsd, dsd, content, style, noise, masks = build_inputs(gold)
 
