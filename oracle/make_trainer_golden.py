@@ -25,7 +25,7 @@ CFG = "configs/cf_IAMslant_noMask_charSpecSingleAppend_GANMedMT_autoAEMoPrcp2tig
 B = 2              # lines (tiny: the CPU trainer step takes seconds)
 L = int(os.environ.get("HWG_TRAINER_L", 15))          # characters per line
 LABEL_SEED = int(os.environ.get("HWG_TRAINER_LABEL_SEED", 5))
-SEEDS = dict(generator=400, hwr=401, discriminator=402, noise=403, masks=404)   # what the tests rebuild the inputs from
+SEEDS = dict(generator=400, hwr=401, discriminator=402, noise=403, masks=404, real=405)   # what the tests rebuild the inputs from
 
 
 class _Log:
@@ -36,7 +36,8 @@ class _Log:
         return lambda *a, **k: None
 
 
-def main():
+def run_lesson(kind):
+    """kind: 'gen' (curriculum slot 1, ["no-step","gen"]) or 'disc' (slot 3, ["disc"])."""
     ref_shim.install()
     cwd = os.getcwd()
     os.chdir(ref_shim.REF)
@@ -85,6 +86,15 @@ def main():
                         "spaced_label": None, "author": ["a"] * B, "name": ["n"] * B}
 
         tr.text_data = Text()
+        real = torch.from_numpy(synth.hwr_case(B, 128, SEEDS["real"]))      # 'disc' lesson: the real lines
+
+        class Loader:                      # trainer :230 uses the py2 iterator protocol
+            def next(self):
+                inst = Text().getInstance()
+                inst.update(image=real.clone(), fg_mask=torch.ones_like(real), a_batch_size=1)
+                return inst
+
+        tr.data_loader_iter = Loader()
         # ---- recorders
         from . import disc as odisc
         dmasks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(B, SEEDS["masks"]).items()}
@@ -119,39 +129,54 @@ def main():
 
         model.generator.forward = gen_forward
         torch.randn_like, F.dropout2d = randn_like, dropout2d
+        slot = {"gen": 1, "disc": 3}[kind]
+        if kind == "disc":                  # 2B rows go through the discriminator: masks for 2B samples
+            dmasks.update({k: torch.from_numpy(v) for k, v in synth.disc_masks(2 * B, SEEDS["masks"]).items()})
         try:
-            tr.iteration = 1
-            log = tr._train_iteration(1)            # curriculum slot 1: ["no-step", "gen"]
+            tr.iteration = slot
+            log = tr._train_iteration(slot)
         finally:
             torch.randn_like, F.dropout2d = orig_randn_like, orig_drop
             model.generator.forward = gen_fwd
-        assert len(tr.saved_grads) == 2, len(tr.saved_grads)
-        names = [n for n, _ in model.named_parameters()]
-        assert len(names) == len(tr.parameters)
         out = {"content": rec["gen_in"][0].numpy(), "style": rec["gen_in"][1].numpy(), "image": rec["gen_out"].numpy(),
                "label": label.numpy(), "label_lengths": lengths.numpy(),
-               "losses": np.array([log.get("genRecogLoss", np.nan), log.get("generatorLoss", np.nan)], np.float64),
+               "noise_shapes": np.array(rec["noise"], np.int64), "mask_sites": np.array(rec["masks"]),
+               "modes": np.array([int(model.generator.training), int(model.hwr.training), int(model.discriminator.training)]),
+               "seeds": np.array([SEEDS[k] for k in ("generator", "hwr", "discriminator", "noise", "masks", "real")], np.int64),
                "loss_keys": np.array(sorted(k for k in log if "Loss" in k))}
-        out["noise_shapes"] = np.array(rec["noise"], np.int64)
-        out["mask_sites"] = np.array(rec["masks"])
-        out["modes"] = np.array([int(model.generator.training), int(model.hwr.training), int(model.discriminator.training)])
-        out["seeds"] = np.array([SEEDS[k] for k in ("generator", "hwr", "discriminator", "noise", "masks")], np.int64)
-        u = model.discriminator.state_dict()["convs1.0.module.weight_u"]
-        out["disc_u_after"] = u.numpy().copy()
-        for si, setname in enumerate(("recog", "adv")):
-            for n, g in zip(names, tr.saved_grads[si]):
-                if g is None or not n.startswith("generator."):
-                    continue
-                dig, samp = digest(g.numpy())
-                out[f"grad/{setname}/{n}/digest"] = dig
-                out[f"grad/{setname}/{n}/sample"] = samp[:256]
-        print("losses", out["losses"], "noise tensors", len(rec["noise"]), "dropout sites", len(rec["masks"]),
+        names = [n for n, _ in model.named_parameters()]
+        if kind == "gen":
+            assert len(tr.saved_grads) == 2 and len(names) == len(tr.parameters)
+            out["losses"] = np.array([log.get("genRecogLoss", np.nan), log.get("generatorLoss", np.nan)], np.float64)
+            out["disc_u_after"] = model.discriminator.state_dict()["convs1.0.module.weight_u"].numpy().copy()
+            for si, setname in enumerate(("recog", "adv")):
+                for n, g in zip(names, tr.saved_grads[si]):
+                    if g is None or not n.startswith("generator."):
+                        continue
+                    dig, samp = digest(g.numpy())
+                    out[f"grad/{setname}/{n}/digest"] = dig
+                    out[f"grad/{setname}/{n}/sample"] = samp[:256]
+            fname = "trainer_gen.npz"
+        else:
+            # the trainer has clipped (clip_grad_value_ 2, :381) and stepped optimizer_discriminator; .grad still holds
+            # the clipped gradients of this iteration
+            out["losses"] = np.array([log["discriminatorLoss"]], np.float64)
+            for n, p in model.named_parameters():
+                if n.startswith("discriminator.") and p.grad is not None:
+                    dig, samp = digest(p.grad.numpy())
+                    out[f"grad/disc/{n}/digest"] = dig
+                    out[f"grad/disc/{n}/sample"] = samp[:256]
+            assert all(p.grad is None or float(p.grad.abs().max()) == 0 for n, p in model.named_parameters()
+                       if n.startswith("generator."))             # fake.detach(): nothing reaches the generator
+            fname = "trainer_disc.npz"
+        print(kind, "losses", out["losses"], "noise tensors", len(rec["noise"]), "dropout sites", len(rec["masks"]),
               "content", out["content"].shape, "image", out["image"].shape)
-        np.savez_compressed(os.path.join(GOLD, "trainer_gen.npz"), **out)
+        np.savez_compressed(os.path.join(GOLD, fname), **out)
         return tmp
     finally:
         os.chdir(cwd)
 
 
 if __name__ == "__main__":
-    main()
+    for k in (sys.argv[1:] or ["gen", "disc"]):
+        run_lesson(k)

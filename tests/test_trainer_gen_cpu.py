@@ -21,7 +21,7 @@ W_RECOG, W_GEN = 1e-4, 1.0          # loss_weights genRecog / generator of the I
 def build_inputs(gold):
     """Weights (seeded drop-in construction == seeded reference construction), inputs, noise and masks of the lesson."""
     from handwriting_line_generation_b200 import CNNOnlyHWR, DiscriminatorAP, SpacedGenerator
-    s_gen, s_hwr, s_disc, s_noise, s_masks = (int(v) for v in gold["seeds"])
+    s_gen, s_hwr, s_disc, s_noise, s_masks = (int(v) for v in gold["seeds"][:5])
     torch.manual_seed(s_gen)
     gsd = SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False, append_style=True, small=False).state_dict()
     torch.manual_seed(s_hwr)
@@ -81,3 +81,37 @@ def test_oracle_chain_reproduces_the_reference_trainers_gen_lesson(golden_dir):
         assert checked >= 60, checked
         assert num / (d1 * d2) ** 0.5 >= 0.99999, (setname, num / (d1 * d2) ** 0.5)
     print("worst relative error vs the trainer's stashed gradient sets:", worst)
+
+
+def test_oracle_reproduces_the_reference_trainers_disc_lesson(golden_dir):
+    """Curriculum slot ["disc"] through the unmodified trainer (:785-806): real lines || generated lines (detached)
+    through the discriminator, hinge loss, `clip_grad_value_(…, 2)` (:381).  The oracle's loss holds 1e-4; the gradients
+    of all 28 trainable discriminator tensors are compared after the same clipping."""
+    gold = np.load(f"{golden_dir}/trainer_disc.npz")
+    gsd, hsd, dsd, content, style, noise, _ = build_inputs(gold)
+    B = style.size(0)
+    with torch.no_grad():
+        fake = ogen.generator_forward(gsd, content, style, noise)
+    assert np.abs(fake.numpy() - gold["image"]).max() <= 1e-4 * np.abs(gold["image"]).max()
+    real = torch.from_numpy(synth.hwr_case(B, fake.size(3), int(gold["seeds"][5])))
+    masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(2 * B, int(gold["seeds"][4])).items()}
+    leaf = {k: v.clone().requires_grad_(not k.endswith(("weight_u", "weight_v"))) for k, v in dsd.items()}
+    loss = odisc.hinge_loss(odisc.disc_forward(leaf, torch.cat((real, fake), 0), masks, training=True), B)
+    assert abs(loss.item() - gold["losses"][0]) <= 1e-4 * abs(gold["losses"][0])
+    loss.backward()
+    checked, worst = 0, 0.0
+    for n, p in leaf.items():
+        key = f"grad/disc/discriminator.{n}"
+        if not p.requires_grad or key + "/digest" not in gold.files:
+            continue
+        dig, ref = gold[key + "/digest"], gold[key + "/sample"].astype(np.float64)
+        samp = digest(p.grad.clamp(-2, 2).numpy())[1][:256].astype(np.float64)
+        if dig[3] < 1e-9:
+            assert np.abs(samp).max() <= 1e-6, n
+        else:
+            err = float(np.abs(samp - ref).max() / dig[3])
+            worst = max(worst, err)
+            assert err <= 1e-3, (n, err)          # 12 fp32 layers, sums over up to 10^6 pixels
+        checked += 1
+    assert checked == 28, checked
+    print("worst relative error vs the trainer's discriminator gradients:", worst)
