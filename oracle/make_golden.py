@@ -263,7 +263,7 @@ def make_disc():
         for n, p in m.named_parameters():
             if p.requires_grad:
                 dig, samp = digest(p.grad.numpy())
-                out[f"{name}/grad/{n}/digest"], out[f"{name}/grad/{n}/sample"] = dig, samp
+                out[f"{name}/grad/{n}/digest"], out[f"{name}/grad/{n}/sample"] = dig, samp[:512]
         print(f"disc/{name}: B={B} W={W} hinge loss {loss.item():.5f}, {len(names)} parameter gradients")
     np.savez_compressed(os.path.join(GOLD, "disc.npz"), **out)
 

