@@ -25,7 +25,14 @@ SHAPES = {
     "t_gen_b0c2_dgrad": (16, 4, 256, 256, 256, (3, 3, 1, 1), "none"),
     "t_gen_b1c2": (16, 8, 256, 128, 128, (3, 3, 1, 1), "noise_stats"),
     "t_gen_b2c2": (16, 16, 256, 64, 64, (3, 3, 1, 1), "noise_stats"),
+    # discriminator, train-step shapes at 16 lines per GPU (HWG_CONV_TILE_W=32 reproduces the module's tile choice)
+    "t_disc_convs1_0": (16, 58, 1024, 64, 64, (3, 3, 0, 1), "lrelu"),
+    "t_disc_convs1_3": (16, 28, 512, 64, 128, (3, 3, 0, 1), "none"),
+    "t_disc_convs2_0": (16, 26, 512, 128, 128, (3, 3, 0, 1), "lrelu"),
+    "t_disc_convs3_0": (16, 12, 256, 128, 128, (3, 3, 0, 1), "stats"),
+    "t_disc_convs3_4": (16, 5, 128, 128, 256, (3, 3, 0, 1), "none"),
 }
+TILE_W = int(os.environ.get("HWG_CONV_TILE_W", "0"))
 which = [a for a in sys.argv[1:] if a in SHAPES] or ([] if sys.argv[1:] else list(SHAPES))
 reps = 10
 for name in which:
@@ -36,8 +43,12 @@ for name in which:
     taps = conv.conv_taps(kh, kw, ph, pw)
     Ho, Wo = H + 2 * ph - kh + 1, W + 2 * pw - kw + 1
     kw_ = dict(bias=b)
+    if TILE_W:
+        kw_.update(tile_w=TILE_W)
     if epi == "relu":
         kw_.update(act=_lib.ACT_RELU)
+    elif epi == "lrelu":
+        kw_.update(act=_lib.ACT_LRELU, slope=0.1)
     elif epi == "stats":
         kw_.update(stats=torch.zeros(N, Cout, 2, device="cuda"))
     elif epi == "noise_stats":
