@@ -91,7 +91,7 @@ def run_lesson(kind):
         class Loader:                      # trainer :230 uses the py2 iterator protocol
             def next(self):
                 inst = Text().getInstance()
-                inst.update(image=real.clone(), fg_mask=torch.ones_like(real), a_batch_size=1)
+                inst.update(image=real.clone(), fg_mask=torch.ones_like(real), a_batch_size=2)
                 return inst
 
         tr.data_loader_iter = Loader()
@@ -129,6 +129,8 @@ def run_lesson(kind):
 
         model.generator.forward = gen_forward
         torch.randn_like, F.dropout2d = randn_like, dropout2d
+        if kind == "balance":
+            return _balance_golden(tr, model, (orig_randn_like, orig_drop), F, tmp)
         slot = {"gen": 1, "disc": 3}[kind]
         if kind == "disc":                  # 2B rows go through the discriminator: masks for 2B samples
             dmasks.update({k: torch.from_numpy(v) for k, v in synth.disc_masks(2 * B, SEEDS["masks"]).items()})
@@ -177,6 +179,76 @@ def run_lesson(kind):
         os.chdir(cwd)
 
 
+def _balance_golden(tr, model, originals, F, tmp):
+    """Lessons 1 -> 2 of the curriculum (["no-step","gen"] then ["auto","auto-gen"]): the second one balances the four
+    stashed gradient sets into p.grad, clips and steps (trainer :340-391).  Recorded for every parameter tensor with at
+    most 4096 elements: the four sets, p.grad before balancing (after the last backward) and after balancing (on entry
+    to clip_grad_value_), plus the statistics that involve all tensors."""
+    torch.randn_like, F.dropout2d = originals            # the auto lesson draws in modules outside the hot path
+    tr.iteration = 1
+    tr._train_iteration(1)
+    assert len(tr.saved_grads) == 2
+    snaps = []
+    orig_backward = torch.Tensor.backward
+    orig_clip = torch.nn.utils.clip_grad_value_
+
+    def backward(self, *a, **k):
+        r = orig_backward(self, *a, **k)
+        snaps.append([None if p.grad is None else p.grad.detach().clone() for p in tr.parameters])
+        return r
+
+    post = {}
+
+    def clip(params, v):
+        post["grads"] = [None if p.grad is None else p.grad.detach().clone() for p in tr.parameters]
+        post["sets"] = len(tr.saved_grads)
+        return orig_clip(params, v)
+
+    saved_before = None
+    torch.Tensor.backward = backward
+    torch.nn.utils.clip_grad_value_ = clip
+    try:
+        tr.iteration = 2
+        # the stash is emptied inside the call: keep a reference to the list objects
+        stash = tr.saved_grads
+        tr._train_iteration(2)
+    finally:
+        torch.Tensor.backward = orig_backward
+        torch.nn.utils.clip_grad_value_ = orig_clip
+    # inside the call: backward #1 = autoGenLoss (stashed, zeroed), #2 = recogLoss (stashed, zeroed), #3 = the rest -> D
+    assert len(snaps) == 3, len(snaps)
+    sets = list(stash[:2]) + [snaps[0], snaps[1]]          # order of self.saved_grads at balancing time
+    D, after = snaps[2], post["grads"]
+    names = [n for n, _ in model.named_parameters()]
+    mult = None
+    for it, m in tr.balance_var_x.items():
+        if int(it) <= 2:
+            mult = m
+    from .balance import abs_means
+    means, fill = abs_means(D)
+    out = {"multipliers": np.array(mult, np.float64), "fill": np.float64(fill), "names": []}
+    keep = [i for i, p in enumerate(tr.parameters) if p.numel() <= 4096 and D[i] is not None]
+    # a spread over the model's parts, and every tensor whose own mean|D| is exactly 0 (the :354-359 rule)
+    pick = [i for i in keep if float(means[i]) == 0][:8]
+    for prefix in ("generator.", "style_extractor.", "spacer.", "hwr.", "discriminator."):
+        pick += [i for i in keep if names[i].startswith(prefix)][:10]
+    pick = sorted(set(pick))
+    for i in pick:
+        n = names[i]
+        out["names"].append(n)
+        out[f"D/{n}"] = D[i].numpy()
+        out[f"after/{n}"] = after[i].numpy()
+        out[f"meanD/{n}"] = np.float64(means[i])
+        for k, st in enumerate(sets):
+            if st[i] is not None:
+                out[f"R{k}/{n}"] = st[i].numpy()
+    out["names"] = np.array(out["names"])
+    out["n_zero_mean"] = np.int64(sum(1 for i in pick if float(means[i]) == 0))
+    print("balance: multipliers", mult, "tensors stored", len(pick), "with zero mean|D|", int(out["n_zero_mean"]), "fill", fill.item())
+    np.savez_compressed(os.path.join(GOLD, "trainer_balance.npz"), **out)
+    return tmp
+
+
 if __name__ == "__main__":
-    for k in (sys.argv[1:] or ["gen", "disc"]):
+    for k in (sys.argv[1:] or ["gen", "disc", "balance"]):
         run_lesson(k)
