@@ -30,6 +30,8 @@ _SIGNATURES = {
     "hwg_conv_fprop": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hwg_logsoftmax_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "hwg_balance_chunk": (c_int, []),
+    "hwg_balance": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     "hwg_shift_expand": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "hwg_shift_collapse": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "hwg_gn_coeffs": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_f, c_vp, c_vp, c_vp]),

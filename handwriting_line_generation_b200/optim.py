@@ -67,6 +67,50 @@ class FlatAdam:
                   float(self.clip_value or 0.0), float(grad_scale), self.step_dev.data_ptr(), 1, _lib.stream())
         torch.autograd.graph.increment_version(self.params)     # derived-weight caches key on (data_ptr, _version)
 
+    # ---- gradient balancing (trainer/hw_with_style_trainer.py:300-377) — NOT YET RUN ON A GPU, see hwg_balance ----
+    def stash(self):
+        """The trainer's `saved_grad` (:303-322, :330-338): keeps the gradient buffer as one more stashed set and zeroes
+        it for the next backward."""
+        self._rebind_grads()
+        if not hasattr(self, "_stash"):
+            self._stash = []
+        self._stash.append(self.flat_g.clone())
+        self.flat_g.zero_()
+
+    @torch.no_grad()
+    def balance(self, multipliers):
+        """:340-377 on the flat buffers: adds every stashed set to the gradient buffer, rescaled per parameter to the
+        gradient's mean magnitude and weighted by `multipliers` (`balance_var_x`); one hwg_balance call (three launches,
+        no host synchronisation).  Clears the stash."""
+        import ctypes
+        sets = getattr(self, "_stash", [])
+        if not sets:
+            return
+        self._rebind_grads()
+        assert len(multipliers) >= len(sets)
+        dev = self.flat_g.device
+        if getattr(self, "_bal", None) is None:
+            chunk = _lib.load().hwg_balance_chunk()
+            offs, lens, tab = [], [], []
+            for si, p in enumerate(self.params):
+                o, k = self.offsets[id(p)]
+                offs.append(o)
+                lens.append(k)
+                tab += [(si, c) for c in range(-(-k // chunk))]
+            self._bal = dict(off=torch.tensor(offs, dtype=torch.int64, device=dev),
+                             len=torch.tensor(lens, dtype=torch.int64, device=dev),
+                             tab=torch.tensor(tab, dtype=torch.int32, device=dev).reshape(-1, 2).contiguous(),
+                             nseg=len(offs))
+        b, K = self._bal, len(sets)
+        x = torch.tensor([float(v) for v in multipliers[:K]], dtype=torch.float32, device=dev)
+        sums = torch.empty((b["nseg"], K + 1), dtype=torch.float32, device=dev)
+        mult = torch.empty((K, b["nseg"]), dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in sets])
+        _lib.call("hwg_balance", self.flat_g.data_ptr(), ctypes.addressof(ptrs), K, x.data_ptr(), b["off"].data_ptr(),
+                  b["len"].data_ptr(), b["nseg"], b["tab"].data_ptr(), b["tab"].size(0), sums.data_ptr(), mult.data_ptr(),
+                  _lib.stream())
+        self._stash = []
+
     def zero_grad(self, set_to_none=False):
         """step() already leaves the gradient buffer zeroed; this is for steps that are skipped."""
         self.flat_g.zero_()

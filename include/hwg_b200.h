@@ -420,6 +420,23 @@ int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const fl
                        void* stream);
 
 /* ------------------------------------------------------------------------
+ * Gradient balancing on flat gradient buffers — SURVEY.md 8 f2, reference
+ * trainer/hw_with_style_trainer.py:340-377 (`balance_loss`), restated in oracle/balance.py:
+ *   for every stashed set R_k and parameter segment s:  D_s += x_k * R_k,s * (mean|D_s| / mean|R_k,s|)
+ * with mean|D_s| taken before any set is added, segments whose mean|D_s| is exactly 0 using the average of the
+ * non-zero means instead (:354-359), and sets with mean|R_k,s| == 0 skipped (:373).
+ * g_main and every set are flat fp32 buffers with the same parameter slots (optim.FlatAdam): seg_off_dev[s] /
+ * seg_len_dev[s] = first element / element count of parameter s; block_tab_dev = nblocks (segment, chunk) int32
+ * pairs, one per hwg_balance_chunk() elements of a segment; sets_host = HOST array of K device pointers (K <= 8);
+ * x_dev = the K multipliers (`balance_var_x`) in device memory; sums_dev [nseg][K+1] and mult_dev [K][nseg] are
+ * workspaces.  Three launches, no host synchronisation.
+ * Status: written after round 1's GPU budget was spent — not yet run on a GPU, not called by default. */
+int hwg_balance_chunk(void);
+int hwg_balance(float* g_main, const float* const* sets_host, int K, const float* x_dev,
+                const int64_t* seg_off_dev, const int64_t* seg_len_dev, int nseg, const int32_t* block_tab_dev,
+                int nblocks, float* sums_dev, float* mult_dev, void* stream);
+
+/* ------------------------------------------------------------------------
  * Discriminator (reference model/discriminator_ap.py:68-161):
  * memory-bound passes around the tensor-core convolutions.  NHWC bf16, C % 8 == 0.
  * ---------------------------------------------------------------------- */
