@@ -268,6 +268,58 @@ def make_disc():
     np.savez_compressed(os.path.join(GOLD, "disc.npz"), **out)
 
 
+# name -> (B, W, weight seed, input seed, training)
+ENC_CASES = {"eval_w128": (2, 128, 500, 501, False), "train_w200": (2, 200, 500, 502, True)}
+
+
+def make_enc():
+    """Features and the perceptual-loss gradient (w.r.t. the reconstructed image) of the unmodified reference Encoder2(32)."""
+    ref_shim.install()
+    from model.autoencoder import Encoder2
+    import torch.nn.functional as F
+    from . import enc as oenc
+    out = {}
+    for name, (B, W, wseed, iseed, training) in ENC_CASES.items():
+        torch.manual_seed(wseed)
+        m = Encoder2(32)
+        m.train(training)
+        out["state_dict_keys"] = keys_fixture(m.state_dict())
+        out[f"{name}/weights_digest"] = weights_digest(m.state_dict())
+        r = np.random.RandomState(iseed + 7)
+        masks = [torch.from_numpy((r.rand(2 * B, c) >= 3 * p).astype(np.float32)) for _, c, p in oenc.DROPOUT_SITES]
+        it = iter(masks)
+        orig = F.dropout2d
+
+        def fake_dropout2d(x, p=0.5, training=True, inplace=False):
+            if not training:
+                return x
+            k = next(it)
+            assert k.shape == (x.size(0), x.size(1))
+            return x * (k / (1.0 - p))[:, :, None, None]
+
+        F.dropout2d = fake_dropout2d
+        try:
+            image = torch.from_numpy(synth.hwr_case(B, W, iseed))
+            recon = torch.from_numpy(synth.hwr_case(B, W, iseed + 1)).requires_grad_()
+            feats = m(torch.cat((image, recon), 0))                      # trainer :740-742
+            loss = 0
+            for f in feats:
+                o_f, r_f = torch.chunk(f, 2, dim=0)
+                loss = loss + F.l1_loss(r_f, o_f)
+            loss.backward()
+        finally:
+            F.dropout2d = orig
+        for i, f in enumerate(feats):
+            dig, samp = digest(f.detach().numpy())
+            out[f"{name}/feat{i}/digest"], out[f"{name}/feat{i}/sample"] = dig, samp[:2048]
+            out[f"{name}/feat{i}/shape"] = np.array(f.shape)
+        out[f"{name}/loss"] = np.float32(loss.item())
+        dig, samp = digest(recon.grad.numpy())
+        out[f"{name}/grad_digest"], out[f"{name}/grad_sample"] = dig, samp[:2048]
+        print(f"enc/{name}: B={B} W={W} train={training} -> {[tuple(f.shape) for f in feats]} loss {loss.item():.5f}")
+    np.savez_compressed(os.path.join(GOLD, "enc.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -279,6 +331,8 @@ def main(argv):
         globals()["make_gen"]()
     if what in ("disc", "all"):
         make_disc()
+    if what in ("enc", "all"):
+        make_enc()
 
 
 if __name__ == "__main__":
