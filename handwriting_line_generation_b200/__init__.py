@@ -9,6 +9,7 @@ from .pure_gen import SpacedGenerator  # noqa: F401
 from .cnn_only_hwr import CNNOnlyHWR  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
 from .discriminator_ap import DiscriminatorAP  # noqa: F401
+from .encoder2 import Encoder2  # noqa: F401  (not yet run on a GPU: see its module docstring)
 
 __all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam",
-           "DiscriminatorAP"]
+           "DiscriminatorAP", "Encoder2"]

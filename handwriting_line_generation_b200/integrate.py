@@ -7,11 +7,24 @@ and generate.py run the sm_100a path without a source change."""
 import importlib
 
 
-def install():
+def install(encoder=False):
     """Call after the reference's root is on sys.path and before HWWithStyle / the trainer are built.
-    Returns the list of (module name, attribute) pairs that were rebound."""
+    Returns the list of (module name, attribute) pairs that were rebound.
+
+    encoder=True also rebinds `Encoder2`, the perceptual encoder the trainer builds for `encoder_type: "2tight"`
+    (`from model.autoencoder import Encoder2`, trainer/hw_with_style_trainer.py:15,148-149) — opt-in until the module has
+    a green GPU parity run (encoder2.py: status)."""
     from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator
     swapped = []
+    if encoder:
+        from .encoder2 import Encoder2
+        for modname in ("model.autoencoder", "trainer.hw_with_style_trainer"):
+            try:
+                mod = importlib.import_module(modname)
+            except ImportError:
+                continue
+            setattr(mod, "Encoder2", Encoder2)
+            swapped.append((modname, "Encoder2"))
     hws = importlib.import_module("model.hw_with_style")
     for name, cls in (("SpacedGenerator", SpacedGenerator), ("CNNOnlyHWR", CNNOnlyHWR),
                       ("DiscriminatorAP", DiscriminatorAP)):

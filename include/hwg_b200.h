@@ -488,6 +488,23 @@ int hwg_spectral_norm_bwd(const void* jobs_dev, int njobs, int64_t max_elems, co
                           float* dots_scratch, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Perceptual encoder (reference model/autoencoder.py:341-410 `Encoder2`; SURVEY.md 8 row f1, second half) and the
+ * perceptual loss built on it (trainer/hw_with_style_trainer.py:740-748).  The convolutions, GroupNorm, AvgPool2d and
+ * Dropout2d + ReLU passes are the discriminator's entry points above; these two are what they do not cover.
+ * Status: written after round 1's GPU budget was spent — compiled, not yet run on a GPU.
+ * ---------------------------------------------------------------------- */
+/* The residual additions `x = self.conv1(x); x += res` (autoencoder.py:400-401, :404-405): y = a + b on NHWC bf16
+ * [N,HW,C] (C in {16,32,64,128,256}; y may alias a or b) and, when stats != NULL (fp32 [N,C,2], zeroed by the caller),
+ * the per-(n,c) sum and sum of squares of y that the GroupNorm which follows consumes (hwg_gn_coeffs). */
+int hwg_add_stats(const void* a, const void* b, void* y, int N, int64_t HW, int C, float* stats, void* stream);
+/* F.l1_loss between the halves of one feature tensor f = [orig ; recon] (trainer :743-747: torch.chunk(b, 2, dim=0)):
+ * *loss += loss_scale * sum |recon - orig| (loss_scale = 1/half_numel for reduction='mean'), and, when g != NULL,
+ * g[i] = grad_scale * sign(recon[i] - orig[i]) as bf16 (the gradient w.r.t. the recon half, sign(0) = 0 as in torch).
+ * dtype: HWG_DT_BF16 or HWG_DT_F32 element type of f; half_numel % 8 == 0; 16-byte aligned pointers. */
+int hwg_l1_halves(const void* f, int dtype, int64_t half_numel, float loss_scale, float grad_scale, float* loss,
+                  void* g, void* stream);
+
+/* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).
  * The reference is single-process: nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79
  * normalise with the statistics of the WHOLE batch.  With the batch sharded

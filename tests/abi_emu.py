@@ -1,0 +1,219 @@
+"""TEST INFRASTRUCTURE — CPU interpreter of the C-ABI entry points a host module calls (include/hwg_b200.h semantics, plain
+torch/numpy on raw addresses), so that the HOST-side composition of a drop-in module — tap lists, operand packing, shapes,
+residual / Dropout2d / GroupNorm bookkeeping, the backward chain — can be checked against the oracle without a GPU.
+
+It is a checker, never a fallback: it is installed by monkeypatching `_lib.call` inside a test (`installed()`), nothing in
+the package imports it, and the GPU tests compare the real kernels with the same oracle.  Storage types follow the kernels
+(NHWC bf16 activations, fp32 statistics); arithmetic is fp32."""
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+from handwriting_line_generation_b200 import _lib, weightmap
+
+from . import ref_map
+
+
+def _view(ptr, n, dtype):
+    """Tensor view (shared memory) of n elements of `dtype` at address ptr."""
+    if ptr is None or ptr == 0:
+        return None
+    if dtype == torch.bfloat16:
+        a = np.frombuffer((ctypes.c_uint16 * n).from_address(ptr), dtype=np.uint16)
+        return torch.from_numpy(a).view(torch.bfloat16)
+    a = np.frombuffer((ctypes.c_float * n).from_address(ptr), dtype=np.float32)
+    return torch.from_numpy(a)
+
+
+def _act(v, act, slope):
+    if act == _lib.ACT_RELU:
+        return torch.relu(v)
+    if act == _lib.ACT_LRELU:
+        return torch.where(v > 0, v, slope * v)
+    assert act == _lib.ACT_NONE
+    return v
+
+
+def hwg_conv_fprop(d_addr, x, w, bias, noise, noise_w, stats, y, stream):
+    d = _lib.ConvDesc.from_address(d_addr)
+    assert noise is None and noise_w is None and d.fold_c == 0 and d.in_stride_h <= 1 and d.in_stride_w <= 1
+    N, H, W, Ci, Cp, Co, Ho, Wo, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps
+    xv = _view(x, N * H * W * Cp, torch.bfloat16).view(N, H, W, Cp)[..., :Ci].float()
+    wv = _view(w, T * Co * Ci, torch.bfloat16).view(T, Co, Ci).float()
+    taps = [(d.tap_dh[t], d.tap_dw[t]) for t in range(T)]
+    P = max(max(abs(a), abs(b)) for a, b in taps) + max(Ho, Wo, H, W)        # out-of-bounds reads are zero
+    xp = torch.nn.functional.pad(xv, (0, 0, P, P, P, P))
+    acc = torch.zeros((N, Ho, Wo, Co))
+    for t, (dh, dw) in enumerate(taps):
+        acc += xp[:, P + dh:P + dh + Ho, P + dw:P + dw + Wo, :] @ wv[t].t()
+    if bias is not None:
+        acc += _view(bias, Co, torch.float32)
+    acc = _act(acc, d.act, d.slope)
+    ydt = torch.float32 if d.y_dtype == _lib.DT_F32 else torch.bfloat16
+    out = acc.to(ydt)
+    if stats is not None:
+        st = _view(stats, N * Co * 2, torch.float32).view(N, Co, 2)
+        st[:, :, 0] += out.float().sum((1, 2))
+        st[:, :, 1] += (out.float() ** 2).sum((1, 2))
+    span = (N - 1) * d.y_stride_n + (Ho - 1) * d.y_stride_h + (Wo - 1) * d.y_stride_w + Co
+    yv = torch.as_strided(_view(y, span, ydt), (N, Ho, Wo, Co), (d.y_stride_n, d.y_stride_h, d.y_stride_w, 1))
+    yv.copy_(out)
+    return 0
+
+
+def hwg_shift_expand(img, out, N, H, W, kw, pad, stream):
+    iv = _view(img, N * H * W, torch.float32).view(N, H, W)
+    ov = _view(out, N * H * W * 16, torch.bfloat16).view(N, H, W, 16)
+    ip = torch.nn.functional.pad(iv, (16, 16))
+    ov.zero_()
+    for j in range(kw):
+        ov[..., j] = ip[:, :, 16 + j - pad:16 + j - pad + W].to(torch.bfloat16)
+    return 0
+
+
+def hwg_shift_collapse(g, dimg, N, H, W, kw, pad, accumulate, stream):
+    gv = _view(g, N * H * W * 16, torch.bfloat16).view(N, H, W, 16).float()
+    dv = _view(dimg, N * H * W, torch.float32).view(N, H, W)
+    gp = torch.nn.functional.pad(gv, (0, 0, 16, 16))
+    acc = torch.zeros((N, H, W))
+    for j in range(kw):
+        acc += gp[:, :, 16 - j + pad:16 - j + pad + W, j]
+    dv.copy_(dv + acc if accumulate else acc)
+    return 0
+
+
+def hwg_gn_coeffs(stats, gamma, beta, N, C, groups, HW, eps, coef, save, stream):
+    st = _view(stats, N * C * 2, torch.float32).view(N, groups, C // groups, 2)
+    cnt = (C // groups) * HW
+    mean = st[..., 0].sum(2) / cnt
+    var = st[..., 1].sum(2) / cnt - mean * mean
+    rstd = 1.0 / torch.sqrt(var + eps)
+    mean_c, rstd_c = (t.repeat_interleave(C // groups, 1) for t in (mean, rstd))
+    gm = _view(gamma, C, torch.float32) if gamma else torch.ones(C)
+    bt = _view(beta, C, torch.float32) if beta else torch.zeros(C)
+    a = gm * rstd_c
+    _view(coef, N * C * 2, torch.float32).view(N, C, 2).copy_(torch.stack((a, bt - mean_c * a), -1))
+    if save:
+        _view(save, N * C * 2, torch.float32).view(N, C, 2).copy_(torch.stack((mean_c, rstd_c), -1))
+    return 0
+
+
+def hwg_scale_shift_act(x, out, coef, per_sample, N, HW, C, act, slope, stream):
+    xv = _view(x, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    cf = _view(coef, (N if per_sample else 1) * C * 2, torch.float32).view(-1, 1, C, 2)
+    _view(out, N * HW * C, torch.bfloat16).view(N, HW, C).copy_(_act(cf[..., 0] * xv + cf[..., 1], act, slope))
+    return 0
+
+
+def hwg_avgpool_nhwc(x, y, N, H, W, C, kh, kw, stream):
+    xv = _view(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float()
+    Ho, Wo = H // kh, W // kw
+    p = xv[:, :Ho * kh, :Wo * kw].reshape(N, Ho, kh, Wo, kw, C).mean((2, 4))
+    _view(y, N * Ho * Wo * C, torch.bfloat16).view(N, Ho, Wo, C).copy_(p)
+    return 0
+
+
+def hwg_add_stats(a, b, y, N, HW, C, stats, stream):
+    s = (_view(a, N * HW * C, torch.bfloat16).float() + _view(b, N * HW * C, torch.bfloat16).float()).to(torch.bfloat16)
+    _view(y, N * HW * C, torch.bfloat16).copy_(s)
+    if stats:
+        st = _view(stats, N * C * 2, torch.float32).view(N, C, 2)
+        sf = s.float().view(N, HW, C)
+        st[:, :, 0] += sf.sum(1)
+        st[:, :, 1] += (sf * sf).sum(1)
+    return 0
+
+
+def hwg_l1_halves(f, dtype, half, loss_scale, grad_scale, loss, g, stream):
+    fv = _view(f, 2 * half, torch.float32 if dtype == _lib.DT_F32 else torch.bfloat16).float()
+    d = fv[half:] - fv[:half]
+    _view(loss, 1, torch.float32).add_(loss_scale * d.abs().sum())
+    if g:
+        _view(g, half, torch.bfloat16).copy_(grad_scale * torch.sign(d))
+    return 0
+
+
+def _up(g, N, H, W, C, kh, kw):
+    """Gradient of the AvgPool2d(kh,kw) output spread back over the [N,H,W,C] grid (zero where the floor drops rows)."""
+    Ho, Wo = H // kh, W // kw
+    gv = _view(g, N * Ho * Wo * C, torch.bfloat16).view(N, Ho, Wo, C).float() / (kh * kw)
+    full = torch.zeros((N, H, W, C))
+    full[:, :Ho * kh, :Wo * kw] = gv.repeat_interleave(kh, 1).repeat_interleave(kw, 2)
+    return full
+
+
+def _gyp(g, z, coef, slope, N, H, W, C, kh, kw):
+    zv = _view(z, N * H * W * C, torch.bfloat16).view(N, H, W, C).float()
+    cf = _view(coef, N * C * 2, torch.float32).view(N, 1, 1, C, 2)
+    pre = cf[..., 0] * zv + cf[..., 1]
+    return _up(g, N, H, W, C, kh, kw) * torch.where(pre > 0, torch.ones(()), torch.full((), slope)), zv
+
+
+def hwg_norm_bwd_reduce(g, z, coef, slope, N, H, W, C, kh, kw, sums, stream):
+    gy, zv = _gyp(g, z, coef, slope, N, H, W, C, kh, kw)
+    sv = _view(sums, N * C * 2, torch.float32).view(N, C, 2)
+    sv[:, :, 0] += gy.sum((1, 2))
+    sv[:, :, 1] += (gy * zv).sum((1, 2))
+    return 0
+
+
+def hwg_gn_bwd_coeffs(sums, save, gamma, N, C, groups, HW, spq, dgamma, dbeta, stream):
+    cg = C // groups
+    sv = _view(sums, N * C * 2, torch.float32).view(N, C, 2)
+    sa = _view(save, N * C * 2, torch.float32).view(N, C, 2)
+    gm = _view(gamma, C, torch.float32) if gamma else torch.ones(C)
+    mu, r = sa[..., 0], sa[..., 1]
+    T = r * (sv[..., 1] - mu * sv[..., 0])
+    cnt = cg * HW
+    A = (gm * sv[..., 0]).view(N, groups, cg).sum(2).repeat_interleave(cg, 1) / cnt
+    B = (gm * T).view(N, groups, cg).sum(2).repeat_interleave(cg, 1) / cnt
+    _view(spq, N * C * 3, torch.float32).view(N, C, 3).copy_(torch.stack((r * gm, -r * r * B, -r * A + r * r * mu * B), -1))
+    if dgamma:
+        _view(dgamma, C, torch.float32).add_(T.sum(0))
+    if dbeta:
+        _view(dbeta, C, torch.float32).add_(sv[..., 0].sum(0))
+    return 0
+
+
+def hwg_norm_bwd_apply(g, z, coef, spq, slope, N, H, W, C, kh, kw, gz, stream):
+    gy, zv = _gyp(g, z, coef, slope, N, H, W, C, kh, kw)
+    sp = _view(spq, N * C * 3, torch.float32).view(N, 1, 1, C, 3)
+    _view(gz, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(sp[..., 0] * gy + sp[..., 1] * zv + sp[..., 2])
+    return 0
+
+
+def hwg_act_bwd(g, y, scale, slope, N, H, W, C, kh, kw, gz, stream):
+    yv = _view(y, N * H * W * C, torch.bfloat16).view(N, H, W, C).float()
+    out = _up(g, N, H, W, C, kh, kw) * torch.where(yv > 0, torch.ones(()), torch.full((), slope))
+    if scale:
+        out = out * _view(scale, N * C, torch.float32).view(N, 1, 1, C)
+    _view(gz, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(out)
+    return 0
+
+
+_TABLE = {f.__name__: f for f in (hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
+                                  hwg_avgpool_nhwc, hwg_add_stats, hwg_l1_halves, hwg_norm_bwd_reduce, hwg_gn_bwd_coeffs,
+                                  hwg_norm_bwd_apply, hwg_act_bwd)}
+
+
+@contextlib.contextmanager
+def installed(monkeypatch):
+    """Routes `_lib.call` to the interpreter above, `JobTable.run` to the CPU job-table interpreter and lifts the
+    CUDA-tensor check, for the duration of one test.  Records the entry points that were called."""
+    calls = []
+
+    def call(name, *args):
+        if name not in _TABLE:
+            raise NotImplementedError(f"abi_emu: {name} is not interpreted")
+        calls.append(name)
+        rc = _TABLE[name](*args)
+        assert rc == 0
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(_lib, "stream", lambda: 0)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(weightmap.JobTable, "run",
+                        lambda self, src_base=None, dst_base=None: ref_map.run_jobs_cpu(self, src_base, dst_base))
+    yield calls

@@ -1,0 +1,100 @@
+"""PENDING (never run on a GPU: written after round 1's GPU budget was spent) — promote to tests/test_enc_gpu.py after a
+green run on a B200:  python -m pytest tools/pending_test_enc_gpu.py -q   (from the repo root)
+
+The Encoder2 drop-in and its fused perceptual loss (handwriting_line_generation_b200/encoder2.py, hwg_add_stats,
+hwg_l1_halves) on the real kernels against the goldens of the UNMODIFIED reference (tests/golden/enc.npz: both feature
+tensors, the loss, its gradient w.r.t. the reconstructed image) and against the oracle on the same inputs.  The host-side
+composition is already pinned on CPU (tests/test_encoder2_cpu.py, through the C-ABI interpreter): a failure here points at
+a kernel or at a launch geometry the other modules do not exercise (valid 3x3 / 1x1 / 5-tap 16-channel launches, out_view
+row offsets of the (6,3) head's input gradient, sliced half-batch tensors)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import enc as oenc                      # noqa: E402
+from oracle import synth                            # noqa: E402
+from oracle.make_golden import ENC_CASES, digest    # noqa: E402
+from tests.test_enc_cpu import encoder2_state_dict  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+BF16_REL = 2e-2            # per-tensor rel-L2 of the bf16 path (north_star)
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def _case(name):
+    from handwriting_line_generation_b200.encoder2 import Encoder2
+    B, W, wseed, iseed, training = ENC_CASES[name]
+    sd = encoder2_state_dict(wseed)
+    r = np.random.RandomState(iseed + 7)
+    masks = [torch.from_numpy((r.rand(2 * B, c) >= 3 * p).astype(np.float32)) for _, c, p in oenc.DROPOUT_SITES]
+    image = torch.from_numpy(synth.hwr_case(B, W, iseed))
+    recon = torch.from_numpy(synth.hwr_case(B, W, iseed + 1))
+    m = Encoder2(32)
+    m.load_state_dict(sd)
+    m = m.cuda().train(training)
+    m.dropout_masks = masks
+    return m, sd, masks, image, recon, training
+
+
+@pytest.mark.parametrize("name", sorted(ENC_CASES))
+def test_encoder2_cuda_matches_reference_golden_and_oracle(name):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "enc.npz"))
+    m, sd, masks, image, recon, training = _case(name)
+    ofeats = oenc.encoder2_forward(sd, torch.cat((image, recon), 0), masks, training)
+    orecon = recon.clone().requires_grad_()
+    oloss = oenc.perceptual_loss(sd, image, orecon, masks, training)
+    oloss.backward()
+    with torch.no_grad():
+        feats = m(torch.cat((image, recon), 0).cuda())
+    r = recon.clone().cuda().requires_grad_()
+    loss = m.perceptual_loss(image.cuda(), r)
+    (2.0 * loss).backward()
+    torch.cuda.synchronize()
+    for i, (f, of) in enumerate(zip(feats, ofeats)):
+        assert list(f.shape) == gold[f"{name}/feat{i}/shape"].tolist()
+        assert rel_l2(f.cpu(), of) <= BF16_REL, (i, rel_l2(f.cpu(), of))
+        _, samp = digest(f.float().cpu().contiguous().numpy())          # the reference's own numbers, same sampling
+        ref = gold[f"{name}/feat{i}/sample"]
+        assert np.linalg.norm(samp[:2048] - ref) <= 3e-2 * np.linalg.norm(ref)
+    assert abs(loss.item() - float(gold[f"{name}/loss"])) <= 1e-2 * abs(float(gold[f"{name}/loss"]))
+    g, og = (r.grad / 2.0).cpu(), orecon.grad
+    cos = float((g.double() * og.double()).sum() / (g.double().norm() * og.double().norm()))
+    # L1 loss: sign gradients flip where a feature difference is inside the bf16 rounding; the CPU interpreter of the same
+    # composition (bf16 storage, fp32 arithmetic) measures cosine 0.982-0.984 and a norm ratio within 0.5 %
+    assert cos >= 0.96, cos
+    assert abs(float(g.norm() / og.norm()) - 1.0) <= 5e-2
+
+
+def test_hwg_add_stats_and_l1_halves_against_torch():
+    from handwriting_line_generation_b200 import _lib
+    g0 = torch.Generator().manual_seed(1)
+    for C, HW, N in ((32, 1000, 3), (64, 4096, 2), (16, 7, 1), (256, 33, 2)):
+        a = torch.randn((N, HW, C), generator=g0).to(torch.bfloat16).cuda()
+        b = torch.randn((N, HW, C), generator=g0).to(torch.bfloat16).cuda()
+        y = torch.empty_like(a)
+        st = torch.zeros((N, C, 2), device="cuda")
+        _lib.call("hwg_add_stats", a.data_ptr(), b.data_ptr(), y.data_ptr(), N, HW, C, st.data_ptr(), _lib.stream())
+        ref = (a.float() + b.float()).to(torch.bfloat16)
+        assert torch.equal(y, ref)
+        assert torch.allclose(st[:, :, 0], ref.float().sum(1), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(st[:, :, 1], (ref.float() ** 2).sum(1), rtol=1e-4, atol=1e-3)
+        _lib.call("hwg_add_stats", a.data_ptr(), b.data_ptr(), a.data_ptr(), N, HW, C, None, _lib.stream())   # in place
+        assert torch.equal(a, ref)
+    for dt, tdt in ((_lib.DT_F32, torch.float32), (_lib.DT_BF16, torch.bfloat16)):
+        f = torch.randn((2, 5000, 32), generator=g0).to(tdt).cuda()
+        f[1, :100] = f[0, :100]                                      # exact ties: sign(0) = 0
+        half = f.numel() // 2
+        loss = torch.zeros((), device="cuda")
+        g = torch.empty((half,), device="cuda", dtype=torch.bfloat16)
+        _lib.call("hwg_l1_halves", f.data_ptr(), dt, half, 1.0 / half, 0.5, loss.data_ptr(), g.data_ptr(), _lib.stream())
+        d = f[1].float() - f[0].float()
+        assert abs(loss.item() - d.abs().mean().item()) <= 1e-5 * d.abs().mean().item()
+        assert torch.equal(g.float(), (0.5 * torch.sign(d)).reshape(-1))
