@@ -8,8 +8,8 @@ One step (trainer/hw_with_style_trainer.py:514-530,752-764 `run_gen` with the ge
   backward           recognizer input-gradient chain (dgrad), generator dgrad + wgrad + norm/noise backward
   gradient all-reduce over NCCL (world > 1), launched from grad-ready hooks on a side stream (dp.GradReducer)
   clip_grad_value_(2) + Adam on the generator (lr 2e-4, betas (0.5, 0.999): configs/cf_IAM*.json:35-46, trainer :381)
-The discriminator and perceptual-encoder branches of the full step (BASELINE configs[2]) are not part
-of this path and are not executed.
+The frozen discriminator's adversarial branch (HWG_BENCH_NO_DISC=1 drops it) runs inside the step; the
+perceptual-encoder branch (Encoder2) is opt-in (HWG_BENCH_PERCEPTUAL=1) until that module has a green GPU parity run.
 
 Batch 16 lines per GPU (weak scaling; 8 GPUs = BASELINE configs[3]'s global batch 128), T_s = 256 -> 64x1024 px,
 IAM charset (80 classes), 40-character targets.
@@ -28,10 +28,18 @@ HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per
 HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
 DISC_GF_FWD_PER_LINE = 11.295     # SURVEY.md §8d / Appendix D, DiscriminatorAP forward conv GFLOP per 64x1024 line
 W_CTC, W_GEN = 1e-4, 1.0          # loss_weights genRecog / generator of the IAM GAN config (config json :58-61)
+W_PERC = 0.5                      # loss_weights perceptual (config json :56)
 
 
 def use_disc():
     return not os.environ.get("HWG_BENCH_NO_DISC")
+
+
+def use_perceptual():
+    """Opt-in (HWG_BENCH_PERCEPTUAL=1) until the Encoder2 drop-in has a green GPU parity run (encoder2.py: status): the
+    perceptual branch of BASELINE configs[2] — L1 between Encoder2 features of a (synthetic) real line batch and of the
+    generated lines (trainer :724-748), backward to the generated image."""
+    return bool(os.environ.get("HWG_BENCH_PERCEPTUAL"))
 
 
 DEFAULT_SYNC_BN = "peer"
@@ -45,7 +53,10 @@ def config(B, world, executed, sync_bn="off"):
                         "CTC loss fwd+bwd, " + disc + "ONE backward over the weighted sum of the two losses (the reference's per-loss gradient "
                         "balancing, trainer :300-377 / SURVEY 8 f2, which runs a backward per loss, is not built), "
                         "gradient all-reduce (N>1), clip + Adam on the generator; "
-                        + ("the perceptual (Encoder2) branch of SURVEY 8 f1 is not included" if use_disc() else
+                        + ("perceptual branch (frozen Encoder2(32) on [synthetic real lines ; generated lines], L1 between the "
+                           "halves of both feature tensors, input-gradient bwd over the generated half) included"
+                           if use_perceptual() else
+                           "the perceptual (Encoder2) branch of SURVEY 8 f1 is not included" if use_disc() else
                            "discriminator/perceptual branches (SURVEY 8 f1) not included"),
             "batch_per_gpu": B, "global_batch": B * world, "line_px": [64, 4 * GAN["Ts"]], "classes": GAN["C"],
             "target_chars": GAN["S"], "parallelism": f"dp{world}",
@@ -152,6 +163,10 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         disc = pkg.DiscriminatorAP(64, use_low=True, use_med=True).to(dev).train()   # IAM GAN config: dim 64, "use low"
         for p in disc.parameters():
             p.requires_grad_(False)        # 'gen' lesson: the discriminator only scores; its optimizer is not stepped
+    enc, real = None, None
+    if use_perceptual():
+        enc = pkg.Encoder2(32).to(dev).train()      # the trainer never calls .eval() on it (:136-158): Dropout2d active
+        real = torch.from_numpy(synth.hwr_case(B, 4 * Ts, 9000 + rank)).to(dev)
     # train-mode BatchNorm over the GLOBAL batch, as in the single-process reference: "peer" = in-kernel exchange over
     # NVLink peer memory (dp.PeerExchange), "nccl" = one NCCL all-reduce per layer and direction, "off" = per-rank
     sync_bn = os.environ.get("HWG_BENCH_SYNC_BN", DEFAULT_SYNC_BN) if world > 1 else "off"
@@ -216,6 +231,8 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             loss = loss + adv
         elif disc is not None:
             loss = loss + adversarial(img)
+        if enc is not None:
+            loss = loss + W_PERC * enc.perceptual_loss(real, img)
         loss.backward()
         if reducer is not None:
             reducer.finish()

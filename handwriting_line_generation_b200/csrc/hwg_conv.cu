@@ -63,7 +63,30 @@ struct ConvKParams {
   // run as one: the four rows of the initial transposed conv, the four parities of FusedUpsample)
   int fold_c, fold_w, stat_c;
   long long fold_sh, fold_sw;
+  // halo mode (development switch HWG_CONV_HALO, default off): the taps of a group are
+  // read as SHIFTED VIEWS of one halo tile instead of one 16 KiB operand tile per tap.  TW = 8, TH = 16, CK = 64.
+  int halo;              // 0: off
+  int halo_bo;           // 1: descriptors carry base_offset = (start >> 7) & 7 (tools/halo_probe.cu decides)
+  int hw_;               // halo tile width in pixels (TW + dw_max - dw_min)
+  int ha_bytes;          // halo tile bytes, rounded up to 1 KiB;  ha_tx: bytes the TMA box transfers
+  int ha_tx;
+  int hstage_bytes;      // ha_bytes + (wstat ? 0 : max group taps * b_bytes)
+  int hgroups;           // tap groups per K chunk (1: full 2-D halo; one per kernel row otherwise)
+  int dw_min;
+  int hg_first[HWG_MAX_TAPS], hg_ntaps[HWG_MAX_TAPS], hg_dh[HWG_MAX_TAPS];   // per group: first tap, taps, box row origin
 };
+
+// K-major SWIZZLE_128B descriptor of a shifted view into a halo tile: rows of 128 bytes, 8-row groups `sbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_view128(uint32_t start, uint32_t sbo, uint32_t use_bo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((start & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (use_bo) d |= (uint64_t)((start >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 // Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
 // Recursive halving: 31 shuffles instead of 32*5.
@@ -86,7 +109,9 @@ __device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %
 
 // Template parameters >= 0 fix an epilogue option at compile time; -1 leaves it to the runtime
 // value in ConvKParams (generic fallback used by uncommon combinations).
-template <int ACT_T, int NOISE_T, int STATS_T, int F32_T>
+// HALO_T: the halo-mode main loop (development, see ConvKParams::halo) lives in its own instantiations so that the code
+// generated for the default path is exactly what the GPU runs of round 1 measured.
+template <int ACT_T, int NOISE_T, int STATS_T, int F32_T, bool HALO_T = false>
 __global__ void __launch_bounds__(320)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ ConvKParams p) {
@@ -95,7 +120,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int stage_bytes = p.gsize * p.unit_bytes;
+  const int stage_bytes = HALO_T ? p.hstage_bytes : p.gsize * p.unit_bytes;
   const int kiters = p.ntaps * p.kchunks;
   unsigned char* wsmem = smem + (size_t)p.stages * stage_bytes;                      // resident weights (wstat)
   float* bias_s = reinterpret_cast<float*>(wsmem + (p.wstat ? (size_t)kiters * p.b_bytes : 0));  // [cpad]
@@ -157,6 +182,24 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int tw_i = pt % p.tiles_w, r = pt / p.tiles_w;
         const int th_i = r % p.tiles_h, n = r / p.tiles_h;
         const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH, n0 = nt * p.BN;
+        if constexpr (HALO_T) {
+          // one halo tile (+ the group's weight tiles) per (K chunk, tap group)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int g = 0; g < p.hgroups; ++g) {
+              const int nt = p.hg_ntaps[g];
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              unsigned char* dst = smem + (size_t)stage * stage_bytes;
+              mbar_expect_tx(&full_bar[stage], (uint32_t)p.ha_tx + (p.wstat ? 0u : b_tx * (uint32_t)nt));
+              tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.dw_min, ho0 + p.hg_dh[g], n);
+              if (!p.wstat)
+                for (int j = 0; j < nt; ++j)
+                  tma_load_2d(dst + p.ha_bytes + (size_t)j * p.b_bytes, &tmap_w, &full_bar[stage], kc * p.CK,
+                              (p.hg_first[g] + j) * p.Cout + n0);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          continue;
+        }
         int tp = 0, kc = 0, it = 0;
         for (int g = 0; g < p.ngroups; ++g) {
           const int nsub = min(p.gsize, kiters - it);
@@ -188,6 +231,35 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
+        if constexpr (HALO_T) {
+          uint32_t acc = 0u;
+          const uint32_t sbo = (uint32_t)p.hw_ * 128u;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            for (int g = 0; g < p.hgroups; ++g) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+              for (int j = 0; j < p.hg_ntaps[g]; ++j) {
+                const int tp = p.hg_first[g] + j;
+                // MMA row (ty, tx) reads halo pixel (ty + dh - origin, tx + dw - dw_min): shifted start, group stride
+                // = one halo row
+                const uint32_t start = a_addr + (uint32_t)(((p.tap_dh[tp] - p.hg_dh[g]) * p.hw_ +
+                                                            (p.tap_dw[tp] - p.dw_min)) * 128);
+                const uint64_t da = umma_desc_view128(start, sbo, (uint32_t)p.halo_bo);
+                const uint64_t db = umma_desc_kmajor(p.wstat ? w_addr + (uint32_t)((tp * p.kchunks + kc) * p.b_bytes)
+                                                             : a_addr + (uint32_t)(p.ha_bytes + j * p.b_bytes), 128u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc);
+                  acc = 1u;
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          umma_commit(&tmem_full[a]);
+          continue;
+        }
         int it = 0;
         for (int g = 0; g < p.ngroups; ++g) {
           const int nsub = min(p.gsize, kiters - it);
@@ -507,6 +579,13 @@ static ConvKernel pick_kernel(const ConvKParams& p) {
   if (f && nz == 0 && !st && a == HWG_ACT_LOGSOFTMAX) return conv_fprop_kernel<HWG_ACT_LOGSOFTMAX, 0, 0, 1>;
   return conv_fprop_kernel<-1, -1, -1, -1>;
 }
+static ConvKernel pick_kernel_halo(const ConvKParams& p) {
+  const int a = p.act, nz = p.noise_mode, st = p.has_stats, f = p.y_f32;
+  if (!f && nz == 0 && !st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 0, 0, true>;
+  if (!f && nz == 0 && st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 1, 0, true>;
+  if (!f && nz == 0 && !st && a == HWG_ACT_RELU) return conv_fprop_kernel<HWG_ACT_RELU, 0, 0, 0, true>;
+  return conv_fprop_kernel<-1, -1, -1, -1, true>;
+}
 
 int conv_small_try(const hwgConvDesc* d, const void* x, const void* w, const float* bias, const float* noise,
                    const float* noise_w, float* stats, void* y, void* stream);   // hwg_conv_small.cu
@@ -563,8 +642,43 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     if ((bn == 64 || bn == 128 || bn == 256) && bn <= cout16 && d->act != HWG_ACT_LOGSOFTMAX) p.BN = bn;
   }
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
+  // ---- halo mode (development switch HWG_CONV_HALO=1|2, default off; never run on a GPU yet: DESIGN section 10) ----
+  // 1: full 2-D halo tile per K chunk when the weights fit next to it, else one halo tile per kernel row; 2: force rows.
+  static const int halo_env = [] { const char* e = getenv("HWG_CONV_HALO"); return e ? atoi(e) : 0; }();
+  static const int halo_bo_env = getenv("HWG_CONV_HALO_BO") != nullptr ? 1 : 0;
+  int halo_mode = 0, h_dh_min = 0, h_dh_max = 0, h_dw_min = 0, h_dw_max = 0, h_wstat = 0, h_maxrow = 0;
+  if (halo_env > 0 && d->Cin % 64 == 0 && d->in_stride_h <= 1 && d->in_stride_w <= 1 && d->ntaps >= 2 && !d->fold_c &&
+      d->Ho >= 12 && d->Wo >= 8) {     // overrides a caller's tile_w: the halo tile is always 8 x 16
+    h_dh_min = h_dh_max = d->tap_dh[0]; h_dw_min = h_dw_max = d->tap_dw[0];
+    bool rows_contiguous = true;          // taps of one kernel row must be adjacent in the list (row-major lists are)
+    int run = 1, dir = 0;
+    h_maxrow = 1;
+    for (int t = 1; t < d->ntaps; ++t) {
+      h_dh_min = d->tap_dh[t] < h_dh_min ? d->tap_dh[t] : h_dh_min; h_dh_max = d->tap_dh[t] > h_dh_max ? d->tap_dh[t] : h_dh_max;
+      h_dw_min = d->tap_dw[t] < h_dw_min ? d->tap_dw[t] : h_dw_min; h_dw_max = d->tap_dw[t] > h_dw_max ? d->tap_dw[t] : h_dw_max;
+      if (d->tap_dh[t] == d->tap_dh[t - 1]) { ++run; }
+      else {
+        const int nd = d->tap_dh[t] > d->tap_dh[t - 1] ? 1 : -1;
+        if (dir != 0 && nd != dir) rows_contiguous = false;
+        dir = nd; run = 1;
+      }
+      h_maxrow = run > h_maxrow ? run : h_maxrow;
+    }
+    if (rows_contiguous && h_dw_max - h_dw_min <= 8 && h_dh_max - h_dh_min <= 8) {
+      const int hw = 8 + h_dw_max - h_dw_min;
+      const int bb = round_up(p.BN * 64 * 2, 1024);
+      const int kit = d->ntaps * (d->Cin / 64);
+      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+      const size_t wall = (size_t)kit * bb;
+      h_wstat = (p.n_tiles == 1 && wall <= 144 * 1024) ? 1 : 0;
+      const size_t avail = 200 * 1024 - fx - (h_wstat ? wall : 0);
+      const size_t ha2 = round_up(hw * (16 + h_dh_max - h_dh_min) * 128, 1024), ha1 = round_up(hw * 16 * 128, 1024);
+      if (halo_env == 1 && 2 * (ha2 + (h_wstat ? 0 : (size_t)d->ntaps * bb)) <= avail) halo_mode = 2;
+      else if (2 * (ha1 + (h_wstat ? 0 : (size_t)h_maxrow * bb)) <= avail) halo_mode = 1;
+    }
+  }
   // output tile TW x TH = 128 pixels
-  int TW = d->tile_w;
+  int TW = halo_mode ? 8 : d->tile_w;
   if (TW == 0) {
     // the power of two that wastes the fewest pixels; ties go to the wider tile
     long best = -1; TW = 128;
@@ -603,8 +717,8 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   if (p.gsize > kiters) p.gsize = kiters;
   p.ngroups = (kiters + p.gsize - 1) / p.gsize;
   p.gsize = (kiters + p.ngroups - 1) / p.ngroups;   // balance the groups
-  const int stage_bytes = p.gsize * p.unit_bytes;
-  const size_t wbytes = p.wstat ? (size_t)kiters * p.b_bytes : 0;
+  int stage_bytes = p.gsize * p.unit_bytes;
+  size_t wbytes = p.wstat ? (size_t)kiters * p.b_bytes : 0;
   // two CTAs per SM when everything is small (the memory-bound layers): more epilogue warps in flight
   const int sms = num_sms();
   int ctas_per_sm = 1;
@@ -616,6 +730,35 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     if (p.stages > 8) p.stages = 8;
   }
   if (p.stages < 2) p.stages = 2;
+  if (halo_mode) {
+    // stage = one halo tile (+ the weight tiles of its tap group unless the weights are resident); one CTA per SM
+    p.halo = 1; p.halo_bo = halo_bo_env;
+    p.wstat = h_wstat;
+    wbytes = p.wstat ? (size_t)kiters * p.b_bytes : 0;
+    p.hw_ = 8 + h_dw_max - h_dw_min;
+    p.dw_min = h_dw_min;
+    const int hh = halo_mode == 2 ? 16 + h_dh_max - h_dh_min : 16;
+    p.ha_tx = p.hw_ * hh * 128;
+    p.ha_bytes = round_up(p.ha_tx, 1024);
+    p.hgroups = 0;
+    if (halo_mode == 2) {
+      p.hgroups = 1; p.hg_first[0] = 0; p.hg_ntaps[0] = d->ntaps; p.hg_dh[0] = h_dh_min;
+    } else {
+      for (int t = 0; t < d->ntaps; ++t) {
+        if (t == 0 || d->tap_dh[t] != d->tap_dh[t - 1]) {
+          p.hg_first[p.hgroups] = t; p.hg_ntaps[p.hgroups] = 0; p.hg_dh[p.hgroups] = d->tap_dh[t]; ++p.hgroups;
+        }
+        ++p.hg_ntaps[p.hgroups - 1];
+      }
+    }
+    const int gmax = halo_mode == 2 ? d->ntaps : h_maxrow;
+    p.hstage_bytes = p.ha_bytes + (p.wstat ? 0 : gmax * p.b_bytes);
+    stage_bytes = p.hstage_bytes;
+    ctas_per_sm = 1;
+    p.stages = (int)((200 * 1024 - fixed - wbytes) / stage_bytes);
+    if (p.stages > 8) p.stages = 8;
+    HWG_REQUIRE(p.stages >= 2, "hwg_conv_fprop: halo mode does not fit shared memory (internal)");
+  }
   p.acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   p.tmem_cols = 2 * p.acc_stride;
   int grid = sms * ctas_per_sm;
@@ -643,6 +786,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     cuuint64_t strides[3] = {(cuuint64_t)d->x_pitch * 2, (cuuint64_t)d->W * d->x_pitch * 2,
                              (cuuint64_t)d->H * d->W * d->x_pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)p.CK, (cuuint32_t)(p.TW * p.isw), (cuuint32_t)(p.TH * p.ish), 1};
+    if (p.halo) { box[1] = (cuuint32_t)p.hw_; box[2] = (cuuint32_t)(p.ha_tx / (p.hw_ * 128)); }   // the halo tile
     cuuint32_t estr[4] = {1, (cuuint32_t)p.isw, (cuuint32_t)p.ish, 1};
     CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -660,7 +804,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return HWG_ERR_CUDA; }
   }
   const size_t smem = (size_t)p.stages * stage_bytes + wbytes + fixed;
-  ConvKernel k = pick_kernel(p);
+  ConvKernel k = p.halo ? pick_kernel_halo(p) : pick_kernel(p);
   HWG_SMEM_OPTIN(k);
   // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently
   k<<<grid, ctas_per_sm == 1 ? 320 : 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
