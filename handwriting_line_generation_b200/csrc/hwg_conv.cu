@@ -186,13 +186,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // one halo tile (+ the group's weight tiles) per (K chunk, tap group)
           for (int kc = 0; kc < p.kchunks; ++kc) {
             for (int g = 0; g < p.hgroups; ++g) {
-              const int nt = p.hg_ntaps[g];
+              const int gtaps = p.hg_ntaps[g];
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               unsigned char* dst = smem + (size_t)stage * stage_bytes;
-              mbar_expect_tx(&full_bar[stage], (uint32_t)p.ha_tx + (p.wstat ? 0u : b_tx * (uint32_t)nt));
+              mbar_expect_tx(&full_bar[stage], (uint32_t)p.ha_tx + (p.wstat ? 0u : b_tx * (uint32_t)gtaps));
               tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.dw_min, ho0 + p.hg_dh[g], n);
               if (!p.wstat)
-                for (int j = 0; j < nt; ++j)
+                for (int j = 0; j < gtaps; ++j)
                   tma_load_2d(dst + p.ha_bytes + (size_t)j * p.b_bytes, &tmap_w, &full_bar[stage], kc * p.CK,
                               (p.hg_first[g] + j) * p.Cout + n0);
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
