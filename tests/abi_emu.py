@@ -193,7 +193,39 @@ def hwg_act_bwd(g, y, scale, slope, N, H, W, C, kh, kw, gz, stream):
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
+def hwg_balance(g_main, sets_host, K, x_dev, seg_off, seg_len, nseg, block_tab, nblocks, sums, mult, stream):
+    """Header semantics (include/hwg_b200.h): D_s += x_k * R_k,s * (mean|D_s| / mean|R_k,s|), mean|D_s| taken first, exact
+    zeros replaced by the average of the non-zero means, sets with mean|R_k,s| == 0 skipped.  Also checks that the
+    (segment, chunk) table covers every segment exactly once per chunk."""
+    chunk = _lib.load().hwg_balance_chunk()
+    off = np.frombuffer((ctypes.c_int64 * nseg).from_address(seg_off), dtype=np.int64)
+    ln = np.frombuffer((ctypes.c_int64 * nseg).from_address(seg_len), dtype=np.int64)
+    tab = np.frombuffer((ctypes.c_int32 * (2 * nblocks)).from_address(block_tab), dtype=np.int32).reshape(-1, 2)
+    want = [(s_, c) for s_ in range(nseg) for c in range(-(-int(ln[s_]) // chunk))]
+    assert sorted(map(tuple, tab.tolist())) == want, "block table does not tile the segments"
+    total = int((off + ln).max())
+    g = _view(g_main, total, torch.float32)
+    ptrs = (ctypes.c_void_p * K).from_address(sets_host)
+    sets = [_view(ptrs[k], total, torch.float32) for k in range(K)]
+    x = _view(x_dev, K, torch.float32)
+    means = [g[int(o):int(o + n)].abs().mean() for o, n in zip(off, ln)]
+    nz = [m for m in means if m != 0]
+    fill = sum(nz) / len(nz) if nz else None
+    for s_, (o, n) in enumerate(zip(off, ln)):
+        o, n = int(o), int(n)
+        mD = means[s_] if (means[s_] != 0 or fill is None) else fill
+        D = g[o:o + n]
+        add = torch.zeros(n)
+        for k in range(K):
+            R = sets[k][o:o + n]
+            r = R.abs().mean()
+            if r != 0:
+                add += x[k] * R * (mD / r)
+        D += add
+    return 0
+
+
+_TABLE = {f.__name__: f for f in (hwg_balance, hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
                                   hwg_avgpool_nhwc, hwg_add_stats, hwg_l1_halves, hwg_norm_bwd_reduce, hwg_gn_bwd_coeffs,
                                   hwg_norm_bwd_apply, hwg_act_bwd)}
 

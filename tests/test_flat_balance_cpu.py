@@ -1,0 +1,42 @@
+"""CPU: the HOST side of `FlatAdam.stash()` / `FlatAdam.balance()` (trainer/hw_with_style_trainer.py:300-377):
+the stash bookkeeping, the segment / block tables and the pointer array handed to `hwg_balance`, run through the CPU
+interpreter of the C-ABI (tests/abi_emu.py, which also checks that the block table tiles every segment) and compared with
+oracle/balance.py — the restatement tests/test_balance_cpu.py pins to the unmodified reference trainer.  The kernel itself
+has not run on a GPU yet: tools/pending_test_balance_gpu.py is the same scenario on the real launches."""
+import torch
+
+from oracle import balance as obal
+
+from . import abi_emu
+
+
+def test_flat_stash_and_balance_match_the_oracle(hwg_lib, monkeypatch):
+    import handwriting_line_generation_b200 as pkg
+    g0 = torch.Generator().manual_seed(0)
+    shapes = [(64, 32, 3, 3), (64,), (5000,), (1,), (3, 7), (128, 128, 3, 3), (17,)]
+    with abi_emu.installed(monkeypatch) as calls:
+        params = [torch.nn.Parameter(torch.randn(s, generator=g0)) for s in shapes]
+        opt = pkg.FlatAdam(params, lr=1e-3)
+        K, mult = 4, [0.6, 0.5, 0.4, 0.75]
+        sets_cpu = []
+        for k in range(K):
+            grads = [torch.randn(s, generator=g0) * (0.1 + k) for s in shapes]
+            if k == 1:
+                grads[2] = torch.zeros(shapes[2])            # a set without a gradient for this tensor: skipped (:373)
+            sets_cpu.append(grads)
+            for p, g in zip(params, grads):
+                opt.grad_view(p).copy_(g)
+            opt.stash()
+            assert float(opt.flat_g.abs().max()) == 0.0
+        main_cpu = [torch.randn(s, generator=g0) * 0.01 for s in shapes]
+        main_cpu[3] = torch.zeros(shapes[3])                 # mean|D| == 0: takes the fill value (:354-359)
+        for p, g in zip(params, main_cpu):
+            opt.grad_view(p).copy_(g)
+        ref = obal.balance([g.clone() for g in main_cpu], sets_cpu, mult)
+        opt.balance(mult)
+        assert opt._stash == [] and calls == ["hwg_balance"]
+        for p, r in zip(params, ref):
+            got = opt.grad_view(p)
+            assert float((got - r).abs().max()) <= 2e-6 * float(r.abs().max()) + 1e-12
+        opt.balance(mult)                                    # nothing stashed: a no-op, no launch
+        assert calls == ["hwg_balance"]
