@@ -808,6 +808,6 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   HWG_SMEM_OPTIN(k);
   // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently
   k<<<grid, ctas_per_sm == 1 ? 320 : 192, smem, (cudaStream_t)stream>>>(tmx, tmw, p);
-  g_last_conv_kernel.store(1);
+  g_last_conv_kernel.store(p.halo ? (p.hgroups == 1 ? 3 : 4) : 1);
   return check_launch("conv_fprop_kernel");
 }

@@ -176,8 +176,9 @@ int hwg_conv_fprop(const hwgConvDesc* desc, const void* x, const void* w, const 
                    const float* noise, const float* noise_w, float* stats, void* y,
                    void* stream);
 /* Which kernel served the most recent hwg_conv_fprop call: 1 = conv_fprop_kernel (tcgen05 implicit GEMM, the
- * tensor-bound layers), 2 = conv_small_kernel (TMA-staged tiles + mma.sync, the HBM-bound 16-64 channel layers).
- * For benchmarks / profiles. */
+ * tensor-bound layers), 2 = conv_small_kernel (TMA-staged tiles + mma.sync, the HBM-bound 16-64 channel layers),
+ * 3 / 4 = conv_fprop_kernel with the halo-tile main loop (development switch HWG_CONV_HALO; 3 = one 2-D halo tile per
+ * K chunk, 4 = one halo tile per kernel row).  For benchmarks / profiles. */
 int hwg_last_conv_kernel(void);
 
 /* ------------------------------------------------------------------------

@@ -67,7 +67,8 @@ for name in which:
     us = e0.elapsed_time(e1) * 1e3 / reps
     fl = 2.0 * N * Ho * Wo * Cout * Cin * kh * kw
     by = (x.numel() + out.numel()) * 2
-    print(f"{name:16s} {us:9.1f} us  {fl / us / 1e6:8.1f} TFLOP/s  act-bytes {by / us / 1e3:8.1f} GB/s", flush=True)
+    kern = {1: "tcgen05", 2: "small", 3: "tcgen05+halo2d", 4: "tcgen05+halo-rows"}.get(_lib.load().hwg_last_conv_kernel(), "?")
+    print(f"{name:16s} {us:9.1f} us  {fl / us / 1e6:8.1f} TFLOP/s  act-bytes {by / us / 1e3:8.1f} GB/s  [{kern}]", flush=True)
 
 if "blur_b4" in sys.argv[1:]:
     from handwriting_line_generation_b200 import ops
