@@ -13,3 +13,5 @@ from .encoder2 import Encoder2  # noqa: F401  (not yet run on a GPU: see its mod
 
 __all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam",
            "DiscriminatorAP", "Encoder2"]
+
+set_retain_graph = _lib.set_retain_graph   # keep saved state over repeated .backward(retain_graph=True) calls (see _lib.py)

@@ -137,6 +137,29 @@ def load():
     return _lib
 
 
+# The autograd.Functions of the drop-in modules keep their saved-for-backward state in a python object on ctx and drop it
+# at the end of backward (what autograd does with retain_graph=False).  The reference trainer's gradient balancing calls
+# .backward(retain_graph=True) several times on ONE graph (trainer/hw_with_style_trainer.py:303,314,325): with
+# RETAIN_SAVED the state is kept until the graph itself is released, so repeated backward passes work.
+RETAIN_SAVED = bool(os.environ.get("HWG_RETAIN_GRAPH"))
+
+
+def set_retain_graph(flag=True):
+    global RETAIN_SAVED
+    RETAIN_SAVED = bool(flag)
+
+
+def saved_state(state):
+    """The saved-for-backward state of a module Function, or torch's own complaint when it has been released."""
+    if state is None:
+        raise RuntimeError("Trying to backward through the graph a second time: the saved state of this "
+                           "handwriting_line_generation_b200 module was released by the first backward.  Call "
+                           "handwriting_line_generation_b200.set_retain_graph(True) (or integrate.install(retain_graph=True)) "
+                           "before the forward when .backward(retain_graph=True) is used, as the reference trainer's "
+                           "gradient balancing does.")
+    return state
+
+
 _DEBUG_SYNC = bool(os.environ.get("HWG_DEBUG_SYNC"))   # development aid: synchronise after every launch, name the faulting one
 
 

@@ -16,7 +16,7 @@ from math import sqrt
 import torch
 import torch.nn.functional as F
 
-from . import conv, ops, weightmap
+from . import _lib, conv, ops, weightmap
 from ._lib import ACT_LRELU, ACT_NONE
 from .pure_gen import TAPS3x3, conv1_forward
 
@@ -342,7 +342,7 @@ class _StyleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_s, g_gb):
-        m, acts = ctx.module, ctx.acts
+        m, acts = ctx.module, _lib.saved_state(ctx.acts)
         c = m._packed()
         sink = getattr(m, "_grad_sink", None)
         sp = _style_params(m)
@@ -383,7 +383,8 @@ class _StyleFn(torch.autograd.Function):
             if ready is not None:
                 for p in sp:
                     ready(p)
-        ctx.acts = None
+        if not _lib.RETAIN_SAVED:
+            ctx.acts = None
         return (None, g) + tuple(grads)
 
 
@@ -398,8 +399,9 @@ class _GenFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         with torch.no_grad():
-            g_content, g_s, g_gb, flat = backward_train(ctx.module, ctx.saved, g)
-        ctx.saved = None
+            g_content, g_s, g_gb, flat = backward_train(ctx.module, _lib.saved_state(ctx.saved), g)
+        if not _lib.RETAIN_SAVED:
+            ctx.saved = None
         return (None, None, g_content, g_s, g_gb) + tuple(flat)
 
 

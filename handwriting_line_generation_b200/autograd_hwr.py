@@ -9,7 +9,7 @@ between them (log-softmax, BatchNorm+ReLU, ReLU+MaxPool, stem) emit the bias gra
 """
 import torch
 
-from . import conv, ops, weightmap
+from . import _lib, conv, ops, weightmap
 from ._lib import ACT_LOGSOFTMAX, ACT_NONE, ACT_RELU
 
 _T3 = conv.conv_taps(3, 3, 1, 1)
@@ -316,8 +316,9 @@ class _HWRFn(torch.autograd.Function):
     def backward(ctx, g):
         needed = {n for n, need in zip(ctx.names, ctx.needs_input_grad[3:]) if need}
         with torch.no_grad():
-            grads, g_img = backward_train(ctx.module, ctx.saved, g, ctx.x_needs_grad, needed)
-        ctx.saved = None
+            grads, g_img = backward_train(ctx.module, _lib.saved_state(ctx.saved), g, ctx.x_needs_grad, needed)
+        if not _lib.RETAIN_SAVED:
+            ctx.saved = None
         return (None, None, g_img) + tuple(grads[n] for n in ctx.names)
 
 

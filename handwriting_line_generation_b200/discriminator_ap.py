@@ -539,10 +539,12 @@ class _DiscFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
+        _lib.saved_state(ctx.saved)
         dev = ctx.saved["mL"].device
         grads = [torch.zeros(shp, device=dev) if g is None else g.contiguous().float()
                  for g, shp in zip(grads, ctx.saved["out_shapes"])]
         with torch.no_grad():
             dimg, pg = ctx.m._backward(ctx.saved, grads, ctx.x_needs_grad, ctx.names)
-        ctx.saved = None
+        if not _lib.RETAIN_SAVED:
+            ctx.saved = None
         return (None, None, dimg) + tuple(pg[n] for n in ctx.names)

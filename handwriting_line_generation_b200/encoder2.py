@@ -337,7 +337,7 @@ class _EncFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_feat, g_mid):
-        N, H, W = ctx.saved["shape"]
+        N, H, W = _lib.saved_state(ctx.saved)["shape"]
         dev = ctx.saved["a4"].device
 
         def nhwc(g, shape):
@@ -349,7 +349,8 @@ class _EncFn(torch.autograd.Function):
             gf = nhwc(g_feat, (N, 1, W // 8 - 4, ctx.m.out_dim))
             gm = None if g_mid is None else nhwc(g_mid, None)
             dimg = ctx.m._backward(ctx.saved, gf, gm, 0)
-        ctx.saved = None
+        if not _lib.RETAIN_SAVED:
+            ctx.saved = None
         return None, dimg
 
 
@@ -376,7 +377,8 @@ class _PerceptualFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         with torch.no_grad():
-            dimg = ctx.m._backward(ctx.saved, ctx.g[0], ctx.g[1], ctx.B)      # the recon half only
+            dimg = ctx.m._backward(_lib.saved_state(ctx.saved), ctx.g[0], ctx.g[1], ctx.B)      # the recon half only
             dimg.mul_(g_loss)                                                # the chain is linear in the loss gradient
-        ctx.saved = ctx.g = None
+        if not _lib.RETAIN_SAVED:
+            ctx.saved = ctx.g = None
         return None, None, dimg

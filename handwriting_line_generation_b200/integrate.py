@@ -7,15 +7,19 @@ and generate.py run the sm_100a path without a source change."""
 import importlib
 
 
-def install(encoder=False):
+def install(encoder=False, retain_graph=False):
     """Call after the reference's root is on sys.path and before HWWithStyle / the trainer are built.
     Returns the list of (module name, attribute) pairs that were rebound.
 
     encoder=True also rebinds `Encoder2`, the perceptual encoder the trainer builds for `encoder_type: "2tight"`
     (`from model.autoencoder import Encoder2`, trainer/hw_with_style_trainer.py:15,148-149) — opt-in until the module has
-    a green GPU parity run (encoder2.py: status)."""
-    from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator
+    a green GPU parity run (encoder2.py: status).
+    retain_graph=True keeps the modules' saved-for-backward state over repeated `.backward(retain_graph=True)` calls on one
+    graph — what the trainer does when `balance_loss` is configured (trainer/hw_with_style_trainer.py:300-338)."""
+    from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator, set_retain_graph
     swapped = []
+    if retain_graph:
+        set_retain_graph(True)
     if encoder:
         from .encoder2 import Encoder2
         for modname in ("model.autoencoder", "trainer.hw_with_style_trainer"):

@@ -127,3 +127,28 @@ def test_cpu_tensors_are_rejected_without_the_interpreter():
     m = Encoder2(32)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 1, 64, 128))
+
+
+def test_repeated_backward_needs_and_honours_set_retain_graph(hwg_lib, monkeypatch):
+    """The reference trainer's gradient balancing backpropagates several losses through ONE graph with retain_graph=True
+    (trainer :300-338).  Default: the saved state goes with the first backward and a second one fails with torch's own
+    wording; with set_retain_graph(True) the second backward reproduces the first."""
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import _lib
+    m, sd, masks, image, recon, training = _case("eval_w128")
+    with abi_emu.installed(monkeypatch):
+        r = recon.clone().requires_grad_()
+        loss = m.perceptual_loss(image, r)
+        loss.backward(retain_graph=True)
+        with pytest.raises(RuntimeError, match="second time"):
+            loss.backward()
+        monkeypatch.setattr(_lib, "RETAIN_SAVED", False)
+        pkg.set_retain_graph(True)
+        assert _lib.RETAIN_SAVED
+        r = recon.clone().requires_grad_()
+        loss = m.perceptual_loss(image, r)
+        loss.backward(retain_graph=True)
+        g1 = r.grad.clone()
+        loss.backward()
+        assert torch.equal(r.grad, 2 * g1)
+        pkg.set_retain_graph(False)
