@@ -42,12 +42,33 @@ def use_perceptual():
     return bool(os.environ.get("HWG_BENCH_PERCEPTUAL"))
 
 
+def use_balanced():
+    """Opt-in (HWG_BENCH_BALANCED=1, one GPU) until FlatAdam.stash()/balance() and Encoder2 have green GPU parity runs: the
+    optimizer step as the reference's curriculum takes it with `balance_loss` — a no-step 'gen' lesson whose adversarial
+    and recognition losses are back-propagated separately and stashed (trainer :300-338), then a lesson whose own gradient
+    (here: the perceptual loss of the 'auto' lesson) the stashed sets are balanced into per parameter tensor
+    (:340-377, `balance_var_x` of the config), then clip + Adam."""
+    return bool(os.environ.get("HWG_BENCH_BALANCED"))
+
+
+BALANCE_VAR_X = [0.6, 0.5]        # config :100 `balance_var_x` [0.6, 0.5, 0.4, 0.75]: the entries of the two sets stashed here
 DEFAULT_SYNC_BN = "peer"
 
 
 def config(B, world, executed, sync_bn="off"):
     disc = ("frozen discriminator_ap fwd (train mode: spectral-norm power iteration, Dropout2d) + input-gradient bwd "
             "for the adversarial loss -mean(D(fake)), " if use_disc() else "")
+    if use_balanced():
+        return {"workload": "HWWithStyle GAN balanced optimizer step (BASELINE configs[2] shapes), the reference curriculum's pair of "
+                            "lessons restricted to the built components: no-step 'gen' lesson = pure_gen generator fwd, frozen "
+                            "discriminator_ap fwd+bwd and frozen cnn_only_hwr fwd+bwd + CTC, the adversarial and the recognition "
+                            "loss back-propagated SEPARATELY through the generator and stashed; second lesson = generator fwd, "
+                            "frozen Encoder2(32) perceptual loss against synthetic real lines, backward; per-tensor gradient "
+                            "balancing of the two stashed sets into it (trainer :340-377), clip + Adam.  Two generator "
+                            "forwards and three generator backwards per step; the style extractor / spacer lessons (SURVEY 8 "
+                            "f3, f4) are not built",
+                "batch_per_gpu": B, "global_batch": B * world, "line_px": [64, 4 * GAN["Ts"]], "classes": GAN["C"],
+                "target_chars": GAN["S"], "parallelism": f"dp{world}", "execution": executed}
     return {"workload": "HWWithStyle GAN 'gen' lesson train step (BASELINE configs[2]/[3] shapes): "
                         "pure_gen generator fwd+bwd, frozen cnn_only_hwr fwd + input-gradient bwd (train-mode BatchNorm), "
                         "CTC loss fwd+bwd, " + disc + "ONE backward over the weighted sum of the two losses (the reference's per-loss gradient "
@@ -164,7 +185,10 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         for p in disc.parameters():
             p.requires_grad_(False)        # 'gen' lesson: the discriminator only scores; its optimizer is not stepped
     enc, real = None, None
-    if use_perceptual():
+    if use_balanced():
+        assert world == 1 and disc is not None, "HWG_BENCH_BALANCED: one GPU, with the discriminator branch"
+        pkg.set_retain_graph(True)         # the generator is back-propagated through twice on one graph
+    if use_perceptual() or use_balanced():
         enc = pkg.Encoder2(32).to(dev).train()      # the trainer never calls .eval() on it (:136-158): Dropout2d active
         real = torch.from_numpy(synth.hwr_case(B, 4 * Ts, 9000 + rank)).to(dev)
     # train-mode BatchNorm over the GLOBAL batch, as in the single-process reference: "peer" = in-kernel exchange over
@@ -238,6 +262,23 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
             reducer.finish()
         opt.step()             # clip + Adam + gradient zeroing, one launch
         return loss
+
+    def train_balanced(c, s, tg):
+        img = gen(c, s)                                       # lesson 1: 'gen', no-step
+        adv = adversarial(img)
+        recog = W_CTC * pkg.CTCLoss(hwr(img), tg, il, tl)
+        adv.backward(retain_graph=True)                       # trainer :300-311 (autoGenLoss first)
+        opt.stash()
+        recog.backward()                                      # :312-323
+        opt.stash()
+        perc = W_PERC * enc.perceptual_loss(real, gen(c, s))  # lesson 2: the 'auto' lesson's perceptual loss (:724-748)
+        perc.backward()
+        opt.balance(BALANCE_VAR_X)                            # :340-377
+        opt.step()                                            # :381-391
+        return adv.detach() + recog.detach() + perc.detach()
+
+    if use_balanced():
+        train = train_balanced                                # noqa: F811 - the opt-in step replaces the default one
 
     def barrier():
         torch.cuda.synchronize()

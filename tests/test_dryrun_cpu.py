@@ -94,3 +94,39 @@ def test_disc_lesson_and_recognizer_training_host_code_runs(recorder):
     raw, dec, dl = pkg.ctc_greedy_decode(lp.detach())
     assert tuple(raw.shape) == (T - 6, B)
     assert {"hwg_spectral_norm_bwd", "hwg_channel_sum", "hwg_hwr_stem", "hwg_ctc_greedy_decode"} <= set(recorder)
+
+
+def test_balanced_two_lesson_step_host_code_runs(recorder):
+    """bench_gan_train.train_balanced() (opt-in, HWG_BENCH_BALANCED=1): two losses back-propagated separately through ONE
+    generator graph and stashed, the perceptual lesson, FlatAdam.balance, FlatAdam.step."""
+    pkg, gen, hwr, disc = _modules()
+    enc = pkg.Encoder2(32).train()
+    for p in list(hwr.parameters()) + list(disc.parameters()):
+        p.requires_grad_(False)
+    opt = pkg.FlatAdam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
+    gen._grad_sink = opt
+    T, B, S = 32, 2, 5
+    content, style = (torch.from_numpy(a) for a in synth.gen_case(T, B, 80, 128, 9))
+    real = torch.from_numpy(synth.hwr_case(B, 4 * T, 3))
+    tg = torch.randint(1, 80, (B, S), dtype=torch.int32)
+    il, tl = torch.full((B,), T - 6, dtype=torch.int32), torch.full((B,), S, dtype=torch.int32)
+    pkg.set_retain_graph(True)
+    try:
+        for _ in range(2):
+            img = gen(content, style)
+            preds = disc(img)
+            adv = -sum(p.mean() for p in preds) / len(preds)
+            recog = 1e-4 * pkg.CTCLoss(hwr(img), tg, il, tl)
+            adv.backward(retain_graph=True)
+            opt.stash()
+            recog.backward()
+            opt.stash()
+            assert len(opt._stash) == 2
+            (0.5 * enc.perceptual_loss(real, gen(content, style))).backward()
+            opt.balance([0.6, 0.5])
+            assert opt._stash == []
+            opt.step()
+    finally:
+        pkg.set_retain_graph(False)
+    assert recorder.count("hwg_balance") == 2 and recorder.count("hwg_adam_flat") == 2
+    assert {"hwg_l1_halves", "hwg_add_stats"} <= set(recorder)
