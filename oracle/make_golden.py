@@ -320,6 +320,56 @@ def make_enc():
     np.savez_compressed(os.path.join(GOLD, "enc.npz"), **out)
 
 
+# name -> (B, W, weight seed, input seed)
+STYLE_CASES = {"b2_w256": (2, 256, 600, 601), "b3_w520": (3, 520, 600, 602)}
+DTW_CASES = {"t58_l9": (58, 3, 9, 611), "t124_l30": (124, 2, 30, 612)}      # name -> (T, B, label length, seed)
+
+
+def style_inputs(B, W, seed, n_class=80):
+    """Image and a recognizer-like log-prob tensor [B, n_class, W/4-6]: spaced random text, sharpened, log-softmax."""
+    image = torch.from_numpy(synth.hwr_case(B, W, seed))
+    T = W // 4 - 6
+    content, _ = synth.gen_case(T, B, n_class, 8, seed + 1)                               # [T,B,C] one-hot
+    r = np.random.RandomState(seed + 2)
+    logits = 5.0 * content + r.standard_normal(content.shape).astype(np.float32)
+    recog = torch.log_softmax(torch.from_numpy(logits), 2).permute(1, 2, 0).contiguous()  # [B,C,T]
+    return image, recog
+
+
+def dtw_inputs(T, B, L, seed, n_class=80):
+    r = np.random.RandomState(seed)
+    pred = torch.log_softmax(torch.from_numpy(2.0 * r.standard_normal((T, B, n_class)).astype(np.float32)), 2)
+    label = torch.from_numpy(r.randint(1, n_class, (L, B)).astype(np.int64))
+    return pred, label
+
+
+def make_style():
+    """Style vectors of the unmodified reference CharStyleEncoder (IAM GAN configuration) and DTW alignments of the
+    unmodified `correct_pred`."""
+    ref_shim.install()
+    from model.char_style import CharStyleEncoder
+    from model.hw_with_style import correct_pred
+    out = {}
+    for name, (B, W, wseed, iseed) in STYLE_CASES.items():
+        torch.manual_seed(wseed)
+        m = CharStyleEncoder(1, 64, 128, 128, 0, 'group', 'relu', 'replicate', 80, global_pool=False,
+                             average_found_char_style=1.0, num_final_g_spacing_style=1, num_char_fc=1, vae=False, window=2,
+                             small=False)
+        m.eval()
+        out["state_dict_keys"] = keys_fixture(m.state_dict())
+        out[f"{name}/weights_digest"] = weights_digest(m.state_dict())
+        image, recog = style_inputs(B, W, iseed)
+        with torch.no_grad():
+            style = m(image, recog)
+        out[f"{name}/style"] = style.numpy()
+        print(f"style/{name}: B={B} W={W} -> {tuple(style.shape)} |style|max {style.abs().max():.4f}")
+    for name, (T, B, L, seed) in DTW_CASES.items():
+        pred, label = dtw_inputs(T, B, L, seed)
+        out[f"dtw/{name}"] = correct_pred(pred, label).numpy()
+        print(f"dtw/{name}: {out[f'dtw/{name}'].shape}")
+    np.savez_compressed(os.path.join(GOLD, "style.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -333,6 +383,8 @@ def main(argv):
         make_disc()
     if what in ("enc", "all"):
         make_enc()
+    if what in ("style", "all"):
+        make_style()
 
 
 if __name__ == "__main__":
