@@ -225,7 +225,61 @@ def hwg_balance(g_main, sets_host, K, x_dev, seg_off, seg_len, nseg, block_tab, 
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_balance, hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
+def _i64(ptr, n):
+    return np.frombuffer((ctypes.c_int64 * n).from_address(ptr), dtype=np.int64)
+
+
+def hwg_spectral_norm(jobs_dev, njobs, max_h, max_wd, norms, inv_sigma, stream):
+    """SpectralNorm._update_u_v (discriminator_ap.py:19-32), one power iteration: v = l2n(W^T u), u = l2n(W v) in place,
+    inv_sigma = 1 / (u . W v); l2n(x) = x / (|x| + 1e-12)."""
+    jobs = _i64(jobs_dev, 4 * njobs).reshape(njobs, 4)
+    inv = _view(inv_sigma, njobs, torch.float32)
+    for i, (w, u, v, hw) in enumerate(jobs.tolist()):
+        h, wd = hw & 0xffffffff, hw >> 32
+        W, uu, vv = _view(w, h * wd, torch.float32).view(h, wd), _view(u, h, torch.float32), _view(v, wd, torch.float32)
+        nv = W.t().mv(uu)
+        vv.copy_(nv / (nv.norm() + 1e-12))
+        nu = W.mv(vv)
+        uu.copy_(nu / (nu.norm() + 1e-12))
+        inv[i] = 1.0 / uu.dot(W.mv(vv))
+    return 0
+
+
+def hwg_spectral_norm_bwd(jobs_dev, njobs, max_elems, inv_sigma, dots, stream):
+    """In place gw -= (<gw, w_bar> * inv_sigma[layer]) * u v^T."""
+    jobs = _i64(jobs_dev, 5 * njobs).reshape(njobs, 5)
+    inv = _view(inv_sigma, njobs, torch.float32)
+    for i, (w, gw, u, v, hw) in enumerate(jobs.tolist()):
+        h, wd = hw & 0xffffffff, hw >> 32
+        W, G = _view(w, h * wd, torch.float32).view(h, wd), _view(gw, h * wd, torch.float32).view(h, wd)
+        G -= ((G * W).sum() * inv[i]) * torch.outer(_view(u, h, torch.float32), _view(v, wd, torch.float32))
+    return 0
+
+
+def hwg_channel_sum(x, rows, C, out, stream):
+    _view(out, C, torch.float32).add_(_view(x, rows * C, torch.bfloat16).view(rows, C).float().sum(0))
+    return 0
+
+
+def hwg_conv_wgrad(d_addr, x, gy, dw, stream):
+    """dw[t][co][ci] += sum_pixels gy[n,ho,wo,co] * x[n,ho+dh_t,wo+dw_t,ci] (plain grid: no strides / phases)."""
+    d = _lib.WgradDesc.from_address(d_addr)
+    assert d.Hi == 0 and d.Wi == 0 and d.gy_stride_h <= 1 and d.gy_stride_w <= 1 and d.gy_off_h == 0 and d.gy_off_w == 0
+    N, H, W, Ci, Cp, Ho, Wo, Co, Gp, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Ho, d.Wo, d.Cout, d.gy_pitch, d.ntaps
+    assert all(d.tap_gy_h[t] == 0 and d.tap_gy_w[t] == 0 for t in range(T))
+    xv = _view(x, N * H * W * Cp, torch.bfloat16).view(N, H, W, Cp)[..., :Ci].float()
+    gv = _view(gy, N * Ho * Wo * Gp, torch.bfloat16).view(N, Ho, Wo, Gp)[..., :Co].float()
+    out = _view(dw, T * Co * Ci, torch.float32).view(T, Co, Ci)
+    P = max(max(abs(d.tap_dh[t]), abs(d.tap_dw[t])) for t in range(T)) + max(Ho, Wo, H, W)
+    xp = torch.nn.functional.pad(xv, (0, 0, P, P, P, P))
+    for t in range(T):
+        xs = xp[:, P + d.tap_dh[t]:P + d.tap_dh[t] + Ho, P + d.tap_dw[t]:P + d.tap_dw[t] + Wo, :]
+        out[t] += torch.einsum("nhwo,nhwi->oi", gv, xs)
+    return 0
+
+
+_TABLE = {f.__name__: f for f in (hwg_balance, hwg_spectral_norm, hwg_spectral_norm_bwd, hwg_channel_sum, hwg_conv_wgrad,
+                                  hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
                                   hwg_avgpool_nhwc, hwg_add_stats, hwg_l1_halves, hwg_norm_bwd_reduce, hwg_gn_bwd_coeffs,
                                   hwg_norm_bwd_apply, hwg_act_bwd)}
 
