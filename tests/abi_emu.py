@@ -32,6 +32,8 @@ def _act(v, act, slope):
         return torch.relu(v)
     if act == _lib.ACT_LRELU:
         return torch.where(v > 0, v, slope * v)
+    if act == _lib.ACT_LOGSOFTMAX:
+        return torch.log_softmax(v, -1)
     assert act == _lib.ACT_NONE
     return v
 
@@ -225,6 +227,122 @@ def hwg_balance(g_main, sets_host, K, x_dev, seg_off, seg_len, nseg, block_tab, 
     return 0
 
 
+# ---- recognizer (cnn_only_hwr.py) ---------------------------------------------------------------------------------
+def hwg_bn_coeffs(stats, N, C, count_per_n, weight, bias, rmean, rvar, momentum, eps, use_batch_stats, coef, save, stream):
+    w = _view(weight, C, torch.float32) if weight else torch.ones(C)
+    b = _view(bias, C, torch.float32) if bias else torch.zeros(C)
+    if use_batch_stats:
+        tot = _view(stats, N * C * 2, torch.float32).view(N, C, 2).sum(0)
+        cnt = float(count_per_n * N)
+        mean = tot[:, 0] / cnt
+        var = (tot[:, 1] / cnt - mean * mean).clamp_min(0)
+        if rmean:
+            rm, rv = _view(rmean, C, torch.float32), _view(rvar, C, torch.float32)
+            rm.copy_((1 - momentum) * rm + momentum * mean)
+            rv.copy_((1 - momentum) * rv + momentum * var * (cnt / max(cnt - 1, 1)))
+    else:
+        mean, var = _view(rmean, C, torch.float32).clone(), _view(rvar, C, torch.float32).clone()
+    rstd = 1.0 / torch.sqrt(var + eps)
+    a = w * rstd
+    _view(coef, 2 * C, torch.float32).view(C, 2).copy_(torch.stack((a, b - mean * a), -1))
+    if save:
+        _view(save, 2 * C, torch.float32).view(C, 2).copy_(torch.stack((mean, rstd), -1))
+    return 0
+
+
+def _stem(img, w, b, N, H, W, Cout):
+    iv = _view(img, N * H * W, torch.float32).view(N, 1, H, W).clone().requires_grad_()
+    wv = _view(w, Cout * 9, torch.float32).view(Cout, 1, 3, 3).clone().requires_grad_()
+    bv = _view(b, Cout, torch.float32).clone().requires_grad_()
+    with torch.enable_grad():                        # the modules call their backward entry points under no_grad
+        y = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(iv, wv, bv, padding=1)), 2, 2)
+    return iv, wv, bv, y
+
+
+def hwg_hwr_stem(img, w, b, N, H, W, Cout, y, stream):
+    with torch.no_grad():
+        out = _stem(img, w, b, N, H, W, Cout)[3]
+    _view(y, out.numel(), torch.bfloat16).view(N, H // 2, W // 2, Cout).copy_(out.permute(0, 2, 3, 1))
+    return 0
+
+
+def _stem_grads(img, w, b, ga, N, H, W, Cout):
+    iv, wv, bv, y = _stem(img, w, b, N, H, W, Cout)
+    g = _view(ga, y.numel(), torch.bfloat16).view(N, H // 2, W // 2, Cout).float().permute(0, 3, 1, 2)
+    return torch.autograd.grad(y, (iv, wv, bv), g)
+
+
+def hwg_hwr_stem_bwd(img, w, b, ga, N, H, W, Cout, dw, db, stream):
+    _, gw, gb = _stem_grads(img, w, b, ga, N, H, W, Cout)
+    _view(dw, Cout * 9, torch.float32).add_(gw.reshape(-1))
+    _view(db, Cout, torch.float32).add_(gb)
+    return 0
+
+
+def hwg_hwr_stem_bwd_image(img, w, b, ga, N, H, W, Cout, gimg, stream):
+    gi, _, _ = _stem_grads(img, w, b, ga, N, H, W, Cout)
+    _view(gimg, N * H * W, torch.float32).add_(gi.reshape(-1))
+    return 0
+
+
+def hwg_maxpool_nhwc(x, y, N, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, stream):
+    xv = _view(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2)
+    out = torch.nn.functional.max_pool2d(xv, (kh, kw), (sh, sw), (ph, pw))
+    assert tuple(out.shape[2:]) == (Ho, Wo)
+    _view(y, N * Ho * Wo * C, torch.bfloat16).view(N, Ho, Wo, C).copy_(out.permute(0, 2, 3, 1))
+    return 0
+
+
+def hwg_relu_maxpool_bwd(ga, c, N, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo, gc, dbias, stream):
+    cv = _view(c, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2).clone().requires_grad_()
+    with torch.enable_grad():
+        out = torch.nn.functional.max_pool2d(cv, (kh, kw), (sh, sw), (ph, pw))   # first maximum wins, as in the kernel
+    g = _view(ga, N * Ho * Wo * C, torch.bfloat16).view(N, Ho, Wo, C).float().permute(0, 3, 1, 2)
+    (gx,) = torch.autograd.grad(out, cv, g)
+    gx = gx * (cv.detach() > 0)
+    _view(gc, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(gx.permute(0, 2, 3, 1))
+    _view(dbias, C, torch.float32).add_(gx.sum((0, 2, 3)))
+    return 0
+
+
+def hwg_logsoftmax_bwd(g, lp, T, B, C, Cp, gz, dbias, stream):
+    gv = _view(g, T * B * C, torch.float32).view(T, B, C)
+    lv = _view(lp, T * B * C, torch.float32).view(T, B, C)
+    z = gv - torch.exp(lv) * gv.sum(2, keepdim=True)
+    out = _view(gz, B * T * Cp, torch.bfloat16).view(B, 1, T, Cp)
+    out.zero_()
+    out[:, 0, :, :C] = z.permute(1, 0, 2).to(torch.bfloat16)
+    _view(dbias, C, torch.float32).add_(z.sum((0, 1)))
+    return 0
+
+
+def _bn_gy(g, z, coef, save, rows, C, relu):
+    gv = _view(g, rows * C, torch.bfloat16).view(rows, C).float()
+    zv = _view(z, rows * C, torch.bfloat16).view(rows, C).float()
+    cf = _view(coef, 2 * C, torch.float32).view(C, 2)
+    sv = _view(save, 2 * C, torch.float32).view(C, 2)
+    gy = gv * ((cf[:, 0] * zv + cf[:, 1]) > 0) if relu else gv
+    return gy, (zv - sv[:, 0]) * sv[:, 1], sv[:, 1]
+
+
+def hwg_bn_bwd_reduce(g, z, coef, save, rows, C, relu, sums, stream):
+    gy, xhat, _ = _bn_gy(g, z, coef, save, rows, C, relu)
+    sv = _view(sums, 2 * C, torch.float32).view(C, 2)
+    sv[:, 0] += gy.sum(0)
+    sv[:, 1] += (gy * xhat).sum(0)
+    return 0
+
+
+def hwg_bn_bwd_apply(g, z, coef, save, weight, sums, rows, norm_rows, C, relu, gz, dconv_bias, stream):
+    gy, xhat, rstd = _bn_gy(g, z, coef, save, rows, C, relu)
+    sv = _view(sums, 2 * C, torch.float32).view(C, 2)
+    M = float(norm_rows if norm_rows > 0 else rows)
+    out = _view(weight, C, torch.float32) * rstd * (gy - sv[:, 0] / M - xhat * sv[:, 1] / M)
+    _view(gz, rows * C, torch.bfloat16).view(rows, C).copy_(out)
+    _view(dconv_bias, C, torch.float32).add_(out.sum(0))
+    return 0
+
+
 def _i64(ptr, n):
     return np.frombuffer((ctypes.c_int64 * n).from_address(ptr), dtype=np.int64)
 
@@ -278,7 +396,9 @@ def hwg_conv_wgrad(d_addr, x, gy, dw, stream):
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_balance, hwg_spectral_norm, hwg_spectral_norm_bwd, hwg_channel_sum, hwg_conv_wgrad,
+_TABLE = {f.__name__: f for f in (hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
+                                  hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,
+                                  hwg_balance, hwg_spectral_norm, hwg_spectral_norm_bwd, hwg_channel_sum, hwg_conv_wgrad,
                                   hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
                                   hwg_avgpool_nhwc, hwg_add_stats, hwg_l1_halves, hwg_norm_bwd_reduce, hwg_gn_bwd_coeffs,
                                   hwg_norm_bwd_apply, hwg_act_bwd)}

@@ -1,0 +1,70 @@
+"""CPU: the HOST side of the CNNOnlyHWR drop-in (forward, the backward through every layer incl. the image gradient, the
+accumulator arena and the one-launch gradient unpack) run through the CPU interpreter of the C-ABI (tests/abi_emu.py) against
+the oracle — the assertions of tests/test_hwr_train_gpu.py, which the real kernels pass on the B200, made in the build
+container on the module's composition."""
+import numpy as np
+import torch
+
+from oracle import hwr as ohwr
+from oracle import synth
+
+from . import abi_emu
+from .test_modules_cpu import _hwr_module
+
+BF16_REL = 2e-2
+ZERO_GRAD = {"cnn.conv2.bias", "cnn.conv4.bias", "cnn.conv6.bias", "cnn1d.0.bias", "cnn1d.3.bias", "cnn1d.6.bias",
+             "cnn1d.9.bias"}  # bias of a conv that feeds BatchNorm: true gradient is identically zero
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def _oracle(sd, img, tg, il, tl, emulate):
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    x = torch.from_numpy(img).requires_grad_()
+    lp = ohwr.hwr_forward(p, x, True, None, emulate_bf16=emulate)
+    loss = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    loss.backward()
+    return loss.item(), {k: v.grad for k, v in p.items() if v.requires_grad and v.grad is not None}, x.grad, lp.detach()
+
+
+def test_recognizer_train_step_through_the_interpreter(hwg_lib, monkeypatch):
+    B, W, S = 2, 128, 6
+    m, sd = _hwr_module(200)
+    sd = {k: v.clone() for k, v in sd.items()}
+    m.train()
+    img = synth.hwr_case(B, W, 31)
+    T = W // 4 - 6
+    tg = np.random.RandomState(5).randint(1, 80, (B, S)).astype(np.int32)
+    il, tl = np.full(B, T, np.int32), np.full(B, S, np.int32)
+    x = torch.from_numpy(img).requires_grad_()
+    with abi_emu.installed(monkeypatch) as calls:
+        lp = m(x)
+        loss = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+        loss.backward()
+    loss32, g32, gx32, lp32 = _oracle(sd, img, tg, il, tl, False)
+    _, gemu, _, _ = _oracle(sd, img, tg, il, tl, True)
+    assert tuple(lp.shape) == (T, B, 80) and rel_l2(lp.detach(), lp32) <= BF16_REL
+    assert abs(loss.item() - loss32) <= BF16_REL * abs(loss32)
+    got = {n: p.grad for n, p in m.named_parameters()}
+    assert set(got) == set(g32)
+    for n, g in g32.items():
+        if n in ZERO_GRAD:
+            assert got[n].abs().max() <= 1e-2 * g32[n.replace("bias", "weight")].abs().max(), n
+            continue
+        ours, emu = rel_l2(got[n], g), rel_l2(gemu[n], g)
+        cos = float((got[n].double() * g.double()).sum() / (got[n].double().norm() * g.double().norm()))
+        assert ours <= 1.3 * emu + BF16_REL, f"{n}: interpreter-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
+        if n.endswith("weight"):
+            assert cos >= 0.85, f"{n}: cosine {cos:.3f}"
+    cos = float((x.grad.double() * gx32.double()).sum() / (x.grad.double().norm() * gx32.double().norm()))
+    assert cos >= 0.8, cos
+    # running statistics advanced as nn.BatchNorm does (momentum 0.1, unbiased variance)
+    upd = {}
+    ohwr.hwr_forward(sd, torch.from_numpy(img), True, upd)
+    for k, v in upd.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_l2(m.state_dict()[k], v) <= 1e-2, k
+    assert {"hwg_hwr_stem", "hwg_maxpool_nhwc", "hwg_bn_coeffs", "hwg_logsoftmax_bwd", "hwg_bn_bwd_apply",
+            "hwg_relu_maxpool_bwd", "hwg_hwr_stem_bwd", "hwg_hwr_stem_bwd_image", "hwg_conv_wgrad"} <= set(calls)
