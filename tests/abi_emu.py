@@ -39,29 +39,55 @@ def _act(v, act, slope):
 
 
 def hwg_conv_fprop(d_addr, x, w, bias, noise, noise_w, stats, y, stream):
+    """The full tap-list convolution of include/hwg_b200.h: input strides, channel folding (union taps or per-fold taps),
+    bias -> noise tensor -> activation -> statistics -> (strided, folded) store.  In-kernel noise is not interpreted."""
     d = _lib.ConvDesc.from_address(d_addr)
-    assert noise is None and noise_w is None and d.fold_c == 0 and d.in_stride_h <= 1 and d.in_stride_w <= 1
+    assert noise_w is None or noise is not None, "abi_emu: in-kernel noise (noise_w without a tensor) is not interpreted"
     N, H, W, Ci, Cp, Co, Ho, Wo, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps
+    sh, sw = max(d.in_stride_h, 1), max(d.in_stride_w, 1)
+    fc = d.fold_c if d.fold_c else Co
+    F = Co // fc
+    fw = d.fold_w if d.fold_w > 0 else 1
+    rows = fc if (d.fold_c and d.fold_taps > 0) else Co                      # rows of one tap matrix
     xv = _view(x, N * H * W * Cp, torch.bfloat16).view(N, H, W, Cp)[..., :Ci].float()
-    wv = _view(w, T * Co * Ci, torch.bfloat16).view(T, Co, Ci).float()
+    wv = _view(w, T * rows * Ci, torch.bfloat16).view(T, rows, Ci).float()
     taps = [(d.tap_dh[t], d.tap_dw[t]) for t in range(T)]
-    P = max(max(abs(a), abs(b)) for a, b in taps) + max(Ho, Wo, H, W)        # out-of-bounds reads are zero
+    P = max(max(abs(a), abs(b)) for a, b in taps) + max(Ho * sh, Wo * sw, H, W)   # out-of-bounds reads are zero
     xp = torch.nn.functional.pad(xv, (0, 0, P, P, P, P))
+
+    def window(dh, dw):
+        return xp[:, P + dh:P + dh + Ho * sh:sh, P + dw:P + dw + Wo * sw:sw, :]
+
     acc = torch.zeros((N, Ho, Wo, Co))
     for t, (dh, dw) in enumerate(taps):
-        acc += xp[:, P + dh:P + dh + Ho, P + dw:P + dw + Wo, :] @ wv[t].t()
+        if d.fold_c and d.fold_taps > 0:
+            f = t // d.fold_taps
+            acc[..., f * fc:(f + 1) * fc] += window(dh, dw) @ wv[t].t()
+        else:
+            acc += window(dh, dw) @ wv[t].t()
     if bias is not None:
         acc += _view(bias, Co, torch.float32)
-    acc = _act(acc, d.act, d.slope)
     ydt = torch.float32 if d.y_dtype == _lib.DT_F32 else torch.bfloat16
-    out = acc.to(ydt)
+
+    def placed(ptr, dt, sn_, sh_, sw_, f):
+        """[N,Ho,Wo,fc] view of fold f's pixels inside a tensor with these pixel strides."""
+        disp = (f // fw) * d.fold_stride_h + (f % fw) * d.fold_stride_w if d.fold_c else 0
+        span = disp + (N - 1) * sn_ + (Ho - 1) * sh_ + (Wo - 1) * sw_ + fc
+        return torch.as_strided(_view(ptr, span, dt), (N, Ho, Wo, fc), (sn_, sh_, sw_, 1), disp)
+
+    if noise is not None:
+        nw = _view(noise_w, Co, torch.float32)
+        for f in range(F):
+            z = placed(noise, torch.float32, d.nz_stride_n, d.nz_stride_h, d.nz_stride_w, f)
+            acc[..., f * fc:(f + 1) * fc] += nw[f * fc:(f + 1) * fc] * z
+    out = _act(acc, d.act, d.slope).to(ydt)
     if stats is not None:
-        st = _view(stats, N * Co * 2, torch.float32).view(N, Co, 2)
-        st[:, :, 0] += out.float().sum((1, 2))
-        st[:, :, 1] += (out.float() ** 2).sum((1, 2))
-    span = (N - 1) * d.y_stride_n + (Ho - 1) * d.y_stride_h + (Wo - 1) * d.y_stride_w + Co
-    yv = torch.as_strided(_view(y, span, ydt), (N, Ho, Wo, Co), (d.y_stride_n, d.y_stride_h, d.y_stride_w, 1))
-    yv.copy_(out)
+        st = _view(stats, N * fc * 2, torch.float32).view(N, fc, 2)
+        of = out.float().view(N, Ho * Wo, F, fc)
+        st[:, :, 0] += of.sum((1, 2))
+        st[:, :, 1] += (of * of).sum((1, 2))
+    for f in range(F):
+        placed(y, ydt, d.y_stride_n, d.y_stride_h, d.y_stride_w, f).copy_(out[..., f * fc:(f + 1) * fc])
     return 0
 
 
@@ -380,23 +406,155 @@ def hwg_channel_sum(x, rows, C, out, stream):
 
 
 def hwg_conv_wgrad(d_addr, x, gy, dw, stream):
-    """dw[t][co][ci] += sum_pixels gy[n,ho,wo,co] * x[n,ho+dh_t,wo+dw_t,ci] (plain grid: no strides / phases)."""
+    """dw[t][co][ci] += sum over the iteration grid (i, j) of gy[n, i*gs_h + go_h + ph_t, j*gs_w + go_w + pw_t, co] *
+    x[n, i + dh_t, j + dw_t, ci]  (grid 0 = the gy extent; strides / offsets / per-tap phases: the up-sampling layers)."""
     d = _lib.WgradDesc.from_address(d_addr)
-    assert d.Hi == 0 and d.Wi == 0 and d.gy_stride_h <= 1 and d.gy_stride_w <= 1 and d.gy_off_h == 0 and d.gy_off_w == 0
     N, H, W, Ci, Cp, Ho, Wo, Co, Gp, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Ho, d.Wo, d.Cout, d.gy_pitch, d.ntaps
-    assert all(d.tap_gy_h[t] == 0 and d.tap_gy_w[t] == 0 for t in range(T))
+    Hi, Wi = (d.Hi or Ho), (d.Wi or Wo)
+    gsh, gsw = max(d.gy_stride_h, 1), max(d.gy_stride_w, 1)
     xv = _view(x, N * H * W * Cp, torch.bfloat16).view(N, H, W, Cp)[..., :Ci].float()
     gv = _view(gy, N * Ho * Wo * Gp, torch.bfloat16).view(N, Ho, Wo, Gp)[..., :Co].float()
     out = _view(dw, T * Co * Ci, torch.float32).view(T, Co, Ci)
-    P = max(max(abs(d.tap_dh[t]), abs(d.tap_dw[t])) for t in range(T)) + max(Ho, Wo, H, W)
+    P = max(max(abs(d.tap_dh[t]), abs(d.tap_dw[t])) for t in range(T)) + max(Hi, Wi, H, W)
     xp = torch.nn.functional.pad(xv, (0, 0, P, P, P, P))
+    Q = max(Hi * gsh, Wi * gsw)
+    gp = torch.nn.functional.pad(gv, (0, 0, 0, Q, 0, Q))                         # grid points beyond gy contribute zero
     for t in range(T):
-        xs = xp[:, P + d.tap_dh[t]:P + d.tap_dh[t] + Ho, P + d.tap_dw[t]:P + d.tap_dw[t] + Wo, :]
-        out[t] += torch.einsum("nhwo,nhwi->oi", gv, xs)
+        xs = xp[:, P + d.tap_dh[t]:P + d.tap_dh[t] + Hi, P + d.tap_dw[t]:P + d.tap_dw[t] + Wi, :]
+        oh, ow = d.gy_off_h + d.tap_gy_h[t], d.gy_off_w + d.tap_gy_w[t]
+        gs = gp[:, oh:oh + Hi * gsh:gsh, ow:ow + Wi * gsw:gsw, :]
+        out[t] += torch.einsum("nhwo,nhwi->oi", gs, xs)
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
+# ---- generator (pure_gen.py) ----------------------------------------------------------------------------------------
+def hwg_linear_f32(inp, W, bias, out, B, K, O, act, slope, stream):
+    v = _view(inp, B * K, torch.float32).view(B, K) @ _view(W, O * K, torch.float32).view(O, K).t()
+    if bias:
+        v = v + _view(bias, O, torch.float32)
+    _view(out, B * O, torch.float32).view(B, O).copy_(_act(v, act, slope))
+    return 0
+
+
+def hwg_linear_bwd_f32(x, y, gy, W, B, K, O, act, slope, gx, gW, gb, accumulate, stream):
+    g = _view(gy, B * O, torch.float32).view(B, O).clone()
+    if act == _lib.ACT_LRELU:
+        g = g * torch.where(_view(y, B * O, torch.float32).view(B, O) > 0, torch.ones(()), torch.full((), slope))
+    xv, Wv = _view(x, B * K, torch.float32).view(B, K), _view(W, O * K, torch.float32).view(O, K)
+    if gx:
+        _view(gx, B * K, torch.float32).view(B, K).add_(g @ Wv)
+    for ptr, val, n in ((gW, g.t() @ xv, O * K), (gb, g.sum(0), O)):
+        if ptr:
+            dst = _view(ptr, n, torch.float32)
+            dst.copy_(dst + val.reshape(-1) if accumulate else val.reshape(-1))
+    return 0
+
+
+def hwg_pixelnorm_f32(inp, out, B, K, stream):
+    v = _view(inp, B * K, torch.float32).view(B, K)
+    _view(out, B * K, torch.float32).view(B, K).copy_(v / torch.sqrt((v * v).mean(1, keepdim=True) + 1e-8))
+    return 0
+
+
+def hwg_gen_pack_input(content, cs_t, cs_b, cs_c, style, T, B, C, S, Cp, x, stream):
+    span = (T - 1) * cs_t + (B - 1) * cs_b + (C - 1) * cs_c + 1
+    cv = torch.as_strided(_view(content, span, torch.float32), (T, B, C), (cs_t, cs_b, cs_c))
+    xv = _view(x, B * T * Cp, torch.bfloat16).view(B, 1, T, Cp)
+    xv.zero_()
+    xv[:, 0, :, :C] = cv.permute(1, 0, 2).to(torch.bfloat16)
+    if style and S:
+        xv[:, 0, :, C:C + S] = _view(style, B * S, torch.float32).view(B, 1, S).to(torch.bfloat16)
+    return 0
+
+
+def hwg_adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps, coef, save, stream):
+    st = _view(stats, N * C * 2, torch.float32).view(N, C, 2)
+    span = (N - 1) * gb_stride + C
+    gm = torch.as_strided(_view(gamma, span, torch.float32), (N, C), (gb_stride, 1))
+    bt = torch.as_strided(_view(beta, span, torch.float32), (N, C), (gb_stride, 1))
+    mean = st[..., 0] / HW
+    var = (st[..., 1] / HW - mean * mean).clamp_min(0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    a = gm * rstd
+    _view(coef, N * C * 2, torch.float32).view(N, C, 2).copy_(torch.stack((a, bt - mean * a), -1))
+    if save:
+        _view(save, N * C * 2, torch.float32).view(N, C, 2).copy_(torch.stack((mean, rstd), -1))
+    return 0
+
+
+def hwg_blur_noise_act_stats(x, y, N, H, W, C, noise, noise_w, seed, subseq, seed_dev, act, slope, stats, stream):
+    assert noise_w is None or noise is not None, "abi_emu: in-kernel noise is not interpreted"
+    xv = _view(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2)
+    k = torch.tensor([1.0, 2.0, 1.0])
+    k = (k[:, None] * k[None, :] / 16.0).expand(C, 1, 3, 3)
+    v = torch.nn.functional.conv2d(xv, k, padding=1, groups=C).permute(0, 2, 3, 1)
+    if noise_w is not None:
+        v = v + _view(noise_w, C, torch.float32) * _view(noise, N * H * W * C, torch.float32).view(N, H, W, C)
+    out = _act(v, act, slope).to(torch.bfloat16)
+    _view(y, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(out)
+    if stats:
+        st = _view(stats, N * C * 2, torch.float32).view(N, C, 2)
+        of = out.float()
+        st[:, :, 0] += of.sum((1, 2))
+        st[:, :, 1] += (of * of).sum((1, 2))
+    return 0
+
+
+def hwg_gen_output(x, coef, w, b0, N, HW, C, out, stream):
+    xv = _view(x, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    cf = _view(coef, N * C * 2, torch.float32).view(N, 1, C, 2)
+    v = ((cf[..., 0] * xv + cf[..., 1]) * _view(w, C, torch.float32)).sum(2) + _view(b0, 1, torch.float32)
+    _view(out, N * HW, torch.float32).view(N, HW).copy_(torch.tanh(v))
+    return 0
+
+
+def hwg_gen_output_bwd(g_out, out, a, coef, w, N, HW, C, gx, dwb, stream):
+    dv = _view(g_out, N * HW, torch.float32).view(N, HW) * (1 - _view(out, N * HW, torch.float32).view(N, HW) ** 2)
+    av = _view(a, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    cf = _view(coef, N * C * 2, torch.float32).view(N, 1, C, 2)
+    wv = _view(w, C, torch.float32)
+    _view(gx, N * HW * C, torch.bfloat16).view(N, HW, C).copy_(dv[..., None] * wv)      # w.r.t. the AdaIN output
+    acc = _view(dwb, C + 1, torch.float32)
+    acc[:C] += (dv[..., None] * (cf[..., 0] * av + cf[..., 1])).sum((0, 1))
+    acc[C] += dv.sum()
+    return 0
+
+
+def _adain_ahat(a, save, N, HW, C):
+    av = _view(a, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    sv = _view(save, N * C * 2, torch.float32).view(N, 1, C, 2)
+    return av, (av - sv[..., 0]) * sv[..., 1]
+
+
+def hwg_adain_bwd_reduce(g, a, save, N, HW, C, sums, stream):
+    gv = _view(g, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    _, ahat = _adain_ahat(a, save, N, HW, C)
+    sv = _view(sums, N * C * 2, torch.float32).view(N, C, 2)
+    sv[:, :, 0] += gv.sum(1)
+    sv[:, :, 1] += (gv * ahat).sum(1)
+    return 0
+
+
+def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, subseq, seed_dev, row_subseq, gy, dch,
+                        stream):
+    HW = H * W
+    gv = _view(g, N * HW * C, torch.bfloat16).view(N, HW, C).float()
+    av, ahat = _adain_ahat(a, save, N, HW, C)
+    A = _view(coef, N * C * 2, torch.float32).view(N, 1, C, 2)[..., 0]
+    sv = _view(sums, N * C * 2, torch.float32).view(N, 1, C, 2)
+    ga = A * (gv - sv[..., 0] / HW - ahat * sv[..., 1] / HW)
+    out = ga * torch.where(av > 0, torch.ones(()), torch.full((), slope))
+    _view(gy, N * HW * C, torch.bfloat16).view(N, HW, C).copy_(out)
+    dc = _view(dch, 2 * C, torch.float32).view(C, 2)
+    dc[:, 0] += out.sum((0, 1))
+    assert noise is not None, "abi_emu: regenerated in-kernel noise is not interpreted"
+    dc[:, 1] += (out * _view(noise, N * HW * C, torch.float32).view(N, HW, C)).sum((0, 1))
+    return 0
+
+
+_TABLE = {f.__name__: f for f in (hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
+                                  hwg_blur_noise_act_stats, hwg_gen_output, hwg_gen_output_bwd, hwg_adain_bwd_reduce,
+                                  hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,
                                   hwg_balance, hwg_spectral_norm, hwg_spectral_norm_bwd, hwg_channel_sum, hwg_conv_wgrad,
                                   hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
@@ -422,4 +580,16 @@ def installed(monkeypatch):
     monkeypatch.setattr(_lib, "require_cuda", lambda *t: None)
     monkeypatch.setattr(weightmap.JobTable, "run",
                         lambda self, src_base=None, dst_base=None: ref_map.run_jobs_cpu(self, src_base, dst_base))
+
+    class _Stream:                       # the generator's backward forks its wgrad launches onto a side stream
+        device = torch.device("cpu")
+        cuda_stream = 0
+
+        def wait_stream(self, other):
+            pass
+
+    main = _Stream()
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: main)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     yield calls
