@@ -42,8 +42,9 @@ def hwg_conv_fprop(d_addr, x, w, bias, noise, noise_w, stats, y, stream):
     """The full tap-list convolution of include/hwg_b200.h: input strides, channel folding (union taps or per-fold taps),
     bias -> noise tensor -> activation -> statistics -> (strided, folded) store.  In-kernel noise is not interpreted."""
     d = _lib.ConvDesc.from_address(d_addr)
-    assert noise_w is None or noise is not None, "abi_emu: in-kernel noise (noise_w without a tensor) is not interpreted"
     N, H, W, Ci, Cp, Co, Ho, Wo, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps
+    # in-kernel noise is not interpreted: only accepted when every noise weight is zero (the strict-parity variant)
+    assert noise_w is None or noise is not None or float(_view(noise_w, Co, torch.float32).abs().max()) == 0
     sh, sw = max(d.in_stride_h, 1), max(d.in_stride_w, 1)
     fc = d.fold_c if d.fold_c else Co
     F = Co // fc
@@ -483,12 +484,12 @@ def hwg_adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps, coef, save, s
 
 
 def hwg_blur_noise_act_stats(x, y, N, H, W, C, noise, noise_w, seed, subseq, seed_dev, act, slope, stats, stream):
-    assert noise_w is None or noise is not None, "abi_emu: in-kernel noise is not interpreted"
+    assert noise_w is None or noise is not None or float(_view(noise_w, C, torch.float32).abs().max()) == 0
     xv = _view(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2)
     k = torch.tensor([1.0, 2.0, 1.0])
     k = (k[:, None] * k[None, :] / 16.0).expand(C, 1, 3, 3)
     v = torch.nn.functional.conv2d(xv, k, padding=1, groups=C).permute(0, 2, 3, 1)
-    if noise_w is not None:
+    if noise_w is not None and noise is not None:
         v = v + _view(noise_w, C, torch.float32) * _view(noise, N * H * W * C, torch.float32).view(N, H, W, C)
     out = _act(v, act, slope).to(torch.bfloat16)
     _view(y, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(out)
