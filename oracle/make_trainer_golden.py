@@ -36,12 +36,17 @@ class _Log:
         return lambda *a, **k: None
 
 
-def run_lesson(kind):
-    """kind: 'gen' (curriculum slot 1, ["no-step","gen"]) or 'disc' (slot 3, ["disc"])."""
+def run_lesson(kind, install=None, hook=None):
+    """kind: 'gen' (curriculum slot 1, ["no-step","gen"]) or 'disc' (slot 3, ["disc"]).
+    install / hook (tests only: the same unmodified trainer with the drop-in modules): `install()` runs before the model
+    is built (the import swap of INTEGRATION.md), `hook(trainer, model, rec)` right before `_train_iteration`; with a hook
+    nothing is written and (trainer, log, rec, model) is returned."""
     ref_shim.install()
     cwd = os.getcwd()
     os.chdir(ref_shim.REF)
     try:
+        if install is not None:
+            install()
         import torch.nn.functional as F
         from model import HWWithStyle
         import model.loss as mloss
@@ -134,12 +139,16 @@ def run_lesson(kind):
         slot = {"gen": 1, "disc": 3}[kind]
         if kind == "disc":                  # 2B rows go through the discriminator: masks for 2B samples
             dmasks.update({k: torch.from_numpy(v) for k, v in synth.disc_masks(2 * B, SEEDS["masks"]).items()})
+        if hook is not None:
+            hook(tr, model, rec)
         try:
             tr.iteration = slot
             log = tr._train_iteration(slot)
         finally:
             torch.randn_like, F.dropout2d = orig_randn_like, orig_drop
             model.generator.forward = gen_fwd
+        if hook is not None:
+            return tr, log, rec, model
         out = {"content": rec["gen_in"][0].numpy(), "style": rec["gen_in"][1].numpy(), "image": rec["gen_out"].numpy(),
                "label": label.numpy(), "label_lengths": lengths.numpy(),
                "noise_shapes": np.array(rec["noise"], np.int64), "mask_sites": np.array(rec["masks"]),

@@ -370,6 +370,48 @@ def hwg_bn_bwd_apply(g, z, coef, save, weight, sums, rows, norm_rows, C, relu, g
     return 0
 
 
+# ---- CTC (model/loss.py:28-30) through torch's own F.ctc_loss ---------------------------------------------------------
+def _i32(ptr, n):
+    return torch.from_numpy(np.frombuffer((ctypes.c_int32 * n).from_address(ptr), dtype=np.int32))
+
+
+def _ctc_args(lp, T, B, C, tg, ts_b, ts_s, S, il, tl):
+    lpv = _view(lp, T * B * C, torch.float32).view(T, B, C)
+    if S:
+        span = (B - 1) * ts_b + (S - 1) * ts_s + 1
+        tgt = torch.as_strided(_i32(tg, span), (B, S), (ts_b, ts_s)).long()
+    else:
+        tgt = torch.zeros((B, 0), dtype=torch.long)
+    return lpv, tgt, _i32(il, B).long(), _i32(tl, B).long()
+
+
+def hwg_ctc_forward(lp, T, B, C, tg, ts_b, ts_s, S, il, tl, blank, nll, log_alpha, log_beta, stream):
+    lpv, tgt, ilv, tlv = _ctc_args(lp, T, B, C, tg, ts_b, ts_s, S, il, tl)
+    _view(nll, B, torch.float32).copy_(torch.nn.functional.ctc_loss(lpv, tgt, ilv, tlv, blank=blank, reduction="none"))
+    return 0
+
+
+def hwg_ctc_reduce_mean(nll, tl, B, loss, unit, stream):
+    n = _view(nll, B, torch.float32)
+    s = _i32(tl, B).float().clamp_min(1)
+    v = (n / s).mean()
+    bad = bool(torch.isinf(v))
+    _view(loss, 1, torch.float32).fill_(0.0 if bad else float(v))
+    _view(unit, B, torch.float32).copy_(torch.zeros(B) if bad else 1.0 / (B * s))
+    return 0
+
+
+def hwg_ctc_backward(go, unit, lp, T, B, C, tg, ts_b, ts_s, S, il, tl, blank, nll, la, lb, beta_ready, grad, stream):
+    lpv, tgt, ilv, tlv = _ctc_args(lp, T, B, C, tg, ts_b, ts_s, S, il, tl)
+    x = lpv.clone().requires_grad_()
+    with torch.enable_grad():
+        per = torch.nn.functional.ctc_loss(x, tgt, ilv, tlv, blank=blank, reduction="none")
+        tot = (per * _view(unit, B, torch.float32)).sum() * _view(go, 1, torch.float32)[0]
+    (g,) = torch.autograd.grad(tot, x)
+    _view(grad, T * B * C, torch.float32).view(T, B, C).copy_(g)
+    return 0
+
+
 def _i64(ptr, n):
     return np.frombuffer((ctypes.c_int64 * n).from_address(ptr), dtype=np.int64)
 
@@ -553,7 +595,7 @@ def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, 
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
+_TABLE = {f.__name__: f for f in (hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
                                   hwg_blur_noise_act_stats, hwg_gen_output, hwg_gen_output_bwd, hwg_adain_bwd_reduce,
                                   hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,
