@@ -123,3 +123,69 @@ def test_reference_trainer_gen_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib, 
         print(f"trainer drop-in: {setname} set against the OTHER loss's reference gradient {cross:.3f}")
         assert cos >= cross + 0.3, (setname, cos, cross)      # it is the gradient of ITS loss
     assert {"hwg_ctc_forward", "hwg_ctc_backward", "hwg_spectral_norm", "hwg_gen_output_bwd"} <= set(calls)
+
+
+def test_reference_trainer_disc_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib, monkeypatch):
+    """Curriculum slot ["disc"] (trainer :785-806, :381-388): real || generated (detached) lines through the drop-in
+    discriminator, the trainer's hinge loss, backward to all 28 discriminator tensors, `clip_grad_value_`, Adam step of
+    the trainer's own optimizer_discriminator — against the golden of the same lesson on the reference's classes."""
+    import importlib
+    import sys
+
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import _lib, integrate
+    from oracle import make_trainer_golden as harness
+    from oracle import synth
+    gold = np.load(f"{golden_dir}/trainer_disc.npz")
+    _, _, _, _, style, noise, _ = build_inputs(gold)
+    B = style.size(0)
+    masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(2 * B, int(gold["seeds"][4])).items()}
+    saved_path, saved_ds = list(sys.path), sys.modules.get("datasets")
+    state = {}
+
+    def install():
+        hws = importlib.import_module("model.hw_with_style")
+        mloss = importlib.import_module("model.loss")
+        state["orig"] = (hws, mloss, hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss)
+        integrate.install(retain_graph=True)
+
+    def hook(tr, model, rec):
+        assert isinstance(model.discriminator, pkg.DiscriminatorAP)
+        model.discriminator.dropout_masks = masks
+        state["before"] = {n: p.detach().clone() for n, p in model.discriminator.named_parameters()}
+        recorded = model.generator.forward
+        model.generator.forward = lambda content, style, *a, **k: recorded(content, style, *a, noise=noise, **k)
+
+    try:
+        with abi_emu.installed(monkeypatch):
+            tr, log, rec, model = harness.run_lesson("disc", install=install, hook=hook)
+    finally:
+        hws, mloss, g, h, d, c = state["orig"]
+        hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss = g, h, d, c
+        _lib.RETAIN_SAVED = False
+        sys.path[:] = saved_path
+        if saved_ds is not None:
+            sys.modules["datasets"] = saved_ds
+        else:
+            sys.modules.pop("datasets", None)
+    assert np.array_equal(rec["gen_in"][0].numpy(), gold["content"]) and np.array_equal(rec["gen_in"][1].numpy(), gold["style"])
+    assert abs(log["discriminatorLoss"] - gold["losses"][0]) <= 2e-2 * abs(gold["losses"][0])
+    num = d1 = d2 = 0.0
+    checked = 0
+    for n, p in model.discriminator.named_parameters():
+        key = f"grad/disc/discriminator.{n}"
+        if key + "/sample" not in gold.files:
+            continue
+        assert p.grad is not None, n
+        ref = gold[key + "/sample"].astype(np.float64)
+        samp = digest(p.grad.numpy())[1][:256].astype(np.float64)          # already clipped by the trainer (:381)
+        num, d1, d2 = num + float((samp * ref).sum()), d1 + float((samp * samp).sum()), d2 + float((ref * ref).sum())
+        checked += 1
+        if p.requires_grad and float(np.abs(ref).max()) > 0:
+            assert not torch.equal(p.detach(), state["before"][n]), n     # the trainer's optimizer stepped it
+    assert checked == 28, checked
+    cos = num / (d1 * d2) ** 0.5
+    print(f"trainer drop-in: clipped discriminator gradients, cosine with the reference trainer's {cos:.3f}")
+    assert cos >= 0.95, cos
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0 for n, p in model.named_parameters()
+               if n.startswith("generator."))                              # fake.detach(): nothing reaches the generator
