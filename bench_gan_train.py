@@ -44,14 +44,15 @@ def use_perceptual():
 
 def use_balanced():
     """Opt-in (HWG_BENCH_BALANCED=1, one GPU) until FlatAdam.stash()/balance() and Encoder2 have green GPU parity runs: the
-    optimizer step as the reference's curriculum takes it with `balance_loss` — a no-step 'gen' lesson whose adversarial
-    and recognition losses are back-propagated separately and stashed (trainer :300-338), then a lesson whose own gradient
+    optimizer step as the reference's curriculum takes it with `balance_loss` — a no-step 'gen' lesson whose recognition
+    and adversarial losses are back-propagated separately and stashed (trainer :312-338), then a lesson whose own gradient
     (here: the perceptual loss of the 'auto' lesson) the stashed sets are balanced into per parameter tensor
     (:340-377, `balance_var_x` of the config), then clip + Adam."""
     return bool(os.environ.get("HWG_BENCH_BALANCED"))
 
 
 BALANCE_VAR_X = [0.6, 0.5]        # config :100 `balance_var_x` [0.6, 0.5, 0.4, 0.75]: the entries of the two sets stashed here
+                                  # (recognition set first, adversarial set second, as the trainer stashes them)
 DEFAULT_SYNC_BN = "peer"
 
 
@@ -267,9 +268,9 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         img = gen(c, s)                                       # lesson 1: 'gen', no-step
         adv = adversarial(img)
         recog = W_CTC * pkg.CTCLoss(hwr(img), tg, il, tl)
-        adv.backward(retain_graph=True)                       # trainer :300-311 (autoGenLoss first)
+        recog.backward(retain_graph=True)                     # trainer :312-323: the 'Recog' losses first, stashed
         opt.stash()
-        recog.backward()                                      # :312-323
+        adv.backward()                                        # :326-338: the rest of a no-step lesson, stashed
         opt.stash()
         perc = W_PERC * enc.perceptual_loss(real, gen(c, s))  # lesson 2: the 'auto' lesson's perceptual loss (:724-748)
         perc.backward()

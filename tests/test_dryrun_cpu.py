@@ -117,9 +117,9 @@ def test_balanced_two_lesson_step_host_code_runs(recorder):
             preds = disc(img)
             adv = -sum(p.mean() for p in preds) / len(preds)
             recog = 1e-4 * pkg.CTCLoss(hwr(img), tg, il, tl)
-            adv.backward(retain_graph=True)
+            recog.backward(retain_graph=True)
             opt.stash()
-            recog.backward()
+            adv.backward()
             opt.stash()
             assert len(opt._stash) == 2
             (0.5 * enc.perceptual_loss(real, gen(content, style))).backward()
