@@ -370,6 +370,47 @@ def make_style():
     np.savez_compressed(os.path.join(GOLD, "style.npz"), **out)
 
 
+# name -> (L, B, weight seed, input seed)
+SPACER_CASES = {"l12_b3": (12, 3, 700, 701), "l40_b2": (40, 2, 700, 702)}
+
+
+def spacer_inputs(L, B, seed, n_class=80):
+    r = np.random.RandomState(seed)
+    label = torch.from_numpy(r.randint(1, n_class, (L, B)).astype(np.int64))
+    lengths = torch.IntTensor([L - (b % 3) for b in range(B)])
+    style = torch.from_numpy(r.standard_normal((B, 128)).astype(np.float32))
+    return label, lengths, style
+
+
+def make_spacer():
+    """Counts of the unmodified reference CountCNN and the spaced text of the unmodified `HWWithStyle.insert_spaces`
+    (called unbound on a stand-in that carries the attributes it reads: no model weights are involved in it)."""
+    ref_shim.install()
+    import types
+    from model.count_cnn import CountCNN
+    from model.hw_with_style import HWWithStyle
+    out = {}
+    for name, (L, B, wseed, iseed) in SPACER_CASES.items():
+        torch.manual_seed(wseed)
+        m = CountCNN(80, 128, 128, 2).eval()
+        out["state_dict_keys"] = keys_fixture(m.state_dict())
+        out[f"{name}/weights_digest"] = weights_digest(m.state_dict())
+        label, lengths, style = spacer_inputs(L, B, iseed)
+        onehot = torch.zeros(L, B, 80).scatter_(2, label[..., None], 1.0)
+        with torch.no_grad():
+            counts = m(onehot, style)
+        for std, tag in ((1e-8, "cfg"), (0.4, "noisy")):           # the config's count_std / dup_std, and a case where the draws matter
+            host = types.SimpleNamespace(count_std=std, dup_std=std / 10, count_duplicates=True, num_class=80)
+            np.random.seed(iseed)
+            spaced, padded = HWWithStyle.insert_spaces(host, label, lengths, counts)
+            out[f"{name}/{tag}/spaced"] = spaced.argmax(2).numpy().astype(np.int16)
+            assert float(spaced.sum(2).min()) == 1.0 and float(spaced.max()) == 1.0
+            out[f"{name}/{tag}/padded"] = np.array(padded, np.float64)
+        out[f"{name}/counts"] = counts.numpy()
+        print(f"spacer/{name}: counts {tuple(counts.shape)} spaced T={spaced.size(0)}")
+    np.savez_compressed(os.path.join(GOLD, "spacer.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -385,6 +426,8 @@ def main(argv):
         make_enc()
     if what in ("style", "all"):
         make_style()
+    if what in ("spacer", "all"):
+        make_spacer()
 
 
 if __name__ == "__main__":
