@@ -506,6 +506,20 @@ int hwg_l1_halves(const void* f, int dtype, int64_t half_numel, float loss_scale
                   void* g, void* stream);
 
 /* ------------------------------------------------------------------------
+ * DTW alignment of a label to the recognizer output — reference `correct_pred`, model/hw_with_style.py:18-74 (SURVEY.md 8
+ * row f3; called by HWWithStyle.autoencode / extract_style, :279-291).  label_with_blanks = blank, c0, blank, c1, ...,
+ * blank (L = 2S+1 columns); dtw[i][j] = (1 - pred[i-1, b, label_with_blanks[j-1]]) + min(dtw[i-1][j], dtw[i-1][j-1],
+ * dtw[i][j-1]) inside the band |i - j| <= w, w = max(T/2, |T - L|) (first minimum wins, as torch.min); the path is
+ * traced back from (T, L) and the label under it written front to back.
+ * pred [T,B,C] fp32 contiguous; label int32, element (s,b) at label[s*label_stride_s + b*label_stride_b];
+ * hist [B,T,L] bytes and scratch [B,T+L] int32 are workspaces; out [T+L,B] int32 (the caller zero-fills it: rows past
+ * out_len[b] are the reference's zero padding), out_len [B].  One CTA per sequence, 2S+2 <= 1024.
+ * Status: written after round 1's GPU budget was spent — compiled, not yet run on a GPU. */
+int hwg_dtw_align(const float* pred, int T, int B, int C, const int32_t* label, int64_t label_stride_s,
+                  int64_t label_stride_b, int S, uint8_t* hist, int32_t* out, int32_t* out_len, int32_t* scratch,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).
  * The reference is single-process: nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79
  * normalise with the statistics of the WHOLE batch.  With the batch sharded
