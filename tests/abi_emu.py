@@ -412,6 +412,23 @@ def hwg_ctc_backward(go, unit, lp, T, B, C, tg, ts_b, ts_s, S, il, tl, blank, nl
     return 0
 
 
+def hwg_adam_flat(p, g, m, v, n, lr, beta1, beta2, eps, clip_value, grad_scale, step_dev, zero_grad, stream):
+    """include/hwg_b200.h: clip_grad_value_ + Adam (bias-corrected, as torch.optim.Adam) + zero_grad over flat buffers."""
+    pv, gv, mv, vv = (_view(x, n, torch.float32) for x in (p, g, m, v))
+    st = _view(step_dev, 1, torch.float32)
+    st += 1
+    t = float(st[0])
+    gg = gv * grad_scale
+    if clip_value > 0:
+        gg = gg.clamp(-clip_value, clip_value)
+    mv.copy_(mv + (gg - mv) * (1 - beta1))
+    vv.copy_(beta2 * vv + (1 - beta2) * gg * gg)
+    pv.sub_(lr / (1 - beta1 ** t) * mv / (vv.sqrt() / (1 - beta2 ** t) ** 0.5 + eps))
+    if zero_grad:
+        gv.zero_()
+    return 0
+
+
 def _i64(ptr, n):
     return np.frombuffer((ctypes.c_int64 * n).from_address(ptr), dtype=np.int64)
 
@@ -595,7 +612,7 @@ def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, 
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
+_TABLE = {f.__name__: f for f in (hwg_adam_flat, hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
                                   hwg_blur_noise_act_stats, hwg_gen_output, hwg_gen_output_bwd, hwg_adain_bwd_reduce,
                                   hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,

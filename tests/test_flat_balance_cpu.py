@@ -40,3 +40,30 @@ def test_flat_stash_and_balance_match_the_oracle(hwg_lib, monkeypatch):
             assert float((got - r).abs().max()) <= 2e-6 * float(r.abs().max()) + 1e-12
         opt.balance(mult)                                    # nothing stashed: a no-op, no launch
         assert calls == ["hwg_balance"]
+
+
+def test_flat_adam_step_equals_clip_plus_torch_adam(hwg_lib, monkeypatch):
+    """FlatAdam's host side (flat slots, .data / .grad re-pointing, version bump) through the interpreter of
+    hwg_adam_flat against `clip_grad_value_` + `torch.optim.Adam` (trainer :381-391), five steps."""
+    import handwriting_line_generation_b200 as pkg
+    g0 = torch.Generator().manual_seed(1)
+    shapes = [(16, 8, 3, 3), (16,), (5,), (3, 7)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g0)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    topt = torch.optim.Adam(ref, lr=2e-4, betas=(0.5, 0.999))
+    with abi_emu.installed(monkeypatch) as calls:
+        opt = pkg.FlatAdam(ours, lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
+        for step in range(5):
+            grads = [torch.randn(s, generator=g0) * (3.0 if step % 2 else 0.3) for s in shapes]     # some beyond the clip
+            for p, q, g in zip(ref, ours, grads):
+                p.grad = g.clone()
+                opt.grad_view(q).copy_(g)
+            torch.nn.utils.clip_grad_value_(ref, 2)
+            topt.step()
+            v0 = [q._version for q in ours]
+            opt.step()
+            assert all(q._version > v for q, v in zip(ours, v0))            # derived-weight caches see the update
+            assert float(opt.flat_g.abs().max()) == 0.0                      # zero_grad is part of the launch
+            for p, q in zip(ref, ours):
+                assert torch.allclose(q, p, rtol=1e-5, atol=1e-7)
+    assert calls.count("hwg_adam_flat") == 5
