@@ -1,0 +1,45 @@
+"""CPU: the GPU parity tests parked under tools/ (written after the round's GPU budget was spent, to be promoted after a
+green B200 run) executed through the CPU interpreter of the C-ABI with `.cuda()` made a no-op — so that their own code and
+thresholds are known to be sound before they meet the real kernels (this is how a 3e-2 image bound and a 0.6 cosine bound
+that the bf16 pipeline cannot meet on the trainer's 2-line case were found and replaced)."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+from . import abi_emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture
+def emulated_gpu(monkeypatch, hwg_lib):
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    with abi_emu.installed(monkeypatch) as calls:
+        yield calls
+
+
+def test_parked_trainer_gen_lesson_test(emulated_gpu):
+    _load("pending_test_trainer_gen_gpu").test_cuda_gen_lesson_against_the_reference_trainer()
+    assert "hwg_ctc_backward" in emulated_gpu
+
+
+@pytest.mark.parametrize("name", ["eval_w128", "train_w200"])
+def test_parked_encoder2_test(emulated_gpu, name):
+    _load("pending_test_enc_gpu").test_encoder2_cuda_matches_reference_golden_and_oracle(name)
+    assert "hwg_l1_halves" in emulated_gpu
+
+
+def test_parked_balance_test(emulated_gpu):
+    _load("pending_test_balance_gpu").test_flat_balance_matches_the_oracle()
+    assert emulated_gpu.count("hwg_balance") == 1
