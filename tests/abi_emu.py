@@ -412,6 +412,24 @@ def hwg_ctc_backward(go, unit, lp, T, B, C, tg, ts_b, ts_s, S, il, tl, blank, nl
     return 0
 
 
+def hwg_dtw_align(pred, T, B, C, label, ls_s, ls_b, S, hist, out, out_len, scratch, stream):
+    """model/hw_with_style.py:18-74 through the oracle's restatement (bit-exact against the reference goldens); checks the
+    host wrapper's buffers: out [T+L,B] zero-filled by the caller, out_len [B]."""
+    from oracle import style as ostyle
+    pv = _view(pred, T * B * C, torch.float32).view(T, B, C).numpy()
+    span = (S - 1) * ls_s + (B - 1) * ls_b + 1
+    lab = torch.as_strided(_i32(label, span), (S, B), (ls_s, ls_b)).numpy()
+    L = 2 * S + 1
+    ov = _i32(out, (T + L) * B).view(T + L, B)
+    assert int(ov.abs().max()) == 0, "out must be zero-filled by the caller"
+    lv = _i32(out_len, B)
+    for b in range(B):
+        path = ostyle.correct_pred(pv[:, b:b + 1], lab[:, b:b + 1])[:, 0]      # per line: its own (unpadded) path
+        ov[:len(path), b] = torch.from_numpy(path.astype(np.int32))
+        lv[b] = len(path)
+    return 0
+
+
 def hwg_adam_flat(p, g, m, v, n, lr, beta1, beta2, eps, clip_value, grad_scale, step_dev, zero_grad, stream):
     """include/hwg_b200.h: clip_grad_value_ + Adam (bias-corrected, as torch.optim.Adam) + zero_grad over flat buffers."""
     pv, gv, mv, vv = (_view(x, n, torch.float32) for x in (p, g, m, v))
@@ -612,7 +630,7 @@ def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, 
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_adam_flat, hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
+_TABLE = {f.__name__: f for f in (hwg_dtw_align, hwg_adam_flat, hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
                                   hwg_blur_noise_act_stats, hwg_gen_output, hwg_gen_output_bwd, hwg_adain_bwd_reduce,
                                   hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,

@@ -43,3 +43,12 @@ def test_parked_encoder2_test(emulated_gpu, name):
 def test_parked_balance_test(emulated_gpu):
     _load("pending_test_balance_gpu").test_flat_balance_matches_the_oracle()
     assert emulated_gpu.count("hwg_balance") == 1
+
+
+@pytest.mark.parametrize("name", ["t58_l9", "t124_l30"])
+def test_parked_dtw_test(emulated_gpu, name):
+    """The host wrapper `dtw.correct_pred` (buffers, zero padding to the longest path, dtype / device of the result) around
+    an interpreter of hwg_dtw_align that is the oracle itself; the kernel's own arithmetic is mirrored in
+    tests/test_dtw_wavefront_cpu.py."""
+    _load("pending_test_dtw_gpu").test_dtw_matches_the_reference_golden(name)
+    assert emulated_gpu.count("hwg_dtw_align") == 1
