@@ -1,5 +1,6 @@
 #!/bin/bash
-# First GPU call of the next round (one GPU, ~4 min).  Everything below was written after round 1's GPU budget was spent.
+# First GPU call of the next round (one GPU; typically 6-8 min, every step under its own timeout):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round2_first.sh'  Everything below was written after round 1's GPU budget was spent.
 # (1) the parked GPU tests (trainer-level gen lesson, flat gradient balancing, Encoder2 / perceptual loss, DTW alignment);
 # (2) tools/halo_probe.cu: do shifted UMMA views of one swizzled halo tile read the right pixels, and with which descriptor;
 # (3) the halo-mode main loop of conv_fprop_kernel (HWG_CONV_HALO=1|2, HWG_CONV_HALO_BO per the probe): numerics through the
@@ -7,6 +8,7 @@
 # (4) the opt-in bench steps (perceptual branch; balanced two-lesson step);
 # (5) the weight-stationary limit experiment on the 64->64 3x3 layers, and the step with each override.
 mkdir -p gpurun_out
+exec > >(tee gpurun_out/round2_first.log) 2>&1      # the whole transcript comes back with gpurun_out/
 timeout 300 python -m pytest tools/pending_test_trainer_gen_gpu.py tools/pending_test_balance_gpu.py tools/pending_test_enc_gpu.py tools/pending_test_dtw_gpu.py -q -p no:cacheprovider 2>&1 | tail -8
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o gpurun_out/halo_probe tools/halo_probe.cu && timeout 60 gpurun_out/halo_probe | tee gpurun_out/halo_probe.txt
 BO=""
