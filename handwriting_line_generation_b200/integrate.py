@@ -7,7 +7,7 @@ and generate.py run the sm_100a path without a source change."""
 import importlib
 
 
-def install(encoder=False, retain_graph=False):
+def install(encoder=False, retain_graph=False, dtw=False):
     """Call after the reference's root is on sys.path and before HWWithStyle / the trainer are built.
     Returns the list of (module name, attribute) pairs that were rebound.
 
@@ -15,11 +15,17 @@ def install(encoder=False, retain_graph=False):
     (`from model.autoencoder import Encoder2`, trainer/hw_with_style_trainer.py:15,148-149) — opt-in until the module has
     a green GPU parity run (encoder2.py: status).
     retain_graph=True keeps the modules' saved-for-backward state over repeated `.backward(retain_graph=True)` calls on one
-    graph — what the trainer does when `balance_loss` is configured (trainer/hw_with_style_trainer.py:300-338)."""
+    graph — what the trainer does when `balance_loss` is configured (trainer/hw_with_style_trainer.py:300-338).
+    dtw=True rebinds `correct_pred` (model/hw_with_style.py:18, the DTW label alignment `autoencode` / `extract_style`
+    call) to the one-launch version — opt-in until it has a green GPU run (dtw.py: status)."""
     from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator, set_retain_graph
     swapped = []
     if retain_graph:
         set_retain_graph(True)
+    if dtw:
+        from .dtw import correct_pred
+        setattr(importlib.import_module("model.hw_with_style"), "correct_pred", correct_pred)
+        swapped.append(("model.hw_with_style", "correct_pred"))
     if encoder:
         from .encoder2 import Encoder2
         for modname in ("model.autoencoder", "trainer.hw_with_style_trainer"):
