@@ -62,12 +62,18 @@ def test_reference_trainer_gen_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib, 
     def install():
         hws = importlib.import_module("model.hw_with_style")
         mloss = importlib.import_module("model.loss")
+        mauto = importlib.import_module("model.autoencoder")
+        mtr = importlib.import_module("trainer.hw_with_style_trainer")
         state["orig"] = (hws, mloss, hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss)
-        integrate.install(retain_graph=True)
+        state["enc"] = (mauto, mtr, mauto.Encoder2, mtr.Encoder2)
+        integrate.install(retain_graph=True, encoder=True)
 
     def hook(tr, model, rec):
         assert isinstance(model.generator, pkg.SpacedGenerator) and isinstance(model.hwr, pkg.CNNOnlyHWR)
         assert isinstance(model.discriminator, pkg.DiscriminatorAP) and tr.balance_loss
+        # the trainer built the perceptual encoder from the drop-in class and loaded the checkpoint into it (:136-158)
+        assert isinstance(tr.encoder, pkg.Encoder2) and tr.encoder.out_dim == 32
+        state["encoder_sum"] = float(sum(p.detach().double().abs().sum() for p in tr.encoder.parameters()))
         model.discriminator.dropout_masks = masks                      # the reference run patched F.dropout2d with these
         recorded = model.generator.forward                              # the harness's recorder around the module's forward
         model.generator.forward = lambda content, style, *a, **k: recorded(content, style, *a, noise=noise, **k)
@@ -78,12 +84,16 @@ def test_reference_trainer_gen_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib, 
     finally:
         hws, mloss, g, h, d, c = state["orig"]
         hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss = g, h, d, c
+        if "enc" in state:
+            mauto, mtr, e1, e2 = state["enc"]
+            mauto.Encoder2, mtr.Encoder2 = e1, e2
         _lib.RETAIN_SAVED = False
         sys.path[:] = saved_path
         if saved_ds is not None:
             sys.modules["datasets"] = saved_ds
         else:
             sys.modules.pop("datasets", None)
+    assert state["encoder_sum"] > 0
     # the trainer fed the drop-in generator exactly what it fed the reference's (same RNG consumption up to that point)
     assert np.array_equal(rec["gen_in"][0].numpy(), gold["content"]) and np.array_equal(rec["gen_in"][1].numpy(), gold["style"])
     # bf16 path: as close to the reference's fp32 image as plain torch with bf16 storage between the layers is (DESIGN
