@@ -6,11 +6,15 @@ the golden of the same lesson run with the reference's own classes (tests/golden
 This is the drop-in claim at the level a user of the reference meets it: no call site changes, the trainer's own
 `self.model(label, label_lengths, style)` / `self.model.hwr(gen_image)` / `CTCLoss` / `self.model.discriminator(fake)`
 calls, its three `.backward(retain_graph=True)` passes over one graph and its gradient stashing (trainer :300-338)."""
+import importlib
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
 
-from oracle import ref_shim
+from oracle import ref_shim, synth
 from oracle.make_golden import digest
 
 from . import abi_emu
@@ -199,3 +203,63 @@ def test_reference_trainer_disc_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib,
     assert cos >= 0.95, cos
     assert all(p.grad is None or float(p.grad.abs().max()) == 0 for n, p in model.named_parameters()
                if n.startswith("generator."))                              # fake.detach(): nothing reaches the generator
+
+
+def test_reference_trainer_balanced_step_runs_on_the_drop_ins(golden_dir, hwg_lib, monkeypatch):
+    """Curriculum slots 1 -> 2 (["no-step","gen"] then ["auto","auto-gen"]) of the unmodified trainer on the drop-ins, incl.
+    `Encoder2` at its own call site (`self.encoder(both_i)`, trainer :742), the DTW `correct_pred` (`autoencode`), the CTC
+    of `reconRecog`, three backward passes over one retained graph per lesson, the trainer's own per-tensor balancing of the
+    four stashed sets (:340-377), `clip_grad_value_` and `optimizer.step()`.  The second lesson draws its noise / dropout
+    from RNG streams the reference run does not share, so this is a "runs end to end, finite, every generator tensor
+    stepped" check; the per-lesson parity is what the two tests above pin."""
+    import handwriting_line_generation_b200 as pkg
+    from handwriting_line_generation_b200 import _lib, integrate
+    from oracle import make_trainer_golden as harness
+    gold = np.load(f"{golden_dir}/trainer_gen.npz")
+    _, _, _, _, _, noise, masks = build_inputs(gold)
+    saved_path, saved_ds = list(sys.path), sys.modules.get("datasets")
+    state = {}
+    def install():
+        hws = importlib.import_module("model.hw_with_style"); mloss = importlib.import_module("model.loss")
+        mauto = importlib.import_module("model.autoencoder"); mtr = importlib.import_module("trainer.hw_with_style_trainer")
+        state["orig"] = (hws, mloss, hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss, hws.correct_pred)
+        state["enc"] = (mauto, mtr, mauto.Encoder2, mtr.Encoder2)
+        integrate.install(retain_graph=True, encoder=True, dtw=True)
+    def hook(tr, model, rec):
+        model.discriminator.dropout_masks = masks
+        recorded = model.generator.forward
+        model.generator.forward = lambda content, style, *a, **k: recorded(content, style, *a, noise=noise, **k)
+    cwd = os.getcwd()
+    try:
+        with abi_emu.installed(monkeypatch) as calls:
+            tr, log, rec, model = harness.run_lesson("gen", install=install, hook=hook)
+            os.chdir(ref_shim.REF)
+            model.discriminator.dropout_masks = None
+            fwd = model.generator.forward
+            def with_noise(content, style, *a, **k):
+                B = style.size(0)
+                nz = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(content.size(0), B), 77)]
+                return fwd(content, style, *a, noise=nz, **k)
+            model.generator.forward = with_noise
+            before = {n: p.detach().clone() for n, p in model.generator.named_parameters()}
+            n0 = len(calls)
+            tr.iteration = 2
+            log2 = tr._train_iteration(2)
+            lesson2 = set(calls[n0:])
+            changed = sum(int(not torch.equal(p.detach(), before[n])) for n, p in model.generator.named_parameters())
+    finally:
+        os.chdir(cwd)
+        hws, mloss, g, h, d, c, cp = state["orig"]
+        hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss, hws.correct_pred = g, h, d, c, cp
+        mauto, mtr, e1, e2 = state["enc"]; mauto.Encoder2, mtr.Encoder2 = e1, e2
+        _lib.RETAIN_SAVED = False
+        sys.path[:] = saved_path
+        if saved_ds is not None: sys.modules["datasets"] = saved_ds
+        else: sys.modules.pop("datasets", None)
+    for k in ("autoLoss", "perceptualLoss", "reconRecogLoss", "generatorLoss"):
+        assert k in log2 and np.isfinite(log2[k]), (k, log2)
+    assert 0.0 < log2["perceptualLoss"] < 5.0 and 0.0 < log2["autoLoss"] < 2.0
+    assert changed == len(before) == 64                       # the balanced gradient reached every generator tensor
+    assert tr.saved_grads == []                               # consumed by the trainer's balancing
+    assert {"hwg_dtw_align", "hwg_add_stats", "hwg_ctc_backward", "hwg_spectral_norm", "hwg_gen_output_bwd",
+            "hwg_hwr_stem_bwd_image", "hwg_norm_bwd_apply"} <= lesson2
