@@ -205,13 +205,14 @@ def test_reference_trainer_disc_lesson_runs_on_the_drop_ins(golden_dir, hwg_lib,
                if n.startswith("generator."))                              # fake.detach(): nothing reaches the generator
 
 
-def test_reference_trainer_balanced_step_runs_on_the_drop_ins(golden_dir, hwg_lib, monkeypatch):
+def test_reference_trainer_curriculum_cycle_runs_on_the_drop_ins(golden_dir, hwg_lib, monkeypatch):
     """Curriculum slots 1 -> 2 (["no-step","gen"] then ["auto","auto-gen"]) of the unmodified trainer on the drop-ins, incl.
     `Encoder2` at its own call site (`self.encoder(both_i)`, trainer :742), the DTW `correct_pred` (`autoencode`), the CTC
     of `reconRecog`, three backward passes over one retained graph per lesson, the trainer's own per-tensor balancing of the
     four stashed sets (:340-377), `clip_grad_value_` and `optimizer.step()`.  The second lesson draws its noise / dropout
     from RNG streams the reference run does not share, so this is a "runs end to end, finite, every generator tensor
-    stepped" check; the per-lesson parity is what the two tests above pin."""
+    stepped" check; the per-lesson parity is what the two tests above pin.  The remaining lessons of the 7-lesson cycle
+    (disc, gen, auto, disc, and the next cycle's count lesson) follow in the same trainer: finite logs throughout."""
     import handwriting_line_generation_b200 as pkg
     from handwriting_line_generation_b200 import _lib, integrate
     from oracle import make_trainer_golden as harness
@@ -247,6 +248,11 @@ def test_reference_trainer_balanced_step_runs_on_the_drop_ins(golden_dir, hwg_li
             log2 = tr._train_iteration(2)
             lesson2 = set(calls[n0:])
             changed = sum(int(not torch.equal(p.detach(), before[n])) for n, p in model.generator.named_parameters())
+            # ... and the rest of the 7-lesson cycle (config :85-95): disc, gen, auto, disc, then the next cycle's count
+            cycle = {}
+            for it in (3, 4, 5, 6, 7):
+                tr.iteration = it
+                cycle[it] = tr._train_iteration(it)
     finally:
         os.chdir(cwd)
         hws, mloss, g, h, d, c, cp = state["orig"]
@@ -263,3 +269,7 @@ def test_reference_trainer_balanced_step_runs_on_the_drop_ins(golden_dir, hwg_li
     assert tr.saved_grads == []                               # consumed by the trainer's balancing
     assert {"hwg_dtw_align", "hwg_add_stats", "hwg_ctc_backward", "hwg_spectral_norm", "hwg_gen_output_bwd",
             "hwg_hwr_stem_bwd_image", "hwg_norm_bwd_apply"} <= lesson2
+    assert "discriminatorLoss" in cycle[3] and "discriminatorLoss" in cycle[6] and "perceptualLoss" in cycle[5]
+    assert "countLoss" in cycle[7], cycle[7]
+    for it, lg in cycle.items():
+        assert all(np.isfinite(v) for k, v in lg.items() if isinstance(v, float)), (it, lg)
