@@ -250,9 +250,13 @@ def test_reference_trainer_curriculum_cycle_runs_on_the_drop_ins(golden_dir, hwg
             changed = sum(int(not torch.equal(p.detach(), before[n])) for n, p in model.generator.named_parameters())
             # ... and the rest of the 7-lesson cycle (config :85-95): disc, gen, auto, disc, then the next cycle's count
             cycle = {}
+            per_lesson = {1: n0, 2: len(calls) - n0}
             for it in (3, 4, 5, 6, 7):
                 tr.iteration = it
+                c0 = len(calls)
                 cycle[it] = tr._train_iteration(it)
+                per_lesson[it] = len(calls) - c0
+            print("library calls per lesson (slot: calls):", per_lesson)
     finally:
         os.chdir(cwd)
         hws, mloss, g, h, d, c, cp = state["orig"]
