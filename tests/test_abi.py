@@ -53,3 +53,18 @@ def test_cpu_tensor_is_rejected():
     lp = torch.zeros(4, 1, 3).log_softmax(2)
     with pytest.raises(RuntimeError, match="CUDA"):
         CTCLoss(lp, torch.ones(1, 1, dtype=torch.int32), torch.tensor([4]), torch.tensor([1]))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/hwg_b200.h is the whole boundary: it must compile as C99 (what a cgo / JNI / FFI binding would include)."""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "hwg_b200.h"\nint main(void) { return hwg_version() == 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0 and "warning" not in r.stderr, r.stderr
