@@ -3,6 +3,7 @@ flavours (initial transposed conv as four channel folds, nearest-upsample row pa
 parities), blur / noise / AdaIN passes, the output head, and the whole backward (strided dgrad launches, gridded / phased
 wgrad launches, the one-launch gradient unpack) — run through the CPU interpreter of the C-ABI (tests/abi_emu.py) against the
 oracle, with the assertions of tests/test_gen_train_gpu.py (which the real kernels pass on the B200)."""
+import pytest
 import torch
 
 from oracle import gen as ogen
@@ -30,8 +31,9 @@ def _oracle(sd, content, style, noise, R, emulate):
     return img.detach(), g
 
 
-def test_generator_forward_and_backward_through_the_interpreter(hwg_lib, monkeypatch):
-    T, B, _, wseed, iseed = GEN_CASES["small"]
+@pytest.mark.parametrize("name", ["small", "odd_T"])
+def test_generator_forward_and_backward_through_the_interpreter(name, hwg_lib, monkeypatch):
+    T, B, _, wseed, iseed = GEN_CASES[name]
     m, sd = _gen_module(wseed)
     sd = {k: v.clone() for k, v in sd.items()}
     m.train()
