@@ -27,6 +27,50 @@ def _view(ptr, n, dtype):
     return torch.from_numpy(a)
 
 
+# ---- the in-kernel NoiseInjection RNG (csrc/noise_rng.cuh): counter-based, any element independently ----------------
+GENERATED_NOISE = []          # forward launches append the N(0,1) tensors they drew (logical NHWC), in launch order
+_M32 = 0xFFFFFFFF
+
+
+def _fmix32(h):
+    h = np.asarray(h, np.uint64) & _M32
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85EBCA6B)) & _M32
+    h ^= h >> np.uint64(13)
+    h = (h * np.uint64(0xC2B2AE35)) & _M32
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def _noise_key(seed, subseq):
+    seed, subseq = int(seed) & 0xFFFFFFFFFFFFFFFF, int(subseq) & 0xFFFFFFFFFFFFFFFF
+    a = int(_fmix32((seed & _M32) ^ 0x9E3779B9)) ^ int(_fmix32(((subseq & _M32) + 0x7F4A7C15) & _M32))
+    b = int(_fmix32(((seed >> 32) + 0x94D049BB) & _M32)) ^ int(_fmix32(((subseq >> 32) & _M32) ^ 0xBF58476D))
+    return a, b
+
+
+def _normals(key, idx):
+    """normal_one(key, idx) for an int64 array of element indices (exact log / sin / cos instead of the MUFU approximations:
+    differences of ~1e-6, irrelevant for what the interpreter checks — that forward and backward address the SAME noise)."""
+    idx = np.asarray(idx, np.uint64)
+    pair = idx >> np.uint64(1)
+    x = _fmix32((((pair & _M32) ^ np.uint64(key[0])) + (pair >> np.uint64(32)) * np.uint64(0x9E3779B1)) & _M32)
+    y = ((x ^ np.uint64(key[1])) * np.uint64(0x2C1B3C6D)) & _M32
+    y ^= y >> np.uint64(15)
+    y = (y * np.uint64(0x297A2D39)) & _M32
+    y ^= y >> np.uint64(16)
+    u1 = ((x >> np.uint64(8)).astype(np.float64) + 0.5) / 2 ** 24
+    ang = (y >> np.uint64(8)).astype(np.float64) * (2 * np.pi / 2 ** 24)
+    r = np.sqrt(-2.0 * np.log(u1))
+    z = np.where((idx & np.uint64(1)) == 0, r * np.cos(ang), r * np.sin(ang))
+    return torch.from_numpy(z.astype(np.float32))
+
+
+def _seed_total(seed, seed_dev):
+    extra = int(np.frombuffer((ctypes.c_uint64 * 1).from_address(seed_dev), dtype=np.uint64)[0]) if seed_dev else 0
+    return (int(seed) + extra) & 0xFFFFFFFFFFFFFFFF
+
+
 def _act(v, act, slope):
     if act == _lib.ACT_RELU:
         return torch.relu(v)
@@ -43,8 +87,7 @@ def hwg_conv_fprop(d_addr, x, w, bias, noise, noise_w, stats, y, stream):
     bias -> noise tensor -> activation -> statistics -> (strided, folded) store.  In-kernel noise is not interpreted."""
     d = _lib.ConvDesc.from_address(d_addr)
     N, H, W, Ci, Cp, Co, Ho, Wo, T = d.N, d.H, d.W, d.Cin, d.x_pitch, d.Cout, d.Ho, d.Wo, d.ntaps
-    # in-kernel noise is not interpreted: only accepted when every noise weight is zero (the strict-parity variant)
-    assert noise_w is None or noise is not None or float(_view(noise_w, Co, torch.float32).abs().max()) == 0
+    rng = noise_w is not None and noise is None          # in-kernel noise: fold f draws from subsequence noise_subseq + f
     sh, sw = max(d.in_stride_h, 1), max(d.in_stride_w, 1)
     fc = d.fold_c if d.fold_c else Co
     F = Co // fc
@@ -81,6 +124,16 @@ def hwg_conv_fprop(d_addr, x, w, bias, noise, noise_w, stats, y, stream):
         for f in range(F):
             z = placed(noise, torch.float32, d.nz_stride_n, d.nz_stride_h, d.nz_stride_w, f)
             acc[..., f * fc:(f + 1) * fc] += nw[f * fc:(f + 1) * fc] * z
+    elif rng:
+        nw = _view(noise_w, Co, torch.float32)
+        seed = _seed_total(d.noise_seed, d.noise_seed_dev)
+        drawn = []
+        for f in range(F):                                 # element index over the fold's logical [N,Ho,Wo,fold_c] output
+            key = _noise_key(seed, d.noise_subseq + (f if d.fold_c else 0))
+            z = _normals(key, np.arange(N * Ho * Wo * fc)).view(N, Ho, Wo, fc)
+            acc[..., f * fc:(f + 1) * fc] += nw[f * fc:(f + 1) * fc] * z
+            drawn.append(z)
+        GENERATED_NOISE.append(torch.cat(drawn, 1) if F > 1 else drawn[0])     # folds of the initial conv = output rows
     out = _act(acc, d.act, d.slope).to(ydt)
     if stats is not None:
         st = _view(stats, N * fc * 2, torch.float32).view(N, fc, 2)
@@ -561,13 +614,17 @@ def hwg_adain_coeffs(stats, gamma, beta, gb_stride, N, C, HW, eps, coef, save, s
 
 
 def hwg_blur_noise_act_stats(x, y, N, H, W, C, noise, noise_w, seed, subseq, seed_dev, act, slope, stats, stream):
-    assert noise_w is None or noise is not None or float(_view(noise_w, C, torch.float32).abs().max()) == 0
     xv = _view(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2)
     k = torch.tensor([1.0, 2.0, 1.0])
     k = (k[:, None] * k[None, :] / 16.0).expand(C, 1, 3, 3)
     v = torch.nn.functional.conv2d(xv, k, padding=1, groups=C).permute(0, 2, 3, 1)
-    if noise_w is not None and noise is not None:
-        v = v + _view(noise_w, C, torch.float32) * _view(noise, N * H * W * C, torch.float32).view(N, H, W, C)
+    if noise_w is not None:
+        if noise is not None:
+            z = _view(noise, N * H * W * C, torch.float32).view(N, H, W, C)
+        else:
+            z = _normals(_noise_key(_seed_total(seed, seed_dev), subseq), np.arange(N * H * W * C)).view(N, H, W, C)
+            GENERATED_NOISE.append(z)
+        v = v + _view(noise_w, C, torch.float32) * z
     out = _act(v, act, slope).to(torch.bfloat16)
     _view(y, N * H * W * C, torch.bfloat16).view(N, H, W, C).copy_(out)
     if stats:
@@ -625,8 +682,16 @@ def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, 
     _view(gy, N * HW * C, torch.bfloat16).view(N, HW, C).copy_(out)
     dc = _view(dch, 2 * C, torch.float32).view(C, 2)
     dc[:, 0] += out.sum((0, 1))
-    assert noise is not None, "abi_emu: regenerated in-kernel noise is not interpreted"
-    dc[:, 1] += (out * _view(noise, N * HW * C, torch.float32).view(N, HW, C)).sum((0, 1))
+    if noise is not None:
+        z = _view(noise, N * HW * C, torch.float32).view(N, HW, C)
+    else:                                               # regenerated from (seed, subsequence), in the FORWARD's numbering
+        st = _seed_total(seed, seed_dev)
+        if row_subseq:                                  # the initial conv's four output rows were four folds
+            rows = [_normals(_noise_key(st, subseq + h), np.arange(N * W * C)).view(N, 1, W, C) for h in range(H)]
+            z = torch.cat(rows, 1).reshape(N, HW, C)
+        else:
+            z = _normals(_noise_key(st, subseq), np.arange(N * HW * C)).view(N, HW, C)
+    dc[:, 1] += (out * z).sum((0, 1))
     return 0
 
 

@@ -3,6 +3,7 @@ flavours (initial transposed conv as four channel folds, nearest-upsample row pa
 parities), blur / noise / AdaIN passes, the output head, and the whole backward (strided dgrad launches, gridded / phased
 wgrad launches, the one-launch gradient unpack) — run through the CPU interpreter of the C-ABI (tests/abi_emu.py) against the
 oracle, with the assertions of tests/test_gen_train_gpu.py (which the real kernels pass on the B200)."""
+import numpy as np
 import pytest
 import torch
 
@@ -68,3 +69,45 @@ def test_generator_forward_and_backward_through_the_interpreter(name, hwg_lib, m
     assert abs(got["out.0.conv.bias"].item() - g32["out.0.conv.bias"].item()) <= 1e-3 * scale
     assert {"hwg_gen_pack_input", "hwg_blur_noise_act_stats", "hwg_adain_bwd_apply", "hwg_gen_output_bwd",
             "hwg_linear_bwd_f32", "hwg_conv_wgrad"} <= set(calls)
+
+
+def test_inkernel_noise_is_addressed_consistently_by_forward_and_backward(hwg_lib, monkeypatch):
+    """The DEFAULT path draws NoiseInjection's N(0,1) inside the kernels from (seed, subsequence, element index) and the
+    backward REGENERATES it for the noise-weight gradients (per-row subsequences for the initial transposed conv, per-fold
+    subsequences in folded launches).  Through the interpreter's port of csrc/noise_rng.cuh: the ten tensors the forward
+    drew are handed to the oracle as its noise; image and every gradient — the noise weights' in particular — must then
+    agree as in the explicit-noise test, which they only do if both passes address the same elements."""
+    T, B, _, wseed, iseed = GEN_CASES["small"]
+    m, sd = _gen_module(wseed)
+    sd = {k: v.clone() for k, v in sd.items()}
+    m.train()
+    content, style = synth.gen_case(T, B, 80, 128, iseed, True)
+    R = torch.randn(B, 1, 64, 4 * T, generator=torch.Generator().manual_seed(2))
+    c = torch.from_numpy(content).requires_grad_()
+    s = torch.from_numpy(style).requires_grad_()
+    with abi_emu.installed(monkeypatch):
+        del abi_emu.GENERATED_NOISE[:]
+        img = m(c, s)                                            # no noise= : in-kernel RNG
+        drawn = [z.permute(0, 3, 1, 2).contiguous().numpy() for z in abi_emu.GENERATED_NOISE]
+        (img * R).sum().backward()
+    shapes = synth.gen_noise_shapes(T, B)
+    assert [tuple(z.shape) for z in drawn] == [tuple(sh) for sh in shapes]
+    zall = torch.cat([torch.from_numpy(z).flatten() for z in drawn])
+    assert abs(float(zall.mean())) < 0.02 and abs(float(zall.std()) - 1.0) < 0.02          # N(0,1)
+    img32, g32 = _oracle(sd, content, style, drawn, R, False)
+    _, gemu = _oracle(sd, content, style, drawn, R, True)
+    assert rel_l2(img.detach(), img32) <= BF16_REL
+    got = {n: p.grad for n, p in m.named_parameters() if not n.startswith("gen.")}
+    for n, g in g32.items():
+        if "noise" not in n:
+            continue
+        ours, emu = rel_l2(got[n], g), rel_l2(gemu[n], g)
+        cos = float((got[n].double() * g.double()).sum() / (got[n].double().norm() * g.double().norm()))
+        assert ours <= 3.5 * emu + BF16_REL and cos >= 0.93, (n, ours, emu, cos)
+    # a second forward draws different noise (fresh host seed / device counter)
+    with abi_emu.installed(monkeypatch):
+        del abi_emu.GENERATED_NOISE[:]
+        with torch.no_grad():
+            m(c.detach(), s.detach())
+        again = abi_emu.GENERATED_NOISE[0].permute(0, 3, 1, 2).numpy()
+    assert not np.array_equal(again, drawn[0])
