@@ -1,10 +1,16 @@
-"""TEST INFRASTRUCTURE — CPU interpreter of the C-ABI entry points a host module calls (include/hwg_b200.h semantics, plain
-torch/numpy on raw addresses), so that the HOST-side composition of a drop-in module — tap lists, operand packing, shapes,
-residual / Dropout2d / GroupNorm bookkeeping, the backward chain — can be checked against the oracle without a GPU.
+"""TEST INFRASTRUCTURE — CPU interpreter of the C-ABI entry points the host modules call (include/hwg_b200.h semantics, plain
+torch/numpy on raw addresses), so that the HOST-side composition of the drop-in modules — tap lists, operand packing, shapes,
+residual / Dropout2d / GroupNorm / BatchNorm bookkeeping, noise seeds and subsequences, accumulator arenas, the backward
+chains, the optimizer plumbing — can be checked against the oracle and the reference goldens without a GPU, up to running
+the UNMODIFIED reference trainer's curriculum on the drop-ins (tests/test_trainer_dropin_cpu.py).
 
 It is a checker, never a fallback: it is installed by monkeypatching `_lib.call` inside a test (`installed()`), nothing in
 the package imports it, and the GPU tests compare the real kernels with the same oracle.  Storage types follow the kernels
-(NHWC bf16 activations, fp32 statistics); arithmetic is fp32."""
+(NHWC bf16 activations and gradients, fp32 statistics); arithmetic is fp32.  The in-kernel NoiseInjection RNG
+(csrc/noise_rng.cuh) is ported bit for bit in its integer part (exact log / sin / cos instead of the MUFU approximations).
+The generator, recognizer and discriminator modules pass the same assertions through this interpreter as on the B200
+(tests/test_*_emulated_cpu.py vs tests/test_*_gpu.py), which is what gives the not-yet-run modules' CPU checks their
+weight."""
 import contextlib
 import ctypes
 
