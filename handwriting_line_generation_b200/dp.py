@@ -142,25 +142,29 @@ class GradReducer:
                 p.grad = v
                 views.append(v)
                 off += -(-p.numel() // 4) * 4          # 16-byte aligned slots
-        self.buckets.append({"params": plist, "flat": flat, "views": views, "pending": len(plist), "work": None})
+        self.buckets.append({"params": plist, "flat": flat, "views": views, "ready": set(), "work": None})
+
+    def _arrived(self, p):
+        """One parameter of a bucket has its gradient.  Idempotent per step: a parameter whose gradient a backward kernel
+        wrote straight into the flat buffer is reported by the producer (`mark_ready`) AND by its post-accumulate hook
+        (autograd runs the hook even when the Function returned None for it) — counting both would launch the bucket's
+        all-reduce before its other parameters have been written."""
+        b = self.buckets[self._bucket_of[id(p)]]
+        if b["work"] is not None:          # already on its way this step
+            return
+        b["ready"].add(id(p))
+        if len(b["ready"]) == len(b["params"]):
+            self._launch(b)
 
     def _make_hook(self, bi):
-        def hook(p):
-            b = self.buckets[bi]
-            b["pending"] -= 1
-            if b["pending"] == 0:
-                self._launch(b)
         self._bucket_of.update({id(p): bi for p in self.buckets[bi]["params"]})
-        return hook
+        return self._arrived
 
     def mark_ready(self, p):
-        """For gradients written straight into the flat buffer by a backward kernel (no AccumulateGrad, so no hook):
-        the producer reports the parameter itself."""
+        """For gradients written straight into the flat buffer by a backward kernel: the producer reports the parameter
+        itself, after the launch that wrote it."""
         if self.world > 1 and id(p) in self._bucket_of:
-            b = self.buckets[self._bucket_of[id(p)]]
-            b["pending"] -= 1
-            if b["pending"] == 0:
-                self._launch(b)
+            self._arrived(p)
 
     def _launch(self, b):
         for p, v in zip(b["params"], b["views"]):
@@ -191,7 +195,7 @@ class GradReducer:
         for b in self.buckets:
             b["work"].wait()
             b["work"] = None
-            b["pending"] = len(b["params"])
+            b["ready"].clear()
         if self.comm is not None:
             torch.cuda.current_stream().wait_stream(self.comm)
 

@@ -39,9 +39,16 @@ def run_jobs_cpu(table, src_base=None, dst_base=None):
             v = np.stack([np.where(pad, 0.0, src[np.where(pad, 0, sb + o)]) for o in j["in_off"]], -1)   # [Rp,Cp,nin]
             res = (v.astype(np.float32) @ j["M"]) * scale
             vals = [res[..., o] for o in range(j["nout"])]
+        touched = []
         for o, val in zip(j["out_off"], vals):
             if j["accumulate"]:
                 np.add.at(out, (db + o)[~pad], val[~pad])
+                touched.append((db + o)[~pad].reshape(-1))
             else:
                 out[db + o] = val
-        dst_t.copy_(torch.from_numpy(out).to(dst_t.dtype))
+                touched.append((db + o).reshape(-1))
+        # write back ONLY what the job addresses, as the kernel does: the destination may share its storage with regions
+        # another thread is working on (the data-parallel tests all-reduce slices of the flat gradient buffer in the
+        # background while later jobs fill other slices)
+        idx = torch.from_numpy(np.unique(np.concatenate(touched)))
+        dst_t[idx] = torch.from_numpy(out[idx.numpy()]).to(dst_t.dtype)
