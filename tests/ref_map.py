@@ -50,5 +50,5 @@ def run_jobs_cpu(table, src_base=None, dst_base=None):
         # write back ONLY what the job addresses, as the kernel does: the destination may share its storage with regions
         # another thread is working on (the data-parallel tests all-reduce slices of the flat gradient buffer in the
         # background while later jobs fill other slices)
-        idx = torch.from_numpy(np.unique(np.concatenate(touched)))
-        dst_t[idx] = torch.from_numpy(out[idx.numpy()]).to(dst_t.dtype)
+        idx = np.concatenate(touched)                  # duplicates carry the same value
+        dst_t[torch.from_numpy(idx)] = torch.from_numpy(out[idx]).to(dst_t.dtype)
