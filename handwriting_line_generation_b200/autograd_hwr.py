@@ -62,7 +62,9 @@ def forward_train(m, x):
     x = x.float().contiguous()
     B = x.size(0)
     dev = x.device
-    ctx = {"x": x, "sync_bn_group": m.sync_bn_group if m.training else None}
+    # eval mode under autograd (a frozen `hwr.eval()` guiding the generator): the running statistics are constants of the
+    # backward, so no batch-statistics terms and no exchange
+    ctx = {"x": x, "sync_bn_group": m.sync_bn_group if m.training else None, "bn_use_batch": bool(m.training)}
     m._bn_counters = []
 
     arena = ops.ZeroArena(B * 2 * (256 + 6 * 512) + 64, dev)     # all BatchNorm statistics of this pass: one memset
@@ -213,6 +215,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     arena = ops.ZeroArena(dw_floats + 32768, lp.device)
     grads = _Grads(m, needed, arena)
     sync = ctx.get("sync_bn_group")        # the forward normalised with joint statistics of this group (SyncBN)
+    ub = ctx.get("bn_use_batch", True)
 
     def dgrad(gz, key, H, W):
         wd, tapsd = dg[key]
@@ -227,7 +230,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- dilated 1-D blocks, last to first
     for (ci, bi, pad, dil), (a_in, z, coef, save) in zip(reversed(_CNN1D), reversed(ctx["head_in"])):
         bn = m.cnn1d[bi]
-        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena, sync_group=sync, sync_key=("b", id(bn)))
+        gz, dgam, dbet, dcb = ops.bn_bwd(g, z, coef, save, bn.weight.detach(), arena=arena, sync_group=sync, sync_key=("b", id(bn)), use_batch=ub)
         grads[f"cnn1d.{bi}.weight"], grads[f"cnn1d.{bi}.bias"] = dgam, dbet
         grads.wgrad(f"cnn1d.{ci}.weight", f"v{ci}", a_in, gz, conv.conv_taps(1, 3, 0, pad, 1, dil), 512, 512)
         grads[f"cnn1d.{ci}.bias"] = dcb
@@ -235,7 +238,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- conv6 + BN + ReLU
     coef, save = ctx["bn6"]
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z6"], coef, save, m.cnn.batchnorm6.weight.detach(), arena=arena, sync_group=sync,
-                                     sync_key=("b", id(m.cnn.batchnorm6)))
+                                     sync_key=("b", id(m.cnn.batchnorm6)), use_batch=ub)
     grads["cnn.batchnorm6.weight"], grads["cnn.batchnorm6.bias"] = dgam, dbet
     a5 = ctx["a5"]
     grads.wgrad("cnn.conv6.weight", "w6", a5, gz, _T3P0, 512, 512)
@@ -250,7 +253,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- conv4 + BN + ReLU
     coef, save = ctx["bn4"]
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z4"], coef, save, m.cnn.batchnorm4.weight.detach(), arena=arena, sync_group=sync,
-                                     sync_key=("b", id(m.cnn.batchnorm4)))
+                                     sync_key=("b", id(m.cnn.batchnorm4)), use_batch=ub)
     grads["cnn.batchnorm4.weight"], grads["cnn.batchnorm4.bias"] = dgam, dbet
     a3 = ctx["a3"]
     grads.wgrad("cnn.conv4.weight", "w4", a3, gz, _T3, 256, 512)
@@ -265,7 +268,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     # ---- conv2 + BN + ReLU
     coef, save = ctx["bn2"]
     gz, dgam, dbet, dcb = ops.bn_bwd(g, ctx["z2"], coef, save, m.cnn.batchnorm2.weight.detach(), arena=arena, sync_group=sync,
-                                     sync_key=("b", id(m.cnn.batchnorm2)))
+                                     sync_key=("b", id(m.cnn.batchnorm2)), use_batch=ub)
     grads["cnn.batchnorm2.weight"], grads["cnn.batchnorm2.bias"] = dgam, dbet
     a1 = ctx["a1"]
     grads.wgrad("cnn.conv2.weight", "w2", a1, gz, _T3, 128, 256)

@@ -60,6 +60,10 @@ struct ChainSmem {
   float* lp;     // [2][TC][Cp] staged log-prob rows
 };
 
+// Labels index the staged log-prob row and the per-class tables: a value outside [0, C) (invalid input — ATen's CPU path
+// raises, the host wrapper checks CPU targets) is clamped so that it can never address memory out of range.
+__device__ __forceinline__ int clamp_label(int l, int C) { return l < 0 ? 0 : (l >= C ? C - 1 : l); }
+
 template <int VEC>
 __global__ void __launch_bounds__(1024)
 ctc_chain_kernel(const float* __restrict__ lp, int T, int B, int C,
@@ -82,7 +86,7 @@ ctc_chain_kernel(const float* __restrict__ lp, int T, int B, int C,
   int* lab = reinterpret_cast<int*>(col + 2 * colpitch);        // [L]
 
   for (int s = tid; s < Lb; s += NT)
-    lab[s] = (s & 1) ? targets[b * ts_b + (int64_t)(s >> 1) * ts_s] : blank;
+    lab[s] = (s & 1) ? clamp_label(targets[b * ts_b + (int64_t)(s >> 1) * ts_s], C) : blank;
   for (int i = tid; i < 2 * colpitch; i += NT) col[i] = -CUDART_INF_F;
 
   float* table = (dir == 0 ? log_alpha : log_beta) + (size_t)b * T * L;
@@ -197,7 +201,7 @@ ctc_grad_kernel(const float* __restrict__ grad_out, const float* __restrict__ un
   int* cls_pos = cls_off + (C + 1);                  // [S_max] label positions grouped by class
   float* occ = reinterpret_cast<float*>(cls_pos + S_max);  // [GRAD_TT][L]
 
-  for (int i = tid; i < Sb; i += NT) lab[i] = targets[b * ts_b + (int64_t)i * ts_s];
+  for (int i = tid; i < Sb; i += NT) lab[i] = clamp_label(targets[b * ts_b + (int64_t)i * ts_s], C);
   __syncthreads();
   // counting sort of label positions by class (stable -> fixed summation order)
   for (int c = tid; c < C; c += NT) {

@@ -32,6 +32,8 @@ class _CTCLossFn(torch.autograd.Function):
         dev = lp.device
         if targets.dim() != 2 or targets.size(0) != B:
             raise RuntimeError("targets must be [B,S] (the trainer passes label.permute(1,0))")
+        if not targets.is_cuda and targets.numel() and (int(targets.max()) >= C or int(targets.min()) < 0):
+            raise RuntimeError(f"targets must be class indices in [0, {C})")   # CUDA targets: clamped in-kernel (no sync)
         tg = targets.to(device=dev, dtype=torch.int32, non_blocking=True)  # keeps strides
         S = tg.size(1)
         # the reference hands over CPU IntTensors: validate there like ATen does, without a sync

@@ -120,7 +120,7 @@ class GradReducer:
             self._close(cur)
         self.cuda = bool(self.params) and self.params[0].is_cuda
         self.comm = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
-        self._handles, self._bucket_of = [], {}
+        self._handles, self._bucket_of, self._producer_streams = [], {}, {}
         if self.world > 1:
             for bi, b in enumerate(self.buckets):
                 for p in b["params"]:
@@ -145,10 +145,11 @@ class GradReducer:
         self.buckets.append({"params": plist, "flat": flat, "views": views, "ready": set(), "work": None})
 
     def _arrived(self, p):
-        """One parameter of a bucket has its gradient.  Idempotent per step: a parameter whose gradient a backward kernel
-        wrote straight into the flat buffer is reported by the producer (`mark_ready`) AND by its post-accumulate hook
-        (autograd runs the hook even when the Function returned None for it) — counting both would launch the bucket's
-        all-reduce before its other parameters have been written."""
+        """Post-accumulate-grad hook: one parameter of a bucket has its gradient for this backward pass.  The autograd
+        engine runs the hook ONCE per pass, after every node that feeds the parameter has run — also when the producing
+        Functions returned None because their kernels wrote the gradient straight into the flat buffer, and also when the
+        module was called several times in the graph (the reference trainer concatenates a reconstruction and a generated
+        batch, trainer :538/:577) — so it is the only readiness signal; `mark_ready` does not count."""
         b = self.buckets[self._bucket_of[id(p)]]
         if b["work"] is not None:          # already on its way this step
             return
@@ -161,23 +162,31 @@ class GradReducer:
         return self._arrived
 
     def mark_ready(self, p):
-        """For gradients written straight into the flat buffer by a backward kernel: the producer reports the parameter
-        itself, after the launch that wrote it."""
-        if self.world > 1 and id(p) in self._bucket_of:
-            self._arrived(p)
+        """For gradients written straight into the flat buffer by a backward kernel: the producer reports, after its
+        launches, the STREAM it wrote on — the all-reduce is ordered after that stream as well as after the stream the
+        hook runs on.  Readiness itself comes from the hook (`_arrived`): a producer that runs twice in one pass must not
+        release the bucket after its first run."""
+        if self.world > 1 and self.comm is not None and id(p) in self._bucket_of:
+            self._producer_streams[torch.cuda.current_stream().cuda_stream] = torch.cuda.current_stream()
 
     def _launch(self, b):
         for p, v in zip(b["params"], b["views"]):
             if p.grad is None:
-                v.zero_()
+                if self.flat is None:                 # (a flat slot is zeroed by step / zero_grad and may already hold what a
+                    v.zero_()                         # backward kernel added)
                 p.grad = v
             elif p.grad.data_ptr() != v.data_ptr():   # autograd installed its own tensor: move it into the bucket
-                v.copy_(p.grad)
+                if self.flat is not None:             # a backward kernel may already have added into the flat slot
+                    v.add_(p.grad)                    # (FlatAdam._rebind_grads does the same; the slot starts zeroed)
+                else:
+                    v.copy_(p.grad)
                 p.grad = v
         if self.comm is not None:
             ev = torch.cuda.Event()
             ev.record()
             self.comm.wait_event(ev)
+            for st in self._producer_streams.values():        # kernels that wrote the flat buffer directly
+                self.comm.wait_stream(st)
             with torch.cuda.stream(self.comm):
                 b["flat"].mul_(1.0 / self.world)
                 b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -196,6 +205,7 @@ class GradReducer:
             b["work"].wait()
             b["work"] = None
             b["ready"].clear()
+        self._producer_streams.clear()       # per step: a stream of an earlier (eager) step must not enter a later capture
         if self.comm is not None:
             torch.cuda.current_stream().wait_stream(self.comm)
 

@@ -144,20 +144,24 @@ def _is_peer(sync):
     return hasattr(sync, "allreduce_")          # dp.PeerExchange (in-kernel NVLink exchange) vs a torch process group
 
 
-def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None, sync_key=None):
+def bn_bwd(g, z, coef, save, weight, relu=True, arena=None, sync_group=None, sync_key=None, use_batch=True):
     """BatchNorm(+ReLU) backward on NHWC bf16: returns (gz bf16, dweight [C], dbias [C], dconv_bias [C]);
     dweight/dbias are strided views of the [C,2] sums.
     sync_group: what the forward normalised JOINT batch statistics with (SyncBN) — a dp.PeerExchange (one
     hwg_peer_allreduce_f32 launch, slot `sync_key`) or a torch.distributed group (NCCL all-reduce): the
     (sum gy, sum gy*xhat) pair that enters the input gradient is summed over the ranks and divided by the global row
-    count; the parameter gradients stay the local sums (the gradient all-reduce averages those)."""
+    count; the parameter gradients stay the local sums (the gradient all-reduce averages those).
+    use_batch=False: the forward normalised with the RUNNING statistics (eval mode under autograd) — mean and variance
+    are constants, so the input gradient is sc*gy: the apply pass gets zeroed sums and no exchange runs."""
     C = z.size(-1)
     rows = z.numel() // C
     sums = _zeros(arena, (C, 2), z.device)
     _lib.call("hwg_bn_bwd_reduce", g.data_ptr(), z.data_ptr(), coef.data_ptr(), save.data_ptr(), rows, C, int(relu),
               sums.data_ptr(), _lib.stream())
     gsums, grows = sums, rows
-    if sync_group is not None:
+    if not use_batch:
+        gsums = _zeros(arena, (C, 2), z.device)
+    elif sync_group is not None:
         gsums = torch.empty_like(sums)
         if _is_peer(sync_group):
             _lib.call("hwg_peer_allreduce_f32", sums.data_ptr(), gsums.data_ptr(), 2 * C, *sync_group.args(sync_key),

@@ -1,7 +1,4 @@
-"""PENDING (never run on a GPU: written after round 1's GPU budget was spent) — promote to tests/test_balance_gpu.py after a
-green run on a B200:  python -m pytest tools/pending_test_balance_gpu.py -q   (from the repo root)
-
-FlatAdam.stash() / FlatAdam.balance() (hwg_balance: three launches over the flat gradient buffers) against
+"""FlatAdam.stash() / FlatAdam.balance() (hwg_balance: three launches over the flat gradient buffers) against
 oracle/balance.py, the restatement of trainer/hw_with_style_trainer.py:340-377 that tests/test_balance_cpu.py pins to the
 unmodified reference trainer."""
 import os
@@ -10,7 +7,6 @@ import sys
 import pytest
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import balance as obal   # noqa: E402
 
 pytestmark = pytest.mark.gpu

@@ -1,7 +1,4 @@
-"""PENDING (never run on a GPU: written after round 1's GPU budget was spent) — promote to tests/test_dtw_gpu.py after a
-green run on a B200:  python -m pytest tools/pending_test_dtw_gpu.py -q   (from the repo root)
-
-`handwriting_line_generation_b200.dtw.correct_pred` (hwg_dtw_align) against the alignments of the UNMODIFIED reference
+"""`handwriting_line_generation_b200.dtw.correct_pred` (hwg_dtw_align) against the alignments of the UNMODIFIED reference
 `correct_pred` (tests/golden/style.npz, `dtw/*`) and against the oracle on more shapes — bit-exact (integer work)."""
 import os
 import sys
@@ -11,7 +8,6 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
 from oracle import style as ostyle                                   # noqa: E402
 from oracle.make_golden import DTW_CASES, dtw_inputs                 # noqa: E402
 

@@ -1,7 +1,4 @@
-"""PENDING (never run on a GPU: written after round 1's GPU budget was spent) — promote to tests/test_enc_gpu.py after a
-green run on a B200:  python -m pytest tools/pending_test_enc_gpu.py -q   (from the repo root)
-
-The Encoder2 drop-in and its fused perceptual loss (handwriting_line_generation_b200/encoder2.py, hwg_add_stats,
+"""The Encoder2 drop-in and its fused perceptual loss (handwriting_line_generation_b200/encoder2.py, hwg_add_stats,
 hwg_l1_halves) on the real kernels against the goldens of the UNMODIFIED reference (tests/golden/enc.npz: both feature
 tensors, the loss, its gradient w.r.t. the reconstructed image) and against the oracle on the same inputs.  The host-side
 composition is already pinned on CPU (tests/test_encoder2_cpu.py, through the C-ABI interpreter): a failure here points at
@@ -15,7 +12,6 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
 from oracle import enc as oenc                      # noqa: E402
 from oracle import synth                            # noqa: E402
 from oracle.make_golden import ENC_CASES, digest    # noqa: E402

@@ -70,3 +70,45 @@ def test_recognizer_train_step_through_the_interpreter(hwg_lib, monkeypatch):
             assert rel_l2(m.state_dict()[k], v) <= 1e-2, k
     assert {"hwg_hwr_stem", "hwg_maxpool_nhwc", "hwg_bn_coeffs", "hwg_logsoftmax_bwd", "hwg_bn_bwd_apply",
             "hwg_relu_maxpool_bwd", "hwg_hwr_stem_bwd", "hwg_hwr_stem_bwd_image", "hwg_conv_wgrad"} <= set(calls)
+
+
+def _eval_case(m, sd):
+    """Non-trivial running statistics (far from the batch statistics of the test image) for the eval-mode tests."""
+    g = torch.Generator().manual_seed(77)
+    for k in list(sd):
+        if k.endswith("running_mean"):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    m.load_state_dict(sd)
+    return sd
+
+
+def test_recognizer_eval_mode_gradient_through_the_interpreter(hwg_lib, monkeypatch):
+    """A frozen `hwr.eval()` under autograd: BatchNorm normalises with the running statistics, which are
+    constants of the backward — the input gradient is sc*gy without the batch-statistics terms."""
+    B, W, S = 2, 128, 6
+    m, sd = _hwr_module(200)
+    sd = _eval_case(m, {k: v.clone() for k, v in sd.items()})
+    m.eval()
+    img = synth.hwr_case(B, W, 31)
+    T = W // 4 - 6
+    tg = np.random.RandomState(5).randint(1, 80, (B, S)).astype(np.int32)
+    il, tl = np.full(B, T, np.int32), np.full(B, S, np.int32)
+    x = torch.from_numpy(img).requires_grad_()
+    with abi_emu.installed(monkeypatch):
+        lp = m(x)
+        loss = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+        loss.backward()
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    xo = torch.from_numpy(img).requires_grad_()
+    lpo = ohwr.hwr_forward(p, xo, False, None)
+    lo = torch.nn.functional.ctc_loss(lpo, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    lo.backward()
+    assert rel_l2(lp.detach(), lpo.detach()) <= BF16_REL
+    cos = float((x.grad.double() * xo.grad.double()).sum() / (x.grad.double().norm() * xo.grad.double().norm()))
+    assert cos >= 0.9, cos
+    for n in ("cnn1d.12.weight", "cnn1d.9.weight", "cnn.conv6.weight", "cnn.batchnorm6.weight"):
+        a, b = dict(m.named_parameters())[n].grad.double(), p[n].grad.double()
+        c = float((a * b).sum() / (a.norm() * b.norm()))
+        assert c >= 0.9, (n, c)

@@ -141,3 +141,31 @@ def test_hwr_input_gradient_for_gan_lessons():
         lp2 = ohwr.hwr_forward(sd, torch.from_numpy(x) - step * gq.float(), True, None)
         l2 = torch.nn.functional.ctc_loss(lp2, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
     assert l2.item() < lo.item()
+
+
+def test_hwr_eval_mode_gradient_uses_running_statistics_as_constants():
+    """A frozen `hwr.eval()` under autograd: BatchNorm's running statistics are constants of the backward (gz = sc*gy),
+    against torch autograd on the fp32 oracle in eval mode."""
+    from handwriting_line_generation_b200 import CTCLoss
+    from tests.test_hwr_emulated_cpu import _eval_case
+    m, sd = _hwr_module(200)
+    sd = _eval_case(m, {k: v.clone() for k, v in sd.items()})
+    m = m.cuda().eval()
+    B, W, S = 2, 128, 6
+    img = synth.hwr_case(B, W, 31)
+    T = W // 4 - 6
+    tg = np.random.RandomState(5).randint(1, 80, (B, S)).astype(np.int32)
+    il, tl = np.full(B, T, np.int32), np.full(B, S, np.int32)
+    xc = torch.from_numpy(img).cuda().requires_grad_()
+    lp = m(xc)
+    CTCLoss(lp, torch.from_numpy(tg).cuda(), torch.from_numpy(il), torch.from_numpy(tl)).backward()
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    xo = torch.from_numpy(img).requires_grad_()
+    lpo = ohwr.hwr_forward(p, xo, False, None)
+    torch.nn.functional.ctc_loss(lpo, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl)).backward()
+    assert rel_l2(lp.detach().cpu().numpy(), lpo.detach().numpy()) <= BF16_REL
+    gq, gr = xc.grad.cpu().double(), xo.grad.double()
+    assert float((gq * gr).sum() / (gq.norm() * gr.norm())) >= 0.9
+    for n in ("cnn1d.12.weight", "cnn1d.9.weight", "cnn.conv6.weight", "cnn.batchnorm6.weight"):
+        a, b = dict(m.named_parameters())[n].grad.cpu().double(), p[n].grad.double()
+        assert float((a * b).sum() / (a.norm() * b.norm())) >= 0.9, n

@@ -1,7 +1,4 @@
-"""PENDING (written when the round's GPU budget was spent, never run on a GPU): move to tests/test_trainer_gen_gpu.py after one
-green run on a B200 (the one attempt ended in a fixture error before reaching the GPU, since fixed) — `python -m pytest tools/pending_test_trainer_gen_gpu.py -q` works from the repo root.
-
-GPU: the CUDA 'gen' lesson against the UNMODIFIED reference TRAINER (tests/golden/trainer_gen.npz, see
+"""GPU: the CUDA 'gen' lesson against the UNMODIFIED reference TRAINER (tests/golden/trainer_gen.npz, see
 tests/test_trainer_gen_cpu.py): same weights (seeded construction), the content / style / labels the trainer fed,
 the same noise and Dropout2d masks.  Forward values are held to the bf16 bounds of DESIGN §5; the two gradient sets the
 trainer stashes (recognition loss, adversarial loss) are compared by direction, like tests/test_gen_train_gpu.py does
