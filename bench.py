@@ -275,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     peaks = load_peaks()
     layers, _ = gen_conv_layers(T)
     kern = {}
-    for e0, e1, fl, kind, by in prof:
+    for e0, e1, fl, kind, by, *_ in prof:
         k = kern.setdefault(kind, {"ms": 0.0, "launches": 0, "issued_flop": 0.0, "bytes": 0.0})
         k["ms"] += e0.elapsed_time(e1) / psteps
         k["launches"] += 1 / psteps

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 # bench.py sets this to a list to time every launch with CUDA events on the launching stream:
-# entries are (start_event, end_event, issued_flops)
+# entries are (start_event, end_event, issued_flops, kernel, activation bytes, (N, Ho, Wo, Cin, Cout, ntaps))
 PROFILE = None
 
 
@@ -115,7 +115,7 @@ def conv_fprop(x, w_packed, taps, Ho, Wo, *, bias=None, act=_lib.ACT_NONE, slope
         kind = "conv_small_kernel" if _lib.load().hwg_last_conv_kernel() == 2 else "conv_fprop_kernel"
         by = N * H * W * Cin * 2 + N * Ho * Wo * Cout * y.element_size()    # activations read once + written once
         flops = 2.0 * N * Ho * Wo * Cin * (w_packed.size(0) * w_packed.size(1))   # MACs actually issued
-        PROFILE.append((e0, e1, flops, kind, by))
+        PROFILE.append((e0, e1, flops, kind, by, (N, Ho, Wo, Cin, Cout, ntaps)))
     return out
 
 
@@ -164,5 +164,5 @@ def conv_wgrad(x, gy, taps, cin, cout, out=None, grid=None, gy_stride=(1, 1), gy
     if PROFILE is not None:
         e1.record()
         PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * len(taps), "conv_wgrad_kernel",
-                        (x.numel() + gy.numel()) * 2))
+                        (x.numel() + gy.numel()) * 2, (N, Ho, Wo, cin, cout, len(taps))))
     return out

@@ -67,7 +67,7 @@ class FlatAdam:
                   float(self.clip_value or 0.0), float(grad_scale), self.step_dev.data_ptr(), 1, _lib.stream())
         torch.autograd.graph.increment_version(self.params)     # derived-weight caches key on (data_ptr, _version)
 
-    # ---- gradient balancing (trainer/hw_with_style_trainer.py:300-377) — NOT YET RUN ON A GPU, see hwg_balance ----
+    # ---- gradient balancing (trainer/hw_with_style_trainer.py:300-377): tests/test_balance_gpu.py ----
     def stash(self):
         """The trainer's `saved_grad` (:303-322, :330-338): keeps the gradient buffer as one more stashed set and zeroes
         it for the next backward."""
@@ -106,7 +106,7 @@ class FlatAdam:
         if b.get("x_key") != key:            # uploaded once per multiplier list: no host copy on the steady-state path,
             b["x_key"], b["x"] = key, torch.tensor(key, dtype=torch.float32, device=dev)   # so a captured step can replay it
         x = b["x"]
-        sums = torch.empty((b["nseg"], K + 1), dtype=torch.float32, device=dev)
+        sums = torch.empty(b["tab"].size(0) * (K + 1) + b["nseg"], dtype=torch.float32, device=dev)   # block partials + first blocks
         mult = torch.empty((K, b["nseg"]), dtype=torch.float32, device=dev)
         ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in sets])
         _lib.call("hwg_balance", self.flat_g.data_ptr(), ctypes.addressof(ptrs), K, x.data_ptr(), b["off"].data_ptr(),

@@ -428,10 +428,11 @@ int hwg_linear_bwd_f32(const float* x, const float* y, const float* gy, const fl
  * non-zero means instead (:354-359), and sets with mean|R_k,s| == 0 skipped (:373).
  * g_main and every set are flat fp32 buffers with the same parameter slots (optim.FlatAdam): seg_off_dev[s] /
  * seg_len_dev[s] = first element / element count of parameter s; block_tab_dev = nblocks (segment, chunk) int32
- * pairs, one per hwg_balance_chunk() elements of a segment; sets_host = HOST array of K device pointers (K <= 8);
- * x_dev = the K multipliers (`balance_var_x`) in device memory; sums_dev [nseg][K+1] and mult_dev [K][nseg] are
- * workspaces.  Three launches, no host synchronisation.
- * Status: written after round 1's GPU budget was spent — not yet run on a GPU, not called by default. */
+ * pairs, one per hwg_balance_chunk() elements of a segment, the rows of a segment consecutive and in chunk order;
+ * sets_host = HOST array of K device pointers (K <= 8); x_dev = the K multipliers (`balance_var_x`) in device memory;
+ * sums_dev (nblocks*(K+1) + nseg floats: per-block partial sums + the first block of every segment) and mult_dev
+ * [K][nseg] are workspaces.  Three launches, no host synchronisation, no atomics: the result is a deterministic function
+ * of the inputs, so data-parallel ranks holding the same all-reduced gradients stay bit-identical. */
 int hwg_balance_chunk(void);
 int hwg_balance(float* g_main, const float* const* sets_host, int K, const float* x_dev,
                 const int64_t* seg_off_dev, const int64_t* seg_len_dev, int nseg, const int32_t* block_tab_dev,

@@ -22,7 +22,7 @@ def test_reference_arm_prints_the_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "GAN train-step lines/sec" and d["unit"] == "lines/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["config"]["global_batch"] == 128 and d["vs_baseline"] is None
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1 and d["data"] == "synthetic"
     assert "discriminator_ap" in d["config"]["workload"] and "model" not in d["config"]
     cb = d["cpu_baseline"]

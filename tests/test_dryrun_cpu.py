@@ -96,8 +96,32 @@ def test_disc_lesson_and_recognizer_training_host_code_runs(recorder):
     assert {"hwg_spectral_norm_bwd", "hwg_channel_sum", "hwg_hwr_stem", "hwg_ctc_greedy_decode"} <= set(recorder)
 
 
+def test_bench_headline_step_host_code_runs(recorder):
+    """bench_gan_train.GanStep (the default bench step, also used by tools/step_runner.py): both step kinds, with the
+    discriminator's forward on its side stream."""
+    import bench_gan_train as bg
+    import handwriting_line_generation_b200 as pkg
+    T, B, S = 32, 2, bg.GAN["S"]
+    content, style = (torch.from_numpy(a) for a in synth.gen_case(T, B, 80, 128, 9))
+    real = torch.from_numpy(synth.hwr_case(B, 4 * T, 3))
+    tg = torch.randint(1, 80, (B, S), dtype=torch.int32)
+    try:
+        for kind in ("balanced", "gen_only"):
+            del recorder[:]
+            st = bg.GanStep(torch.device("cpu"), B, kind=kind, Ts=T)
+            for _ in range(2):
+                loss = st.train(content, style, tg, real)
+                assert loss.dim() == 0
+            assert recorder.count("hwg_adam_flat") == 2
+            assert recorder.count("hwg_balance") == (2 if kind == "balanced" else 0)
+            gf = st.conv_gflop(bg.gen_layers(T)[0])
+            assert gf["conv_fprop_kernel"]["gflop"] > 0 and gf["conv_wgrad_kernel"]["gflop"] > 0
+    finally:
+        pkg.set_retain_graph(False)
+
+
 def test_balanced_two_lesson_step_host_code_runs(recorder):
-    """bench_gan_train.train_balanced() (opt-in, HWG_BENCH_BALANCED=1): two losses back-propagated separately through ONE
+    """The balanced step spelled out (bench_gan_train.GanStep.train_balanced): two losses back-propagated separately through ONE
     generator graph and stashed, the perceptual lesson, FlatAdam.balance, FlatAdam.step."""
     pkg, gen, hwr, disc = _modules()
     enc = pkg.Encoder2(32).train()

@@ -1,7 +1,8 @@
 """Runs a few steps of one workload (development aid; run it under `ncu --metrics gpu__time_duration.sum` for a launch
 list, or bare for an eager/graphed device time).
 
-  python tools/step_runner.py {gen_infer|hwr_train|gen_train} [--B n] [--steps k] [--graph]
+  python tools/step_runner.py {gen_infer|hwr_train|gen_train|gan_step} [--B n] [--steps k] [--graph]
+gan_step = bench.py's headline step (bench_gan_train.GanStep; HWG_BENCH_STEP=balanced|gen_only)
 """
 import argparse
 import os
@@ -80,6 +81,15 @@ elif a.workload == "gen_train":
         loss.backward()
         opt.step()
         return loss
+elif a.workload == "gan_step":
+    import bench_gan_train as bg
+    st = bg.GanStep(dev, B)
+    content, style = synth.gen_case(Ts, B, 80, 128, 3)
+    ins = [torch.from_numpy(content).to(dev), torch.from_numpy(style).to(dev),
+           torch.randint(1, 80, (B, bg.GAN["S"]), dtype=torch.int32, device=dev),
+           torch.from_numpy(synth.hwr_case(B, 4 * Ts, 9)).to(dev)]
+    mods = [st.gen, st.hwr]
+    step = st.train
 else:
     raise SystemExit("unknown workload")
 
