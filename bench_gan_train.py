@@ -463,6 +463,10 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     barrier()
     hconv.PROFILE = None
     kern = {}
+    if os.environ.get("HWG_BENCH_DUMP_CONV") and rank == 0:      # development aid: per-launch table of the profiled steps
+        rows = [dict(kind=kind, geom=list(geo[0]) if geo else None, ms=e0.elapsed_time(e1), gflop=fl / 1e9, mb=by / 1e6)
+                for e0, e1, fl, kind, by, *geo in prof]
+        json.dump({"batch": B, "steps": psteps, "launches": rows}, open(os.environ["HWG_BENCH_DUMP_CONV"], "w"))
     for e0, e1, fl, kind, by, *_ in prof:
         k = kern.setdefault(kind, {"ms": 0.0, "launches": 0.0, "issued_flop": 0.0, "bytes": 0.0})
         k["ms"] += e0.elapsed_time(e1) / psteps
@@ -554,12 +558,14 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         torch.cuda.empty_cache()
         if not os.environ.get("HWG_BENCH_NO_GPU_BASELINE"):
             line["gpu_baseline"] = gpu_baseline(dev, B, min(args.steps, 10))
-        torch.set_num_threads(os.cpu_count() or 1)
-        tb = time.time()
-        lps, times = cpu_lines_per_s(4, 4)
-        line["cpu_baseline"] = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{len(times)} timed optimizer steps on a 4-line sample of the batch (T_s={Ts}), stock "
-                                          f"torch fp32, {time.time() - tb:.1f}s of CPU work"}
+        line["cpu_baseline"] = None
+        if not os.environ.get("HWG_BENCH_NO_CPU_BASELINE"):
+            torch.set_num_threads(os.cpu_count() or 1)
+            tb = time.time()
+            lps, times = cpu_lines_per_s(4, 4)
+            line["cpu_baseline"] = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{len(times)} timed optimizer steps on a 4-line sample of the batch (T_s={Ts}), "
+                                              f"stock torch fp32, {time.time() - tb:.1f}s of CPU work"}
         if not os.environ.get("HWG_BENCH_NO_EXTRAS"):
             try:   # the other configs, measured briefly in the same run (bench.py --workload gen_infer / hwr_train)
                 import bench_hwr_train

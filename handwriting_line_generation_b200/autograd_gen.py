@@ -338,7 +338,7 @@ class _StyleFn(torch.autograd.Function):
             acts.append(ops.linear(acts[-1], w, b, ACT_LRELU, 0.2))
         gb = ops.linear(acts[-1], c["gb_w"], c["gb_b"])
         ctx.module, ctx.acts = module, acts
-        return acts[-1], gb
+        return acts[-1].detach(), gb               # detached alias: see _GenFn.forward
 
     @staticmethod
     def backward(ctx, g_s, g_gb):
@@ -394,7 +394,10 @@ class _GenFn(torch.autograd.Function):
         with torch.no_grad():
             out, saved = forward_train(module, content, s, gb, noise)
         ctx.module, ctx.saved = module, saved
-        return out
+        # a detached alias: the saved state keeps the tensor itself, and an output that is ALSO reachable from ctx would
+        # close a reference cycle through its grad_fn (output -> node -> ctx -> saved -> output) that is only broken when
+        # backward drops the state — never, with set_retain_graph(True) or when no backward runs
+        return out.detach()
 
     @staticmethod
     def backward(ctx, g):

@@ -313,7 +313,7 @@ class _HWRFn(torch.autograd.Function):
             out, saved = forward_train(module, x)
         ctx.module, ctx.names, ctx.saved = module, names, saved
         ctx.x_needs_grad = x.requires_grad
-        return out
+        return out.detach()          # detached alias of the saved log-probs: no output -> node -> ctx -> output cycle
 
     @staticmethod
     def backward(ctx, g):

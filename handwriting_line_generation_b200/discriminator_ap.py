@@ -535,7 +535,7 @@ class _DiscFn(torch.autograd.Function):
             outs, saved = m._forward_impl(x, keep=True)
         ctx.m, ctx.names, ctx.saved = m, names, saved
         ctx.x_needs_grad = x.requires_grad
-        return tuple(outs)
+        return tuple(o.detach() for o in outs)       # detached aliases: no output -> node -> ctx -> output cycle
 
     @staticmethod
     def backward(ctx, *grads):

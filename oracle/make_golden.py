@@ -411,6 +411,161 @@ def make_spacer():
     np.savez_compressed(os.path.join(GOLD, "spacer.npz"), **out)
 
 
+# ---- BASELINE-size cases (parity only at toy sizes) ---------------------------------------------------------
+# cfg1: BASELINE configs[0] — CNNOnlyHWR + CTC fwd+bwd, B=8, 64x1024, 60-char targets
+# cfg2: configs[1] — SpacedGenerator inference, B=32, T_s=256 -> [32,1,64,1024]
+# step16: the bench step's forward at 16 lines: generator -> {recognizer + CTC, discriminator}
+# cfg5: configs[4] — RIMES charset (78 classes), B=64, T_s=512 -> 64x2048 lines, recognizer, 120-char targets, CTC fwd+bwd
+FULL = dict(cfg1=dict(B=8, W=1024, S=60, wseed=900, iseed=901),
+            cfg2=dict(B=32, T=256, wseed=910, iseed=911),
+            step16=dict(B=16, T=256, S=40, gseed=920, hseed=921, dseed=922, iseed=923),
+            cfg5=dict(B=64, T=512, S=120, C=78, gseed=930, hseed=931, iseed=932))
+
+
+def full_labels(B, S, C, seed):
+    return np.random.RandomState(seed).randint(1, C, (S, B)).astype(np.int32)          # [S,B] like the trainer's `label`
+
+
+def _ref_generate(m, content, style, noise):
+    it = iter(noise)
+    orig = torch.randn_like
+
+    def fake_randn_like(x, **kw):
+        z = next(it)
+        assert z.shape == x.shape, (z.shape, x.shape)
+        return z
+
+    torch.randn_like = fake_randn_like
+    try:
+        return m(torch.from_numpy(content), torch.from_numpy(style))
+    finally:
+        torch.randn_like = orig
+
+
+def _put(out, key, t, nsamp=8192):
+    dig, samp = digest(t.detach().numpy() if torch.is_tensor(t) else t)
+    out[key + "/digest"], out[key + "/sample"] = dig, samp[:nsamp]
+
+
+def make_full():
+    """Goldens of the UNMODIFIED reference modules at BASELINE.json's configuration sizes: digests + strided samples (the
+    tensors themselves are tens of MB).  Written to tests/golden/full.npz."""
+    ref_shim.install()
+    from model.cnn_only_hwr import CNNOnlyHWR
+    from model.discriminator_ap import DiscriminatorAP
+    from model.loss import CTCLoss
+    from model.pure_gen import SpacedGenerator
+    import torch.nn.functional as F
+    from . import disc as odisc
+    out = {}
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def gen_module(seed, C=80):
+        return synth.state_dict_from_seed(lambda: SpacedGenerator(C, 128, 256, n_style_trans=6, emb_dropout=False,
+                                                                  append_style=True, small=False), seed)
+
+    # ---- cfg1
+    c = FULL["cfg1"]
+    m, sd = synth.state_dict_from_seed(lambda: CNNOnlyHWR(80, norm='batch'), c["wseed"])
+    m.train()
+    out["cfg1/weights_digest"] = weights_digest(sd)
+    x = torch.from_numpy(synth.hwr_case(c["B"], c["W"], c["iseed"])).requires_grad_()
+    label = torch.from_numpy(full_labels(c["B"], c["S"], 80, c["iseed"] + 1))
+    T = c["W"] // 4 - 6
+    lp = m(x)
+    loss = CTCLoss(lp, label.permute(1, 0), torch.IntTensor([T] * c["B"]), torch.IntTensor([c["S"]] * c["B"]))
+    loss.backward()
+    _put(out, "cfg1/log_probs", lp)
+    out["cfg1/loss"] = np.float64(loss.item())
+    _put(out, "cfg1/grad/input", x.grad)
+    for n, p in m.named_parameters():
+        _put(out, f"cfg1/grad/{n}", p.grad, 1024)
+    out["cfg1/argmax"] = lp.argmax(2).numpy().astype(np.int16)
+    print(f"full/cfg1: lp {tuple(lp.shape)} loss {loss.item():.5f}")
+
+    # ---- cfg2
+    c = FULL["cfg2"]
+    m, sd = gen_module(c["wseed"])
+    m.eval()
+    out["cfg2/weights_digest"] = weights_digest(sd)
+    content, style = synth.gen_case(c["T"], c["B"], 80, 128, c["iseed"])
+    noise = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(c["T"], c["B"]), c["iseed"] + 7)]
+    with torch.no_grad():
+        img = _ref_generate(m, content, style, noise)
+    _put(out, "cfg2/image", img)
+    _put(out, "cfg2/image_line0", img[0], 4096)
+    del noise
+    print(f"full/cfg2: image {tuple(img.shape)} absmax {float(img.abs().max()):.4f}")
+
+    # ---- step16
+    c = FULL["step16"]
+    g, gsd = gen_module(c["gseed"])
+    g.train()
+    h, hsd = synth.state_dict_from_seed(lambda: CNNOnlyHWR(80, norm='batch'), c["hseed"])
+    h.train()
+    torch.manual_seed(c["dseed"])
+    d = DiscriminatorAP(64, use_low=True, use_med=True)
+    synth.perturb_disc(d.state_dict(), c["dseed"] + 1)
+    d.train()
+    for k, sdx in (("gen", gsd), ("hwr", hsd), ("disc", d.state_dict())):
+        out[f"step16/{k}_weights_digest"] = weights_digest(sdx)
+    content, style = synth.gen_case(c["T"], c["B"], 80, 128, c["iseed"])
+    noise = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(c["T"], c["B"]), c["iseed"] + 7)]
+    masks = {k: torch.from_numpy(v) for k, v in synth.disc_masks(c["B"], c["iseed"] + 8).items()}
+    label = torch.from_numpy(full_labels(c["B"], c["S"], 80, c["iseed"] + 1))
+    order = iter(odisc.DROPOUT_ORDER)
+    orig = F.dropout2d
+
+    def fake_dropout2d(x, p=0.5, training=True, inplace=False):
+        site = next(order)
+        return x * (masks[site] / (1.0 - p))[:, :, None, None]
+
+    F.dropout2d = fake_dropout2d
+    try:
+        with torch.no_grad():
+            img = _ref_generate(g, content, style, noise)
+            lp = h(img)
+            preds = d(img)
+            T = c["T"] - 6
+            ctc = CTCLoss(lp, label.permute(1, 0), torch.IntTensor([T] * c["B"]), torch.IntTensor([c["S"]] * c["B"]))
+            adv = -sum(p.mean() for p in preds) / len(preds)
+    finally:
+        F.dropout2d = orig
+    _put(out, "step16/image", img)
+    _put(out, "step16/log_probs", lp)
+    for i, pr in enumerate(preds):
+        out[f"step16/pred{i}"] = pr.numpy()
+    out["step16/ctc"], out["step16/adv"] = np.float64(ctc.item()), np.float64(adv.item())
+    del noise
+    print(f"full/step16: ctc {ctc.item():.4f} adv {adv.item():.5f}")
+
+    # ---- cfg5
+    c = FULL["cfg5"]
+    g, gsd = gen_module(c["gseed"], c["C"])
+    g.eval()
+    h, hsd = synth.state_dict_from_seed(lambda: CNNOnlyHWR(c["C"], norm='batch'), c["hseed"])
+    h.train()
+    out["cfg5/gen_weights_digest"], out["cfg5/hwr_weights_digest"] = weights_digest(gsd), weights_digest(hsd)
+    content, style = synth.gen_case(c["T"], c["B"], c["C"], 128, c["iseed"])
+    noise = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(c["T"], c["B"]), c["iseed"] + 7)]
+    label = torch.from_numpy(full_labels(c["B"], c["S"], c["C"], c["iseed"] + 1))
+    with torch.no_grad():
+        img = _ref_generate(g, content, style, noise)
+    del noise
+    lp = h(img).detach().requires_grad_()
+    T = 4 * c["T"] // 4 - 6
+    loss = CTCLoss(lp, label.permute(1, 0), torch.IntTensor([T] * c["B"]), torch.IntTensor([c["S"]] * c["B"]))
+    loss.backward()
+    _put(out, "cfg5/image", img)
+    _put(out, "cfg5/image_lines0_1", img[:2], 4096)
+    _put(out, "cfg5/log_probs", lp)
+    out["cfg5/loss"] = np.float64(loss.item())
+    _put(out, "cfg5/ctc_grad", lp.grad)
+    out["cfg5/argmax"] = lp.argmax(2).numpy().astype(np.int16)
+    print(f"full/cfg5: image {tuple(img.shape)} lp {tuple(lp.shape)} loss {loss.item():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "full.npz"), **out)
+
+
 def main(argv):
     what = argv[1] if len(argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -428,6 +583,8 @@ def main(argv):
         make_style()
     if what in ("spacer", "all"):
         make_spacer()
+    if what in ("full", "all"):
+        make_full()
 
 
 if __name__ == "__main__":

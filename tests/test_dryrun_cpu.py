@@ -154,3 +154,27 @@ def test_balanced_two_lesson_step_host_code_runs(recorder):
         pkg.set_retain_graph(False)
     assert recorder.count("hwg_balance") == 2 and recorder.count("hwg_adam_flat") == 2
     assert {"hwg_l1_halves", "hwg_add_stats"} <= set(recorder)
+
+
+def test_module_outputs_do_not_keep_their_graph_alive(recorder):
+    """An output tensor that is also held by the Function's saved state closes a cycle output -> grad_fn -> ctx -> output
+    that Python cannot collect (it runs through the C++ node): with set_retain_graph(True), or whenever no backward runs,
+    every forward leaked its activations and left stale AccumulateGrad nodes behind (which is what broke the CUDA-graph
+    capture of the balanced step).  The outputs are detached aliases; the graph dies with the last reference."""
+    import gc
+    import weakref
+    pkg, gen, hwr, disc = _modules()
+    pkg.set_retain_graph(True)
+    try:
+        T, B = 32, 2
+        content, style = (torch.from_numpy(a) for a in synth.gen_case(T, B, 80, 128, 9))
+        img = gen(content, style)
+        lp = hwr(img)
+        preds = disc(img)
+        refs = [weakref.ref(t.grad_fn) for t in (img, lp, preds[0])]
+        assert all(r() is not None for r in refs)
+        del img, lp, preds
+        gc.collect()
+        assert all(r() is None for r in refs), "a module output keeps its own autograd graph alive"
+    finally:
+        pkg.set_retain_graph(False)
