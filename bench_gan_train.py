@@ -232,16 +232,20 @@ class GanStep:
         # of it, stash / balance / clip + Adam + zero are flat launches
         self.opt = pkg.FlatAdam(self.gen.parameters(), lr=2e-4, betas=(0.5, 0.999), clip_value=2.0)
         self.gen._grad_sink = self.opt
-        self.reducer = dp.GradReducer(self.gen.parameters(), flat=self.opt) if world > 1 else None
+        # gen_only step: bucketed all-reduce from grad-ready hooks (dp.GradReducer); balanced step: one all-reduce per gradient
+        # set on a communication stream (_allreduce)
+        self.reducer = dp.GradReducer(self.gen.parameters(), flat=self.opt) if (world > 1 and self.kind != "balanced") else None
         if self.reducer is not None:
             self.gen._grad_ready_cb = self.reducer.mark_ready
+        self.comm = torch.cuda.Stream(device=dev) if world > 1 else None
         T = (Ts or GAN["Ts"]) - 6
         self.il = torch.full((B,), T, dtype=torch.int32, device=dev)
         self.tl = torch.full((B,), GAN["S"], dtype=torch.int32, device=dev)
         # the two critics of the generated image are independent: the discriminator's forward runs on a side stream next
         # to recognizer + CTC (autograd replays each branch's backward on the stream of its forward)
         self.parallel = bool(overlap) and not os.environ.get("HWG_BENCH_NO_OVERLAP")
-        self.side = torch.cuda.Stream(device=dev) if self.parallel else None
+        self.s2 = self.side = torch.cuda.Stream(device=dev)
+        self.s3 = torch.cuda.Stream(device=dev)
 
     def adversarial(self, img):                # generator's adversarial loss, trainer :810-821
         preds = self.disc(img)
@@ -273,18 +277,58 @@ class GanStep:
         self.opt.step()
         return loss
 
+    def _allreduce(self, buf):
+        """Gradient all-reduce (average over the ranks) of one whole gradient set on the communication stream, ordered after
+        the stream that produced it; it overlaps whatever the step issues next (the balancing is nonlinear, so every set
+        is reduced before it)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            buf.mul_(1.0 / self.world)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+
     def train_balanced(self, c, s, tg, real):
-        opt = self.opt
-        recog, adv = self._critics(self.gen(c, s), tg)             # lesson 1: 'gen', no-step
-        recog.backward(retain_graph=True)                          # trainer :312-323: the 'Recog' losses first ...
-        self._reduce()                                             # (the balancing is nonlinear: reduce every set first)
-        opt.stash()                                                # ... stashed
-        adv.backward()                                             # :326-338: the rest of a no-step lesson, stashed
-        self._reduce()
-        opt.stash()
-        perc = W_PERC * self.enc.perceptual_loss(real, self.gen(c, s))   # lesson 2: 'auto''s perceptual loss (:724-748)
-        perc.backward()
-        self._reduce()
+        """Three independent chains on three streams; each backward pass leaves its gradient set in its own buffer
+        (FlatAdam.sink: the trainer's backward -> clone into saved_grad -> zero, :312-338, without the copies):
+          main  generator fwd -> recognizer fwd -> CTC -> backward (recognizer, generator)                      -> stash slot 0
+          s2    (after the generator fwd) discriminator fwd -> backward (discriminator; generator on main)      -> stash slot 1
+          s3    (after the generator fwd) generator fwd #2 -> Encoder2 perceptual loss -> backward (both)       -> main buffer
+        then all-reduces (N > 1), balancing, clip + Adam on the main stream."""
+        opt, gen = self.opt, self.gen
+        main = torch.cuda.current_stream()
+        par = self.parallel
+        img = gen(c, s)                                            # lesson 1: 'gen', no-step (trainer :577)
+        if par:
+            self.s2.wait_stream(main)
+            self.s3.wait_stream(main)                              # (the weight re-pack of this step ran inside gen fwd #1)
+            with torch.cuda.stream(self.s2):
+                adv = self.adversarial(img)                        # :810-821
+            with torch.cuda.stream(self.s3):                       # lesson 2: 'auto''s perceptual loss (:724-748)
+                perc = W_PERC * self.enc.perceptual_loss(real, gen(c, s))
+        recog = W_CTC * self.pkg.CTCLoss(self.hwr(img), tg, self.il, self.tl)      # :760-764
+        if not par:
+            adv = self.adversarial(img)
+        gen._grad_sink = opt.sink(0)
+        recog.backward(retain_graph=True)                          # :312-323: the 'Recog' losses first -> first stashed set
+        self._allreduce(opt.sink(0).buf)
+        gen._grad_sink = opt.sink(1)
+        adv.backward()                                             # :326-338: the rest of a no-step lesson -> second set
+        self._allreduce(opt.sink(1).buf)
+        gen._grad_sink = opt
+        if par:
+            with torch.cuda.stream(self.s3):
+                perc.backward()
+                self._allreduce(opt.flat_g)
+            main.wait_stream(self.s2)
+            main.wait_stream(self.s3)
+        else:
+            perc = W_PERC * self.enc.perceptual_loss(real, gen(c, s))
+            perc.backward()
+            self._allreduce(opt.flat_g)
+        if self.world > 1:
+            main.wait_stream(self.comm)
         opt.balance(BALANCE_VAR_X)                                 # :340-377
         opt.step()                                                 # :381-391: clip + Adam + gradient zeroing, one launch
         return recog.detach() + adv.detach() + perc.detach()
@@ -380,8 +424,9 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         try:
             graphed = graphs.GraphedStep(train, list(devsets[0]), modules=[gen, hwr], warmup=3)
             executed = ("one CUDA graph per step (fixed shapes; every forward, CTC, the three backward passes, "
-                        + ("discriminator forward on a parallel stream, " if st.parallel else "")
-                        + ("NCCL all-reduces on a side stream, " if world > 1 else "") + "balancing, Adam), replayed")
+                        + ("as three parallel branches (recognizer / discriminator / second lesson), " if st.parallel else "")
+                        + ("one NCCL all-reduce per gradient set on a communication stream, " if world > 1 else "")
+                        + "balancing, Adam), replayed")
         except Exception:             # noqa: BLE001 - a failed capture poisons the process: say why, then run eagerly afresh
             traceback.print_exc()
             sys.stderr.write("[bench] CUDA-graph capture failed (above); restarting with HWG_BENCH_NO_GRAPH=1\n")

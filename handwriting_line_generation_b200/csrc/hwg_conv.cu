@@ -63,10 +63,11 @@ struct ConvKParams {
   // run as one: the four rows of the initial transposed conv, the four parities of FusedUpsample)
   int fold_c, fold_w, stat_c;
   long long fold_sh, fold_sw;
-  // halo mode (development switch HWG_CONV_HALO, default off): the taps of a group are
+  // halo mode (HWG_CONV_HALO, default on for the eligible launches): the taps of a group are
   // read as SHIFTED VIEWS of one halo tile instead of one 16 KiB operand tile per tap.  TW = 8, TH = 16, CK = 64.
   int halo;              // 0: off
-  int halo_bo;           // 1: descriptors carry base_offset = (start >> 7) & 7 (tools/halo_probe.cu decides)
+  int halo_bo;           // 1: descriptors carry base_offset = (start >> 7) & 7 (tools/halo_probe.cu on B200: NOT needed, the
+                         //    swizzle follows the absolute shared-memory address; kept as HWG_CONV_HALO_BO for other parts)
   int hw_;               // halo tile width in pixels (TW + dw_max - dw_min)
   int ha_bytes;          // halo tile bytes, rounded up to 1 KiB;  ha_tx: bytes the TMA box transfers
   int ha_tx;
@@ -109,8 +110,8 @@ __device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %
 
 // Template parameters >= 0 fix an epilogue option at compile time; -1 leaves it to the runtime
 // value in ConvKParams (generic fallback used by uncommon combinations).
-// HALO_T: the halo-mode main loop (development, see ConvKParams::halo) lives in its own instantiations so that the code
-// generated for the default path is exactly what the GPU runs of round 1 measured.
+// HALO_T: the halo-tile main loop (see ConvKParams::halo) lives in its own instantiations; launches that are not eligible
+// run the per-tap loop unchanged.
 template <int ACT_T, int NOISE_T, int STATS_T, int F32_T, bool HALO_T = false>
 __global__ void __launch_bounds__(320)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -642,9 +643,11 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
     if ((bn == 64 || bn == 128 || bn == 256) && bn <= cout16 && d->act != HWG_ACT_LOGSOFTMAX) p.BN = bn;
   }
   p.n_tiles = (d->Cout + p.BN - 1) / p.BN;
-  // ---- halo mode (development switch HWG_CONV_HALO=1|2, default off; never run on a GPU yet: DESIGN section 10) ----
-  // 1: full 2-D halo tile per K chunk when the weights fit next to it, else one halo tile per kernel row; 2: force rows.
-  static const int halo_env = [] { const char* e = getenv("HWG_CONV_HALO"); return e ? atoi(e) : 0; }();
+  // ---- halo-tile main loop (default since round 2; HWG_CONV_HALO=0 switches it off, 2 forces one halo tile per kernel row) ----
+  // 1: full 2-D halo tile per K chunk when the weights fit next to it, else one halo tile per kernel row.
+  // B200, 16 lines: discriminator convs1.3 60.7 -> 39.0 us (805 TFLOP/s), convs2.0 100.9 -> 79.9 us, whole step -3 %
+  // (profiles/README.md, round 2); numerics: the conv / discriminator / recognizer parity tests run in this mode.
+  static const int halo_env = [] { const char* e = getenv("HWG_CONV_HALO"); return e ? atoi(e) : 1; }();
   static const int halo_bo_env = getenv("HWG_CONV_HALO_BO") != nullptr ? 1 : 0;
   int halo_mode = 0, h_dh_min = 0, h_dh_max = 0, h_dw_min = 0, h_dw_max = 0, h_wstat = 0, h_maxrow = 0;
   if (halo_env > 0 && d->Cin % 64 == 0 && d->in_stride_h <= 1 && d->in_stride_w <= 1 && d->ntaps >= 2 && !d->fold_c &&

@@ -17,6 +17,21 @@ import torch
 from . import _lib
 
 
+class _Sink:
+    """A gradient destination with the optimizer's slot layout: the main gradient buffer or one of its stash slots.  The
+    backward kernels of a module whose `_grad_sink` is set ADD their parameter gradients straight into it."""
+
+    def __init__(self, opt, buf):
+        self.opt, self.buf = opt, buf
+
+    def owns(self, p):
+        return id(p) in self.opt.offsets
+
+    def grad_view(self, p):
+        o, k = self.opt.offsets[id(p)]
+        return self.buf[o:o + k].view_as(p)
+
+
 class FlatAdam:
     def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8, clip_value=None):
         self.params = [p for p in params if p.requires_grad]
@@ -45,6 +60,22 @@ class FlatAdam:
     def grad_view(self, p):
         o, k = self.offsets[id(p)]
         return self.flat_g[o:o + k].view_as(p)
+
+    # ---- stash slots: the trainer's `saved_grad` sets (:303-338) without the clone + zero round trip ----
+    def sink(self, slot=None):
+        """Gradient destination for `module._grad_sink`: None = the main gradient buffer (this optimizer itself), an int =
+        stash slot `slot` (a persistent zero-initialised buffer with the same layout).  A backward pass whose module
+        points at slot k leaves its gradient set there directly — the trainer's "backward, clone into saved_grad, zero"
+        (:312-338) becomes "backward into the slot" — and the passes of one optimizer step no longer share a buffer, so
+        they can run concurrently on different streams.  `balance()` consumes and re-zeroes the slots that were handed
+        out."""
+        if slot is None:
+            return self
+        slots = self.__dict__.setdefault("_slots", {})
+        if slot not in slots:
+            slots[slot] = _Sink(self, torch.zeros_like(self.flat_g))
+        self.__dict__.setdefault("_slots_used", set()).add(slot)
+        return slots[slot]
 
     def owns(self, p):
         return id(p) in self.offsets
@@ -83,7 +114,8 @@ class FlatAdam:
         gradient's mean magnitude and weighted by `multipliers` (`balance_var_x`); one hwg_balance call (three launches,
         no host synchronisation).  Clears the stash."""
         import ctypes
-        sets = getattr(self, "_stash", [])
+        used = sorted(getattr(self, "_slots_used", ()))
+        sets = [self._slots[k].buf for k in used] + getattr(self, "_stash", [])     # slot order, then stash() order
         if not sets:
             return
         self._rebind_grads()
@@ -113,6 +145,10 @@ class FlatAdam:
                   b["len"].data_ptr(), b["nseg"], b["tab"].data_ptr(), b["tab"].size(0), sums.data_ptr(), mult.data_ptr(),
                   _lib.stream())
         self._stash = []
+        for k in used:                       # ready for the next step's backward passes
+            self._slots[k].buf.zero_()
+        if used:
+            self._slots_used = set()
 
     def zero_grad(self, set_to_none=False):
         """step() already leaves the gradient buffer zeroed; this is for steps that are skipped."""

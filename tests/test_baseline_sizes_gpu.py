@@ -97,8 +97,12 @@ def test_config1_recognizer_ctc_fwd_bwd_all_gradients(golden_dir):
     raw, _, _ = ctc_greedy_decode(lp.detach())
     oraw, _ = octc.greedy_decode(lp.detach().cpu().numpy())
     assert np.array_equal(raw.cpu().numpy(), oraw)
-    # and the argmax agrees with the reference's on all but the frames bf16 rounding can tip (observed: < 1 %)
-    assert float((raw.cpu().numpy() != gold["cfg1/argmax"]).mean()) <= 0.03
+    # against the reference's own best path: a random-init recognizer is nearly undecided (top-2 gaps of ~1e-2), so bf16
+    # rounding tips some frames — wherever the paths differ, the reference's class is within the bf16 error of our maximum
+    ref_arg = torch.from_numpy(gold["cfg1/argmax"].astype(np.int64))
+    lpc = lp.detach().cpu()
+    gap = lpc.max(2).values - lpc.gather(2, ref_arg.unsqueeze(2)).squeeze(2)
+    assert float(gap.max()) <= 0.05, float(gap.max())
 
 
 def test_config2_generator_inference_32_lines(golden_dir):
@@ -184,3 +188,87 @@ def test_config5_long_lines_generation_recognition_ctc(golden_dir):
     assert float(np.abs(lpg.grad.cpu().numpy() - ograd).max()) <= 2e-3 * float(np.abs(ograd).max())
     # against the reference's gradient (computed on ITS fp32 log-probs): bf16 log-prob error moves the occupancies
     assert _vs_golden(lpg.grad, gold, "cfg5/ctc_grad", 0.25) >= 0.0
+
+
+def test_gen_lesson_gradient_sets_at_line_size():
+    """The two gradient sets the reference trainer stashes in its 'gen' lesson (recognition loss through the frozen
+    recognizer, adversarial loss through the frozen discriminator; trainer :300-338) at 8 lines of 64x1024 px, against torch
+    autograd over the fp32 oracle chain and over its bf16-storage emulation.  What decides these gradients is the bf16 rounding
+    of the FORWARD activations (ReLU / LeakyReLU / max-pool decisions of 30+ stacked layers); rounding the gradients between
+    the layers is immaterial (tools/grad_sensitivity.py: 0.735 vs 0.737 on the trainer's own lesson).  Asserted: the CUDA sets
+    are as close to the fp32 gradient as the emulation is (cosine within 0.05, per-tensor rel-L2 <= emu + 2e-2 on the
+    adversarial set), and at this size both are well aligned with it."""
+    import handwriting_line_generation_b200 as pkg
+    B, T, S = 8, 256, 40
+    gm, gsd = synth.state_dict_from_seed(lambda: pkg.SpacedGenerator(80, 128, 256, n_style_trans=6, emb_dropout=False,
+                                                                     append_style=True, small=False), 940)
+    hm, hsd = synth.state_dict_from_seed(lambda: pkg.CNNOnlyHWR(80, norm='batch'), 941)
+    torch.manual_seed(942)
+    dm = pkg.DiscriminatorAP(64, use_low=True, use_med=True)
+    dsd = synth.perturb_disc(dm.state_dict(), 943)
+    gsd, hsd, dsd = ({k: v.clone() for k, v in sd.items()} for sd in (gsd, hsd, dsd))
+    gm, hm, dm = gm.cuda().train(), hm.cuda().train(), dm.cuda().train()
+    for p in list(hm.parameters()) + list(dm.parameters()):
+        p.requires_grad_(False)
+    content, style = synth.gen_case(T, B, 80, 128, 944)
+    noise = synth.gen_noise(synth.gen_noise_shapes(T, B), 945)
+    masks = synth.disc_masks(B, 946)
+    dm.dropout_masks = {k: torch.from_numpy(v) for k, v in masks.items()}
+    label = torch.from_numpy(full_labels(B, S, 80, 947))
+    il, tl = torch.IntTensor([T - 6] * B), torch.IntTensor([S] * B)
+    names = [n for n, _ in gm.named_parameters()]
+    pkg.set_retain_graph(True)
+    try:
+        img = gm(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), noise=[torch.from_numpy(z).cuda() for z in noise])
+        recog = 1e-4 * pkg.CTCLoss(hm(img), label.permute(1, 0).cuda(), il, tl)
+        preds = dm(img)
+        adv = -sum(p.mean() for p in preds) / len(preds)
+        plist = [p for _, p in gm.named_parameters()]
+        got = {}
+        for nm, loss in (("recog", recog), ("adv", adv)):
+            gs = torch.autograd.grad(loss, plist, retain_graph=True, allow_unused=True)
+            got[nm] = {n: (None if g is None else g.detach().cpu().double()) for n, g in zip(names, gs)}
+    finally:
+        pkg.set_retain_graph(False)
+
+    def oracle(emu):
+        gp = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in gsd.items()}
+        oimg = ogen.generator_forward(gp, torch.from_numpy(content), torch.from_numpy(style), [torch.from_numpy(z) for z in noise],
+                                      emulate_bf16=emu)
+        lo = 1e-4 * torch.nn.functional.ctc_loss(ohwr.hwr_forward({k: v.clone() for k, v in hsd.items()}, oimg, True, {},
+                                                                  emulate_bf16=emu), label.permute(1, 0), il, tl)
+        la = odisc.gen_loss(odisc.disc_forward(dsd, oimg, {k: torch.from_numpy(v) for k, v in masks.items()}, training=True,
+                                               update={}, emulate_bf16=emu))
+        out = {}
+        for nm, loss in (("recog", lo), ("adv", la)):
+            gs = torch.autograd.grad(loss, [gp[n] for n in names], retain_graph=True, allow_unused=True)
+            out[nm] = {n: (None if g is None else g.double()) for n, g in zip(names, gs)}
+        return out, float(lo), float(la)
+
+    g32, lo32, la32 = oracle(False)
+    gemu, _, _ = oracle(True)
+    assert abs(recog.item() - lo32) <= BF16_REL * abs(lo32) and abs(adv.item() - la32) <= 2 * BF16_REL * abs(la32) + 2e-3
+
+    def set_cos(a, b):
+        num = d1 = d2 = 0.0
+        for n in names:
+            if a[n] is None or b[n] is None:
+                continue
+            num, d1, d2 = num + float((a[n] * b[n]).sum()), d1 + float((a[n] ** 2).sum()), d2 + float((b[n] ** 2).sum())
+        return num / (d1 * d2) ** 0.5
+
+    report = {}
+    for nm in ("recog", "adv"):
+        report[nm] = (set_cos(got[nm], g32[nm]), set_cos(gemu[nm], g32[nm]))
+    print("gen-lesson gradient sets at 8 lines of 64x1024: cosine with the fp32 chain (cuda, bf16-emulated torch):", report)
+    for nm, (c_cuda, c_emu) in report.items():
+        assert c_cuda >= c_emu - 0.05, (nm, c_cuda, c_emu)
+    assert report["adv"][0] >= 0.95 and report["recog"][0] >= 0.8, report
+    worst = 0.0
+    for n in names:
+        if got["adv"][n] is None or g32["adv"][n] is None or float(g32["adv"][n].norm()) == 0:
+            continue
+        ours, emu = rel_l2(got["adv"][n], g32["adv"][n]), rel_l2(gemu["adv"][n], g32["adv"][n])
+        worst = max(worst, ours - emu)
+        assert ours <= 1.3 * emu + BF16_REL, f"adv/{n}: cuda-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
+    print(f"adversarial set: worst per-tensor excess of the CUDA path over the emulation {worst:.3f}")

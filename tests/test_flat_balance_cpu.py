@@ -1,8 +1,8 @@
 """CPU: the HOST side of `FlatAdam.stash()` / `FlatAdam.balance()` (trainer/hw_with_style_trainer.py:300-377):
 the stash bookkeeping, the segment / block tables and the pointer array handed to `hwg_balance`, run through the CPU
 interpreter of the C-ABI (tests/abi_emu.py, which also checks that the block table tiles every segment) and compared with
-oracle/balance.py — the restatement tests/test_balance_cpu.py pins to the unmodified reference trainer.  The kernel itself
-has not run on a GPU yet: tools/pending_test_balance_gpu.py is the same scenario on the real launches."""
+oracle/balance.py — the restatement tests/test_balance_cpu.py pins to the unmodified reference trainer.
+tests/test_balance_gpu.py is the same scenario on the real launches."""
 import torch
 
 from oracle import balance as obal
@@ -40,6 +40,35 @@ def test_flat_stash_and_balance_match_the_oracle(hwg_lib, monkeypatch):
             assert float((got - r).abs().max()) <= 2e-6 * float(r.abs().max()) + 1e-12
         opt.balance(mult)                                    # nothing stashed: a no-op, no launch
         assert calls == ["hwg_balance"]
+
+
+def test_stash_slots_equal_the_stash_path(hwg_lib, monkeypatch):
+    """FlatAdam.sink(k): backward passes that write their gradient set straight into stash slot k (bench step: one slot
+    per loss, no clone + zero) balance to the same result as the stash() path, and the slots come back zeroed."""
+    import handwriting_line_generation_b200 as pkg
+    g0 = torch.Generator().manual_seed(2)
+    shapes = [(32, 16, 3, 3), (32,), (700,), (5, 3)]
+    with abi_emu.installed(monkeypatch) as calls:
+        params = [torch.nn.Parameter(torch.randn(s, generator=g0)) for s in shapes]
+        opt = pkg.FlatAdam(params, lr=1e-3)
+        mult = [0.6, 0.5]
+        sets_cpu = [[torch.randn(s, generator=g0) * (0.2 + k) for s in shapes] for k in range(2)]
+        main_cpu = [torch.randn(s, generator=g0) * 0.05 for s in shapes]
+        for rep in range(2):                                 # twice: the slots are re-zeroed by balance()
+            for k in range(2):
+                sink = opt.sink(k)
+                assert sink is opt.sink(k) and sink.owns(params[0]) and float(sink.buf.abs().max()) == 0.0
+                for p, g in zip(params, sets_cpu[k]):
+                    sink.grad_view(p).add_(g)                # what a backward kernel does
+            assert opt.sink() is opt
+            for p, g in zip(params, main_cpu):
+                opt.grad_view(p).copy_(g)
+            ref = obal.balance([g.clone() for g in main_cpu], sets_cpu, mult)
+            opt.balance(mult)
+            for p, r in zip(params, ref):
+                assert float((opt.grad_view(p) - r).abs().max()) <= 2e-6 * float(r.abs().max()) + 1e-12
+            opt.flat_g.zero_()
+        assert calls == ["hwg_balance", "hwg_balance"]
 
 
 def test_flat_adam_step_equals_clip_plus_torch_adam(hwg_lib, monkeypatch):
