@@ -9,9 +9,10 @@ from .pure_gen import SpacedGenerator  # noqa: F401
 from .cnn_only_hwr import CNNOnlyHWR  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
 from .discriminator_ap import DiscriminatorAP  # noqa: F401
-from .encoder2 import Encoder2  # noqa: F401  (not yet run on a GPU: see its module docstring)
+from .encoder2 import Encoder2  # noqa: F401
+from .count_cnn import CountCNN  # noqa: F401
 
 __all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam",
-           "DiscriminatorAP", "Encoder2"]
+           "DiscriminatorAP", "Encoder2", "CountCNN"]
 
 set_retain_graph = _lib.set_retain_graph   # keep saved state over repeated .backward(retain_graph=True) calls (see _lib.py)

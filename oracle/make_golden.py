@@ -382,6 +382,15 @@ def spacer_inputs(L, B, seed, n_class=80):
     return label, lengths, style
 
 
+def spacer_train_extras(L, B, seed):
+    """Dropout2d keep-masks of the two sites ([B,128], [B,64]; drop rate inflated to 0.3 so small batches really drop
+    channels) and the weights of the linear test loss."""
+    r = np.random.RandomState(seed + 5)
+    masks = [torch.from_numpy((r.rand(B, c) >= 0.3).astype(np.float32)) for c in (128, 64)]
+    R = torch.from_numpy(r.standard_normal((L, B, 2)).astype(np.float32))
+    return masks, R
+
+
 def make_spacer():
     """Counts of the unmodified reference CountCNN and the spaced text of the unmodified `HWWithStyle.insert_spaces`
     (called unbound on a stand-in that carries the attributes it reads: no model weights are involved in it)."""
@@ -408,6 +417,35 @@ def make_spacer():
             out[f"{name}/{tag}/padded"] = np.array(padded, np.float64)
         out[f"{name}/counts"] = counts.numpy()
         print(f"spacer/{name}: counts {tuple(counts.shape)} spaced T={spaced.size(0)}")
+    # train mode (the 'count' lesson trains the spacer): Dropout2d keep-masks injected, a linear loss, every gradient
+    import torch.nn.functional as F
+    for name, (L, B, wseed, iseed) in SPACER_CASES.items():
+        torch.manual_seed(wseed)
+        m = CountCNN(80, 128, 128, 2).train()
+        label, lengths, style = spacer_inputs(L, B, iseed)
+        style = style.clone().requires_grad_()
+        onehot = torch.zeros(L, B, 80).scatter_(2, label[..., None], 1.0).requires_grad_()
+        masks, R = spacer_train_extras(L, B, iseed)
+        it = iter(masks)
+        orig = F.dropout2d
+
+        def fake_dropout2d(x, p=0.5, training=True, inplace=False):
+            mk = next(it)
+            assert training and abs(p - 0.1) < 1e-9 and tuple(mk.shape) == tuple(x.shape[:2]), (p, x.shape)
+            return x * (mk / (1.0 - p))[:, :, None]
+
+        F.dropout2d = fake_dropout2d
+        try:
+            counts = m(onehot, style)
+        finally:
+            F.dropout2d = orig
+        (counts * R).sum().backward()
+        out[f"{name}/train/counts"] = counts.detach().numpy()
+        out[f"{name}/train/grad/style"] = style.grad.numpy()
+        out[f"{name}/train/grad/input"] = onehot.grad.numpy()
+        for n, p_ in m.named_parameters():
+            out[f"{name}/train/grad/{n}"] = p_.grad.numpy()
+        print(f"spacer/{name}: train-mode counts + {len(list(m.parameters()))} parameter gradients")
     np.savez_compressed(os.path.join(GOLD, "spacer.npz"), **out)
 
 

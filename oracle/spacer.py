@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE — CPU restatement of the text-spacing front end of `HWWithStyle.forward`:
 the spacer `CountCNN` (model/count_cnn.py:7-45, built by hw_with_style.py:200-204 as CountCNN(num_class, style_dim, 128, 2)
-for `spacer: "CNN duplicates"`) and `insert_spaces` (hw_with_style.py:302-328).  No CUDA counterpart: in the product these
-two stay the reference's Python.  Pinned by tests/golden/spacer.npz (tests/test_spacer_cpu.py).
+for `spacer: "CNN duplicates"`) and `insert_spaces` (hw_with_style.py:302-328) — the checker of the product's
+`count_cnn.CountCNN` and `spacing.insert_spaces`.  Pinned by tests/golden/spacer.npz (tests/test_spacer_cpu.py).
 
 The reference's insert_spaces walks batch x characters in Python with two `np.random.normal(...)` + `.item()` per character
 (2*L*B host synchronisations on a GPU).  The restatement draws the same normals in ONE vectorised call (same legacy
@@ -14,12 +14,16 @@ import torch
 import torch.nn.functional as F
 
 
-def count_cnn_forward(sd, label_onehot, style):
-    """label_onehot [L,B,C], style [B,S] -> counts [L,B,2] = (blanks before the character, repetitions of it); eval mode
-    (Dropout2d off)."""
+def count_cnn_forward(sd, label_onehot, style, masks=None):
+    """label_onehot [L,B,C], style [B,S] -> counts [L,B,2] = (blanks before the character, repetitions of it).  masks: None
+    = eval mode (Dropout2d off), else the two [B,C] keep-masks of the train-mode Dropout2d(0.1) sites (count_cnn.py:14,18;
+    on a [B,C,L] tensor Dropout2d drops whole (sample, channel) rows)."""
+    def drop(t, i):
+        return t if masks is None else t * (masks[i] / 0.9)[:, :, None]
+
     x = torch.cat((label_onehot.permute(1, 2, 0), style[..., None].expand(-1, -1, label_onehot.size(0))), 1)
-    x = F.relu(F.group_norm(F.conv1d(x, sd["cnn.0.weight"], sd["cnn.0.bias"], padding=1), 8, sd["cnn.1.weight"], sd["cnn.1.bias"]))
-    x = F.relu(F.group_norm(F.conv1d(x, sd["cnn.4.weight"], sd["cnn.4.bias"], padding=1), 8, sd["cnn.5.weight"], sd["cnn.5.bias"]))
+    x = F.relu(drop(F.group_norm(F.conv1d(x, sd["cnn.0.weight"], sd["cnn.0.bias"], padding=1), 8, sd["cnn.1.weight"], sd["cnn.1.bias"]), 0))
+    x = F.relu(drop(F.group_norm(F.conv1d(x, sd["cnn.4.weight"], sd["cnn.4.bias"], padding=1), 8, sd["cnn.5.weight"], sd["cnn.5.bias"]), 1))
     x = F.relu(F.group_norm(F.conv1d(x, sd["cnn.8.weight"], sd["cnn.8.bias"], padding=1), 8, sd["cnn.9.weight"], sd["cnn.9.bias"]))
     x = F.conv1d(x, sd["cnn.11.weight"], sd["cnn.11.bias"])
     return x.permute(2, 0, 1) * sd["std"] + sd["mean"]

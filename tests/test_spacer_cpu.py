@@ -43,3 +43,24 @@ def test_spacer_and_insert_spaces_match_the_reference(name, golden_dir):
         assert np.array_equal(spaced.argmax(2).numpy(), gold[f"{name}/{tag}/spaced"]), tag
         assert float(spaced.sum(2).min()) == 1.0
         assert np.allclose(padded, gold[f"{name}/{tag}/padded"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(SPACER_CASES))
+def test_oracle_spacer_train_mode_gradients_match_the_reference(name, golden_dir):
+    """Train mode (the 'count' lesson trains the spacer): injected Dropout2d keep-masks, a linear loss; counts and the
+    gradients of all 16 parameters, of the style vector and of the text input against the unmodified reference."""
+    from oracle.make_golden import spacer_train_extras
+    gold = np.load(f"{golden_dir}/spacer.npz")
+    L, B, wseed, iseed = SPACER_CASES[name]
+    sd = {k: v.clone().requires_grad_(True) for k, v in count_cnn_state_dict(wseed).items()}
+    label, lengths, style = spacer_inputs(L, B, iseed)
+    style = style.clone().requires_grad_()
+    onehot = torch.zeros(L, B, 80).scatter_(2, label[..., None], 1.0).requires_grad_()
+    masks, R = spacer_train_extras(L, B, iseed)
+    counts = ospacer.count_cnn_forward(sd, onehot, style, masks)
+    (counts * R).sum().backward()
+    ref = gold[f"{name}/train/counts"]
+    assert np.abs(counts.detach().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    for key, t in [("style", style), ("input", onehot)] + list(sd.items()):
+        g = gold[f"{name}/train/grad/{key}"]
+        assert np.abs(t.grad.numpy() - g).max() <= 1e-4 * np.abs(g).max() + 1e-7, key
