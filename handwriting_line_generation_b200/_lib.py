@@ -43,6 +43,9 @@ _SIGNATURES = {
     "hwg_spectral_norm": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_channel_sum": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "hwg_dtw_align": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hwg_insert_spaces_plan": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, ctypes.c_double, ctypes.c_double, c_vp, c_vp,
+                                       c_vp, c_vp]),
+    "hwg_insert_spaces_fill": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hwg_add_stats": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
     "hwg_l1_halves": (c_int, [c_vp, c_int, c_i64, c_f, c_f, c_vp, c_vp, c_vp]),
     "hwg_spectral_norm_bwd": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

@@ -7,7 +7,7 @@ and generate.py run the sm_100a path without a source change."""
 import importlib
 
 
-def install(encoder=False, retain_graph=False, dtw=False):
+def install(encoder=False, retain_graph=False, dtw=False, spacer=False):
     """Call after the reference's root is on sys.path and before HWWithStyle / the trainer are built.
     Returns the list of (module name, attribute) pairs that were rebound.
 
@@ -17,9 +17,19 @@ def install(encoder=False, retain_graph=False, dtw=False):
     retain_graph=True keeps the modules' saved-for-backward state over repeated `.backward(retain_graph=True)` calls on one
     graph — what the trainer does when `balance_loss` is configured (trainer/hw_with_style_trainer.py:300-338).
     dtw=True rebinds `correct_pred` (model/hw_with_style.py:18, the DTW label alignment `autoencode` / `extract_style`
-    call) to the one-launch version — opt-in until it has a green GPU run (dtw.py: status)."""
+    call) to the one-launch version.
+    spacer=True rebinds `CountCNN` (hw_with_style.py:204) and `HWWithStyle.insert_spaces` (:302-328)."""
     from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator, set_retain_graph
     swapped = []
+    if spacer:
+        # the text -> spacing front end of HWWithStyle.forward (hw_with_style.py:236-238): the CountCNN spacer and
+        # insert_spaces (one host read instead of 2*L*B `.item()` calls; same numpy RNG stream, bit-identical text)
+        from .count_cnn import CountCNN
+        from .spacing import insert_spaces
+        hws_ = importlib.import_module("model.hw_with_style")
+        setattr(hws_, "CountCNN", CountCNN)
+        setattr(hws_.HWWithStyle, "insert_spaces", insert_spaces)
+        swapped += [("model.hw_with_style", "CountCNN"), ("model.hw_with_style", "HWWithStyle.insert_spaces")]
     if retain_graph:
         set_retain_graph(True)
     if dtw:

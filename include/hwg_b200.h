@@ -521,6 +521,26 @@ int hwg_dtw_align(const float* pred, int T, int B, int C, const int32_t* label, 
                   void* stream);
 
 /* ------------------------------------------------------------------------
+ * Text spacing (reference HWWithStyle.insert_spaces, model/hw_with_style.py:302-328):
+ *   line b = for every character i < lengths[b]:  [blank] * round(N(counts[i,b,0], count_std))
+ *                                               + [label[i,b]] * round(N(counts[i,b,1], dup_std))   (1 when n_out == 1)
+ *   spaced [T,B,C] one-hot with T = max line length + max(ceil(max counts), 3), blank (class 0) behind every line.
+ * z: the standard normals of the reference's np.random.normal calls, drawn by the host from the same stream in one call
+ *    (order: line, character, count before duplicates); z_off[b] = index of line b's first draw.  The kernel evaluates
+ *    loc + std * z in doubles with two roundings and rounds half to even — numpy's arithmetic and Python's round().
+ * hwg_insert_spaces_plan: reps [B][L][2] = (blanks, repetitions), offsets [B][L+1] = exclusive prefix sums (entries from
+ *    lengths[b] on hold the line length), info [B+1] = line lengths, then ceil(max over ALL entries of counts) (:303).
+ * hwg_insert_spaces_fill: writes every element of spaced [T,B,C] fp32 (label: int32 or int64 [L,B] with element strides).
+ * The caller reads info (ONE device->host copy of B+1 integers, instead of the reference's 2*L*B `.item()` calls) to size
+ * `spaced`.  Integer work: bit-exact against the reference's goldens. */
+int hwg_insert_spaces_plan(const int32_t* lengths, const float* counts, int n_out, const double* z, const int64_t* z_off,
+                           int L, int B, double count_std, double dup_std, int32_t* reps, int32_t* offsets,
+                           int32_t* info, void* stream);
+int hwg_insert_spaces_fill(const void* label, int label_is_i64, int64_t label_stride_l, int64_t label_stride_b,
+                           const int32_t* lengths, const int32_t* reps, const int32_t* offsets, int L, int B, int T,
+                           int C, float* spaced, void* stream);
+
+/* ------------------------------------------------------------------------
  * Peer-memory exchange for data-parallel BatchNorm (coupling 1).
  * The reference is single-process: nn.BatchNorm2d/1d in cnn_only_hwr.py:36,79
  * normalise with the statistics of the WHOLE batch.  With the batch sharded

@@ -701,7 +701,55 @@ def hwg_adain_bwd_apply(g, a, save, coef, sums, N, H, W, C, slope, noise, seed, 
     return 0
 
 
-_TABLE = {f.__name__: f for f in (hwg_dtw_align, hwg_adam_flat, hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
+# ---- text spacing (spacing.py) -------------------------------------------------------------------------------------
+def _iview(ptr, n, ctype, npdtype):
+    return np.frombuffer((ctype * n).from_address(ptr), dtype=npdtype)
+
+
+def hwg_insert_spaces_plan(lengths, counts, n_out, z, z_off, L, B, count_std, dup_std, reps, offsets, info, stream):
+    """Header semantics: per line the rounded normal draws (doubles, half to even), exclusive prefix sums, line length,
+    ceil(max counts) — plain Python loops, as the reference itself walks them."""
+    ln = _iview(lengths, B, ctypes.c_int32, np.int32)
+    c = _view(counts, L * B * n_out, torch.float32).view(L, B, n_out).numpy()
+    zoff = _iview(z_off, B, ctypes.c_int64, np.int64)
+    nz = int(sum(int(v) for v in ln) * n_out)
+    zz = _iview(z, max(nz, 1), ctypes.c_double, np.float64)
+    rp = _iview(reps, B * L * 2, ctypes.c_int32, np.int32).reshape(B, L, 2)
+    off = _iview(offsets, B * (L + 1), ctypes.c_int32, np.int32).reshape(B, L + 1)
+    inf = _iview(info, B + 1, ctypes.c_int32, np.int32)
+    for b in range(B):
+        n = min(max(int(ln[b]), 0), L)
+        tot = 0
+        for i in range(n):
+            cnt = max(0, int(round(np.float64(c[i, b, 0]) + np.float64(count_std) * zz[zoff[b] + i * n_out])))
+            dup = max(0, int(round(np.float64(c[i, b, 1]) + np.float64(dup_std) * zz[zoff[b] + i * n_out + 1]))) if n_out > 1 else 1
+            rp[b, i] = (cnt, dup)
+            off[b, i] = tot
+            tot += cnt + dup
+        off[b, n:] = tot
+        inf[b] = tot
+    inf[B] = int(np.ceil(c.max()))
+    return 0
+
+
+def hwg_insert_spaces_fill(label, is_i64, ls_l, ls_b, lengths, reps, offsets, L, B, T, C, spaced, stream):
+    ln = _iview(lengths, B, ctypes.c_int32, np.int32)
+    rp = _iview(reps, B * L * 2, ctypes.c_int32, np.int32).reshape(B, L, 2)
+    out = _view(spaced, T * B * C, torch.float32).view(T, B, C)
+    ct, dt = (ctypes.c_int64, np.int64) if is_i64 else (ctypes.c_int32, np.int32)
+    span = (L - 1) * ls_l + (B - 1) * ls_b + 1
+    lab = _iview(label, span, ct, dt)
+    out.zero_()
+    for b in range(B):
+        line = []
+        for i in range(min(max(int(ln[b]), 0), L)):
+            line += [0] * int(rp[b, i, 0]) + [int(lab[i * ls_l + b * ls_b])] * int(rp[b, i, 1])
+        line += [0] * (T - len(line))
+        out[torch.arange(T), b, torch.tensor(line[:T])] = 1.0
+    return 0
+
+
+_TABLE = {f.__name__: f for f in (hwg_insert_spaces_plan, hwg_insert_spaces_fill, hwg_dtw_align, hwg_adam_flat, hwg_ctc_forward, hwg_ctc_reduce_mean, hwg_ctc_backward, hwg_linear_f32, hwg_linear_bwd_f32, hwg_pixelnorm_f32, hwg_gen_pack_input, hwg_adain_coeffs,
                                   hwg_blur_noise_act_stats, hwg_gen_output, hwg_gen_output_bwd, hwg_adain_bwd_reduce,
                                   hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,

@@ -129,3 +129,73 @@ def test_hwwithstyle_forward_with_the_drop_ins_equals_the_reference(hwg_lib, mon
     assert lp.shape == ref_lp.shape and rel(lp, ref_lp) <= 2e-2, rel(lp, ref_lp)
     assert torch.equal(lp.argmax(2), ref_lp.argmax(2)) or (lp.argmax(2) != ref_lp.argmax(2)).float().mean() < 0.02
     assert "hwg_conv_fprop" in calls and "hwg_gen_output" in calls and "hwg_hwr_stem" in calls
+
+
+def test_hwwithstyle_forward_with_the_spacer_drop_ins(hwg_lib, monkeypatch):
+    """`integrate.install(spacer=True)` also swaps the spacer `CountCNN` and binds
+    `HWWithStyle.insert_spaces` to the device version.  The UNMODIFIED `HWWithStyle.forward(label, label_lengths, style)` then
+    runs text -> counts -> spaced text -> image entirely on the library (here: through the CPU interpreter): same initial
+    weights as the reference's spacer, counts within the bf16 bound, and the spaced text is exactly what the reference's
+    arithmetic (oracle restatement, same numpy stream) makes of those counts."""
+    import importlib
+    import sys
+
+    import numpy as np
+
+    from oracle import spacer as ospacer
+
+    from . import abi_emu
+    saved_path, saved_ds = list(sys.path), sys.modules.get("datasets")
+    ref_shim.install()
+    cwd = os.getcwd()
+    os.chdir(ref_shim.REF)
+    try:
+        hws = importlib.import_module("model.hw_with_style")
+        mloss = importlib.import_module("model.loss")
+        orig = (hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss, hws.DiscriminatorAP, hws.CountCNN,
+                hws.HWWithStyle.insert_spaces)
+        ref_model = _build()
+        ref_model.eval()
+        L, B = 24, 2
+        r = np.random.RandomState(3)
+        label = torch.from_numpy(r.randint(1, 80, (L, B)).astype(np.int64))
+        lengths = torch.IntTensor([L, L - 2])
+        style = torch.from_numpy(r.standard_normal((B, 128)).astype(np.float32))
+        with torch.no_grad():               # before the swap: insert_spaces is rebound on the CLASS
+            np.random.seed(11)
+            ref_model(label, lengths, style)
+        from handwriting_line_generation_b200 import CountCNN, integrate
+        swapped = integrate.install(spacer=True)
+        try:
+            assert ("model.hw_with_style", "CountCNN") in swapped
+            ours = _build()
+            assert isinstance(ours.spacer, CountCNN)
+            a, b = ref_model.spacer.state_dict(), ours.spacer.state_dict()
+            assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+            ours.eval()
+            with torch.no_grad():
+                with abi_emu.installed(monkeypatch) as calls:
+                    np.random.seed(11)
+                    img = ours(label, lengths, style)
+        finally:
+            (hws.SpacedGenerator, hws.CNNOnlyHWR, mloss.CTCLoss, hws.DiscriminatorAP, hws.CountCNN,
+             hws.HWWithStyle.insert_spaces) = orig
+    finally:
+        os.chdir(cwd)
+        sys.path[:] = saved_path
+        if saved_ds is not None:
+            sys.modules["datasets"] = saved_ds
+        else:
+            sys.modules.pop("datasets", None)
+    rel = float((ours.counts.double() - ref_model.counts.double()).norm() / ref_model.counts.double().norm())
+    assert rel <= 2e-2, rel
+    want, _ = ospacer.insert_spaces(label.numpy(), lengths, ours.counts.numpy(), 80, ours.count_std, ours.dup_std,
+                                    np.random.RandomState(11))
+    assert torch.equal(ours.gen_spaced, want)
+    assert img.size(3) == 4 * ours.gen_spaced.size(0)
+    # bf16 counts can tip a rounding that sits within 1e-2 of .5; everywhere else the reference's spacing is reproduced
+    same_len = ours.gen_spaced.size(0) == ref_model.gen_spaced.size(0)
+    if same_len:
+        agree = float((ours.gen_spaced.argmax(2) == ref_model.gen_spaced.argmax(2)).float().mean())
+        assert agree >= 0.9, agree
+    assert {"hwg_insert_spaces_plan", "hwg_insert_spaces_fill", "hwg_gn_coeffs", "hwg_gen_output"} <= set(calls)

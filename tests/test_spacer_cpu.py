@@ -64,3 +64,24 @@ def test_oracle_spacer_train_mode_gradients_match_the_reference(name, golden_dir
     for key, t in [("style", style), ("input", onehot)] + list(sd.items()):
         g = gold[f"{name}/train/grad/{key}"]
         assert np.abs(t.grad.numpy() - g).max() <= 1e-4 * np.abs(g).max() + 1e-7, key
+
+
+@pytest.mark.parametrize("name", sorted(SPACER_CASES))
+def test_spacing_host_wrapper_through_the_interpreter(name, golden_dir, hwg_lib, monkeypatch):
+    """`spacing.insert_spaces` (the product's host side: one vectorised draw from the reference's numpy stream, draw offsets
+    per line, the single read-back that sizes the result) with the two launches interpreted on CPU: the spaced text of the
+    unmodified reference, bit for bit."""
+    import types
+    from handwriting_line_generation_b200.spacing import insert_spaces
+    from . import abi_emu
+    gold = np.load(f"{golden_dir}/spacer.npz")
+    L, B, wseed, iseed = SPACER_CASES[name]
+    label, lengths, _ = spacer_inputs(L, B, iseed)
+    counts = torch.from_numpy(gold[f"{name}/counts"])
+    with abi_emu.installed(monkeypatch) as calls:
+        for std, tag in ((1e-8, "cfg"), (0.4, "noisy")):
+            host = types.SimpleNamespace(count_std=std, dup_std=std / 10, count_duplicates=True, num_class=80)
+            spaced, padded = insert_spaces(host, label, lengths, counts, rng=np.random.RandomState(iseed))
+            assert np.array_equal(spaced.argmax(2).numpy(), gold[f"{name}/{tag}/spaced"]), tag
+            assert np.allclose(padded, gold[f"{name}/{tag}/padded"], rtol=0, atol=1e-12)
+    assert calls == ["hwg_insert_spaces_plan", "hwg_insert_spaces_fill"] * 2
