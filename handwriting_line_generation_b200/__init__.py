@@ -11,8 +11,9 @@ from .optim import FlatAdam  # noqa: F401
 from .discriminator_ap import DiscriminatorAP  # noqa: F401
 from .encoder2 import Encoder2  # noqa: F401
 from .count_cnn import CountCNN  # noqa: F401
+from .char_style import CharStyleEncoder  # noqa: F401
 
 __all__ = ["CTCLoss", "ctc_greedy_decode", "naive_decode", "SpacedGenerator", "CNNOnlyHWR", "FlatAdam",
-           "DiscriminatorAP", "Encoder2", "CountCNN"]
+           "DiscriminatorAP", "Encoder2", "CountCNN", "CharStyleEncoder"]
 
 set_retain_graph = _lib.set_retain_graph   # keep saved state over repeated .backward(retain_graph=True) calls (see _lib.py)

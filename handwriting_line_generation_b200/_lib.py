@@ -179,6 +179,22 @@ def call(name, *args):
             raise RuntimeError(f"{name}: device fault after this launch: {e}") from None
 
 
+def named_params(module):
+    """[(name, parameter)] of a module, computed once: `nn.Module.named_parameters()` walks the whole module tree on every
+    call (65 parameters x ten calls per train step of the generator alone = 40 % of the step's host time).  Parameter
+    OBJECTS persist over `.to()`, `load_state_dict` and optimizer steps (those change `.data` / `_version`, which the
+    derived-weight caches key on), so the list is cached on the module; registering a new parameter invalidates it."""
+    cache = module.__dict__.get("_hwg_named_params")
+    n = sum(len(m._parameters) for m in module.modules()) if cache is None else cache[0]
+    if cache is None:
+        cache = module.__dict__["_hwg_named_params"] = (n, list(module.named_parameters()))
+    return cache[1]
+
+
+def params(module):
+    return [p for _, p in named_params(module)]
+
+
 def launch_count():
     return int(load().hwg_launch_count())
 

@@ -206,7 +206,7 @@ def backward_train(m, ctx, g_lp, want_input_grad=False, needed=None):
     lp = ctx["lp"]
     T, B, C = lp.shape
     Cp = ((C + 15) // 16) * 16
-    params = dict(m.named_parameters())
+    params = dict(_lib.named_params(m))
     # one zero-filled arena: every per-channel accumulator of this pass and the tap-major wgrad outputs
     wnames = {"w%d" % i: "cnn.conv%d.weight" % i for i in range(1, 7)}
     wnames.update({"v%d" % ci: "cnn1d.%d.weight" % ci for ci in (0, 3, 6, 9, 12)})
@@ -326,6 +326,6 @@ class _HWRFn(torch.autograd.Function):
 
 
 def hwr_apply(module, input):
-    named = [(n, p) for n, p in module.named_parameters()]
+    named = _lib.named_params(module)
     names = tuple(n for n, _ in named)
     return _HWRFn.apply(module, names, input, *[p for _, p in named])

@@ -113,7 +113,7 @@ class CNNOnlyHWR(nn.Module):
         return {"table": t, "c": c}
 
     def _packed(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in _lib.params(self))
         if self._cache_key == key:
             return self._cache
         ptrs = tuple(k[0] for k in key)
@@ -143,7 +143,7 @@ class CNNOnlyHWR(nn.Module):
 
     def forward(self, input, style=None):
         _lib.require_cuda(input)
-        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in _lib.params(self))):
             from .autograd_hwr import hwr_apply  # backward pass lives there
             return hwr_apply(self, input)
         return self._forward_impl(input)

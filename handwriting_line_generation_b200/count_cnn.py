@@ -105,7 +105,7 @@ class CountCNN(nn.Module):
     def forward(self, input, style):
         """input [L,B,class_size] (the one-hot text), style [B,style_size] -> [L,B,n_out] (count_cnn.py:34-45)."""
         _lib.require_cuda(input, style)
-        named = [(n, p) for n, p in self.named_parameters() if n.startswith("cnn.")]
+        named = [(n, p) for n, p in _lib.named_params(self) if n.startswith("cnn.")]
         if torch.is_grad_enabled() and (input.requires_grad or style.requires_grad or any(p.requires_grad for _, p in named)):
             raw = _CountFn.apply(self, tuple(n for n, _ in named), input, style, *[p for _, p in named])
         else:

@@ -194,7 +194,7 @@ class DiscriminatorAP(nn.Module):
     def _prepare(self):
         """Per forward (the reference updates u, v and re-derives weight = w_bar / sigma on EVERY forward, :62-64):
         hwg_spectral_norm (three small launches for all layers) + one hwg_linear_map launch."""
-        ptrs = tuple(p.data_ptr() for p in self.parameters())
+        ptrs = tuple(p.data_ptr() for p in _lib.params(self))
         if self._plan is None or self._plan_ptrs != ptrs:
             self._plan, self._plan_ptrs = self._build_plan(), ptrs
         p = self._plan
@@ -235,7 +235,7 @@ class DiscriminatorAP(nn.Module):
         if return_features:
             raise NotImplementedError("return_features=True is not used by the training step")
         if torch.is_grad_enabled():
-            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            named = [(n, p) for n, p in _lib.named_params(self) if p.requires_grad]
             if named or x.requires_grad:
                 return list(_DiscFn.apply(self, tuple(n for n, _ in named), x, *[p for _, p in named]))
         outs, _ = self._forward_impl(x, keep=False)
@@ -338,7 +338,7 @@ class DiscriminatorAP(nn.Module):
         if plan is not None:
             return plan
         layers = self.conv_layers()
-        params = dict(self.named_parameters())
+        params = dict(_lib.named_params(self))
         inv_sigma, sn_sites = self._plan["inv_sigma"], [s for s, _, _, sp in layers if sp]
         off, slots = 0, {}
 

@@ -115,7 +115,7 @@ class Encoder2(nn.Module):
 
     def _prepare(self):
         """Packed operands, re-derived by one launch when a parameter changed (data_ptr / _version)."""
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in _lib.params(self))
         if self._plan is None or self._plan_key != key:
             dev = self.down_conv1[0].weight.device
             if self._plan is None or self._plan["ptrs"] != tuple(k[0] for k in key):

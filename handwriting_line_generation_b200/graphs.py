@@ -48,3 +48,50 @@ class GraphedStep:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphCache:
+    """One captured graph per input-shape key, for steps whose shapes vary between calls (the reference trainer's batches:
+    the generated width follows the text, the real lines are padded to the widest of the batch).
+
+        step = GraphCache(fn, modules=[gen, hwr]);  out = step(*inputs)
+
+    The first call with a new key captures (`GraphedStep`), later calls with that key replay; at most `max_graphs` graphs
+    are kept (least recently used first out — a captured step holds its activations).  `key(*inputs)` defaults to the
+    inputs' shapes; `bucket(*inputs)` may return padded inputs first (e.g. spaced text padded with blank rows up to a
+    multiple of 32 columns: fewer distinct widths at the price of InstanceNorm statistics taken over the padded line — a
+    change of the result, which is why no padding is applied by default)."""
+
+    def __init__(self, fn, modules=(), warmup=3, max_graphs=8, key=None, bucket=None):
+        self.fn, self.modules, self.warmup, self.max_graphs = fn, tuple(modules), warmup, max_graphs
+        self.key = key or (lambda *ins: tuple((tuple(x.shape), x.dtype) for x in ins))
+        self.bucket = bucket
+        self._graphs = {}            # insertion order = recency
+        self.captures = 0
+
+    def __call__(self, *inputs):
+        if self.bucket is not None:
+            inputs = self.bucket(*inputs)
+        k = self.key(*inputs)
+        g = self._graphs.pop(k, None)
+        if g is None:
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = GraphedStep(self.fn, list(inputs), modules=self.modules, warmup=self.warmup)
+            self.captures += 1
+        self._graphs[k] = g
+        return g(*inputs)
+
+
+def pad_spaced_text(multiple=32, blank=0):
+    """`bucket` for GraphCache over (content [T,B,C], ...): pads the spaced one-hot text with blank rows up to a multiple
+    of `multiple` columns (the generated line gets 4 x as many extra blank pixel columns)."""
+    def bucket(content, *rest):
+        T = content.size(0)
+        Tp = -(-T // multiple) * multiple
+        if Tp != T:
+            pad = torch.zeros((Tp - T,) + tuple(content.shape[1:]), device=content.device, dtype=content.dtype)
+            pad[..., blank] = 1
+            content = torch.cat((content, pad), 0)
+        return (content,) + rest
+    return bucket

@@ -7,7 +7,7 @@ and generate.py run the sm_100a path without a source change."""
 import importlib
 
 
-def install(encoder=False, retain_graph=False, dtw=False, spacer=False):
+def install(encoder=False, retain_graph=False, dtw=False, spacer=False, style=False):
     """Call after the reference's root is on sys.path and before HWWithStyle / the trainer are built.
     Returns the list of (module name, attribute) pairs that were rebound.
 
@@ -18,7 +18,8 @@ def install(encoder=False, retain_graph=False, dtw=False, spacer=False):
     graph — what the trainer does when `balance_loss` is configured (trainer/hw_with_style_trainer.py:300-338).
     dtw=True rebinds `correct_pred` (model/hw_with_style.py:18, the DTW label alignment `autoencode` / `extract_style`
     call) to the one-launch version.
-    spacer=True rebinds `CountCNN` (hw_with_style.py:204) and `HWWithStyle.insert_spaces` (:302-328)."""
+    spacer=True rebinds `CountCNN` (hw_with_style.py:204) and `HWWithStyle.insert_spaces` (:302-328).
+    style=True rebinds `CharStyleEncoder` (hw_with_style.py:122)."""
     from . import CNNOnlyHWR, CTCLoss, DiscriminatorAP, SpacedGenerator, set_retain_graph
     swapped = []
     if spacer:
@@ -30,6 +31,11 @@ def install(encoder=False, retain_graph=False, dtw=False, spacer=False):
         setattr(hws_, "CountCNN", CountCNN)
         setattr(hws_.HWWithStyle, "insert_spaces", insert_spaces)
         swapped += [("model.hw_with_style", "CountCNN"), ("model.hw_with_style", "HWWithStyle.insert_spaces")]
+    if style:
+        # the style extractor of the 'auto' / 'count' lessons (hw_with_style.py:122): model/char_style.py CharStyleEncoder
+        from .char_style import CharStyleEncoder
+        setattr(importlib.import_module("model.hw_with_style"), "CharStyleEncoder", CharStyleEncoder)
+        swapped.append(("model.hw_with_style", "CharStyleEncoder"))
     if retain_graph:
         set_retain_graph(True)
     if dtw:

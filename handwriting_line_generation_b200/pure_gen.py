@@ -289,7 +289,7 @@ class SpacedGenerator(nn.Module):
         return {"table": t, "c": c}
 
     def _packed(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in _lib.params(self))
         if self._cache_key == key:
             return self._cache
         ptrs = tuple(k[0] for k in key)
@@ -308,7 +308,7 @@ class SpacedGenerator(nn.Module):
         noise is generated inside the kernels (counter-based hash + Box-Muller), seeded from torch's CPU generator."""
         _lib.require_cuda(content, style)
         if torch.is_grad_enabled() and (content.requires_grad or style.requires_grad
-                                        or any(p.requires_grad for p in self.parameters())):
+                                        or any(p.requires_grad for p in _lib.params(self))):
             from .autograd_gen import generator_apply  # backward pass lives there
             return generator_apply(self, content, style, noise)
         return self._forward_impl(content, style, noise)[0]

@@ -225,29 +225,39 @@ def test_reference_trainer_curriculum_cycle_runs_on_the_drop_ins(golden_dir, hwg
         mauto = importlib.import_module("model.autoencoder"); mtr = importlib.import_module("trainer.hw_with_style_trainer")
         state["orig"] = (hws, mloss, hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss, hws.correct_pred)
         state["enc"] = (mauto, mtr, mauto.Encoder2, mtr.Encoder2)
-        integrate.install(retain_graph=True, encoder=True, dtw=True)
+        state["f34"] = (hws.CountCNN, hws.HWWithStyle.insert_spaces, hws.CharStyleEncoder)
+        integrate.install(retain_graph=True, encoder=True, dtw=True, spacer=True, style=True)
     def hook(tr, model, rec):
         model.discriminator.dropout_masks = masks
         recorded = model.generator.forward
-        model.generator.forward = lambda content, style, *a, **k: recorded(content, style, *a, noise=noise, **k)
+
+        def first_lesson_noise(content, style, *a, **k):    # by shape: with the spacer drop-in the width is the product's own
+            nz = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(content.size(0), style.size(0)), 76)]
+            return recorded(content, style, *a, noise=nz, **k)
+        model.generator.forward = first_lesson_noise
     cwd = os.getcwd()
     try:
         with abi_emu.installed(monkeypatch) as calls:
             tr, log, rec, model = harness.run_lesson("gen", install=install, hook=hook)
             os.chdir(ref_shim.REF)
             model.discriminator.dropout_masks = None
-            fwd = model.generator.forward
+            fwd = recorded_fwd = type(model.generator).forward.__get__(model.generator)
             def with_noise(content, style, *a, **k):
                 B = style.size(0)
                 nz = [torch.from_numpy(z) for z in synth.gen_noise(synth.gen_noise_shapes(content.size(0), B), 77)]
                 return fwd(content, style, *a, noise=nz, **k)
             model.generator.forward = with_noise
+            assert isinstance(model.style_extractor, pkg.CharStyleEncoder) and isinstance(model.spacer, pkg.CountCNN)
             before = {n: p.detach().clone() for n, p in model.generator.named_parameters()}
+            before_style = {n: p.detach().clone() for n, p in model.style_extractor.named_parameters()}
+            before_spacer = {n: p.detach().clone() for n, p in model.spacer.named_parameters()}
             n0 = len(calls)
             tr.iteration = 2
             log2 = tr._train_iteration(2)
             lesson2 = set(calls[n0:])
             changed = sum(int(not torch.equal(p.detach(), before[n])) for n, p in model.generator.named_parameters())
+            # the 'auto' lesson trains the style extractor (its image path and the heads of the characters that occur)
+            changed_style = [n for n, p in model.style_extractor.named_parameters() if not torch.equal(p.detach(), before_style[n])]
             # ... and the rest of the 7-lesson cycle (config :85-95): disc, gen, auto, disc, then the next cycle's count
             cycle = {}
             per_lesson = {1: n0, 2: len(calls) - n0}
@@ -262,6 +272,7 @@ def test_reference_trainer_curriculum_cycle_runs_on_the_drop_ins(golden_dir, hwg
         hws, mloss, g, h, d, c, cp = state["orig"]
         hws.SpacedGenerator, hws.CNNOnlyHWR, hws.DiscriminatorAP, mloss.CTCLoss, hws.correct_pred = g, h, d, c, cp
         mauto, mtr, e1, e2 = state["enc"]; mauto.Encoder2, mtr.Encoder2 = e1, e2
+        hws.CountCNN, hws.HWWithStyle.insert_spaces, hws.CharStyleEncoder = state["f34"]
         _lib.RETAIN_SAVED = False
         sys.path[:] = saved_path
         if saved_ds is not None: sys.modules["datasets"] = saved_ds
@@ -275,5 +286,10 @@ def test_reference_trainer_curriculum_cycle_runs_on_the_drop_ins(golden_dir, hwg
             "hwg_hwr_stem_bwd_image", "hwg_norm_bwd_apply"} <= lesson2
     assert "discriminatorLoss" in cycle[3] and "discriminatorLoss" in cycle[6] and "perceptualLoss" in cycle[5]
     assert "countLoss" in cycle[7], cycle[7]
+    assert any(n.startswith("down.0.") for n in changed_style) and any(n.startswith("char_extractor.") for n in changed_style)
+    assert any(n.startswith("prep.") for n in changed_style) and len(changed_style) >= 40, len(changed_style)
+    changed_spacer = [n for n, p in model.spacer.named_parameters() if not torch.equal(p.detach(), before_spacer[n])]
+    assert len(changed_spacer) >= 14, changed_spacer          # the 'count' lesson stepped the spacer
+    assert {"hwg_insert_spaces_plan", "hwg_insert_spaces_fill", "hwg_shift_expand"} <= set(calls)
     for it, lg in cycle.items():
         assert all(np.isfinite(v) for k, v in lg.items() if isinstance(v, float)), (it, lg)
