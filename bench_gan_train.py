@@ -599,6 +599,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         line["config"]["peer_exchange_timeouts"] = peer_fault      # 0 = every in-kernel exchange completed
     if world == 1:
         # free the product's memory, then the two baselines of the same step
+        pkg_ = pkg
         del graphed, st, gen, hwr, opt, train, devsets
         torch.cuda.empty_cache()
         if not os.environ.get("HWG_BENCH_NO_GPU_BASELINE"):
@@ -620,6 +621,14 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
                 line["extra_workloads"].update(quick_step_b16(dev))
             except Exception as e:   # never lose the headline over the extras
                 line["extra_workloads"] = {"error": repr(e)}
+            try:   # the curriculum's 7-lesson cycle with every module on the drop-ins, driven eagerly (bench_cycle.py)
+                import bench_cycle
+                torch.cuda.empty_cache()
+                line["extra_workloads"].update(bench_cycle.measure(dev, 16, cycles=4, warmup=2))
+            except Exception as e:   # noqa: BLE001
+                line["extra_workloads"]["cycle_B16"] = {"error": repr(e)[:300]}
+            finally:
+                pkg_.set_retain_graph(False)
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

@@ -48,4 +48,7 @@ for n, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out[n] = {"launches": v[0], "us": round(v[1], 1), "dram_read_mb": round(v[2] / 1e6, 2), "dram_write_mb": round(v[3] / 1e6, 2)}
 print('TOTAL %d launches, %.1f us, read %.1f MB, write %.1f MB' % (len(window), tot[0], tot[1] / 1e6, tot[2] / 1e6))
 if len(sys.argv) > 3:
-    json.dump({"launches_per_step": len(window), "total_us": round(tot[0], 1), "kernels": out}, open(sys.argv[3], 'w'), indent=1)
+    meta = dict(a.split("=", 1) for a in sys.argv[4:])         # e.g. batch=128 step=balanced
+    if "batch" in meta:
+        meta["batch"] = int(meta["batch"])
+    json.dump(dict(meta, launches_per_step=len(window), total_us=round(tot[0], 1), kernels=out), open(sys.argv[3], 'w'), indent=1)
