@@ -3,7 +3,7 @@
 // do not already cover: the residual addition with the GroupNorm statistics of the sum, and the L1 loss between the two
 // halves of a feature tensor with its gradient.  NHWC bf16, 16-byte vectors of 8 channels, fp32 arithmetic; every kernel's
 // roofline is HBM (operands read once, result written once).
-// STATUS: written after round 1's GPU budget was spent — compiled for sm_100a, not yet run on a GPU.
+// GPU parity: tests/test_enc_gpu.py.
 #include "common.cuh"
 
 namespace hwg {

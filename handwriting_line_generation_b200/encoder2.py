@@ -2,10 +2,8 @@
 `Encoder2(32)`, trainer/hw_with_style_trainer.py:148-149) and the perceptual loss of the 'auto' lessons built on it
 (trainer :724-748) — SURVEY.md §8 row f1, second half.
 
-STATUS: written after round 1's GPU budget was spent.  Everything here is compiled / CPU-checked (state_dict contract,
-weight job tables against the CPU interpreter), but the module has NOT yet run on a GPU; its parity test against the
-reference goldens (tests/golden/enc.npz) is parked in tools/pending_test_enc_gpu.py until a B200 run is green.  Nothing
-in the bench or the other modules uses it.
+GPU parity against the goldens of the unmodified reference: tests/test_enc_gpu.py; the module runs inside bench.py's
+headline step (the perceptual loss of the 'auto' lesson).
 
 Same constructor signature, module names, construction order (same seed -> same initial weights) and `state_dict` keys
 as the reference.  The torch sub-modules are parameter containers; the forward runs on libhwg_b200:

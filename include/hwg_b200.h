@@ -493,7 +493,7 @@ int hwg_spectral_norm_bwd(const void* jobs_dev, int njobs, int64_t max_elems, co
  * Perceptual encoder (reference model/autoencoder.py:341-410 `Encoder2`; SURVEY.md 8 row f1, second half) and the
  * perceptual loss built on it (trainer/hw_with_style_trainer.py:740-748).  The convolutions, GroupNorm, AvgPool2d and
  * Dropout2d + ReLU passes are the discriminator's entry points above; these two are what they do not cover.
- * Status: written after round 1's GPU budget was spent — compiled, not yet run on a GPU.
+ * GPU parity: tests/test_enc_gpu.py (goldens of the unmodified reference).
  * ---------------------------------------------------------------------- */
 /* The residual additions `x = self.conv1(x); x += res` (autoencoder.py:400-401, :404-405): y = a + b on NHWC bf16
  * [N,HW,C] (C in {16,32,64,128,256}; y may alias a or b) and, when stats != NULL (fp32 [N,C,2], zeroed by the caller),
@@ -515,7 +515,7 @@ int hwg_l1_halves(const void* f, int dtype, int64_t half_numel, float loss_scale
  * pred [T,B,C] fp32 contiguous; label int32, element (s,b) at label[s*label_stride_s + b*label_stride_b];
  * hist [B,T,L] bytes and scratch [B,T+L] int32 are workspaces; out [T+L,B] int32 (the caller zero-fills it: rows past
  * out_len[b] are the reference's zero padding), out_len [B].  One CTA per sequence, 2S+2 <= 1024.
- * Status: written after round 1's GPU budget was spent — compiled, not yet run on a GPU. */
+ * Bit-exact against the reference's alignments: tests/test_dtw_gpu.py. */
 int hwg_dtw_align(const float* pred, int T, int B, int C, const int32_t* label, int64_t label_stride_s,
                   int64_t label_stride_b, int S, uint8_t* hist, int32_t* out, int32_t* out_len, int32_t* scratch,
                   void* stream);
