@@ -21,6 +21,7 @@ _SIGNATURES = {
     "hwg_last_error": (ctypes.c_char_p, []),
     "hwg_launch_count": (ctypes.c_uint64, []),
     "hwg_last_conv_kernel": (c_int, []),
+    "hwg_last_wgrad_kernel": (c_int, []),
     "hwg_ctc_forward": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
                                 c_int, c_vp, c_vp, c_vp, c_vp]),
     "hwg_ctc_reduce_mean": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),

@@ -46,6 +46,7 @@ struct ConvKParams {
   int unit_bytes;        // bytes of one (tap, chunk) slot inside a stage: a_bytes (+ b_bytes unless wstat)
   int tmem_cols, acc_stride;
   int cpad;              // floats reserved per staged per-channel vector
+  int epi_stage;         // 1: bf16 output rows go through a per-warp shared-memory tile and leave as whole 32-byte sectors
   int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
   long long ysn, ysh, ysw;
   long long zsn, zsh, zsw;
@@ -127,7 +128,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* bias_s = reinterpret_cast<float*>(wsmem + (p.wstat ? (size_t)kiters * p.b_bytes : 0));  // [cpad]
   float* nw_s = bias_s + p.cpad;                                                    // [cpad]
   float* stat_all = nw_s + p.cpad;                                                  // [2 groups][256][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat_all + 1024);
+  uint4* stg_all = reinterpret_cast<uint4*>(stat_all + 1024);                       // [8 warps][32 rows][4 x 16 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 8 * 128);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -309,6 +311,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const unsigned long long nseed = p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull);
     const uint2 nkey0 = noise_key(nseed, p.noise_subseq);
     int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
+    // staged stores (p.epi_stage): a thread's 32-channel chunk of ITS row is 64 bytes, and a warp-wide 16-byte store of
+    // 32 different rows touches 32 sectors half-way (ncu, round 2: 235 MB sent to L2 for a 117 MB output, tensor pipe
+    // 30 % active on the 64-channel layers whose epilogue is as long as their main loop).  The chunk goes through a
+    // per-warp swizzled tile instead and leaves as 8 rows x 64 contiguous bytes per instruction: lane l writes piece
+    // l & 3 of row 8*i + (l >> 2).
+    uint4* const stg = stg_all + (warp - 2) * 128;
+    int s_hl[4], s_wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int mi = q * 32 + 8 * i + (lane >> 2);
+      s_hl[i] = mi / p.TW; s_wl[i] = mi - s_hl[i] * p.TW;
+    }
     int ti = 0;
     for (int t = t_begin; t < t_end; ++t, ++ti) {
       if (ngrp == 2 && (ti & 1) != grp) continue;
@@ -435,7 +449,37 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] -= lse;
         }
-        if (valid) {
+        if (!y_f32 && p.epi_stage) {
+          const int sx = (lane >> 1) & 3;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            if (jj * 8 < nc) {
+              const int j = jj * 8;
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              stg[lane * 4 + (jj ^ sx)] = pk;
+            }
+          }
+          __syncwarp();
+          const int jq = lane & 3;
+          if (jq * 8 < nc) {
+            __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + (long long)n * p.ysn + n0 + c0 + jq * 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2);
+              const int ho_i = th_i * p.TH + s_hl[i], wo_i = tw_i * p.TW + s_wl[i];
+              if (ho_i < p.Ho && wo_i < p.Wo)
+                *reinterpret_cast<uint4*>(yb + (long long)ho_i * p.ysh + (long long)wo_i * p.ysw) =
+                    stg[r * 4 + (jq ^ ((r >> 1) & 3))];
+            }
+          }
+          __syncwarp();
+        } else if (valid) {
           if (y_f32) {
             float* yp = reinterpret_cast<float*>(p.y) + yoff + c0;
             if (nc == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
@@ -575,6 +619,7 @@ static ConvKernel pick_kernel(const ConvKParams& p) {
   if (!f && nz == 0 && !st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 0, 0>;
   if (!f && nz == 0 && st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 1, 0>;
   if (!f && nz == 0 && !st && a == HWG_ACT_RELU) return conv_fprop_kernel<HWG_ACT_RELU, 0, 0, 0>;
+  if (!f && nz == 0 && !st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 0, 0, 0>;
   if (!f && nz == 2 && st && a == HWG_ACT_LRELU && p.BN <= 32) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 2, 0>;
   if (!f && nz == 2 && st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 1, 0>;
   if (f && nz == 0 && !st && a == HWG_ACT_LOGSOFTMAX) return conv_fprop_kernel<HWG_ACT_LOGSOFTMAX, 0, 0, 1>;
@@ -585,6 +630,8 @@ static ConvKernel pick_kernel_halo(const ConvKParams& p) {
   if (!f && nz == 0 && !st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 0, 0, true>;
   if (!f && nz == 0 && st && a == HWG_ACT_NONE) return conv_fprop_kernel<HWG_ACT_NONE, 0, 1, 0, true>;
   if (!f && nz == 0 && !st && a == HWG_ACT_RELU) return conv_fprop_kernel<HWG_ACT_RELU, 0, 0, 0, true>;
+  if (!f && nz == 0 && !st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 0, 0, 0, true>;
+  if (!f && nz == 2 && st && a == HWG_ACT_LRELU) return conv_fprop_kernel<HWG_ACT_LRELU, 2, 1, 0, true>;
   return conv_fprop_kernel<-1, -1, -1, -1, true>;
 }
 
@@ -671,7 +718,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
       const int hw = 8 + h_dw_max - h_dw_min;
       const int bb = round_up(p.BN * 64 * 2, 1024);
       const int kit = d->ntaps * (d->Cin / 64);
-      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + 16384 + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
       const size_t wall = (size_t)kit * bb;
       h_wstat = (p.n_tiles == 1 && wall <= 144 * 1024) ? 1 : 0;
       const size_t avail = 200 * 1024 - fx - (h_wstat ? wall : 0);
@@ -706,7 +753,12 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
   const int kiters = p.ntaps * p.kchunks;
   p.cpad = round_up(d->Cout, 32) + 32;
-  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+  // per-channel vectors, statistics scratch, the epilogue warps' staging tiles (8 x 2 KiB), barriers, alignment slack
+  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + 16384 + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+  static const bool epi_stage_off = getenv("HWG_CONV_EPI_STAGE") != nullptr && atoi(getenv("HWG_CONV_EPI_STAGE")) == 0;
+  p.epi_stage = (!epi_stage_off && d->y_dtype == HWG_DT_BF16 && !d->fold_c && d->Cout % 8 == 0 && p.BN % 8 == 0 &&
+                 d->y_stride_w % 8 == 0 && d->y_stride_h % 8 == 0 && d->y_stride_n % 8 == 0 &&
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
   // Small layers: keep every weight tile resident (one load per CTA) and put several (tap, chunk) operand
   // tiles behind one mbarrier round trip, so the single-thread producer / MMA loops are not the bottleneck.
   // development override (next experiment): HWG_CONV_WSTAT_KB raises the residency limit, e.g. 80 makes

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hwg {
 using namespace sm100;
@@ -56,9 +57,12 @@ __device__ __forceinline__ uint32_t swz(uint32_t pix, uint32_t chunk) {
   return o ^ (((o >> 7) & (PITCH / 16u - 1u)) << 4);
 }
 
-// MT = Cout/16, NT = Cin/8, TPW = taps per warp
-template <int MT, int NT, int TPW>
-__global__ void __launch_bounds__(512)
+// MT = Cout/16, NT = Cin/8, TPW = taps per warp, MINB = resident CTAs per SM the register budget is cut for.
+// Occupancy decides here (ncu, round 2: the <1,2,9> launch held 8 warps per SM — 12 % — with 44 % of the stalls on
+// fixed-latency dependencies and 23 % on ldmatrix results): the MINB = 2 variants give a warp fewer taps (24-32
+// accumulator registers instead of 72-96), so that two CTAs of 12-16 warps fit an SM.
+template <int MT, int NT, int TPW, int MINB>
+__global__ void __launch_bounds__(512, MINB)
 wgrad_small_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ WgSmallParams p) {
   constexpr int PA = MT * 32, PB = NT * 16;  // bytes per pixel of gy / x in shared memory
@@ -248,41 +252,61 @@ int wgrad_small_try(const hwgWgradDesc* d, const void* x, const void* gy, float*
   p.Cout = d->Cout; p.Cin = d->Cin; p.ntaps = d->ntaps;
   p.Hi = Hi; p.Wi = Wi; p.gsh = gsh; p.gsw = gsw; p.goh = d->gy_off_h; p.gow = d->gy_off_w;
   p.dh_min = dh_min; p.dw_min = dw_min;
-  p.TJ = Wi >= 64 ? 64 : (Wi > 16 ? 32 : 16);
-  // tile rows: keep a stage near 40-60 KB
+  const int MT = d->Cout / 16, NT = d->Cin / 8;
+  static const int variant_env = getenv("HWG_WGS_VARIANT") ? atoi(getenv("HWG_WGS_VARIANT")) : 1;   // development A/B switch
   const int pa = d->Cout * 2, pb = d->Cin * 2;
-  int TI = 8;
-  auto stage_bytes_for = [&](int ti, int* gb) {
-    const int g = ((ti * gsh) * (p.TJ * gsw) * pa + 1023) / 1024 * 1024;
-    const int xb = ((ti + dh_max - dh_min) * (p.TJ + dw_max - dw_min) * pb + 1023) / 1024 * 1024;
-    if (gb) *gb = g;
-    return g + xb;
+  const int nred_bytes = d->ntaps * d->Cout * d->Cin * 4;
+  WgsKernel k = nullptr;
+  int ctas_per_sm = 1;
+  // variant 1: few taps per warp, two CTAs per SM; variant 0: all accumulators of a tap group in one warp, one CTA
+  // per SM (also the fall-back when two CTAs' stages do not fit next to the reduction tiles)
+  auto configure = [&](int variant) -> bool {
+    int TPW;
+    if (variant == 0) {
+      ctas_per_sm = 1;
+      if (MT == 1 && NT == 2) { TPW = 9; k = wgrad_small_kernel<1, 2, 9, 1>; }
+      else if (MT == 1 && NT == 4) { TPW = 4; k = wgrad_small_kernel<1, 4, 4, 1>; }
+      else if (MT == 2 && NT == 2) { TPW = 4; k = wgrad_small_kernel<2, 2, 4, 1>; }
+      else { TPW = 3; k = wgrad_small_kernel<2, 4, 3, 1>; }
+    } else {
+      ctas_per_sm = 2;
+      if (MT == 1 && NT == 2) { TPW = 3; k = wgrad_small_kernel<1, 2, 3, 2>; }
+      else if (MT == 1 && NT == 4) { TPW = 2; k = wgrad_small_kernel<1, 4, 2, 2>; }
+      else if (MT == 2 && NT == 2) { TPW = 2; k = wgrad_small_kernel<2, 2, 2, 2>; }
+      else { TPW = 1; k = wgrad_small_kernel<2, 4, 1, 2>; }
+    }
+    p.TG = (d->ntaps + TPW - 1) / TPW;
+    if (p.TG > 16) return false;
+    p.KS = 16 / p.TG;
+    if (variant == 0 && p.KS > 8) p.KS = 8;
+    if (p.KS < 1) p.KS = 1;
+    p.TJ = Wi >= 64 ? 64 : (Wi > 16 ? 32 : 16);
+    auto stage_bytes_for = [&](int ti, int* gb) {
+      const int g = ((ti * gsh) * (p.TJ * gsw) * pa + 1023) / 1024 * 1024;
+      const int xb = ((ti + dh_max - dh_min) * (p.TJ + dw_max - dw_min) * pb + 1023) / 1024 * 1024;
+      if (gb) *gb = g;
+      return g + xb;
+    };
+    // two resident CTAs share the SM's shared memory: two stages of each must fit next to the reduction tile
+    const int per_cta = ctas_per_sm == 2 ? (220 * 1024) / 2 - nred_bytes - 2048 : 200 * 1024 - nred_bytes - 2048;
+    int stage_limit = 48 * 1024;   // a stage near 40-60 KB
+    if (ctas_per_sm == 2 && per_cta / 2 < stage_limit) stage_limit = per_cta / 2;
+    int TI = 8;
+    while (TI > 1 && (stage_bytes_for(TI, nullptr) > stage_limit || TI / 2 >= Hi)) TI >>= 1;
+    p.TI = TI;
+    p.stage_bytes = stage_bytes_for(TI, &p.g_bytes);
+    const int max_stages = ctas_per_sm == 2 ? 3 : 4;
+    p.stages = per_cta / p.stage_bytes;
+    if (p.stages > max_stages) p.stages = max_stages;
+    return p.stages >= 2;
   };
-  while (TI > 1 && (stage_bytes_for(TI, nullptr) > 48 * 1024 || TI / 2 >= Hi)) TI >>= 1;
-  p.TI = TI;
-  p.stage_bytes = stage_bytes_for(TI, &p.g_bytes);
+  if (!((variant_env != 0 && configure(1)) || configure(0))) return -1;
   p.gbox_w = p.TJ * gsw; p.xbox_w = p.TJ + dw_max - dw_min;
   p.tiles_j = (Wi + p.TJ - 1) / p.TJ;
   p.tiles_i = (Hi + p.TI - 1) / p.TI;
   p.total_tiles = p.tiles_i * p.tiles_j * d->N;
-  const int nred_bytes = d->ntaps * d->Cout * d->Cin * 4;
-  p.stages = (int)((200 * 1024 - nred_bytes - 2048) / p.stage_bytes);
-  if (p.stages > 4) p.stages = 4;
-  if (p.stages < 2) return -1;
   // expect_tx counts the full boxes (zero-filled parts included)
   p.tx_bytes = (p.TI + dh_max - dh_min) * p.xbox_w * pb + (p.TI * gsh) * p.gbox_w * pa;
-
-  const int MT = d->Cout / 16, NT = d->Cin / 8;
-  int TPW; WgsKernel k;
-  if (MT == 1 && NT == 2) { TPW = 9; k = wgrad_small_kernel<1, 2, 9>; }
-  else if (MT == 1 && NT == 4) { TPW = 4; k = wgrad_small_kernel<1, 4, 4>; }
-  else if (MT == 2 && NT == 2) { TPW = 4; k = wgrad_small_kernel<2, 2, 4>; }
-  else { TPW = 3; k = wgrad_small_kernel<2, 4, 3>; }
-  p.TG = (d->ntaps + TPW - 1) / TPW;
-  if (p.TG > 16) return -1;
-  p.KS = 16 / p.TG;
-  if (p.KS > 8) p.KS = 8;
-  if (p.KS < 1) p.KS = 1;
   p.dw = dw;
 
   CUtensorMap tmg, tmx;
@@ -292,7 +316,7 @@ int wgrad_small_try(const hwgWgradDesc* d, const void* x, const void* gy, float*
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 64 + nred_bytes + 1024;
   HWG_SMEM_OPTIN(k);
-  int grid = wgs_sms();
+  int grid = wgs_sms() * ctas_per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
   k<<<grid, 32 * p.TG * p.KS, smem, (cudaStream_t)stream>>>(tmg, tmx, p);
   return check_launch("wgrad_small_kernel");

@@ -278,6 +278,11 @@ typedef struct hwgWgradDesc {
 } hwgWgradDesc;
 
 int hwg_conv_wgrad(const hwgWgradDesc* desc, const void* x, const void* gy, float* dw, void* stream);
+/* Which kernel served the most recent hwg_conv_wgrad call: 0 = wgrad_small_kernel (staged tiles + mma.sync, Cout and
+ * Cin in {16, 32}), 1 = conv_wgrad_kernel (tcgen05, split-K, the gy tile of a pixel chunk staged once for a group of
+ * taps, one x box per tap), 2 = conv_wgrad_kernel in halo mode (one x box per chunk that covers every tap's shifted
+ * window; Cin a multiple of 64; development switch HWG_WGRAD_HALO=1, off by default: verified but measured slower).  For benchmarks / profiles. */
+int hwg_last_wgrad_kernel(void);
 
 /* ------------------------------------------------------------------------
  * Memory-bound backward passes of the recognizer (NHWC bf16 gradients).

@@ -24,6 +24,11 @@ CASES = [
     (2, 512, 80, 1, 28, (1, 3), (0, 0), (1, 1)),      # head at W=128: 26 frames, 2-row pixel chunks on H=1
     (2, 512, 512, 1, 26, (1, 3), (0, 8), (1, 8)),     # dilation wider than a chunk
     (2, 256, 512, 3, 32, (3, 3), (0, 0), (1, 1)),
+    # halo-mode tiles of conv_wgrad_kernel: 8x16 / 4x32 pixel chunks, several tap groups, ragged edges
+    (2, 64, 64, 16, 40, (3, 3), (1, 1), (1, 1)),
+    (3, 128, 64, 4, 50, (3, 3), (1, 1), (1, 1)),
+    (2, 64, 192, 11, 23, (3, 3), (1, 1), (1, 1)),
+    (1, 128, 128, 2, 70, (3, 3), (1, 1), (1, 1)),
 ]
 
 
@@ -50,6 +55,19 @@ def test_dgrad_and_wgrad_match_autograd(case):
     dw = conv.conv_wgrad(xc, gyc, taps, Cin, Cout)                     # [ntaps, Cout, Cin]
     got = dw.view(k[0], k[1], Cout, Cin).permute(2, 3, 0, 1).cpu().double()
     assert _rel(got, gw_ref) <= TOL, _rel(got, gw_ref)
+
+
+def test_wgrad_kernel_selection():
+    """Which kernel serves which shape (hwg_last_wgrad_kernel): staged tiles for 16/32 channels, the tcgen05 kernel with a
+    halo box of x for Cin % 64 == 0, one x box per tap otherwise."""
+    import os
+    from handwriting_line_generation_b200 import conv, _lib
+    want_halo = 1 if os.environ.get("HWG_WGRAD_HALO") == "1" else 0
+    for Cin, Cout, mode in [(16, 16, 0), (32, 32, 0), (64, 64, 1 + want_halo), (16, 64, 1), (128, 32, 1 + want_halo)]:
+        x = torch.randn(1, 12, 40, Cin, device="cuda").to(torch.bfloat16)
+        gy = torch.randn(1, 12, 40, Cout, device="cuda").to(torch.bfloat16)
+        conv.conv_wgrad(x, gy, conv.conv_taps(3, 3, 1, 1), Cin, Cout)
+        assert _lib.load().hwg_last_wgrad_kernel() == mode, (Cin, Cout)
 
 
 @pytest.mark.parametrize("case", [(2, 64, 32, 12, 40, (2, 2)), (1, 32, 16, 16, 64, (2, 2)), (2, 128, 64, 8, 50, (2, 1))])
