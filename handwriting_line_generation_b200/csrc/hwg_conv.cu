@@ -67,8 +67,6 @@ struct ConvKParams {
   // halo mode (HWG_CONV_HALO, default on for the eligible launches): the taps of a group are
   // read as SHIFTED VIEWS of one halo tile instead of one 16 KiB operand tile per tap.  TW = 8, TH = 16, CK = 64.
   int halo;              // 0: off
-  int halo_bo;           // 1: descriptors carry base_offset = (start >> 7) & 7 (tools/halo_probe.cu on B200: NOT needed, the
-                         //    swizzle follows the absolute shared-memory address; kept as HWG_CONV_HALO_BO for other parts)
   int hw_;               // halo tile width in pixels (TW + dw_max - dw_min)
   int ha_bytes;          // halo tile bytes, rounded up to 1 KiB;  ha_tx: bytes the TMA box transfers
   int ha_tx;
@@ -76,19 +74,11 @@ struct ConvKParams {
   int hgroups;           // tap groups per K chunk (1: full 2-D halo; one per kernel row otherwise)
   int dw_min;
   int hg_first[HWG_MAX_TAPS], hg_ntaps[HWG_MAX_TAPS], hg_dh[HWG_MAX_TAPS];   // per group: first tap, taps, box row origin
+  // per tap, for the MMA issuer: start of the tap's shifted view inside its halo tile (16-byte units), index of the tap
+  // inside its group (its weight tile in the stage); bit t of hg_mask: tap t opens a group
+  int h_aoff[HWG_MAX_TAPS], h_bsub[HWG_MAX_TAPS];
+  unsigned hg_mask;
 };
-
-// K-major SWIZZLE_128B descriptor of a shifted view into a halo tile: rows of 128 bytes, 8-row groups `sbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_view128(uint32_t start, uint32_t sbo, uint32_t use_bo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((start & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  if (use_bo) d |= (uint64_t)((start >> 7) & 7u) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // Sum over the 32 lanes of 32 per-lane values: afterwards lane l holds sum over lanes of v[l].
 // Recursive halving: 31 shuffles instead of 32*5.
@@ -165,32 +155,33 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t a_tx = (uint32_t)(128 * p.CK * 2), b_tx = (uint32_t)(p.BN * p.CK * 2);
-      if (p.wstat) {
-        // weight-stationary: every (tap, chunk) weight tile of this CTA's channel tile, once
-        const int n0w = (t_begin / p.tiles_m) * p.BN;   // wstat implies a single channel tile
-        mbar_expect_tx(w_bar, b_tx * (uint32_t)kiters);
-        int tp = 0, kc = 0;
-        for (int it = 0; it < kiters; ++it) {
-          tma_load_2d(wsmem + (size_t)it * p.b_bytes, &tmap_w, w_bar, kc * p.CK, tp * p.Cout + n0w);
-          if (++kc == p.kchunks) { kc = 0; ++tp; }
-        }
+    // ===== TMA producer: the whole warp walks the loop, the elected lane issues =====
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t a_tx = (uint32_t)(128 * p.CK * 2), b_tx = (uint32_t)(p.BN * p.CK * 2);
+    if (p.wstat && leader) {
+      // weight-stationary: every (tap, chunk) weight tile of this CTA's channel tile, once
+      const int n0w = (t_begin / p.tiles_m) * p.BN;   // wstat implies a single channel tile
+      mbar_expect_tx(w_bar, b_tx * (uint32_t)kiters);
+      int tp = 0, kc = 0;
+      for (int it = 0; it < kiters; ++it) {
+        tma_load_2d(wsmem + (size_t)it * p.b_bytes, &tmap_w, w_bar, kc * p.CK, tp * p.Cout + n0w);
+        if (++kc == p.kchunks) { kc = 0; ++tp; }
       }
-      const uint32_t unit_tx = a_tx + (p.wstat ? 0u : b_tx);
-      for (int t = t_begin; t < t_end; ++t) {
-        const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
-        const int tw_i = pt % p.tiles_w, r = pt / p.tiles_w;
-        const int th_i = r % p.tiles_h, n = r / p.tiles_h;
-        const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH, n0 = nt * p.BN;
-        if constexpr (HALO_T) {
-          // one halo tile (+ the group's weight tiles) per (K chunk, tap group)
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int g = 0; g < p.hgroups; ++g) {
-              const int gtaps = p.hg_ntaps[g];
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
+    }
+    const uint32_t unit_tx = a_tx + (p.wstat ? 0u : b_tx);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int nt = t / p.tiles_m, pt = t - nt * p.tiles_m;
+      const int tw_i = pt % p.tiles_w, r = pt / p.tiles_w;
+      const int th_i = r % p.tiles_h, n = r / p.tiles_h;
+      const int wo0 = tw_i * p.TW, ho0 = th_i * p.TH, n0 = nt * p.BN;
+      if constexpr (HALO_T) {
+        // one halo tile (+ the group's weight tiles) per (K chunk, tap group)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < p.hgroups; ++g) {
+            const int gtaps = p.hg_ntaps[g];
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (leader) {
               unsigned char* dst = smem + (size_t)stage * stage_bytes;
               mbar_expect_tx(&full_bar[stage], (uint32_t)p.ha_tx + (p.wstat ? 0u : b_tx * (uint32_t)gtaps));
               tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 + p.dw_min, ho0 + p.hg_dh[g], n);
@@ -198,91 +189,124 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 for (int j = 0; j < gtaps; ++j)
                   tma_load_2d(dst + p.ha_bytes + (size_t)j * p.b_bytes, &tmap_w, &full_bar[stage], kc * p.CK,
                               (p.hg_first[g] + j) * p.Cout + n0);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          continue;
         }
-        int tp = 0, kc = 0, it = 0;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const int nsub = min(p.gsize, kiters - it);
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          unsigned char* dst = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], unit_tx * (uint32_t)nsub);
-          for (int sub = 0; sub < nsub; ++sub, ++it) {
+        continue;
+      }
+      int tp = 0, kc = 0, it = 0;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int nsub = min(p.gsize, kiters - it);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        unsigned char* dst = smem + (size_t)stage * stage_bytes;
+        if (leader) mbar_expect_tx(&full_bar[stage], unit_tx * (uint32_t)nsub);
+        for (int sub = 0; sub < nsub; ++sub, ++it) {
+          if (leader) {
             tma_load_4d(dst, &tmap_x, &full_bar[stage], kc * p.CK, wo0 * p.isw + p.tap_dw[tp], ho0 * p.ish + p.tap_dh[tp], n);
             if (!p.wstat) tma_load_2d(dst + p.a_bytes, &tmap_w, &full_bar[stage], kc * p.CK, tp * p.Cout + n0);
-            dst += p.unit_bytes;
-            if (++kc == p.kchunks) { kc = 0; ++tp; }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          dst += p.unit_bytes;
+          if (++kc == p.kchunks) { kc = 0; ++tp; }
         }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
-      const uint32_t row_bytes = (uint32_t)p.CK * 2u;
-      const int kk_n = p.CK / 16;
-      int stage = 0; uint32_t phase = 0;
-      int ti = 0;
-      if (p.wstat) { mbar_wait(w_bar, 0); tc_fence_after(); }
-      const uint32_t w_addr = smem_u32(wsmem);
+    // ===== MMA issuer: the whole warp walks the loop, the elected lane issues =====
+    // The issuing lane is the serial resource of the layers with N <= 128: an MMA of N = 64 occupies the tensor pipe
+    // for ~32-48 cycles, and the round-1 loop spent ~17 dependent uniform-datapath instructions (~120 cycles) on each:
+    // a 64-bit descriptor rebuilt from the tap tables in constant memory per tap, 64-bit adds per K step and the
+    // compiler's vote / elect / branch loop around every tcgen05.mma issued under `if (lane == 0)` (ncu, round 2:
+    // tensor pipe 30 % active at N = 64, 49 % at N = 128, ~60-88 % at N = 256, epilogue warps idle in their mbarrier wait).
+    // Now: descriptor high words are loop constants, low words are start addresses in 16-byte units advanced with
+    // 32-bit adds, and the per-tap offsets of the halo views come from a host-made table held in registers.
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    const uint32_t row_bytes = (uint32_t)p.CK * 2u;
+    const uint32_t hi_k = umma_desc_hi(8u * row_bytes, row_bytes);      // dense K-major operand tiles (A and B)
+    const int kk_n = p.CK / 16;
+    int stage = 0; uint32_t phase = 0;
+    int ti = 0;
+    if (p.wstat) { mbar_wait(w_bar, 0); tc_fence_after(); }
+    const uint32_t w_lo = umma_desc_lo(smem_u32(wsmem));
+    const uint32_t b16 = (uint32_t)p.b_bytes >> 4, a16 = (uint32_t)p.a_bytes >> 4, u16 = (uint32_t)p.unit_bytes >> 4;
+    const uint32_t ring_lo = umma_desc_lo(smem_u32(smem));
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+    if constexpr (HALO_T) {
+      const uint32_t hi_a = umma_desc_hi((uint32_t)p.hw_ * 128u, 128u);   // shifted view: 8-row groups one halo row apart
+      const uint32_t ha16 = (uint32_t)p.ha_bytes >> 4;
+      uint32_t aoff[HWG_MAX_TAPS], bsub[HWG_MAX_TAPS];
+#pragma unroll
+      for (int j = 0; j < HWG_MAX_TAPS; ++j) { aoff[j] = (uint32_t)p.h_aoff[j]; bsub[j] = (uint32_t)p.h_bsub[j] * b16; }
+      const uint32_t gmask = p.hg_mask;
       for (int t = t_begin; t < t_end; ++t, ++ti) {
         const int a = ti & 1;
         mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
-        if constexpr (HALO_T) {
-          uint32_t acc = 0u;
-          const uint32_t sbo = (uint32_t)p.hw_ * 128u;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            for (int g = 0; g < p.hgroups; ++g) {
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-              for (int j = 0; j < p.hg_ntaps[g]; ++j) {
-                const int tp = p.hg_first[g] + j;
-                // MMA row (ty, tx) reads halo pixel (ty + dh - origin, tx + dw - dw_min): shifted start, group stride
-                // = one halo row
-                const uint32_t start = a_addr + (uint32_t)(((p.tap_dh[tp] - p.hg_dh[g]) * p.hw_ +
-                                                            (p.tap_dw[tp] - p.dw_min)) * 128);
-                const uint64_t da = umma_desc_view128(start, sbo, (uint32_t)p.halo_bo);
-                const uint64_t db = umma_desc_kmajor(p.wstat ? w_addr + (uint32_t)((tp * p.kchunks + kc) * p.b_bytes)
-                                                             : a_addr + (uint32_t)(p.ha_bytes + j * p.b_bytes), 128u);
-                for (int kk = 0; kk < 4; ++kk) {
-                  umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, acc);
-                  acc = 1u;
+        uint32_t acc = 0u;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          uint32_t a_base = 0u;
+#pragma unroll
+          for (int j = 0; j < HWG_MAX_TAPS; ++j) {
+            if (j < p.ntaps) {
+              if ((gmask >> j) & 1u) {       // tap j opens a tap group = a pipeline stage
+                if (j > 0) {
+                  if (leader) umma_commit(&empty_bar[stage]);
+                  if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                a_base = ring_lo + (uint32_t)stage * stage16;
               }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              // MMA row (ty, tx) reads halo pixel (ty + dh - origin, tx + dw - dw_min): shifted start address
+              const uint32_t a_lo = a_base + aoff[j];
+              const uint32_t b_lo = p.wstat ? w_lo + (uint32_t)(j * p.kchunks + kc) * b16 : a_base + ha16 + bsub[j];
+              if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_a, b_lo + 2u * kk, hi_k, idesc, kk == 0 ? acc : 1u);
+              }
+              acc = 1u;
             }
           }
-          umma_commit(&tmem_full[a]);
-          continue;
+          if (leader) umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (leader) umma_commit(&tmem_full[a]);
+      }
+    } else {
+      for (int t = t_begin; t < t_end; ++t, ++ti) {
+        const int a = ti & 1;
+        mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
         int it = 0;
         for (int g = 0; g < p.ngroups; ++g) {
           const int nsub = min(p.gsize, kiters - it);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+          uint32_t a_lo = ring_lo + (uint32_t)stage * stage16;
           for (int sub = 0; sub < nsub; ++sub, ++it) {
-            const uint64_t da = umma_desc_kmajor(a_addr, row_bytes);
-            const uint64_t db = umma_desc_kmajor(p.wstat ? w_addr + (uint32_t)(it * p.b_bytes)
-                                                         : a_addr + (uint32_t)p.a_bytes, row_bytes);
-            for (int kk = 0; kk < kk_n; ++kk) {
+            const uint32_t b_lo = p.wstat ? w_lo + (uint32_t)it * b16 : a_lo + a16;
+            if (leader) {
               // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
-              umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (it | kk) != 0 ? 1u : 0u);
+              if (kk_n == 4) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | kk) != 0 ? 1u : 0u);
+              } else {
+                for (int kk = 0; kk < kk_n; ++kk)
+                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | kk) != 0 ? 1u : 0u);
+              }
             }
-            a_addr += (uint32_t)p.unit_bytes;
+            a_lo += u16;
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (leader) umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full[a]);        // accumulator complete
+        if (leader) umma_commit(&tmem_full[a]);        // accumulator complete
       }
     }
   } else {
@@ -695,7 +719,6 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   // B200, 16 lines: discriminator convs1.3 60.7 -> 39.0 us (805 TFLOP/s), convs2.0 100.9 -> 79.9 us, whole step -3 %
   // (profiles/README.md, round 2); numerics: the conv / discriminator / recognizer parity tests run in this mode.
   static const int halo_env = [] { const char* e = getenv("HWG_CONV_HALO"); return e ? atoi(e) : 1; }();
-  static const int halo_bo_env = getenv("HWG_CONV_HALO_BO") != nullptr ? 1 : 0;
   int halo_mode = 0, h_dh_min = 0, h_dh_max = 0, h_dw_min = 0, h_dw_max = 0, h_wstat = 0, h_maxrow = 0;
   if (halo_env > 0 && d->Cin % 64 == 0 && d->in_stride_h <= 1 && d->in_stride_w <= 1 && d->ntaps >= 2 && !d->fold_c &&
       d->Ho >= 12 && d->Wo >= 8) {     // overrides a caller's tile_w: the halo tile is always 8 x 16
@@ -787,7 +810,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   if (p.stages < 2) p.stages = 2;
   if (halo_mode) {
     // stage = one halo tile (+ the weight tiles of its tap group unless the weights are resident); one CTA per SM
-    p.halo = 1; p.halo_bo = halo_bo_env;
+    p.halo = 1;
     p.wstat = h_wstat;
     wbytes = p.wstat ? (size_t)kiters * p.b_bytes : 0;
     p.hw_ = 8 + h_dw_max - h_dw_min;
@@ -804,6 +827,14 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
           p.hg_first[p.hgroups] = t; p.hg_ntaps[p.hgroups] = 0; p.hg_dh[p.hgroups] = d->tap_dh[t]; ++p.hgroups;
         }
         ++p.hg_ntaps[p.hgroups - 1];
+      }
+    }
+    for (int g = 0; g < p.hgroups; ++g) {
+      p.hg_mask |= 1u << p.hg_first[g];
+      for (int j = 0; j < p.hg_ntaps[g]; ++j) {
+        const int t = p.hg_first[g] + j;
+        p.h_aoff[t] = (((d->tap_dh[t] - p.hg_dh[g]) * p.hw_ + (d->tap_dw[t] - p.dw_min)) * 128) >> 4;
+        p.h_bsub[t] = j;
       }
     }
     const int gmax = halo_mode == 2 ? d->ntaps : h_maxrow;

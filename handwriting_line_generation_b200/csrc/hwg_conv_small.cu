@@ -66,7 +66,10 @@ constexpr int CS_WARPS = 8;
 // CIN input channels, NTF 8-channel n-tiles per fold, F folds, MB 16-pixel m-tiles per warp pass, STATS: per-(n,c)
 // statistics.  Two CTAs per SM (<= 128 registers): the per-element epilogue is latency-bound, so resident warps
 // matter more than the size of a warp's register tile.
-template <int CIN, int NTF, int F, int MB, int STATS>
+// ACT_T / NOISE_T >= 0 fix the epilogue's activation / noise mode at compile time (-1: runtime values of CsParams):
+// the epilogue is ~2/3 of this kernel's instructions, and with every option behind a runtime branch the 16 -> 16
+// instantiation was 8192 SASS instructions with 23 % of its stall samples on instruction fetch (ncu, round 2).
+template <int CIN, int NTF, int F, int MB, int STATS, int ACT_T = -1, int NOISE_T = -1>
 __global__ void __launch_bounds__(CS_WARPS * 32, 2)
 conv_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CsParams p) {
@@ -124,6 +127,8 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint2 nkey = noise_key(p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull), p.noise_subseq);
   constexpr bool has_stats = STATS != 0;
   constexpr int NS = STATS ? NT : 1;
+  const int act = ACT_T >= 0 ? ACT_T : p.act;
+  const int noise_mode = NOISE_T >= 0 ? NOISE_T : p.noise_mode;
 
   float s1[NS][2], s2[NS][2];   // per-thread statistics of the current image (channels 8*nt + 2tq, +1)
 #pragma unroll
@@ -221,7 +226,7 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // pair index of (this pixel, channel 2tq) in the logical [N,Ho,Wo,Cf] output of a fold
           const unsigned long long pair0 =
               (((unsigned long long)n * p.Ho + ho) * p.Wo + wo) * (unsigned long long)half_cf + tq;
-          const float* zpix = p.noise_mode == 1
+          const float* zpix = noise_mode == 1
               ? p.noise + ((long long)n * p.zsn + (long long)ho * p.zsh + (long long)wo * p.zsw) + 2 * tq : nullptr;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
@@ -230,17 +235,17 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const int c = f * p.Cf + q * 8 + 2 * tq;   // channel in the launch (bias / noise weight index)
             const float2 bb = *reinterpret_cast<const float2*>(bias_s + c);
             float v0 = acc[a][nt][2 * h] + bb.x, v1 = acc[a][nt][2 * h + 1] + bb.y;
-            if (p.noise_mode == 2) {
+            if (noise_mode == 2) {
               const float2 z = normal_pair(nkey, pair0 + 4 * q);
               const float2 ww = *reinterpret_cast<const float2*>(nw_s + c);
               v0 = fmaf(ww.x, z.x, v0); v1 = fmaf(ww.y, z.y, v1);
-            } else if (p.noise_mode == 1) {
+            } else if (noise_mode == 1) {
               if (valid) {
                 v0 = fmaf(nw_s[c], zpix[f * p.Cf + q * 8], v0); v1 = fmaf(nw_s[c + 1], zpix[f * p.Cf + q * 8 + 1], v1);
               }
             }
-            if (p.act == HWG_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            else if (p.act == HWG_ACT_LRELU) { v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope); }
+            if (act == HWG_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            else if (act == HWG_ACT_LRELU) { v0 = fmaxf(v0, v0 * p.slope); v1 = fmaxf(v1, v1 * p.slope); }
             if (valid) {
               *reinterpret_cast<__nv_bfloat162*>(ypix + fold_off[f] + q * 8) = __floats2bfloat162_rn(v0, v1);
               if constexpr (STATS != 0) {
@@ -303,10 +308,17 @@ int conv_small_try(const hwgConvDesc* d, const void* x, const void* w, const flo
   CsKernel k = nullptr; int MB = 0;
   const int cin = d->Cin;
   const bool st = stats != nullptr;
+  // the two epilogues the train step uses get their own instantiations: generator forward (in-kernel noise + LeakyReLU +
+  // statistics) and plain (input gradients, up-sampling convolutions)
+  const int nmode = noise_w ? (noise ? 1 : 2) : 0;
+  const bool gen_fwd = st && nmode == 2 && d->act == HWG_ACT_LRELU;
+  const bool plain = !st && nmode == 0 && d->act == HWG_ACT_NONE;
 #define CS_PICK(CI, NF, FF, MBS, MBN)                                                              \
   if (cin == CI && NTF == NF && F == FF) {                                                         \
-    if (st) { k = conv_small_kernel<CI, NF, FF, MBS, 1>; MB = MBS; }                               \
-    else { k = conv_small_kernel<CI, NF, FF, MBN, 0>; MB = MBN; }                                  \
+    if (st) { k = gen_fwd ? conv_small_kernel<CI, NF, FF, MBS, 1, HWG_ACT_LRELU, 2>                \
+                          : conv_small_kernel<CI, NF, FF, MBS, 1>; MB = MBS; }                     \
+    else { k = plain ? conv_small_kernel<CI, NF, FF, MBN, 0, HWG_ACT_NONE, 0>                      \
+                     : conv_small_kernel<CI, NF, FF, MBN, 0>; MB = MBN; }                          \
   }
   CS_PICK(16, 2, 1, 4, 4)    // 16 -> 16  (block 4 conv2 and its input gradient)
   CS_PICK(16, 4, 1, 2, 4)    // 16 -> 32  (input gradient of block 4's FusedUpsample, stride 2)

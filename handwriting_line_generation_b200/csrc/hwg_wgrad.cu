@@ -39,19 +39,8 @@ struct WgradKParams {
   float* dw;
 };
 
-// MN-major operand made of TMA boxes {CB channels, pixels}: a pixel row is CB*2 = 128/64/32 bytes (the
-// swizzle span), 8-pixel groups are 8 rows apart (SBO), CB-channel blocks `lbo_bytes` apart (LBO).
-__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t row_bytes, uint32_t lbo_bytes) {
-  const uint32_t mode = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)mode << 61;
-  return d;
-}
-
+// MN-major operands made of TMA boxes {CB channels, pixels}: a pixel row is CB*2 = 128/64/32 bytes (the swizzle span),
+// 8-pixel groups are 8 rows apart (SBO), CB-channel blocks one box apart (LBO): sm100::umma_desc_lo / umma_desc_hi.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -110,16 +99,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
   if (kiters <= 0 || ntap <= 0) {
     // nothing to do for this split (grid rounded up); still release TMEM below
   } else if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)nblk_a * boxa_bytes +
-                          (p.halo ? (uint32_t)(nblk_b * p.hb_w * p.hb_h * p.CBb * 2)
-                                  : (uint32_t)(ntap * nblk_b) * boxb_bytes);
-      for (int c = c_begin; c < c_end; ++c) {
-        const int wc = c % p.chunks_w, r = c / p.chunks_w;
-        const int hc = r % p.chunks_h, n = r / p.chunks_h;
-        const int w0 = wc * p.PW, h0 = hc * p.PH;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // TMA producer: the whole warp walks the loop, the elected lane issues (see sm100::elect_one)
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx = (uint32_t)nblk_a * boxa_bytes +
+                        (p.halo ? (uint32_t)(nblk_b * p.hb_w * p.hb_h * p.CBb * 2)
+                                : (uint32_t)(ntap * nblk_b) * boxb_bytes);
+    for (int c = c_begin; c < c_end; ++c) {
+      const int wc = c % p.chunks_w, r = c / p.chunks_w;
+      const int hc = r % p.chunks_h, n = r / p.chunks_h;
+      const int w0 = wc * p.PW, h0 = hc * p.PH;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (leader) {
         unsigned char* a_dst = ring + (size_t)stage * stage_bytes;
         unsigned char* b_dst = a_dst + p.a_bytes;
         mbar_expect_tx(&full_bar[stage], tx);
@@ -136,53 +127,70 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_cons
               tma_load_4d(b_dst + (size_t)(t * nblk_b + b) * boxb_bytes, &tmap_x, &full_bar[stage], ci0 + p.CBb * b,
                           w0 + p.tap_dw[tap0 + t], h0 + p.tap_dh[tap0 + t], n);
         }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN) | (1u << 15) | (1u << 16);
-      const uint32_t rowa = (uint32_t)p.CBa * 2u, rowb = (uint32_t)p.CBb * 2u;
-      const int segs = p.PW >> 4;           // halo mode: 16-pixel K steps per tile row
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < kiters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
-        const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
-        const uint64_t da = umma_desc_mnmajor(a_addr, rowa, boxa_bytes);
-        if (p.halo) {
-          const uint64_t db = umma_desc_mnmajor(b_addr, rowb, (uint32_t)p.hb_bytes);
-          for (int t = 0; t < ntap; ++t) {
-            const int oh = p.tap_dh[tap0 + t] - p.dh_min, ow = p.tap_dw[tap0 + t] - p.dw_min;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.BN);
-            for (int i = 0; i < p.PH; ++i)
-              for (int sgm = 0; sgm < segs; ++sgm) {
-                // K step = pixels (i, 16*sgm .. 16*sgm+15): rows i*PW + 16*sgm of the gy tile, rows
-                // (i+oh)*hb_w + 16*sgm + ow of the halo tile (the swizzle follows the absolute shared-memory
-                // address, so a view may start at any 128-byte row: tools/halo_probe.cu)
-                const uint32_t ra = (uint32_t)(i * p.PW + 16 * sgm);
-                const uint32_t rb = (uint32_t)((i + oh) * p.hb_w + 16 * sgm + ow);
-                umma_bf16(d_tmem, da + (uint64_t)((ra * rowa) >> 4), db + (uint64_t)((rb * rowb) >> 4), idesc,
-                          (it | i | sgm) != 0 ? 1u : 0u);
-              }
-          }
-        } else {
-          const int ksteps = p.pix >> 4;
-          for (int t = 0; t < ntap; ++t) {
-            const uint64_t db = umma_desc_mnmajor(b_addr + (uint32_t)(t * nblk_b) * boxb_bytes, rowb, boxb_bytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.BN);
-            // 16 pixels = two 8-row groups = 16 rows further into the box (start address is in 16-byte units)
-            for (int kk = 0; kk < ksteps; ++kk)
-              umma_bf16(d_tmem, da + (uint64_t)(kk * (int)rowa), db + (uint64_t)(kk * (int)rowb), idesc,
-                        (it | kk) != 0 ? 1u : 0u);
+    // MMA issuer: whole warp in the loop, elected lane issues; descriptors as (lo, hi) words, only the start-address
+    // field of the low words moves (see hwg_conv.cu: the issuing lane is the serial resource of the small-N layers)
+    const bool leader = elect_one();
+    // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN) | (1u << 15) | (1u << 16);
+    const uint32_t rowa = (uint32_t)p.CBa * 2u, rowb = (uint32_t)p.CBb * 2u;
+    const uint32_t hi_a = umma_desc_hi(8u * rowa, rowa), hi_b = umma_desc_hi(8u * rowb, rowb);
+    const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFFu) >> 4;
+    const uint32_t lbo_a = ((boxa_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t lbo_b = (((p.halo ? (uint32_t)p.hb_bytes : boxb_bytes) >> 4) & 0x3FFFu) << 16;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, a16 = (uint32_t)p.a_bytes >> 4;
+    const int segs = p.PW >> 4;           // halo mode: 16-pixel K steps per tile row
+    const int ksteps = p.pix >> 4;
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < kiters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_lo = (ring_lo + (uint32_t)stage * stage16) | lbo_a;
+      const uint32_t b_lo0 = (ring_lo + (uint32_t)stage * stage16 + a16) | lbo_b;
+      if (p.halo) {
+        for (int t = 0; t < ntap; ++t) {
+          const int oh = p.tap_dh[tap0 + t] - p.dh_min, ow = p.tap_dw[tap0 + t] - p.dw_min;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.BN);
+          for (int i = 0; i < p.PH; ++i)
+            for (int sgm = 0; sgm < segs; ++sgm) {
+              // K step = pixels (i, 16*sgm .. 16*sgm+15): rows i*PW + 16*sgm of the gy tile, rows
+              // (i+oh)*hb_w + 16*sgm + ow of the halo tile (the swizzle follows the absolute shared-memory
+              // address, so a view may start at any 128-byte row: tools/halo_probe.cu)
+              const uint32_t ra = (uint32_t)(i * p.PW + 16 * sgm);
+              const uint32_t rb = (uint32_t)((i + oh) * p.hb_w + 16 * sgm + ow);
+              if (leader)
+                umma_bf16_lh(d_tmem, a_lo + ((ra * rowa) >> 4), hi_a, b_lo0 + ((rb * rowb) >> 4), hi_b, idesc,
+                             (it | i | sgm) != 0 ? 1u : 0u);
+            }
+        }
+      } else {
+        const uint32_t tap16 = (uint32_t)nblk_b * (boxb_bytes >> 4);
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t b_lo = b_lo0 + (uint32_t)t * tap16;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.BN);
+          // 16 pixels = two 8-row groups = 16 rows further into the box (start address is in 16-byte units)
+          if (leader) {
+            if (ksteps == 4) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16_lh(d_tmem, a_lo + (uint32_t)kk * rowa, hi_a, b_lo + (uint32_t)kk * rowb, hi_b, idesc,
+                             (it | kk) != 0 ? 1u : 0u);
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16_lh(d_tmem, a_lo + (uint32_t)kk * rowa, hi_a, b_lo + (uint32_t)kk * rowb, hi_b, idesc,
+                             (it | kk) != 0 ? 1u : 0u);
+            }
           }
         }
+      }
+      if (leader) {
         umma_commit(&empty_bar[stage]);
         if (it == kiters - 1) umma_commit(tmem_full);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else {
     const int q = warp & 3;

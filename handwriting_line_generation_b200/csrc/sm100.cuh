@@ -89,6 +89,36 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, descriptors given as (lo, hi) 32-bit halves: only the 14-bit start-address field of the low word changes between
+// the MMAs of a main loop, so the issuing lane keeps the high words in registers and advances the low words with 32-bit
+// adds (a 64-bit descriptor rebuilt per MMA was ~17 dependent uniform-datapath instructions per MMA: ncu, round 2).
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// low / high word of a K-major (or MN-major: pass the LBO) shared-memory matrix descriptor, see umma_desc_kmajor below
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 16u) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t swizzle_row_bytes) {
+  const uint32_t mode = swizzle_row_bytes == 128 ? 2u : (swizzle_row_bytes == 64 ? 4u : 6u);
+  return (sbo_bytes >> 4) | (1u << 14) | (mode << 29);
+}
+// One lane of a converged warp (the CUTLASS elect_one_sync idiom): code that every lane of the warp walks and in which
+// only the elected lane issues TMA / tcgen05 instructions compiles to a predicated uniform-datapath instruction; the same
+// instruction under `if (lane == 0)` is wrapped by the compiler in a vote / elect / branch loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
