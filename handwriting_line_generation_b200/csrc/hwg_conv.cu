@@ -46,7 +46,6 @@ struct ConvKParams {
   int unit_bytes;        // bytes of one (tap, chunk) slot inside a stage: a_bytes (+ b_bytes unless wstat)
   int tmem_cols, acc_stride;
   int cpad;              // floats reserved per staged per-channel vector
-  int epi_stage;         // 1: bf16 output rows go through a per-warp shared-memory tile and leave as whole 32-byte sectors
   int tap_dh[HWG_MAX_TAPS], tap_dw[HWG_MAX_TAPS];
   long long ysn, ysh, ysw;
   long long zsn, zsh, zsw;
@@ -96,6 +95,22 @@ __device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// NT taps x 4 K steps of one halo stage as straight-line code (no per-tap branches: the issuing lane's dependent chain
+// per tap — table look-up, address adds, vector -> uniform register moves — then overlaps across taps).  Tap j reads the
+// shifted view a_base + aoff[j0 + j] and the weight tile b_base + j * b_stride (16-byte units).
+template <int NT>
+__device__ __forceinline__ void issue_halo_taps(uint32_t d_tmem, uint32_t a_base, const uint32_t (&aoff)[HWG_MAX_TAPS], int j0,
+                                                uint32_t b_base, uint32_t b_stride, uint32_t hi_a, uint32_t hi_b,
+                                                uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const uint32_t a_lo = a_base + aoff[j0 + j], b_lo = b_base + (uint32_t)j * b_stride;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_a, b_lo + 2u * kk, hi_b, idesc, (j | kk) != 0 ? 1u : acc0);
+  }
+}
+
 // named barrier of one 128-thread epilogue group (ids 1 and 2; 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
@@ -118,8 +133,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* bias_s = reinterpret_cast<float*>(wsmem + (p.wstat ? (size_t)kiters * p.b_bytes : 0));  // [cpad]
   float* nw_s = bias_s + p.cpad;                                                    // [cpad]
   float* stat_all = nw_s + p.cpad;                                                  // [2 groups][256][2]
-  uint4* stg_all = reinterpret_cast<uint4*>(stat_all + 1024);                       // [8 warps][32 rows][4 x 16 B]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_all + 8 * 128);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stat_all + 1024);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -240,12 +254,51 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
       for (int j = 0; j < HWG_MAX_TAPS; ++j) { aoff[j] = (uint32_t)p.h_aoff[j]; bsub[j] = (uint32_t)p.h_bsub[j] * b16; }
       const uint32_t gmask = p.hg_mask;
+      // the two shapes every 3x3 layer takes: one stage of nine taps, or three stages of one kernel row each
+      const int fast = (p.ntaps == 9 && p.hgroups == 1) ? 1
+                     : (p.ntaps == 9 && p.hgroups == 3 && p.hg_ntaps[0] == 3 && p.hg_ntaps[1] == 3) ? 2 : 0;
+      const uint32_t b_stride = p.wstat ? (uint32_t)p.kchunks * b16 : b16;
       for (int t = t_begin; t < t_end; ++t, ++ti) {
         const int a = ti & 1;
         mbar_wait(&tmem_empty[a], (uint32_t)(((ti >> 1) & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_stride);
         uint32_t acc = 0u;
+        if (fast == 1) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = ring_lo + (uint32_t)stage * stage16;
+            const uint32_t b_base = p.wstat ? w_lo + (uint32_t)kc * b16 : a_base + ha16;
+            if (leader) {
+              issue_halo_taps<9>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc);
+              umma_commit(&empty_bar[stage]);
+            }
+            acc = 1u;
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          if (leader) umma_commit(&tmem_full[a]);
+          continue;
+        }
+        if (fast == 2) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_base = ring_lo + (uint32_t)stage * stage16;
+              const uint32_t b_base = p.wstat ? w_lo + (uint32_t)(3 * g * p.kchunks + kc) * b16 : a_base + ha16;
+              if (leader) {
+                issue_halo_taps<3>(d_tmem, a_base, aoff, 3 * g, b_base, b_stride, hi_a, hi_k, idesc, acc);
+                umma_commit(&empty_bar[stage]);
+              }
+              acc = 1u;
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (leader) umma_commit(&tmem_full[a]);
+          continue;
+        }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           uint32_t a_base = 0u;
 #pragma unroll
@@ -287,22 +340,28 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const int nsub = min(p.gsize, kiters - it);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          uint32_t a_lo = ring_lo + (uint32_t)stage * stage16;
-          for (int sub = 0; sub < nsub; ++sub, ++it) {
-            const uint32_t b_lo = p.wstat ? w_lo + (uint32_t)it * b16 : a_lo + a16;
-            if (leader) {
-              // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
-              if (kk_n == 4) {
+          const uint32_t a_lo0 = ring_lo + (uint32_t)stage * stage16;
+          if (leader) {
+            // advancing K inside the swizzle span = +32 bytes on the start address (>>4 -> +2)
+            if (kk_n == 4) {
+#pragma unroll 3
+              for (int sub = 0; sub < nsub; ++sub) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)sub * u16;
+                const uint32_t b_lo = p.wstat ? w_lo + (uint32_t)(it + sub) * b16 : a_lo + a16;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | kk) != 0 ? 1u : 0u);
-              } else {
+                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | sub | kk) != 0 ? 1u : 0u);
+              }
+            } else {
+              for (int sub = 0; sub < nsub; ++sub) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)sub * u16;
+                const uint32_t b_lo = p.wstat ? w_lo + (uint32_t)(it + sub) * b16 : a_lo + a16;
                 for (int kk = 0; kk < kk_n; ++kk)
-                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | kk) != 0 ? 1u : 0u);
+                  umma_bf16_lh(d_tmem, a_lo + 2u * kk, hi_k, b_lo + 2u * kk, hi_k, idesc, (it | sub | kk) != 0 ? 1u : 0u);
               }
             }
-            a_lo += u16;
           }
+          it += nsub;
           if (leader) umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -335,18 +394,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const unsigned long long nseed = p.noise_seed + (p.noise_seed_dev ? *p.noise_seed_dev : 0ull);
     const uint2 nkey0 = noise_key(nseed, p.noise_subseq);
     int stat_n = -1, stat_n0 = 0;  // key of the statistics currently held in stat_s
-    // staged stores (p.epi_stage): a thread's 32-channel chunk of ITS row is 64 bytes, and a warp-wide 16-byte store of
-    // 32 different rows touches 32 sectors half-way (ncu, round 2: 235 MB sent to L2 for a 117 MB output, tensor pipe
-    // 30 % active on the 64-channel layers whose epilogue is as long as their main loop).  The chunk goes through a
-    // per-warp swizzled tile instead and leaves as 8 rows x 64 contiguous bytes per instruction: lane l writes piece
-    // l & 3 of row 8*i + (l >> 2).
-    uint4* const stg = stg_all + (warp - 2) * 128;
-    int s_hl[4], s_wl[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int mi = q * 32 + 8 * i + (lane >> 2);
-      s_hl[i] = mi / p.TW; s_wl[i] = mi - s_hl[i] * p.TW;
-    }
     int ti = 0;
     for (int t = t_begin; t < t_end; ++t, ++ti) {
       if (ngrp == 2 && (ti & 1) != grp) continue;
@@ -473,37 +520,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] -= lse;
         }
-        if (!y_f32 && p.epi_stage) {
-          const int sx = (lane >> 1) & 3;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            if (jj * 8 < nc) {
-              const int j = jj * 8;
-              uint4 pk;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-              pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-              stg[lane * 4 + (jj ^ sx)] = pk;
-            }
-          }
-          __syncwarp();
-          const int jq = lane & 3;
-          if (jq * 8 < nc) {
-            __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + (long long)n * p.ysn + n0 + c0 + jq * 8;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = 8 * i + (lane >> 2);
-              const int ho_i = th_i * p.TH + s_hl[i], wo_i = tw_i * p.TW + s_wl[i];
-              if (ho_i < p.Ho && wo_i < p.Wo)
-                *reinterpret_cast<uint4*>(yb + (long long)ho_i * p.ysh + (long long)wo_i * p.ysw) =
-                    stg[r * 4 + (jq ^ ((r >> 1) & 3))];
-            }
-          }
-          __syncwarp();
-        } else if (valid) {
+        if (valid) {
           if (y_f32) {
             float* yp = reinterpret_cast<float*>(p.y) + yoff + c0;
             if (nc == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
@@ -741,7 +758,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
       const int hw = 8 + h_dw_max - h_dw_min;
       const int bb = round_up(p.BN * 64 * 2, 1024);
       const int kit = d->ntaps * (d->Cin / 64);
-      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + 16384 + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
       const size_t wall = (size_t)kit * bb;
       h_wstat = (p.n_tiles == 1 && wall <= 144 * 1024) ? 1 : 0;
       const size_t avail = 200 * 1024 - fx - (h_wstat ? wall : 0);
@@ -776,12 +793,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
   const int kiters = p.ntaps * p.kchunks;
   p.cpad = round_up(d->Cout, 32) + 32;
-  // per-channel vectors, statistics scratch, the epilogue warps' staging tiles (8 x 2 KiB), barriers, alignment slack
-  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + 16384 + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
-  static const bool epi_stage_off = getenv("HWG_CONV_EPI_STAGE") != nullptr && atoi(getenv("HWG_CONV_EPI_STAGE")) == 0;
-  p.epi_stage = (!epi_stage_off && d->y_dtype == HWG_DT_BF16 && !d->fold_c && d->Cout % 8 == 0 && p.BN % 8 == 0 &&
-                 d->y_stride_w % 8 == 0 && d->y_stride_h % 8 == 0 && d->y_stride_n % 8 == 0 &&
-                 (reinterpret_cast<uintptr_t>(y) & 15) == 0) ? 1 : 0;
+  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
   // Small layers: keep every weight tile resident (one load per CTA) and put several (tap, chunk) operand
   // tiles behind one mbarrier round trip, so the single-thread producer / MMA loops are not the bottleneck.
   // development override (next experiment): HWG_CONV_WSTAT_KB raises the residency limit, e.g. 80 makes
