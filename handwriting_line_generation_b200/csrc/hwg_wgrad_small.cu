@@ -116,6 +116,22 @@ wgrad_small_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_con
   const int a_k = rr + 8 * (mi >> 1), a_chunk = mi & 1;   // A: matrices (k0-7,c0) (k0-7,c1) (k8-15,c0) (k8-15,c1)
   const int b_k = rr + 8 * (mi & 1), b_chunk = mi >> 1;   // B: matrices (k0-7,c0) (k8-15,c0) (k0-7,c1) (k8-15,c1)
   const int ksteps_j = p.TJ >> 4, ksteps = p.TI * ksteps_j;
+  const int kj_shift = ksteps_j == 4 ? 2 : (ksteps_j == 2 ? 1 : 0);   // TJ is 16, 32 or 64
+
+  // Per-warp tap constants, in registers: the round-2 profile of this loop showed ~140 instructions per K step for six
+  // MMAs — an integer division per step, four dynamically indexed constant loads and a full address rebuild per tap.
+  //   xoff: the tap's pixel offset inside the x halo box;  goff: its phase's pixel offset inside the gy box;
+  //   reload bit tt: tap tt reads gy at another phase than tap tt-1 (bit 0 always set)
+  int xoff[TPW], goff[TPW];
+  unsigned reload = 0u;
+  const int ntw = max(0, min(TPW, p.ntaps - tap0));
+#pragma unroll
+  for (int tt = 0; tt < TPW; ++tt) {
+    const int tap = min(tap0 + tt, p.ntaps - 1);
+    xoff[tt] = (p.tap_dh[tap] - p.dh_min) * p.xbox_w + (p.tap_dw[tap] - p.dw_min);
+    goff[tt] = p.tap_ph[tap] * p.gbox_w + p.tap_pw[tap];
+    if (tt == 0 || goff[tt] != goff[tt > 0 ? tt - 1 : 0]) reload |= 1u << tt;
+  }
 
   for (int it = 0; it < ntile; ++it) {
     const int s = it % p.stages;
@@ -126,22 +142,20 @@ wgrad_small_kernel(const __grid_constant__ CUtensorMap tmap_gy, const __grid_con
     const uint32_t g_base = smem_u32(smem + (size_t)s * p.stage_bytes);
     const uint32_t x_base = g_base + (uint32_t)p.g_bytes;
     for (int kq = ks; kq < ksteps; kq += p.KS) {
-      const int il = kq / ksteps_j, j0 = (kq - il * ksteps_j) << 4;
+      const int il = kq >> kj_shift, j0 = (kq & (ksteps_j - 1)) << 4;
       if (il >= i_lim) break;
+      const uint32_t gpix0 = (uint32_t)((il * p.gsh) * p.gbox_w + (j0 + a_k) * p.gsw);
+      const uint32_t xpix0 = (uint32_t)(il * p.xbox_w + j0 + b_k);
       uint32_t afr[MT][4];
-      int cur_ph = -1, cur_pw = -1;
 #pragma unroll
       for (int tt = 0; tt < TPW; ++tt) {
-        const int tap = tap0 + tt;
-        if (tap < p.ntaps) {
-          const int ph = p.tap_ph[tap], pw = p.tap_pw[tap];
-          if (ph != cur_ph || pw != cur_pw) {
-            cur_ph = ph; cur_pw = pw;
-            const uint32_t pix = (uint32_t)((il * p.gsh + ph) * p.gbox_w + (j0 + a_k) * p.gsw + pw);
+        if (tt < ntw) {
+          if ((reload >> tt) & 1u) {
+            const uint32_t pix = gpix0 + (uint32_t)goff[tt];
 #pragma unroll
             for (int m = 0; m < MT; ++m) ldsm_x4_trans(g_base + swz<PA>(pix, (uint32_t)(2 * m + a_chunk)), afr[m]);
           }
-          const uint32_t xpix = (uint32_t)((il + p.tap_dh[tap] - p.dh_min) * p.xbox_w + j0 + b_k + p.tap_dw[tap] - p.dw_min);
+          const uint32_t xpix = xpix0 + (uint32_t)xoff[tt];
 #pragma unroll
           for (int n2 = 0; n2 < NT / 2; ++n2) {
             uint32_t bfr[4];
