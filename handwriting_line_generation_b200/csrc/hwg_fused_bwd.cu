@@ -299,8 +299,10 @@ relu_maxpool_bwd_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ 
 // (windows wo = w and w+1, two outputs) — so every activation is read once per window that contains it by the thread
 // that needs it, with no per-pixel division chains or data-dependent loops.  First maximum in row-major scan order
 // wins, as in ATen's max_pool2d_with_indices.
+// three resident blocks per SM: the pass waits on its (up to eight) 16-byte loads per item (ncu, round 2: long_scoreboard 65 %,
+// 99 registers = two blocks), so resident warps are what it needs
 template <int MODE>
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, 3)
 relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ c, int N, int H, int W, int C,
                             int Ho, int Wo, uint4* __restrict__ gc, float* __restrict__ dbias) {
   extern __shared__ float sacc[];  // [1][C]
@@ -647,6 +649,61 @@ gen_output_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__
   for (int c = threadIdx.x; c <= C; c += blockDim.x) atomicAdd(&dwb[c], accs[c]);
 }
 
+// The same pass for C = 8*CV <= 32 channels (the generator's last block has 16) with the weight-gradient sums kept in
+// registers: a thread walks a strided set of pixels and adds gp * x_last[c] into its own C accumulators; the warps are
+// folded once per block.  The generic kernel above folds every channel of every pixel over the warp as it goes
+// (5 shuffles + a shared atomic per channel and pixel): 283 us for 555 MB at 128 lines (ncu, round 2: short_scoreboard 59 %).
+template <int CV>
+__global__ void __launch_bounds__(BW_THREADS)
+gen_output_bwd_acc_kernel(const float* __restrict__ g_out, const float* __restrict__ out, const uint4* __restrict__ a,
+                          const float* __restrict__ coef, const float* __restrict__ w, long long HW,
+                          uint4* __restrict__ gx, float* __restrict__ dwb) {
+  constexpr int C = CV * 8;
+  __shared__ float As[C], Bs[C], ws[C], red[C + 1];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    As[c] = coef[((size_t)n * C + c) * 2]; Bs[c] = coef[((size_t)n * C + c) * 2 + 1]; ws[c] = w[c];
+  }
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) red[c] = 0.f;
+  __syncthreads();
+  float dacc[C], sg = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) dacc[c] = 0.f;
+  const float* gon = g_out + (size_t)n * HW;
+  const float* on = out + (size_t)n * HW;
+  const uint4* an = a + (size_t)n * HW * CV;
+  uint4* gn = gx + (size_t)n * HW * CV;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += (long long)gridDim.x * blockDim.x) {
+    const float o = on[pix];
+    const float gp = gon[pix] * (1.f - o * o);
+    sg += gp;
+    uint4 av[CV];
+#pragma unroll
+    for (int v = 0; v < CV; ++v) av[v] = ldg_stream(an + pix * CV + v);
+#pragma unroll
+    for (int v = 0; v < CV; ++v) {
+      float af[8], o8[8];
+      unpack8b(av[v], af);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j;
+        o8[j] = ws[c] * gp;
+        dacc[c] = fmaf(gp, fmaf(As[c], af[j], Bs[c]), dacc[c]);
+      }
+      gn[pix * CV + v] = pack8b(o8);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float t = warp_sum(dacc[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[c], t);
+  }
+  sg = warp_sum(sg);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&red[C], sg);
+  __syncthreads();
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) atomicAdd(&dwb[c], red[c]);
+}
+
 // thread = (pooled pixel, 8-channel group): writes the four conv0-output gradients of its 2x2 window
 __global__ void __launch_bounds__(BW_THREADS)
 hwr_stem_bwd_expand_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
@@ -874,7 +931,7 @@ extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H,
     const int mode = sw == 2 ? 0 : 1;
     const long long items = (long long)N * ((H + 1) / 2) * (mode == 0 ? (W + 1) / 2 : W) * (C / 8);
     auto kern = mode == 0 ? relu_maxpool_bwd_win_kernel<0> : relu_maxpool_bwd_win_kernel<1>;
-    kern<<<bw_blocks_persistent(items, BW_THREADS * BW_ITER), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
+    kern<<<bw_blocks_persistent(items, BW_THREADS * BW_ITER, 1, 3), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(ga), reinterpret_cast<const uint4*>(c), N, H, W, C, Ho, Wo,
         reinterpret_cast<uint4*>(gc), dbias);
     return check_launch("relu_maxpool_bwd_win_kernel");
@@ -927,6 +984,21 @@ extern "C" int hwg_gen_output_bwd(const float* g_out, const float* out, const vo
                                   const float* w, int N, int64_t HW, int C, void* gx, float* dwb, void* stream) {
   HWG_REQUIRE(g_out && out && a && coef && w && gx && dwb && N > 0 && HW > 0 && C % 8 == 0,
               "hwg_gen_output_bwd: bad argument");
+  if (C == 16 || C == 32) {
+    // a few blocks per image, each thread keeping its sums over ~HW / (blocks x 256) pixels
+    long long bx = (148LL * 8 + N - 1) / N;
+    const long long need = bw_blocks(HW, BW_THREADS);
+    if (bx > need) bx = need;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, N);
+    if (C == 16)
+      gen_output_bwd_acc_kernel<2><<<grid, BW_THREADS, 0, (cudaStream_t)stream>>>(
+          g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, reinterpret_cast<uint4*>(gx), dwb);
+    else
+      gen_output_bwd_acc_kernel<4><<<grid, BW_THREADS, 0, (cudaStream_t)stream>>>(
+          g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, reinterpret_cast<uint4*>(gx), dwb);
+    return check_launch("gen_output_bwd_acc_kernel");
+  }
   dim3 grid(bw_blocks(HW, BW_THREADS), N);
   gen_output_bwd_kernel<<<grid, BW_THREADS, (size_t)(4 * C + 1) * sizeof(float), (cudaStream_t)stream>>>(
       g_out, out, reinterpret_cast<const uint4*>(a), coef, w, HW, C, reinterpret_cast<uint4*>(gx), dwb);
