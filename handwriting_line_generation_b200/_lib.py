@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhwg_b200.so")
+# HWG_LIB_PATH: development switch for same-box A/B timing of two builds of THIS library (tools/gpu_*.sh)
+LIB_PATH = os.environ.get("HWG_LIB_PATH") or os.path.join(_HERE, "lib", "libhwg_b200.so")
 _lib = None
 
 c_int, c_i64, c_vp, c_f = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float

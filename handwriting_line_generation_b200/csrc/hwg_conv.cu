@@ -255,7 +255,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int j = 0; j < HWG_MAX_TAPS; ++j) { aoff[j] = (uint32_t)p.h_aoff[j]; bsub[j] = (uint32_t)p.h_bsub[j] * b16; }
       const uint32_t gmask = p.hg_mask;
       // the two shapes every 3x3 layer takes: one stage of nine taps, or three stages of one kernel row each
-      const int fast = (p.ntaps == 9 && p.hgroups == 1) ? 1
+      const int fast = (p.ntaps >= 2 && p.ntaps <= 9 && p.hgroups == 1) ? 1
                      : (p.ntaps == 9 && p.hgroups == 3 && p.hg_ntaps[0] == 3 && p.hg_ntaps[1] == 3) ? 2 : 0;
       const uint32_t b_stride = p.wstat ? (uint32_t)p.kchunks * b16 : b16;
       for (int t = t_begin; t < t_end; ++t, ++ti) {
@@ -271,7 +271,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint32_t a_base = ring_lo + (uint32_t)stage * stage16;
             const uint32_t b_base = p.wstat ? w_lo + (uint32_t)kc * b16 : a_base + ha16;
             if (leader) {
-              issue_halo_taps<9>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc);
+              switch (p.ntaps) {      // straight-line code per tap count (3x3, the discriminator's 7x1 / 5x1 columns, ...)
+                case 9: issue_halo_taps<9>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 8: issue_halo_taps<8>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 7: issue_halo_taps<7>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 6: issue_halo_taps<6>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 5: issue_halo_taps<5>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 4: issue_halo_taps<4>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                case 3: issue_halo_taps<3>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+                default: issue_halo_taps<2>(d_tmem, a_base, aoff, 0, b_base, b_stride, hi_a, hi_k, idesc, acc); break;
+              }
               umma_commit(&empty_bar[stage]);
             }
             acc = 1u;
