@@ -139,6 +139,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint64_t* w_bar = tmem_empty + 2;             // resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  // per epilogue warp: a 32 x 16 fp32 tile through which the per-channel statistics are transposed (see below)
+  float* tr_all = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(tmem_slot) + 16 + 15) & ~static_cast<uintptr_t>(15));
 
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(p.total_tiles, t_begin + p.tiles_per_cta);
@@ -587,18 +590,38 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             ts1[j] += x; ts2[j] = fmaf(x, x, ts2[j]);
           }
         } else if (has_stats) {
-          // per-(n,c) sum and sum of squares over this warp's 32 pixels
-          float sq[32];
+          // per-(n,c) sum and sum of squares over this warp's 32 pixels: the chunk goes through a swizzled 32 x 16 shared
+          // memory tile, 16 columns at a time — a lane writes its row with four 16-byte stores and then sums half a column
+          // (16 independent loads), the two halves meet with one shuffle.  The butterfly reduction this replaces was
+          // 2 x 31 dependent shuffle / select / add steps per chunk and made the small-K layers epilogue-bound (ncu,
+          // round 2: the discriminator's in_conv, 7 MMAs per tile, ran at 7 % tensor-pipe activity).
+          float* tr = tr_all + (warp - 2) * 512;
+          const int wsw = (lane >> 1) & 3, hsel = lane >> 4, col = lane & 15;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = valid ? v[j] : 0.f;
-            sq[j] = v[j] * v[j];
-          }
-          const float s1 = butterfly_reduce32(v, lane);
-          const float s2 = butterfly_reduce32(sq, lane);
-          if (lane < nc) {
-            atomicAdd(&stat_s[2 * (c0 + lane)], s1);
-            atomicAdd(&stat_s[2 * (c0 + lane) + 1], s2);
+          for (int hf = 0; hf < 2; ++hf) {
+            if (hf * 16 < nc) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int j = hf * 16 + 4 * j4;
+                *reinterpret_cast<float4*>(&tr[lane * 16 + ((j4 ^ wsw) << 2)]) =
+                    valid ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              __syncwarp();
+              float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = hsel * 16 + (i ^ hsel);      // the upper half-warp walks its rows in the other parity order
+                const float x = tr[r * 16 + ((((col >> 2) ^ ((r >> 1) & 3))) << 2) + (col & 3)];
+                a1 += x; a2 = fmaf(x, x, a2);
+              }
+              a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+              a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+              __syncwarp();
+              if (lane < 16 && hf * 16 + lane < nc) {
+                atomicAdd(&stat_s[2 * (c0 + hf * 16 + lane)], a1);
+                atomicAdd(&stat_s[2 * (c0 + hf * 16 + lane) + 1], a2);
+              }
+            }
           }
         }
       }
@@ -767,7 +790,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
       const int hw = 8 + h_dw_max - h_dw_min;
       const int bb = round_up(p.BN * 64 * 2, 1024);
       const int kit = d->ntaps * (d->Cin / 64);
-      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+      const size_t fx = (size_t)(2 * (round_up(d->Cout, 32) + 32) + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 32 + 1024;
       const size_t wall = (size_t)kit * bb;
       h_wstat = (p.n_tiles == 1 && wall <= 144 * 1024) ? 1 : 0;
       const size_t avail = 200 * 1024 - fx - (h_wstat ? wall : 0);
@@ -802,7 +825,7 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
   p.b_bytes = round_up(p.BN * p.CK * 2, 1024);
   const int kiters = p.ntaps * p.kchunks;
   p.cpad = round_up(d->Cout, 32) + 32;
-  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 16 + 1024;
+  const size_t fixed = (size_t)(2 * p.cpad + 1024) * sizeof(float) + (2 * 8 + 5) * sizeof(uint64_t) + 32 + 1024;
   // Small layers: keep every weight tile resident (one load per CTA) and put several (tap, chunk) operand
   // tiles behind one mbarrier round trip, so the single-thread producer / MMA loops are not the bottleneck.
   // development override (next experiment): HWG_CONV_WSTAT_KB raises the residency limit, e.g. 80 makes
@@ -910,7 +933,10 @@ extern "C" int hwg_conv_fprop(const hwgConvDesc* d, const void* x, const void* w
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("hwg_conv_fprop: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return HWG_ERR_CUDA; }
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + wbytes + fixed;
+  // the statistics tiles of the epilogue warps (2 KiB each) live in the slack between the 200 KiB the stages are
+  // budgeted against and the 227 KiB a CTA may have
+  const size_t smem = (size_t)p.stages * stage_bytes + wbytes + fixed +
+                      (p.has_stats ? (size_t)(ctas_per_sm == 1 ? 8 : 4) * 2048 : 0);
   ConvKernel k = p.halo ? pick_kernel_halo(p) : pick_kernel(p);
   HWG_SMEM_OPTIN(k);
   // one CTA per SM: two epilogue groups (320 threads) so that both TMEM buffers drain concurrently

@@ -31,6 +31,10 @@ SHAPES = {
     "t_disc_convs2_0": (16, 26, 512, 128, 128, (3, 3, 0, 1), "lrelu"),
     "t_disc_convs3_0": (16, 12, 256, 128, 128, (3, 3, 0, 1), "stats"),
     "t_disc_convs3_4": (16, 5, 128, 128, 256, (3, 3, 0, 1), "none"),
+    # the discriminator's in_conv as the module runs it: 7 vertical taps over the 16 shifted copies of the image
+    "t_disc_in_conv": (16, 64, 1024, 16, 64, (7, 1, 0, 0), "stats"),
+    "t_disc_in_conv_plain": (16, 64, 1024, 16, 64, (7, 1, 0, 0), "none"),
+    "t_disc_in_conv_dgrad": (16, 64, 1024, 64, 16, (7, 1, 3, 0), "none"),
 }
 TILE_W = int(os.environ.get("HWG_CONV_TILE_W", "0"))
 which = [a for a in sys.argv[1:] if a in SHAPES] or ([] if sys.argv[1:] else list(SHAPES))
