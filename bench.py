@@ -178,7 +178,7 @@ def workload_config(B):
 def run_ours(args, rank, world, local_rank):
     import handwriting_line_generation_b200 as pkg
     from handwriting_line_generation_b200 import conv as hconv
-    from oracle import synth  # input builder only (numpy), not the checker
+    import bench_inputs as synth  # input builders (numpy)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (no CPU fallback exists)"
     torch.cuda.set_device(local_rank)

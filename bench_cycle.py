@@ -29,7 +29,7 @@ class GanCycle:
     def __init__(self, dev, B=16, a_batch=2, W=1024, L=40, C=80, seed=0):
         import handwriting_line_generation_b200 as pkg
         from handwriting_line_generation_b200 import dtw, spacing
-        from oracle import synth                       # input builders only (numpy)
+        import bench_inputs as synth                   # input builders (numpy)
         self.pkg, self.dev, self.B, self.a, self.W, self.L, self.C = pkg, dev, B, a_batch, W, L, C
         self.dtw, self.spacing = dtw, spacing
         torch.manual_seed(seed)

@@ -362,7 +362,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
     if args.impl == "reference":
         return run_reference(args, rank)
     from handwriting_line_generation_b200 import conv as hconv, dp, graphs
-    from oracle import synth   # input builders only (numpy)
+    import bench_inputs as synth   # input builders (numpy)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (no CPU fallback exists)"
     torch.cuda.set_device(local_rank)
@@ -651,7 +651,7 @@ def _time_graph(g, ins, steps):
 def quick_step_b16(dev, steps=20):
     """The same balanced step at 16 lines on one GPU — the per-GPU share of the 8-GPU strong-scaling point."""
     from handwriting_line_generation_b200 import graphs
-    from oracle import synth
+    import bench_inputs as synth
     B, Ts = 16, GAN["Ts"]
     st = GanStep(dev, B)
     content, style = synth.gen_case(Ts, B, GAN["C"], GAN["style"], 5)
@@ -672,7 +672,7 @@ def quick_gen_infer(dev, steps=20):
     """BASELINE configs[1] (generator inference, batch 32), device-timed graph replays."""
     import handwriting_line_generation_b200 as pkg
     from handwriting_line_generation_b200 import graphs
-    from oracle import synth
+    import bench_inputs as synth
     B, Ts = 32, GAN["Ts"]
     torch.manual_seed(0)
     gen = pkg.SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False,
@@ -697,7 +697,7 @@ def quick_disc_lesson(dev, steps=20):
     weights (tcgen05 wgrad, spectral-norm backward), clip + Adam on the discriminator; one replayed CUDA graph."""
     import handwriting_line_generation_b200 as pkg
     from handwriting_line_generation_b200 import graphs
-    from oracle import synth
+    import bench_inputs as synth
     B, Ts = 16, GAN["Ts"]
     torch.manual_seed(0)
     gen = pkg.SpacedGenerator(GAN["C"], GAN["style"], GAN["dim"], n_style_trans=6, emb_dropout=False,

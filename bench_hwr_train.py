@@ -69,7 +69,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
 
     import handwriting_line_generation_b200 as pkg
     from handwriting_line_generation_b200 import conv as hconv, dp
-    from oracle import synth
+    import bench_inputs as synth
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -218,7 +218,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
 # ----------------------------------------------------------------------------------------------------------
 def quick_train_numbers(dev, steps=10, gen_lesson=True):
     import handwriting_line_generation_b200 as pkg
-    from oracle import synth
+    import bench_inputs as synth
     out = {}
 
     from handwriting_line_generation_b200 import graphs

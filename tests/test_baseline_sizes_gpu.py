@@ -198,7 +198,7 @@ def test_gen_lesson_gradient_sets_at_line_size():
     recognizer, adversarial loss through the frozen discriminator; trainer :300-338) at 8 lines of 64x1024 px, against torch
     autograd over the fp32 oracle chain and over its bf16-storage emulation.  What decides these gradients is the bf16 rounding
     of the FORWARD activations (ReLU / LeakyReLU / max-pool decisions of 30+ stacked layers); rounding the gradients between
-    the layers is immaterial (tools/grad_sensitivity.py: 0.735 vs 0.737 on the trainer's own lesson).  Asserted: the CUDA sets
+    the layers is immaterial (tests/tools/grad_sensitivity.py: 0.735 vs 0.737 on the trainer's own lesson).  Asserted: the CUDA sets
     are as close to the fp32 gradient as the emulation is (cosine within 0.05, per-tensor rel-L2 <= emu + 2e-2 on the
     adversarial set), and the adversarial set is aligned with it to 0.99."""
     import handwriting_line_generation_b200 as pkg

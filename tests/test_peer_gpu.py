@@ -2,7 +2,7 @@
 
 On the one-GPU box the process group has world size 1: the kernels still run their full protocol against the rank's
 own mailbox (flagged stores, epoch counters, parity buffers, CUDA-graph replay), and hwg_bn_coeffs_peer must equal
-hwg_bn_coeffs.  With >= 2 GPUs visible the two-rank SyncBN parity check (tools/dp_syncbn_check.py: exchange vs NCCL,
+hwg_bn_coeffs.  With >= 2 GPUs visible the two-rank SyncBN parity check (tests/tools/dp_syncbn_check.py: exchange vs NCCL,
 sharded recognizer vs one process on the whole batch) is launched under torchrun."""
 import os
 import socket
@@ -99,6 +99,6 @@ def test_bn_coeffs_peer_equals_bn_coeffs(px, N, C, HW):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_syncbn_two_ranks_torchrun():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "dp_syncbn_check.py")]
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "tools", "dp_syncbn_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert "SYNCBN_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

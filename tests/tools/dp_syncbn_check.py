@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node 2 tools/dp_syncbn_check.py — SyncBN parity on two (or more) GPUs (development aid / evidence).
+"""torchrun --nproc-per-node 2 tests/tools/dp_syncbn_check.py — SyncBN parity on two (or more) GPUs (development aid / evidence).
 
 1. dp.PeerExchange.allreduce_ (hwg_peer_allreduce_f32, in-kernel NVLink exchange) against NCCL all_reduce on random
    vectors over many epochs (both parities of a slot, several slots), eager and replayed from a CUDA graph.
@@ -9,7 +9,7 @@ import copy
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 

@@ -1,6 +1,6 @@
 """Per-layer comparison of the CUDA generator with the CPU oracle (development aid)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import gen as ogen, synth
 from oracle.make_golden import GEN_CASES

@@ -1,9 +1,9 @@
 """Development aid (CPU, build container): what limits the fidelity of the generator gradients on the reference trainer s own
 'gen' lesson (tests/golden/trainer_gen.npz, 2 lines of 64x128 px) — bf16 rounding of the FORWARD activations (cosine 0.74 of
 the recognition set with the fp32 chain) and not of the gradients between the layers (0.735 with, 0.737 without gradient
-rounding); fp32 with inputs perturbed by 1e-3: 0.997.  python tools/grad_sensitivity.py"""
+rounding); fp32 with inputs perturbed by 1e-3: 0.997.  python tests/tools/grad_sensitivity.py"""
 import numpy as np, torch, sys
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from oracle import gen as ogen, hwr as ohwr, disc as odisc
 from tests.test_trainer_gen_cpu import build_inputs
 gold=np.load(__import__('os').path.join(sys.path[0],'tests','golden','trainer_gen.npz'))

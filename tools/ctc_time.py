@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import handwriting_line_generation_b200 as pkg
-from oracle import synth
+import bench_inputs as synth
 
 def timeit(fn, n=20, warm=5):
     for _ in range(warm): fn()

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 NP=${NPROC:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1"
 if [ -z "$SKIP_CHECK" ]; then
-  timeout 300 $TR --master-port 29513 tools/dp_syncbn_check.py > gpurun_out/syncbn_w2.log 2>&1; echo "w2 check exit $?"
+  timeout 300 $TR --master-port 29513 tests/tools/dp_syncbn_check.py > gpurun_out/syncbn_w2.log 2>&1; echo "w2 check exit $?"
   grep -v "^frame\|^\*\|OMP_NUM\|^$" gpurun_out/syncbn_w2.log | tail -${CHECK_TAIL:-14}
 fi
 export HWG_BENCH_NO_EXTRAS=1

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import handwriting_line_generation_b200 as pkg
-from oracle import synth
+import bench_inputs as synth
 B, W, S = int(os.environ.get("B", 8)), 1024, 60
 torch.manual_seed(0)
 m = pkg.CNNOnlyHWR(80, norm='batch').cuda().train()

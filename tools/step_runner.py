@@ -14,7 +14,7 @@ import torch
 
 import handwriting_line_generation_b200 as pkg
 from handwriting_line_generation_b200 import graphs
-from oracle import synth  # input builders only
+import bench_inputs as synth  # input builders (numpy)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workload")

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 import handwriting_line_generation_b200 as pkg
-from oracle import synth
+import bench_inputs as synth
 
 dev = torch.device("cuda", 0)
 B, Ts, C, S = 64, 512, 78, 120
