@@ -373,9 +373,11 @@ extern "C" int hwg_conv_wgrad(const hwgWgradDesc* d, const void* x, const void* 
     HWG_REQUIRE(p.tmem_cols <= 512, "hwg_conv_wgrad: %d accumulator columns", cols);
   }
   p.dw = dw;
-  // split the pixel range so that the grid covers the SMs ~2x
   const int units = p.tap_groups * p.co_tiles * p.ci_tiles;
-  int cta_target = 2 * 148;
+  // split the pixel range so that the grid covers the SMs ~2x — or once when there is little work: every CTA ends with
+  // 128 x BN x taps fp32 reductions into the arena, which at 16 lines per GPU cost as much as the operand stream
+  // (B200, 16 lines: step 7.29 -> 7.09 ms with one wave)
+  int cta_target = ((long long)p.total_chunks * (p.tap_groups * p.co_tiles * p.ci_tiles) >= 296LL * 16) ? 2 * 148 : 148;
   if (const char* ov = getenv("HWG_WGRAD_CTAS")) {   // development override (tools/step_runner.py sweeps)
     const int v = atoi(ov);
     if (v > 0) cta_target = v;
