@@ -2,7 +2,7 @@
 // The noise is generated inside the producing kernel's epilogue instead of being materialised in HBM
 // (a randn tensor costs 8 bytes of traffic per element next to the 2-byte bf16 activation).  On the
 // 16/32-channel layers the epilogue is instruction-bound, so the generator is built for few
-// instructions per sample: one 2x32-bit integer hash of (element pair index, seed, subsequence) feeds
+// instructions per sample: one 32-bit integer hash of (element pair index, seed, subsequence), stretched to 2x32 bits, feeds
 // one Box-Muller transform with 24-bit uniforms and the fast lg2/sin/cos units -> two normals for
 // ~27 instructions.  Any element can be generated independently (no state), so results do not depend
 // on the tiling.
@@ -24,14 +24,19 @@ __device__ __forceinline__ uint2 noise_key(unsigned long long seed, unsigned lon
 }
 
 // two independent standard normals for elements (2*pair, 2*pair+1)
+// Round 2: the passes that draw the noise are bound by instruction issue (ncu: 74-78 % issue activity, ~13 instructions per
+// element for the noise alone), so the generator was trimmed: the second 32-bit word is ONE odd multiply + xorshift of the
+// (already avalanched) first word instead of a second two-round hash, and the logarithm is lg2.approx.ftz (u1 >= 2^-25 is
+// never subnormal, so the compiler's denormal guard around __log2f was dead weight).
 __device__ __forceinline__ float2 normal_pair(uint2 key, unsigned long long pair) {
-  uint32_t x = fmix32(((uint32_t)pair ^ key.x) + (uint32_t)(pair >> 32) * 0x9E3779B1u);
+  const uint32_t x = fmix32(((uint32_t)pair ^ key.x) + (uint32_t)(pair >> 32) * 0x9E3779B1u);
   uint32_t y = (x ^ key.y) * 0x2C1B3C6Du;
-  y ^= y >> 15; y *= 0x297A2D39u; y ^= y >> 16;
+  y ^= y >> 16;
   const float u1 = fmaf((float)(x >> 8), 5.9604645e-8f, 2.9802322e-8f);   // (0,1): (k + 0.5) / 2^24
   const float ang = (float)(y >> 8) * 3.7450704e-7f;                       // 2*pi*k / 2^24
-  float r;                                                                 // sqrt(-2 ln u1), ln = lg2 * ln2
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862944f * __log2f(u1)));   // one MUFU op instead of the IEEE sequence
+  float l2, r;                                                             // sqrt(-2 ln u1), ln = lg2 * ln2
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862944f * l2));   // one MUFU op instead of the IEEE sequence
   float s, c;
   __sincosf(ang, &s, &c);
   return make_float2(r * c, r * s);

@@ -62,8 +62,6 @@ def _normals(key, idx):
     pair = idx >> np.uint64(1)
     x = _fmix32((((pair & _M32) ^ np.uint64(key[0])) + (pair >> np.uint64(32)) * np.uint64(0x9E3779B1)) & _M32)
     y = ((x ^ np.uint64(key[1])) * np.uint64(0x2C1B3C6D)) & _M32
-    y ^= y >> np.uint64(15)
-    y = (y * np.uint64(0x297A2D39)) & _M32
     y ^= y >> np.uint64(16)
     u1 = ((x >> np.uint64(8)).astype(np.float64) + 0.5) / 2 ** 24
     ang = (y >> np.uint64(8)).astype(np.float64) * (2 * np.pi / 2 ** 24)

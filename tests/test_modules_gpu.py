@@ -92,6 +92,12 @@ def test_inkernel_noise_is_standard_normal():
     z = y.flatten().double()
     assert abs(z.mean().item()) < 5e-3 and abs(z.var().item() - 1) < 1e-2
     assert abs((z ** 4).mean().item() - 3) < 0.1
+    assert abs((z ** 3).mean().item()) < 2e-2 and abs((z ** 6).mean().item() - 15) < 1.5
+    # the two normals of a Box-Muller pair (even / odd element), neighbouring pairs, |z| of the pair (shared radius)
+    a, b = z[0::2], z[1::2]
+    cc = lambda u, v: abs(torch.corrcoef(torch.stack([u, v]))[0, 1].item())
+    assert cc(a, b) < 5e-3 and cc(a[:-1], a[1:]) < 5e-3 and cc(a[:-1], b[1:]) < 5e-3
+    assert cc(a * a + b * b, torch.atan2(b, a)) < 5e-3          # radius vs angle of the pair: the two hash words
     y2 = conv.conv_fprop(x, w, conv.conv_taps(3, 3, 1, 1), H, W, noise_w=torch.ones(C, device="cuda"),
                          noise_seed=1234, noise_subseq=4, out_dtype=torch.float32)
     assert abs(torch.corrcoef(torch.stack([y.flatten(), y2.flatten()]))[0, 1].item()) < 1e-2
