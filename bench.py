@@ -3,12 +3,14 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Default workload (`--workload gan_train`, bench_gan_train.py) = BASELINE.json's metric: the HWWithStyle GAN "gen"
-lesson train step on the SURVEY 8(a) rows — generator fwd+bwd, frozen recognizer fwd + input-gradient bwd, CTC
-fwd+bwd, gradient all-reduce (N>1), Adam — 16 lines of 64x1024 px per GPU.
+Default workload (`--workload gan_train`, bench_gan_train.py) = BASELINE.json's metric on configs[2] / configs[3]: the
+reference's balanced optimizer step of the GAN curriculum (trainer :300-391, :724-748) — generator forward, frozen recognizer
++ CTC and frozen discriminator, the two losses back-propagated separately through the generator and stashed, second generator
+forward + Encoder2 perceptual loss, per-tensor gradient balancing, clip + Adam; gradient all-reduce at N > 1 — at a GLOBAL
+batch of 128 lines of 64x1024 px (strong scaling: 128 / N lines per GPU).
 `--workload gen_infer` (this file) = configs[1]: pure_gen generator inference, batch 32 per GPU, T_s=256;
 `--workload hwr_train` (bench_hwr_train.py) = configs[0]: recognizer + CTC train step, batch 8 per GPU.
-A "step" is one pass of that path over one batch of synthetic input.
+A "step" is one pass of that path over one batch of synthetic input (bench_inputs.py).
 
   value     lines/s with the inputs already resident in HBM (device-timed, CUDA events)
   e2e       the same through the public API (SpacedGenerator.forward) from pinned HOST buffers:
