@@ -35,6 +35,7 @@ _SIGNATURES = {
     "hwg_balance_chunk": (c_int, []),
     "hwg_balance": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     "hwg_shift_expand": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "hwg_stem_conv": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hwg_shift_collapse": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "hwg_gn_coeffs": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_f, c_vp, c_vp, c_vp]),
     "hwg_avgpool_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),

@@ -7,8 +7,9 @@ forward runs on libhwg_b200:
 
 * every spectral-normalised layer's power iteration in ONE launch (`hwg_spectral_norm`), every weight re-layout —
   tap-major bf16 forward and dgrad operands scaled by the fresh 1/sigma — in ONE `hwg_linear_map` launch;
-* `in_conv` (7x7, one input channel) as a 7-tap implicit GEMM over the 16-channel shift expansion of the image
-  (`hwg_shift_expand`), GroupNorm statistics from the convolution epilogue, GroupNorm + LeakyReLU as one scale-shift
+* `in_conv` (7x7, one input channel) by `hwg_stem_conv` straight from the fp32 image while the discriminator is frozen
+  (the 'gen' lessons); as a 7-tap implicit GEMM over the 16-channel shift expansion of the image (`hwg_shift_expand`)
+  when its weight gradient is needed; GroupNorm statistics from the convolution epilogue, GroupNorm + LeakyReLU as one scale-shift
   pass, all other convolutions on the tcgen05 kernel with bias + LeakyReLU epilogues, `hwg_avgpool_nhwc`,
   Dropout2d as a per-(sample, channel) scale fused with the LeakyReLU pass;
 * backward to the INPUT image (what the generator's adversarial loss needs, trainer/hw_with_style_trainer.py:810-821):
@@ -33,6 +34,7 @@ from . import _lib, conv, ops, weightmap
 from ._lib import ACT_LRELU, ACT_NONE
 
 LEAK = 0.1
+_NO_STEM = bool(__import__("os").environ.get("HWG_NO_STEM_CONV"))   # development A/B switch: shift-expansion route for in_conv
 
 
 def get_group_size(channels):
@@ -241,7 +243,7 @@ class DiscriminatorAP(nn.Module):
         outs, _ = self._forward_impl(x, keep=False)
         return outs
 
-    def _forward_impl(self, x, keep):
+    def _forward_impl(self, x, keep, need_wgrad=False):
         c = self._prepare()
         x = x.float().contiguous()
         B, _, H, W = x.shape
@@ -283,12 +285,20 @@ class DiscriminatorAP(nn.Module):
             _lib.call("hwg_avgpool_nhwc", a.data_ptr(), y.data_ptr(), N, Hh, Ww, C, kh, kw, _lib.stream())
             return y
 
-        x7 = torch.empty((B, H, W, 16), device=dev, dtype=torch.bfloat16)
-        _lib.call("hwg_shift_expand", x.data_ptr(), x7.data_ptr(), B, H, W, 7, 3, _lib.stream())
-        if keep:
-            ctx["x7"] = x7
         st = torch.zeros((B, dim, 2), device=dev, dtype=torch.float32)
-        z0 = cv(x7, "in_conv.0", [(dy, 0) for dy in range(7)], H - 6, W, stats=st)
+        if need_wgrad or dim != 64 or _NO_STEM:
+            # the 'disc' lesson needs the shift expansion as the x operand of in_conv's weight gradient
+            x7 = torch.empty((B, H, W, 16), device=dev, dtype=torch.bfloat16)
+            _lib.call("hwg_shift_expand", x.data_ptr(), x7.data_ptr(), B, H, W, 7, 3, _lib.stream())
+            if keep:
+                ctx["x7"] = x7
+            z0 = cv(x7, "in_conv.0", [(dy, 0) for dy in range(7)], H - 6, W, stats=st)
+        else:
+            # frozen discriminator ('gen' lessons, inference): the stem straight from the fp32 image (hwg_stem_conv reads
+            # the same packed [7][64][16] operand)
+            z0 = torch.empty((B, H - 6, W, dim), device=dev, dtype=torch.bfloat16)
+            _lib.call("hwg_stem_conv", x.data_ptr(), c["in_conv.0"].data_ptr(), c["bias"]["in_conv.0"][0].data_ptr(),
+                      B, H, W, 7, 7, 0, 3, dim, z0.data_ptr(), st.data_ptr(), _lib.stream())
         a = gn_lrelu(z0, st, self.in_conv[1], "gn0")                                  # [B,58,W,64]
         y1 = cv(a, "convs1.0", _T31, a.size(1) - 2, W, act=ACT_LRELU)               # [B,56,W,64]
         if keep:
@@ -507,7 +517,7 @@ class DiscriminatorAP(nn.Module):
         collect("convs1.0", a_in, gz)
         g = dgrad(gz, "convs1.0", a_in.size(1), a_in.size(2))              # [B,58,W,64]
         gz = gn_bwd(g, "gn0", self.in_conv[1], 1, 1, "in_conv.1")
-        collect("in_conv.0", ctx["x7"], gz)
+        collect("in_conv.0", ctx.get("x7"), gz)
         dimg = None
         if want_input:
             g7 = dgrad(gz, "in_conv.0", H, W)                              # [B,64,W,16]
@@ -532,7 +542,7 @@ class _DiscFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, m, names, x, *params):
         with torch.no_grad():
-            outs, saved = m._forward_impl(x, keep=True)
+            outs, saved = m._forward_impl(x, keep=True, need_wgrad=bool(names))
         ctx.m, ctx.names, ctx.saved = m, names, saved
         ctx.x_needs_grad = x.requires_grad
         return tuple(o.detach() for o in outs)       # detached aliases: no output -> node -> ctx -> output cycle

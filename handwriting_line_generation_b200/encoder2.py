@@ -8,8 +8,8 @@ headline step (the perceptual loss of the 'auto' lesson).
 Same constructor signature, module names, construction order (same seed -> same initial weights) and `state_dict` keys
 as the reference.  The torch sub-modules are parameter containers; the forward runs on libhwg_b200:
 
-* `down_conv1[0]` (5x5, ONE input channel, padding 2) as a 5-tap (dy, 0) implicit GEMM over the 16-channel shift
-  expansion of the image (`hwg_shift_expand`, the discriminator's in_conv trick), the other ten convolutions on
+* `down_conv1[0]` (5x5, ONE input channel, padding 2) by `hwg_stem_conv` straight from the fp32 image (round 1: a 5-tap
+  implicit GEMM over the 16-channel shift expansion of the image; its input gradient still is, with `hwg_shift_collapse`), the other ten convolutions on
   `hwg_conv_fprop` (staged-tile kernel for the 16/32-channel layers, tcgen05 for >= 64), the (6,3) head as two 9-tap
   launches (HWG_MAX_TAPS = 16);
 * GroupNorm statistics from the producing kernel's epilogue (`stats`) or from `hwg_add_stats` for the two residual sums,
@@ -27,6 +27,8 @@ as the reference.  The torch sub-modules are parameter containers; the forward r
 
 There is no PyTorch fallback."""
 import numpy as np
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -40,6 +42,7 @@ DROPOUT_SITES = (("conv1.2", 32, 0.1), ("conv2.0", 64, 0.1), ("conv2.4", 64, 0.1
 _T33 = conv.conv_taps(3, 3, 1, 1)          # 3x3, padding 1
 _T33V = conv.conv_taps(3, 3, 0, 0)         # 3x3, no padding
 _T11 = [(0, 0)]
+_NO_STEM = bool(os.environ.get("HWG_NO_STEM_CONV"))
 _T5 = [(dy - 2, 0) for dy in range(5)]     # rows of the 5x5 kernel; the columns are channels of the shift expansion
 
 
@@ -191,10 +194,15 @@ class Encoder2(nn.Module):
             return y
 
         # down_conv1 (:344-351): 5x5 conv -> GroupNorm -> ReLU -> AvgPool2d(2) -> 1x1 conv [-> the ReLU opening conv1]
-        x5 = torch.empty((N, H, W, 16), device=dev, dtype=torch.bfloat16)
-        _lib.call("hwg_shift_expand", x.data_ptr(), x5.data_ptr(), N, H, W, 5, 2, s())
         st = zstats(32)
-        z0 = cv(x5, "down_conv1.0", _T5, H, W, self.down_conv1[0], stats=st)                   # [N,64,W,32]
+        if _NO_STEM:       # development A/B switch: the round-1 route (5-tap implicit GEMM over the shift expansion)
+            x5 = torch.empty((N, H, W, 16), device=dev, dtype=torch.bfloat16)
+            _lib.call("hwg_shift_expand", x.data_ptr(), x5.data_ptr(), N, H, W, 5, 2, s())
+            z0 = cv(x5, "down_conv1.0", _T5, H, W, self.down_conv1[0], stats=st)
+        else:
+            z0 = torch.empty((N, H, W, 32), device=dev, dtype=torch.bfloat16)                  # [N,64,W,32]
+            _lib.call("hwg_stem_conv", x.data_ptr(), c["down_conv1.0"][0].data_ptr(), self.down_conv1[0].bias.data_ptr(),
+                      N, H, W, 5, 5, 2, 2, 32, z0.data_ptr(), st.data_ptr(), s())
         p0 = pool(gn_relu(z0, st, self.down_conv1[1], "gn0"))                                  # [N,32,W/2,32]
         r1 = cv(p0, "down_conv1.4", _T11, H // 2, W // 2, self.down_conv1[4], act=ACT_RELU)    # res = ReLU(x), aliased
         # conv1 (:354-362) + residual (:399-401)
@@ -227,7 +235,7 @@ class Encoder2(nn.Module):
         feat = conv.conv_fprop(a4, fa, _T33V, 1, Wf, bias=head.bias.detach(), out_dtype=torch.float32)
         feat.add_(conv.conv_fprop(a4, fb, [(dh + 3, dw) for dh, dw in _T33V], 1, Wf, out_dtype=torch.float32))
         if keep:
-            ctx.update(x5=x5, p0=p0, r1=r1, a1=a1, p1=p1, a2=a2, a3=a3, p2=p2, a4=a4, c=c)
+            ctx.update(p0=p0, r1=r1, a1=a1, p1=p1, a2=a2, a3=a3, p2=p2, a4=a4, c=c)
         return feat, mid, ctx                                            # [N,1,Wf,out_dim] fp32, [N,16,W/4,64] bf16
 
     # -- backward ---------------------------------------------------------------------------------------------------

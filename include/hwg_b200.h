@@ -452,6 +452,17 @@ int hwg_balance(float* g_main, const float* const* sets_host, int K, const float
  * (dy, 0) hwg_conv_fprop over these 16 channels.  hwg_shift_collapse is the adjoint (image gradient from the
  * dgrad of that convolution): dimg[n,0,h,x] (+)= sum_j g[n,h,x-j+pad,j]. */
 int hwg_shift_expand(const float* img, void* out, int N, int H, int W, int kw, int pad, void* stream);
+
+/* One-input-channel stem convolution straight from the fp32 image: the 7x7 in_conv of DiscriminatorAP
+ * (model/discriminator_ap.py:75, padding (0,3)) and the 5x5 down_conv1[0] of Encoder2 (model/autoencoder.py:345, padding 2),
+ * forward only.  img [N,1,H,W] fp32 (rounded to bf16 on the way in, like hwg_shift_expand does); w = the tap-major bf16
+ * operand of the shift-expansion route, [kh][Cout][16] with column j = kernel column j (columns >= kw are ignored);
+ * bias [Cout] fp32 or NULL; y [N,Ho,Wo,Cout] bf16 NHWC contiguous, Ho = H + 2*pad_h - kh + 1, Wo = W + 2*pad_w - kw + 1
+ * (zero padding); stats [N][Cout][2] fp32 (sum, sum of squares of y before rounding; accumulated, caller zeroes) or
+ * NULL.  kh, kw <= 8, Cout 32 or 64.  Write-bound (2*Cout bytes per pixel): staged image tile + mma.sync im2col fragments.
+ * Same result as hwg_shift_expand + a kh-tap hwg_conv_fprop up to the fp32 summation order. */
+int hwg_stem_conv(const float* img, const void* w, const float* bias, int N, int H, int W, int kh, int kw,
+                  int pad_h, int pad_w, int Cout, void* y, float* stats, void* stream);
 int hwg_shift_collapse(const void* g, float* dimg, int N, int H, int W, int kw, int pad, int accumulate,
                        void* stream);
 /* nn.GroupNorm(groups, C) (:76,101) from the per-(n,c) sums of the conv epilogue: coef[n,c] = (a, b) with

@@ -159,6 +159,21 @@ def hwg_shift_expand(img, out, N, H, W, kw, pad, stream):
     return 0
 
 
+def hwg_stem_conv(img, w, bias, N, H, W, kh, kw, pad_h, pad_w, Cout, y, stats, stream):
+    iv = _view(img, N * H * W, torch.float32).view(N, 1, H, W).to(torch.bfloat16).float()
+    wv = _view(w, kh * Cout * 16, torch.bfloat16).view(kh, Cout, 16).float()[:, :, :kw]        # [kh][Cout][kw]
+    wt = wv.permute(1, 0, 2).reshape(Cout, 1, kh, kw)
+    b = _view(bias, Cout, torch.float32) if bias else None
+    out = torch.nn.functional.conv2d(iv, wt, b, padding=(pad_h, pad_w))                        # [N,Cout,Ho,Wo] fp32
+    Ho, Wo = out.shape[2], out.shape[3]
+    if stats:
+        st = _view(stats, N * Cout * 2, torch.float32).view(N, Cout, 2)
+        st[:, :, 0] += out.sum((2, 3))
+        st[:, :, 1] += (out * out).sum((2, 3))
+    _view(y, N * Ho * Wo * Cout, torch.bfloat16).view(N, Ho, Wo, Cout).copy_(out.permute(0, 2, 3, 1).to(torch.bfloat16))
+    return 0
+
+
 def hwg_shift_collapse(g, dimg, N, H, W, kw, pad, accumulate, stream):
     gv = _view(g, N * H * W * 16, torch.bfloat16).view(N, H, W, 16).float()
     dv = _view(dimg, N * H * W, torch.float32).view(N, H, W)
@@ -752,7 +767,7 @@ _TABLE = {f.__name__: f for f in (hwg_insert_spaces_plan, hwg_insert_spaces_fill
                                   hwg_adain_bwd_apply, hwg_bn_coeffs, hwg_hwr_stem, hwg_hwr_stem_bwd, hwg_hwr_stem_bwd_image, hwg_maxpool_nhwc,
                                   hwg_relu_maxpool_bwd, hwg_logsoftmax_bwd, hwg_bn_bwd_reduce, hwg_bn_bwd_apply,
                                   hwg_balance, hwg_spectral_norm, hwg_spectral_norm_bwd, hwg_channel_sum, hwg_conv_wgrad,
-                                  hwg_conv_fprop, hwg_shift_expand, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
+                                  hwg_conv_fprop, hwg_shift_expand, hwg_stem_conv, hwg_shift_collapse, hwg_gn_coeffs, hwg_scale_shift_act,
                                   hwg_avgpool_nhwc, hwg_add_stats, hwg_l1_halves, hwg_norm_bwd_reduce, hwg_gn_bwd_coeffs,
                                   hwg_norm_bwd_apply, hwg_act_bwd)}
 

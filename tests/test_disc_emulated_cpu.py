@@ -59,7 +59,7 @@ def test_gen_lesson_predictions_and_input_gradient(name, golden_dir, hwg_lib, mo
     e, e_emul = _rel_l2(img.grad, img2.grad), _rel_l2(img3.grad, img2.grad)
     cos = F.cosine_similarity(img.grad.double().flatten(), img2.grad.double().flatten(), dim=0).item()
     assert e <= 1.3 * e_emul + 2e-2 and cos >= 0.95, (e, e_emul, cos)
-    assert {"hwg_spectral_norm", "hwg_shift_expand", "hwg_shift_collapse", "hwg_conv_fprop", "hwg_act_bwd"} <= set(calls)
+    assert {"hwg_spectral_norm", "hwg_stem_conv", "hwg_shift_collapse", "hwg_conv_fprop", "hwg_act_bwd"} <= set(calls)
 
 
 def test_disc_lesson_parameter_gradients(golden_dir, hwg_lib, monkeypatch):

@@ -57,6 +57,43 @@ def test_shift_expand_and_collapse_are_adjoint_and_match_definition():
     assert abs(lhs - rhs) <= 1e-4 * abs(lhs)
 
 
+@pytest.mark.parametrize("N,H,W,kh,kw,ph,pw,Cout", [
+    (2, 64, 200, 7, 7, 0, 3, 64),        # DiscriminatorAP.in_conv (discriminator_ap.py:75), ragged width
+    (3, 64, 128, 5, 5, 2, 2, 32),        # Encoder2.down_conv1[0] (autoencoder.py:345)
+    (1, 9, 37, 7, 7, 0, 3, 64),          # fewer rows / columns than one tile
+    (2, 21, 70, 3, 4, 1, 2, 32),         # even kernel width, odd tile remainders
+])
+def test_stem_conv_matches_conv2d(N, H, W, kh, kw, ph, pw, Cout):
+    """hwg_stem_conv (one-input-channel convolution straight from the fp32 image) against F.conv2d in fp64 on the bf16-rounded
+    operands, its statistics epilogue, and against the route it replaces (hwg_shift_expand + kh-tap hwg_conv_fprop)."""
+    from handwriting_line_generation_b200 import _lib, conv
+    g0 = torch.Generator().manual_seed(N * 1000 + W)
+    img = torch.randn(N, 1, H, W, generator=g0)
+    w = (torch.randn(Cout, 1, kh, kw, generator=g0) / (kh * kw) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g0)
+    packed = torch.zeros(kh, Cout, 16, dtype=torch.bfloat16)
+    packed[:, :, :kw] = w[:, 0].permute(1, 0, 2)
+    packed[:, :, kw:] = 7.0                       # columns past kw must be ignored
+    ref = F.conv2d(_bf(img), w.double(), b.double(), padding=(ph, pw))           # [N,Cout,Ho,Wo]
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    img_d, pk_d, b_d = img.cuda(), packed.cuda(), b.cuda()
+    y = torch.empty((N, Ho, Wo, Cout), device="cuda", dtype=torch.bfloat16)
+    st = torch.zeros((N, Cout, 2), device="cuda")
+    _lib.call("hwg_stem_conv", img_d.data_ptr(), pk_d.data_ptr(), b_d.data_ptr(), N, H, W, kh, kw, ph, pw, Cout,
+              y.data_ptr(), st.data_ptr(), _lib.stream())
+    got = _nchw(y)
+    assert ((got - ref).abs().max() / ref.abs().max()).item() <= 6e-3
+    s_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1)
+    assert ((st.cpu().double() - s_ref).abs().max() / s_ref.abs().max()).item() <= 1e-3
+    if ph == 0 and kw <= 7:
+        # the shift-expansion route on the tensor-core kernel: same operands, fp32 accumulation in another order
+        x16 = torch.empty((N, H, W, 16), device="cuda", dtype=torch.bfloat16)
+        _lib.call("hwg_shift_expand", img_d.data_ptr(), x16.data_ptr(), N, H, W, kw, pw, _lib.stream())
+        pk0 = packed.clone(); pk0[:, :, kw:] = 0
+        y2 = conv.conv_fprop(x16, pk0.cuda(), [(dy, 0) for dy in range(kh)], Ho, Wo, bias=b_d)
+        assert ((_nchw(y2) - got).abs().max() / ref.abs().max()).item() <= 8e-3
+
+
 @pytest.mark.parametrize("N,C,H,W", [(2, 64, 10, 33), (3, 128, 5, 16)])
 def test_gn_coeffs(N, C, H, W):
     from handwriting_line_generation_b200 import _lib

@@ -64,7 +64,7 @@ def test_gen_lesson_step_host_code_runs(recorder):
         loss.backward()
         opt.step()
     need = {"hwg_conv_fprop", "hwg_conv_wgrad", "hwg_ctc_forward", "hwg_ctc_backward", "hwg_adam_flat", "hwg_linear_map",
-            "hwg_spectral_norm", "hwg_shift_expand", "hwg_shift_collapse", "hwg_adain_bwd_apply", "hwg_bn_bwd_apply"}
+            "hwg_spectral_norm", "hwg_stem_conv", "hwg_shift_collapse", "hwg_adain_bwd_apply", "hwg_bn_bwd_apply"}
     assert need <= set(recorder), need - set(recorder)
 
 

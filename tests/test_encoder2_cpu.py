@@ -99,7 +99,7 @@ def test_composition_through_the_abi_interpreter_matches_the_oracle(name, hwg_li
     cos = float((g.double() * og.double()).sum() / (g.double().norm() * og.double().norm()))
     assert cos >= 0.95, cos                                              # measured 0.984 / 0.982
     assert abs(float(g.norm() / og.norm()) - 1.0) <= 5e-2
-    assert {"hwg_conv_fprop", "hwg_shift_expand", "hwg_shift_collapse", "hwg_gn_coeffs", "hwg_scale_shift_act",
+    assert {"hwg_conv_fprop", "hwg_stem_conv", "hwg_shift_collapse", "hwg_gn_coeffs", "hwg_scale_shift_act",
             "hwg_avgpool_nhwc", "hwg_add_stats", "hwg_l1_halves", "hwg_norm_bwd_reduce", "hwg_gn_bwd_coeffs",
             "hwg_norm_bwd_apply", "hwg_act_bwd"} == set(calls)
 
