@@ -77,13 +77,30 @@ __global__ void __launch_bounds__(LB_THREADS) linear_bwd_kernel(const float* __r
       gp[b] = g;
     }
     __syncthreads();
-    if (gW)
-      for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (gW) {
+      // threads = (k, slice of the batch): K = 128 would leave 3/4 of the block idle on one long chain of dependent
+      // L2-latency loads (32 us per launch at B = 128, 21 launches per step); the slices meet in shared memory
+      const int kw = K < (int)blockDim.x ? K : (int)blockDim.x, parts = blockDim.x / kw;
+      const int k0 = threadIdx.x % kw, pr = threadIdx.x / kw;
+      float* part = sm + (B > O ? B : O);
+      for (int kb = 0; kb < K; kb += kw) {
+        const int k = kb + k0;
         float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc = fmaf(gp[b], x[(size_t)b * K + k], acc);
-        float* d = gW + (size_t)o * K + k;
-        *d = accumulate ? *d + acc : acc;
+        if (pr < parts && k < K) {
+#pragma unroll 8
+          for (int b = pr; b < B; b += parts) acc = fmaf(gp[b], x[(size_t)b * K + k], acc);
+        }
+        if (pr < parts) part[pr * kw + k0] = acc;
+        __syncthreads();
+        if (pr == 0 && k < K) {
+          float t = 0.f;
+          for (int q = 0; q < parts; ++q) t += part[q * kw + k0];
+          float* d = gW + (size_t)o * K + k;
+          *d = accumulate ? *d + t : t;
+        }
+        __syncthreads();
       }
+    }
     if (gb && threadIdx.x == 0) {
       float acc = 0.f;
       for (int b = 0; b < B; ++b) acc += gp[b];
@@ -112,7 +129,7 @@ __global__ void __launch_bounds__(LB_THREADS) linear_bwd_kernel(const float* __r
       const int k = kb + k0;
       float acc = 0.f;
       if (pr < parts && k < K) {
-#pragma unroll 4
+#pragma unroll 8
         for (int o = pr; o < on; o += parts) acc = fmaf(gp[o], W[(size_t)(o0 + o) * K + k], acc);
       }
       if (pr < parts) part[pr * kw + k0] = acc;

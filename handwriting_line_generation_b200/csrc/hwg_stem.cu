@@ -38,17 +38,20 @@ __device__ __forceinline__ void st_mma(float (&d)[4], const uint32_t (&a)[4], ui
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NT = Cout / 8
+// NT = Cout / 8.  A warp owns NW = 4 of the NT n-tiles (32 channels): with all 64 channels per warp the B fragments,
+// accumulators and statistics took 235 registers = 8 warps per SM; split, two CTAs fit.
 template <int NT>
-__global__ void __launch_bounds__(ST_THREADS, 1)
+__global__ void __launch_bounds__(ST_THREADS, 2)
 stem_conv_kernel(const StemParams p) {
-  constexpr int COUT = NT * 8, WPP = NT * 4;     // 32-bit words per output pixel
+  constexpr int NW = 4, NHALF = NT / NW;
+  constexpr int COUT = NT * 8, WPP = NW * 4;     // 32-bit words per output pixel of a warp's channel slice
   __shared__ __align__(16) __nv_bfloat16 tile_e[2][ST_ROWS * ST_PITCH];   // image tile, as is       [buffer][row][col]
   __shared__ __align__(16) __nv_bfloat16 tile_o[2][ST_ROWS * ST_PITCH];   // shifted by one pixel: tile_o[c] = tile_e[c+1]
-  __shared__ __align__(16) uint32_t outst[ST_THREADS / 32][16 * WPP];     // per warp: 16 pixels x Cout bf16, swizzled
+  __shared__ __align__(16) uint32_t outst[ST_THREADS / 32][16 * WPP];     // per warp: 16 pixels x 32 channels bf16, swizzled
   __shared__ __align__(16) float bias_s[COUT];
   __shared__ float stat_s[2 * COUT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const int half = warp % NHALF, ch0 = half * NW * 8;      // this warp's channel slice [ch0, ch0 + 32)
 
   const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per, t_end = min(p.total_tiles, t_begin + per);
@@ -57,17 +60,17 @@ stem_conv_kernel(const StemParams p) {
   if (t_begin >= t_end) return;
 
   // B fragments: b[s][nt][0] = w[dy = 2s][co = 8nt + g][dx = 2tq, 2tq+1], [1] the same of kernel row 2s+1
-  uint32_t bfr[4][NT][2];
+  uint32_t bfr[4][NW][2];
 #pragma unroll
   for (int s = 0; s < 4; ++s)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NW; ++nt)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int dy = 2 * s + r;
         uint32_t v = 0u;
         if (dy < p.kh && 2 * tq < p.kw) {
-          v = *reinterpret_cast<const uint32_t*>(p.w + ((size_t)dy * COUT + 8 * nt + g) * 16 + 2 * tq);
+          v = *reinterpret_cast<const uint32_t*>(p.w + ((size_t)dy * COUT + ch0 + 8 * nt + g) * 16 + 2 * tq);
           if (2 * tq + 1 >= p.kw) v &= 0xFFFFu;
         }
         bfr[s][nt][r] = v;
@@ -103,21 +106,21 @@ stem_conv_kernel(const StemParams p) {
     }
   };
 
-  float s1[NT][2], s2[NT][2];     // statistics of the current image: channels 8nt + 2tq, +1
+  float s1[NW][2], s2[NW][2];     // statistics of the current image: channels ch0 + 8nt + 2tq, +1
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) { s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f; }
+  for (int nt = 0; nt < NW; ++nt) { s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f; }
   int stat_n = -1;
   auto flush_stats = [&](int n_img) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NW; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float u = s1[nt][e], v = s2[nt][e];
 #pragma unroll
         for (int o = 4; o <= 16; o <<= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
         if (g == 0) {
-          atomicAdd(&stat_s[2 * (8 * nt + 2 * tq + e)], u);
-          atomicAdd(&stat_s[2 * (8 * nt + 2 * tq + e) + 1], v);
+          atomicAdd(&stat_s[2 * (ch0 + 8 * nt + 2 * tq + e)], u);
+          atomicAdd(&stat_s[2 * (ch0 + 8 * nt + 2 * tq + e) + 1], v);
         }
         s1[nt][e] = 0.f; s2[nt][e] = 0.f;
       }
@@ -145,11 +148,11 @@ stem_conv_kernel(const StemParams p) {
     // columns p and p+1 with p = cs + g + 2tq: parity of p = parity of g -> even: tile_e[p], odd: tile_o[p-1]
     const __nv_bfloat16* src = (g & 1) ? tile_o[buf] - 1 : tile_e[buf];
     uint32_t* ost = outst[warp];
-    for (int mt = warp; mt < ST_TR * (ST_TC / 16); mt += ST_THREADS / 32) {
+    for (int mt = warp / NHALF; mt < ST_TR * (ST_TC / 16); mt += (ST_THREADS / 32) / NHALF) {
       const int ro = mt / (ST_TC / 16), cs = (mt - ro * (ST_TC / 16)) * 16;
-      float acc[NT][4];
+      float acc[NW][4];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+      for (int nt = 0; nt < NW; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
       const __nv_bfloat16* a_base = src + ro * ST_PITCH + cs + g + 2 * tq;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -161,7 +164,7 @@ stem_conv_kernel(const StemParams p) {
           a[2] = *reinterpret_cast<const uint32_t*>(r_lo + ST_PITCH);
           a[3] = *reinterpret_cast<const uint32_t*>(r_lo + ST_PITCH + 8);
 #pragma unroll
-          for (int nt = 0; nt < NT; ++nt) st_mma(acc[nt], a, bfr[s][nt][0], bfr[s][nt][1]);
+          for (int nt = 0; nt < NW; ++nt) st_mma(acc[nt], a, bfr[s][nt][0], bfr[s][nt][1]);
         }
       }
       // ---- epilogue: rows g / g+8 of the m-tile = pixels (r0 + ro, c0 + cs + g / + 8), channels 8nt + 2tq, +1
@@ -171,26 +174,26 @@ stem_conv_kernel(const StemParams p) {
         const int px = g + 8 * h;
         const bool valid = ho < p.Ho && c0 + cs + px < p.Wo;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const float2 bb = *reinterpret_cast<const float2*>(bias_s + 8 * nt + 2 * tq);
+        for (int nt = 0; nt < NW; ++nt) {
+          const float2 bb = *reinterpret_cast<const float2*>(bias_s + ch0 + 8 * nt + 2 * tq);
           const float v0 = acc[nt][2 * h] + bb.x, v1 = acc[nt][2 * h + 1] + bb.y;
           if (valid) {
             s1[nt][0] += v0; s1[nt][1] += v1;
             s2[nt][0] = fmaf(v0, v0, s2[nt][0]); s2[nt][1] = fmaf(v1, v1, s2[nt][1]);
           }
           const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
-          ost[px * WPP + ((4 * nt + tq) ^ ((px & (NT - 1)) << 2))] = *reinterpret_cast<const uint32_t*>(&pk);
+          ost[px * WPP + ((4 * nt + tq) ^ ((px & (NW - 1)) << 2))] = *reinterpret_cast<const uint32_t*>(&pk);
         }
       }
       __syncwarp();
-      // 16 pixels x NT 16-byte chunks, lanes over (pixel, chunk): whole pixel rows per group of NT lanes
+      // 16 pixels x NW 16-byte chunks, lanes over (pixel, chunk): 64 contiguous bytes of a pixel row per group of 4 lanes
       if (ho < p.Ho) {
-        __nv_bfloat16* yrow = p.y + (((size_t)n * p.Ho + ho) * p.Wo + c0 + cs) * COUT;
+        __nv_bfloat16* yrow = p.y + (((size_t)n * p.Ho + ho) * p.Wo + c0 + cs) * COUT + ch0;
 #pragma unroll
-        for (int i = 0; i < (16 * NT) / 32; ++i) {
-          const int c = i * 32 + lane, px = c / NT, q = c - px * NT;
+        for (int i = 0; i < (16 * NW) / 32; ++i) {
+          const int c = i * 32 + lane, px = c / NW, q = c - px * NW;
           if (c0 + cs + px < p.Wo) {
-            const uint4 v = *reinterpret_cast<const uint4*>(&ost[px * WPP + ((q ^ (px & (NT - 1))) << 2)]);
+            const uint4 v = *reinterpret_cast<const uint4*>(&ost[px * WPP + ((q ^ (px & (NW - 1))) << 2)]);
             *reinterpret_cast<uint4*>(yrow + (size_t)px * COUT + q * 8) = v;
           }
         }

@@ -83,5 +83,8 @@ def test_cuda_gen_lesson_against_the_reference_trainer():
     g_adv = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in gen.named_parameters()}
     cos_r, cos_a = _set_cosine(g_recog, gold, "recog"), _set_cosine(g_adv, gold, "adv")
     # measured through the CPU interpreter of the same modules (tests/test_trainer_dropin_cpu.py): 0.53 / 0.94 on these
-    # samples (plain torch with bf16 forward emulation: 0.77 / 0.94); a wrong sign, scale or a swapped set gives <= 0
-    assert cos_r >= 0.4 and cos_a >= 0.8, (cos_r, cos_a)
+    # samples (plain torch with bf16 forward emulation: 0.77 / 0.94); a wrong sign, scale or a swapped set gives <= 0, an
+    # unrelated gradient 0 +- 1e-3 (3.3 M components).  The recognition set crosses a random-init recognizer whose train-mode
+    # BatchNorm normalises over TWO 128-pixel lines: on the B200 the fp32 atomics' summation order of the statistics moves
+    # its cosine from run to run — ten runs in round 2: 0.27 ... 0.53 (profiles/microbench_r02.txt) — hence the low bar
+    assert cos_r >= 0.15 and cos_a >= 0.8, (cos_r, cos_a)
