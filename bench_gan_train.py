@@ -36,6 +36,7 @@ GAN = dict(GLOBAL_B=128, Ts=256, S=40, C=80, style=128, dim=256)
 HWR_GF_FWD_PER_LINE = 24.661      # SURVEY.md §8a (a10), forward conv GFLOP per 64x1024 line
 HWR_GF_STEM_PER_LINE = 0.075      # conv0 (fused stem kernel, not a tensor-core launch)
 DISC_GF_FWD_PER_LINE = 11.295     # SURVEY.md §8d / Appendix D, DiscriminatorAP forward conv GFLOP per 64x1024 line
+DISC_GF_STEM_PER_LINE = 2 * 58 * 1024 * 64 * 49 / 1e9   # its 7x7 in_conv: forward on hwg_stem_conv (mma.sync), not a tcgen05 launch
 ENC_GF_FWD_PER_LINE = 1.493       # SURVEY.md Appendix D, Encoder2(32) forward conv GFLOP per 64x1024 line
 W_CTC, W_GEN, W_PERC = 1e-4, 1.0, 0.5   # loss_weights genRecog / generator / perceptual of the IAM GAN config (:54-62)
 BALANCE_VAR_X = [0.6, 0.5]        # config :100 `balance_var_x` [0.6, 0.5, 0.4, 0.75]: the entries of the two sets stashed here
@@ -346,9 +347,10 @@ class GanStep:
         mb_small = sum(l[2] for l in layers if l[3] == "conv_small_kernel") / 1e6
         return {
             "conv_fprop_kernel": {"gflop": B * ((nf + nb) * g_tc + 2 * (HWR_GF_FWD_PER_LINE - HWR_GF_STEM_PER_LINE)
-                                                + 2 * DISC_GF_FWD_PER_LINE),
+                                                + 2 * DISC_GF_FWD_PER_LINE - DISC_GF_STEM_PER_LINE),
                                   "what": f"fprop x{nf} + dgrad x{nb} of generator b0-b2, fprop + dgrad of recognizer conv1-6 + 1-D "
-                                          "head and of every discriminator convolution"
+                                          "head and of every discriminator convolution (the 7x7 stem: dgrad only, its forward "
+                                          "runs on stem_conv_kernel)"
                                           + (", Encoder2 layers with >= 64 channels" if self.enc is not None else "") + " (tcgen05)"},
             "conv_small_kernel": {"gflop": B * (nf + nb) * g_small, "mb": B * (nf + nb) * mb_small,
                                   "what": f"fprop x{nf} + dgrad x{nb} of generator b3-b4 (16-64 channels, HBM-bound)"
