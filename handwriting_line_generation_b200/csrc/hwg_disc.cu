@@ -33,6 +33,17 @@ inline unsigned grid_for(long long items, int per_block, long long cap = 148LL *
   return (unsigned)(b < 1 ? 1 : b);
 }
 
+// grid of the row-indexed passes: blockIdx.y = image, blockIdx.x strides over the rows (~16 blocks per SM in total)
+inline dim3 row_grid(int H, int N) {
+  long long bx = H, cap = (148LL * 16 + N - 1) / N;
+  if (bx > cap) bx = cap;
+  return dim3((unsigned)(bx < 1 ? 1 : bx), (unsigned)N);
+}
+inline int log2_or_neg(int v) {
+  for (int s = 0; s < 31; ++s) if ((1 << s) == v) return s;
+  return -1;
+}
+
 // ---- image -> [N,H,W,16] bf16, channel j = image[h, w + j - pad] (zero outside), j < kw ----------------------
 __global__ void __launch_bounds__(DT)
 shift_expand_kernel(const float* __restrict__ img, uint4* __restrict__ out, long long pixels, int W, int kw, int pad) {
@@ -120,30 +131,41 @@ avgpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H,
 
 // ---- backward of  y = LeakyReLU(scale[n,c] * conv) [-> AvgPool(kh,kw)] ------------------------------------------
 // gz[n,h,w,c] = scale[n,c] * (y > 0 ? 1 : slope) * g[n, h/kh, w/kw, c] / (kh*kw)   (0 where the pool's floor cut)
+// Indexing of the three backward passes below (round 2): blockIdx.y = image, blocks stride over the image ROWS, threads
+// over the W*CV 16-byte items of a row — all 32-bit; round 1 decoded a flat 64-bit item index with six 64-bit divisions
+// per item (~240 instructions around a 16-byte load: ncu showed these passes at 44-56 % issue activity, 3-4 TB/s).
+__device__ __forceinline__ int pool_index(int v, int k) { return k == 1 ? v : (k == 2 ? v >> 1 : v / k); }
+
 __global__ void __launch_bounds__(DT)
 act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y, const float* __restrict__ scale, float slope,
-               int N, int H, int W, int CV, int kh, int kw, int Ho, int Wo, uint4* __restrict__ gz) {
-  const long long total = (long long)N * H * W * CV;
+               int H, int W, int CV, int cv_shift, int kh, int kw, int Ho, int Wo, uint4* __restrict__ gz) {
+  const int n = blockIdx.y, row_items = W * CV;
   const float inv = 1.f / (float)(kh * kw);
-  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
-    const int cv = (int)(i % CV);
-    long long p = i / CV;
-    const int w = (int)(p % W);
-    p /= W;
-    const int h = (int)(p % H), n = (int)(p / H);
-    const int ho = h / kh, wo = w / kw;
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ho < Ho && wo < Wo) {
-      float gv[8], yv[8];
-      unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
-      unpack8d(y[i], yv);
+  for (int h = blockIdx.x; h < H; h += gridDim.x) {
+    const int ho = pool_index(h, kh);
+    const size_t row = ((size_t)n * H + h) * row_items;
+    const uint4* grow = g + ((size_t)n * Ho + (ho < Ho ? ho : 0)) * Wo * CV;
+    for (int j = threadIdx.x; j < row_items; j += DT) {
+      const int w = cv_shift >= 0 ? j >> cv_shift : j / CV, cv = j - w * CV;
+      const int wo = pool_index(w, kw);
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ho < Ho && wo < Wo) {
+        float gv[8], yv[8], sv[8];
+        unpack8d(grow[(size_t)wo * CV + cv], gv);
+        unpack8d(y[row + j], yv);
+        if (scale) {
+          const float4* sp = reinterpret_cast<const float4*>(scale + ((size_t)n * CV + cv) * 8);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+          sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+        } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float s = scale ? scale[(size_t)n * CV * 8 + cv * 8 + k] : 1.f;
-        o[k] = gv[k] * inv * s * (yv[k] > 0.f ? 1.f : slope);
+          for (int k = 0; k < 8; ++k) sv[k] = 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = gv[k] * inv * sv[k] * (yv[k] > 0.f ? 1.f : slope);
       }
+      gz[row + j] = pack8d(o);
     }
-    gz[i] = pack8d(o);
   }
 }
 
@@ -165,19 +187,23 @@ norm_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z,
   }
   float s0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float inv = 1.f / (float)(kh * kw);
-  const long long HW = (long long)H * W;
-  for (long long p = (long long)blockIdx.x * LANES + lane; p < HW; p += (long long)gridDim.x * LANES) {
-    const int h = (int)(p / W), w = (int)(p % W);
-    const int ho = h / kh, wo = w / kw;
-    if (ho >= Ho || wo >= Wo) continue;
-    float gv[8], zv[8];
-    unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
-    unpack8d(z[((long long)n * HW + p) * CV + cv], zv);
+  for (int h = blockIdx.x; h < H; h += gridDim.x) {
+    const int ho = pool_index(h, kh);
+    if (ho >= Ho) continue;
+    const uint4* grow = g + ((size_t)n * Ho + ho) * Wo * CV + cv;
+    const uint4* zrow = z + ((size_t)n * H + h) * W * CV + cv;
+    for (int w = lane; w < W; w += LANES) {
+      const int wo = pool_index(w, kw);
+      if (wo >= Wo) continue;
+      float gv[8], zv[8];
+      unpack8d(grow[(size_t)wo * CV], gv);
+      unpack8d(zrow[(size_t)w * CV], zv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gy = gv[k] * inv * (fmaf(a[k], zv[k], b[k]) > 0.f ? 1.f : slope);
-      s0[k] += gy;
-      s1[k] = fmaf(gy, zv[k], s1[k]);
+      for (int k = 0; k < 8; ++k) {
+        const float gy = gv[k] * inv * (fmaf(a[k], zv[k], b[k]) > 0.f ? 1.f : slope);
+        s0[k] += gy;
+        s1[k] = fmaf(gy, zv[k], s1[k]);
+      }
     }
   }
 #pragma unroll
@@ -226,36 +252,51 @@ __global__ void gn_bwd_coeffs_kernel(const float* __restrict__ sums, const float
 // ---- pass 2: gz = sc*gy' + P*z + Q ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DT)
 norm_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ coef,
-                      const float* __restrict__ spq, float slope, int H, int W, int CV, int kh, int kw, int Ho, int Wo,
-                      uint4* __restrict__ gz) {
-  extern __shared__ float cs[];                    // [C][5]: a, b, sc, P, Q
-  const int n = blockIdx.y, C = CV * 8;
+                      const float* __restrict__ spq, float slope, int H, int W, int CV, int cv_shift, int kh, int kw,
+                      int Ho, int Wo, uint4* __restrict__ gz) {
+  // per-channel constants a, b, sc, P, Q as [5][2 halves][C/2] floats: a lane's two float4 reads per constant are
+  // 16 bytes apart from its neighbour's (conflict-free); round 1's [C][5] scalar layout was 40 bank-conflicted loads per item
+  extern __shared__ __align__(16) float cs[];
+  const int n = blockIdx.y, C = CV * 8, C2 = C / 2;
   for (int c = threadIdx.x; c < C; c += DT) {
-    cs[c * 5] = coef[((size_t)n * C + c) * 2];
-    cs[c * 5 + 1] = coef[((size_t)n * C + c) * 2 + 1];
-    cs[c * 5 + 2] = spq[((size_t)n * C + c) * 3];
-    cs[c * 5 + 3] = spq[((size_t)n * C + c) * 3 + 1];
-    cs[c * 5 + 4] = spq[((size_t)n * C + c) * 3 + 2];
+    const int at = (c & 4 ? C2 : 0) + (c >> 3) * 4 + (c & 3);
+    cs[at] = coef[((size_t)n * C + c) * 2];
+    cs[C + at] = coef[((size_t)n * C + c) * 2 + 1];
+    cs[2 * C + at] = spq[((size_t)n * C + c) * 3];
+    cs[3 * C + at] = spq[((size_t)n * C + c) * 3 + 1];
+    cs[4 * C + at] = spq[((size_t)n * C + c) * 3 + 2];
   }
   __syncthreads();
   const float inv = 1.f / (float)(kh * kw);
-  const long long total = (long long)H * W * CV;
-  for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
-    const int cv = (int)(i % CV);
-    const long long p = i / CV;
-    const int h = (int)(p / W), w = (int)(p % W);
-    const int ho = h / kh, wo = w / kw;
-    float zv[8], gv[8], o[8];
-    unpack8d(z[(long long)n * total + i], zv);
-    const bool in = ho < Ho && wo < Wo;
-    if (in) unpack8d(g[(((long long)n * Ho + ho) * Wo + wo) * CV + cv], gv);
+  const int row_items = W * CV;
+  for (int h = blockIdx.x; h < H; h += gridDim.x) {
+    const int ho = pool_index(h, kh);
+    const size_t row = ((size_t)n * H + h) * row_items;
+    const uint4* grow = g + ((size_t)n * Ho + (ho < Ho ? ho : 0)) * Wo * CV;
+    for (int j = threadIdx.x; j < row_items; j += DT) {
+      const int w = cv_shift >= 0 ? j >> cv_shift : j / CV, cv = j - w * CV;
+      const int wo = pool_index(w, kw);
+      float zv[8], gv[8], o[8];
+      unpack8d(z[row + j], zv);
+      const bool in = ho < Ho && wo < Wo;
+      if (in) unpack8d(grow[(size_t)wo * CV + cv], gv);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float* c5 = cs + (cv * 8 + k) * 5;
-      const float gy = in ? gv[k] * inv * (fmaf(c5[0], zv[k], c5[1]) > 0.f ? 1.f : slope) : 0.f;
-      o[k] = fmaf(c5[2], gy, fmaf(c5[3], zv[k], c5[4]));
+      for (int hf = 0; hf < 2; ++hf) {
+        const float* base = cs + hf * C2 + cv * 4;
+        const float4 ca = *reinterpret_cast<const float4*>(base), cb = *reinterpret_cast<const float4*>(base + C);
+        const float4 sc = *reinterpret_cast<const float4*>(base + 2 * C), P = *reinterpret_cast<const float4*>(base + 3 * C);
+        const float4 Q = *reinterpret_cast<const float4*>(base + 4 * C);
+        const float av[4] = {ca.x, ca.y, ca.z, ca.w}, bv[4] = {cb.x, cb.y, cb.z, cb.w}, sv[4] = {sc.x, sc.y, sc.z, sc.w};
+        const float pv[4] = {P.x, P.y, P.z, P.w}, qv[4] = {Q.x, Q.y, Q.z, Q.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = 4 * hf + kk;
+          const float gy = in ? gv[k] * inv * (fmaf(av[kk], zv[k], bv[kk]) > 0.f ? 1.f : slope) : 0.f;
+          o[k] = fmaf(sv[kk], gy, fmaf(pv[kk], zv[k], qv[kk]));
+        }
+      }
+      gz[row + j] = pack8d(o);
     }
-    gz[(long long)n * total + i] = pack8d(o);
   }
 }
 
@@ -428,9 +469,10 @@ extern "C" int hwg_avgpool_nhwc(const void* x, void* y, int N, int H, int W, int
 extern "C" int hwg_act_bwd(const void* g, const void* y, const float* scale, float slope, int N, int H, int W, int C,
                            int kh, int kw, void* gz, void* stream) {
   HWG_REQUIRE(g && y && gz && N > 0 && C > 0 && C % 8 == 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "hwg_act_bwd: bad argument");
-  act_bwd_kernel<<<grid_for((long long)N * H * W * (C / 8), DT), DT, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(y), scale, slope, N, H, W, C / 8, kh, kw, H / kh,
-      W / kw, reinterpret_cast<uint4*>(gz));
+  HWG_REQUIRE((long long)W * (C / 8) < (1LL << 30) && N <= 65535, "hwg_act_bwd: row of %d x %d channels / N=%d too large", W, C, N);
+  act_bwd_kernel<<<row_grid(H, N), DT, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(y), scale, slope, H, W, C / 8, log2_or_neg(C / 8), kh,
+      kw, H / kh, W / kw, reinterpret_cast<uint4*>(gz));
   return check_launch("act_bwd_kernel");
 }
 
@@ -438,11 +480,9 @@ extern "C" int hwg_norm_bwd_reduce(const void* g, const void* z, const float* co
                                    int C, int kh, int kw, float* sums, void* stream) {
   HWG_REQUIRE(g && z && coef && sums && N > 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw, "hwg_norm_bwd_reduce: bad argument");
   HWG_REQUIRE(cv_supported(C), "hwg_norm_bwd_reduce: C=%d not in {16,32,64,128,256}", C);
-  const long long HW = (long long)H * W;
-  const int CV = C / 8, lanes = DT / CV;
-  long long bx = (HW + lanes - 1) / lanes, cap = (148LL * 8 + N - 1) / N;
-  if (bx > cap) bx = cap;
-  dim3 grid((unsigned)bx, N);
+  HWG_REQUIRE(N <= 65535, "hwg_norm_bwd_reduce: N=%d too large", N);
+  const int CV = C / 8;
+  const dim3 grid = row_grid(H, N);
   const uint4* gp = reinterpret_cast<const uint4*>(g);
   const uint4* zp = reinterpret_cast<const uint4*>(z);
   const int Ho = H / kh, Wo = W / kw;
@@ -472,13 +512,10 @@ extern "C" int hwg_norm_bwd_apply(const void* g, const void* z, const float* coe
   HWG_REQUIRE(g && z && coef && spq && gz && N > 0 && C > 0 && C % 8 == 0 && kh >= 1 && kw >= 1 && H >= kh && W >= kw,
               "hwg_norm_bwd_apply: bad argument");
   HWG_REQUIRE(C <= 1024, "hwg_norm_bwd_apply: C=%d too large", C);
-  const long long total = (long long)H * W * (C / 8);
-  long long bx = (total + DT - 1) / DT, cap = (148LL * 16 + N - 1) / N;
-  if (bx > cap) bx = cap;
-  dim3 grid((unsigned)bx, N);
-  norm_bwd_apply_kernel<<<grid, DT, (size_t)C * 5 * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z), coef, spq, slope, H, W, C / 8, kh, kw, H / kh,
-      W / kw, reinterpret_cast<uint4*>(gz));
+  HWG_REQUIRE((long long)W * (C / 8) < (1LL << 30) && N <= 65535, "hwg_norm_bwd_apply: row of %d x %d channels / N=%d too large", W, C, N);
+  norm_bwd_apply_kernel<<<row_grid(H, N), DT, (size_t)C * 5 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(z), coef, spq, slope, H, W, C / 8, log2_or_neg(C / 8), kh,
+      kw, H / kh, W / kw, reinterpret_cast<uint4*>(gz));
   return check_launch("norm_bwd_apply_kernel");
 }
 
