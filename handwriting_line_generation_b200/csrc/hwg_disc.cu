@@ -110,11 +110,14 @@ avgpool_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H,
   const long long total = (long long)N * Ho * Wo * CV;
   const float inv = 1.f / (float)(kh * kw);
   for (long long i = (long long)blockIdx.x * DT + threadIdx.x; i < total; i += (long long)gridDim.x * DT) {
-    const int cv = (int)(i % CV);
-    long long p = i / CV;
-    const int wo = (int)(p % Wo);
-    p /= Wo;
-    const int ho = (int)(p % Ho), n = (int)(p / Ho);
+    int cv, wo, ho, n;
+    if (i < (1LL << 31)) {     // 32-bit divisions when the index fits
+      const unsigned u = (unsigned)i, q1 = u / (unsigned)CV, q2 = q1 / (unsigned)Wo, q3 = q2 / (unsigned)Ho;
+      cv = (int)(u - q1 * (unsigned)CV); wo = (int)(q1 - q2 * (unsigned)Wo); ho = (int)(q2 - q3 * (unsigned)Ho); n = (int)q3;
+    } else {
+      const long long q1 = i / CV, q2 = q1 / Wo, q3 = q2 / Ho;
+      cv = (int)(i - q1 * CV); wo = (int)(q1 - q2 * Wo); ho = (int)(q2 - q3 * Ho); n = (int)q3;
+    }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int a = 0; a < kh; ++a)
       for (int b = 0; b < kw; ++b) {

@@ -6,6 +6,17 @@
 #include <math_constants.h>
 
 namespace hwg {
+// flat item index -> (a, b, c, d) with item = ((d * C + c) * B + b) * A + a; 32-bit divisions when the index fits
+__device__ __forceinline__ void decode4(long long item, int A, int B, int C, int& a, int& b, int& c, int& d) {
+  if (item < (1LL << 31)) {
+    const unsigned i = (unsigned)item, q1 = i / (unsigned)A, q2 = q1 / (unsigned)B, q3 = q2 / (unsigned)C;
+    a = (int)(i - q1 * (unsigned)A); b = (int)(q1 - q2 * (unsigned)B); c = (int)(q2 - q3 * (unsigned)C); d = (int)q3;
+  } else {
+    const long long q1 = item / A, q2 = q1 / B, q3 = q2 / C;
+    a = (int)(item - q1 * A); b = (int)(q1 - q2 * B); c = (int)(q2 - q3 * C); d = (int)q3;
+  }
+}
+
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -338,11 +349,8 @@ hwr_stem_kernel(const float* __restrict__ img, const float* __restrict__ w, cons
   const int CV = Cout / 8, Hp = H / 2, Wp = W / 2;
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= (long long)N * Hp * Wp * CV) return;
-  const int cv = (int)(item % CV);
-  long long pix = item / CV;
-  const int wp = (int)(pix % Wp); pix /= Wp;
-  const int hp = (int)(pix % Hp);
-  const int n = (int)(pix / Hp);
+  int cv, wp, hp, n;
+  decode4(item, CV, Wp, Hp, cv, wp, hp, n);
   float patch[4][4];
   const float* im = img + (size_t)n * H * W;
 #pragma unroll
@@ -381,11 +389,8 @@ maxpool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, i
   const int CV = C / 8;
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= (long long)N * Ho * Wo * CV) return;
-  const int cv = (int)(item % CV);
-  long long pix = item / CV;
-  const int wo = (int)(pix % Wo); pix /= Wo;
-  const int ho = (int)(pix % Ho);
-  const int n = (int)(pix / Ho);
+  int cv, wo, ho, n;
+  decode4(item, CV, Wo, Ho, cv, wo, ho, n);
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -CUDART_INF_F;

@@ -301,7 +301,9 @@ relu_maxpool_bwd_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ 
 // wins, as in ATen's max_pool2d_with_indices.
 // three resident blocks per SM: the pass waits on its (up to eight) 16-byte loads per item (ncu, round 2: long_scoreboard 65 %,
 // 99 registers = two blocks), so resident warps are what it needs
-template <int MODE>
+// IDX = unsigned when the item count fits 31 bits (always, at the sizes of this path): the flat index is decoded with
+// 32-bit divisions instead of four 64-bit ones per item
+template <int MODE, typename IDX>
 __global__ void __launch_bounds__(BW_THREADS, 3)
 relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restrict__ c, int N, int H, int W, int C,
                             int Ho, int Wo, uint4* __restrict__ gc, float* __restrict__ dbias) {
@@ -315,16 +317,17 @@ relu_maxpool_bwd_win_kernel(const uint4* __restrict__ ga, const uint4* __restric
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   const int HP = (H + 1) / 2;                               // row pairs (the last one may be half)
   const int WP = MODE == 0 ? (W + 1) / 2 : W;               // column groups
-  const long long total = (long long)N * HP * WP * CV;
-  for (long long chunk = blockIdx.x; chunk * (BW_THREADS * BW_ITER) < total; chunk += gridDim.x) {   // persistent blocks
-  const long long base = chunk * (BW_THREADS * BW_ITER);
+  const IDX total = (IDX)N * HP * WP * CV;
+  for (IDX chunk = blockIdx.x; chunk * (BW_THREADS * BW_ITER) < total; chunk += gridDim.x) {   // persistent blocks
+  const IDX base = chunk * (BW_THREADS * BW_ITER);
   for (int it = 0; it < BW_ITER; ++it) {
-    const long long item = base + it * BW_THREADS + threadIdx.x;
+    const IDX item = base + it * BW_THREADS + threadIdx.x;
     if (item >= total) break;
-    long long q = item / CV;
-    const int wg = (int)(q % WP); q /= WP;
-    const int hp = (int)(q % HP);
-    const int n = (int)(q / HP);
+    IDX q = item / (IDX)CV;
+    const IDX q2 = q / (IDX)WP;
+    const int wg = (int)(q - q2 * (IDX)WP);
+    const int n = (int)(q2 / (IDX)HP);
+    const int hp = (int)(q2 - (IDX)n * (IDX)HP);
     const int h0 = 2 * hp, h1 = h0 + 1;
     const bool row1 = h1 < H;
     const bool win_h = hp < Ho;                              // a pooling window covers this row pair
@@ -930,7 +933,9 @@ extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H,
   if (kh == 2 && kw == 2 && sh == 2 && ph == 0 && ((sw == 2 && pw == 0) || (sw == 1 && pw == 1)) && cv_ok(C)) {
     const int mode = sw == 2 ? 0 : 1;
     const long long items = (long long)N * ((H + 1) / 2) * (mode == 0 ? (W + 1) / 2 : W) * (C / 8);
-    auto kern = mode == 0 ? relu_maxpool_bwd_win_kernel<0> : relu_maxpool_bwd_win_kernel<1>;
+    const bool small = items < (1LL << 31) - (long long)BW_THREADS * BW_ITER * 148 * 4;
+    auto kern = small ? (mode == 0 ? relu_maxpool_bwd_win_kernel<0, unsigned> : relu_maxpool_bwd_win_kernel<1, unsigned>)
+                      : (mode == 0 ? relu_maxpool_bwd_win_kernel<0, long long> : relu_maxpool_bwd_win_kernel<1, long long>);
     kern<<<bw_blocks_persistent(items, BW_THREADS * BW_ITER, 1, 3), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(ga), reinterpret_cast<const uint4*>(c), N, H, W, C, Ho, Wo,
         reinterpret_cast<uint4*>(gc), dbias);
