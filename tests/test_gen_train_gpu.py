@@ -13,7 +13,7 @@ the input (torch shows the same with bf16 storage emulation).  Asserted here:
     gen_grad_spread.py on the B200, 60 runs over seven builds of round 2: the AdaIN projection of the 32-channel block sat
     anywhere in 0.09 ... 0.145 against 0.088 for the emulation (one build clustering at 0.14), the style-MLP weights in
     0.133 ... 0.174 against 0.108-0.117; a factor of 1.3 failed one run in two on some builds;
-  * cosine(cuda, fp32) >= 0.95 on every gradient tensor;
+  * cosine(cuda, fp32) >= 0.95 on every gradient tensor (0.9 for tensors with fewer than 256 entries);
   * the tensors next to the output (out conv weight, last AdaIN projection) within 3e-2.
 The backward kernels themselves are held to <= 1e-2 on identical inputs in test_gen_bwd_ops_gpu.py /
 test_conv_bwd_gpu.py."""
@@ -73,7 +73,8 @@ def test_generator_backward_matches_oracle(name):
         # tensors with a handful of entries (per-channel bias sums with heavy cancellation) fluctuate more
         k = 1.6 if g.numel() >= 256 else 2.5
         assert ours <= k * emu + BF16_REL, f"{n}: cuda-vs-fp32 {ours:.3f}, bf16-emulated-torch-vs-fp32 {emu:.3f}"
-        assert cos >= 0.95, f"{n}: cosine {cos:.3f}"
+        # (16-entry bias sums: 0.9 — B200, round 2: conv.4.conv1.0.bias at 0.9499 in one of five suite runs)
+        assert cos >= (0.95 if g.numel() >= 256 else 0.9), f"{n}: cosine {cos:.3f}"
     for n in ("out.0.conv.weight_orig", "conv.4.adain2.style.weight"):
         assert rel_l2(got[n].numpy(), g32[n].numpy()) <= 3e-2, n
     # out.0.conv.bias is ONE number: a sum over every pixel of +/- terms; compare against the size of the terms
