@@ -197,63 +197,82 @@ scale_shift_act_stream_kernel(const uint4* __restrict__ x, uint4* __restrict__ y
 }
 
 // ---- blur + noise + activation + statistics ---------------------------------------------------
-// Separable rolling window: a thread owns one 16-byte channel vector of one image column and walks BLUR_ROWS
-// rows downwards.  Per row it loads the three horizontal neighbours once (l + 2c + r), and combines the
-// horizontal sums of the rows above / at / below: 3(R+2)/R loads per output instead of 9, no integer
-// divisions, coalesced 16-byte accesses along (w, c).
+// A block owns BLUR_ROWS rows x EW_THREADS 16-byte items of one line.  One thread pulls the tile plus its halo
+// (one row above / below, one pixel left / right) into shared memory with 1-D bulk copies, one per row
+// (cp.async.bulk, completion on an mbarrier): the whole tile is in flight at once — a register-only rolling window
+// kept three loads per thread outstanding and measured 2.2 TB/s.  A thread then owns one channel vector of one
+// image column and walks the rows downwards with a separable rolling window (l + 2c + r per row, combined over the
+// rows above / at / below), all from shared memory.
 constexpr int BLUR_ROWS = 8;
 
-__device__ __forceinline__ void blur_hrow(const uint4* __restrict__ xn, int h, int H, long long row_items, int ci,
-                                          int CV, bool has_l, bool has_r, float (&hb)[8]) {
-  if (h < 0 || h >= H) {
+__device__ __forceinline__ void blur_hrow(const uint4* __restrict__ tile, int r, bool valid, int pitch, int CV,
+                                          bool has_l, bool has_r, float (&hb)[8]) {
+  if (!valid) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) hb[j] = 0.f;
     return;
   }
-  const uint4* p = xn + (long long)h * row_items + ci;
-  float c[8], l[8], r[8];
+  const uint4* p = tile + r * pitch + CV + threadIdx.x;
+  float c[8], l[8], q[8];
   unpack8(p[0], c);
   if (has_l) unpack8(p[-CV], l);
-  if (has_r) unpack8(p[CV], r);
+  if (has_r) unpack8(p[CV], q);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) hb[j] = 2.f * c[j] + (has_l ? l[j] : 0.f) + (has_r ? r[j] : 0.f);
+  for (int j = 0; j < 8; ++j) hb[j] = 2.f * c[j] + (has_l ? l[j] : 0.f) + (has_r ? q[j] : 0.f);
 }
 
+__host__ __device__ constexpr size_t blur_tile_bytes(int CV) { return (size_t)(BLUR_ROWS + 2) * (EW_THREADS + 2 * CV) * 16; }
+
 template <bool RNG>
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 3)
 blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C, int cv_shift,
                             const float* __restrict__ noise, const float* __restrict__ noise_w,
                             unsigned long long seed, unsigned long long subseq,
                             const unsigned long long* __restrict__ seed_dev, int act, float slope,
                             float* __restrict__ stats) {
-  extern __shared__ float sacc[];  // [C][2] block-level statistics
-  const int n = blockIdx.z, CV = C / 8;
-  if (stats) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
-  }
+  extern __shared__ __align__(128) unsigned char blur_smem[];
+  const int n = blockIdx.z, CV = C / 8, pitch = EW_THREADS + 2 * CV;
+  const uint4* tile = reinterpret_cast<const uint4*>(blur_smem);          // [BLUR_ROWS + 2][pitch]
+  float* sacc = reinterpret_cast<float*>(blur_smem + blur_tile_bytes(CV));   // [C][2] block-level statistics
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sacc + 2 * C);
   const long long row_items = (long long)W * CV;
   const long long total = (long long)H * row_items;
-  const int ci = blockIdx.x * EW_THREADS + threadIdx.x;   // (w, cv) inside a row
+  const int seg0 = blockIdx.x * EW_THREADS;
+  const int h0 = blockIdx.y * BLUR_ROWS, h1 = min(H, h0 + BLUR_ROWS);
+  const uint4* xn = x + (size_t)n * total;
+  if (threadIdx.x == 0) {
+    sm100::mbar_init(bar, 1);
+    sm100::fence_barrier_init();
+    const long long s0 = max(seg0 - CV, 0), s1 = min((long long)seg0 + EW_THREADS + CV, row_items);
+    const int r0 = max(h0 - 1, 0), r1 = min(h1 + 1, H);
+    const uint32_t row_bytes = (uint32_t)(s1 - s0) * 16u;
+    sm100::mbar_expect_tx(bar, row_bytes * (uint32_t)(r1 - r0));
+    for (int h = r0; h < r1; ++h)
+      bulk_load_1d(blur_smem + ((size_t)(h - (h0 - 1)) * pitch + (s0 - (seg0 - CV))) * 16, xn + (long long)h * row_items + s0,
+                   row_bytes, bar);
+  }
+  if (stats)
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int ci = seg0 + threadIdx.x;   // (w, cv) inside a row
   const int cv = ci & (CV - 1);
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  float nw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
+  const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
+  sm100::mbar_wait(bar, 0);
   if (ci < row_items) {
     const int w = ci >> cv_shift;
     const bool has_l = w > 0, has_r = w < W - 1;
-    const uint4* xn = x + (size_t)n * total;
     uint4* yn = y + (size_t)n * total;
-    float nw[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
-    const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
-    const int h0 = blockIdx.y * BLUR_ROWS, h1 = min(H, h0 + BLUR_ROWS);
     float prev[8], cur[8], nxt[8];
-    blur_hrow(xn, h0 - 1, H, row_items, ci, CV, has_l, has_r, prev);
-    blur_hrow(xn, h0, H, row_items, ci, CV, has_l, has_r, cur);
+    blur_hrow(tile, 0, h0 > 0, pitch, CV, has_l, has_r, prev);
+    blur_hrow(tile, 1, true, pitch, CV, has_l, has_r, cur);
     for (int h = h0; h < h1; ++h) {
-      blur_hrow(xn, h + 1, H, row_items, ci, CV, has_l, has_r, nxt);
+      blur_hrow(tile, h - h0 + 2, h + 1 < H, pitch, CV, has_l, has_r, nxt);
       const long long item = (long long)h * row_items + ci;
       float acc[8];
 #pragma unroll
@@ -409,6 +428,36 @@ maxpool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, i
   y[item] = pack8(m);
 }
 
+// 2x2 windows (both poolings of CNNOnlyHWR): the four loads are issued together and the maximum is taken on packed
+// bf16 pairs (comparisons of bf16 values are exact) — no unpacking, no dependent load chain
+__global__ void __launch_bounds__(EW_THREADS)
+maxpool22_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int C, int sh, int sw,
+                      int ph, int pw, int Ho, int Wo) {
+  const int CV = C / 8;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (long long)N * Ho * Wo * CV) return;
+  int cv, wo, ho, n;
+  decode4(item, CV, Wo, Ho, cv, wo, ho, n);
+  const uint4 NEG = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // -inf: padding never wins
+  const int h0 = ho * sh - ph, w0 = wo * sw - pw;
+  const uint4* xn = x + (size_t)n * H * W * CV;
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int hh = h0 + i, ww = w0 + j;
+      v[2 * i + j] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? xn[((size_t)hh * W + ww) * CV + cv] : NEG;
+    }
+  auto mx = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const __nv_bfloat162 m = __hmax2(__hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b)),
+                                     __hmax2(*reinterpret_cast<__nv_bfloat162*>(&c), *reinterpret_cast<__nv_bfloat162*>(&d)));
+    return *reinterpret_cast<const uint32_t*>(&m);
+  };
+  y[item] = make_uint4(mx(v[0].x, v[1].x, v[2].x, v[3].x), mx(v[0].y, v[1].y, v[2].y, v[3].y),
+                       mx(v[0].z, v[1].z, v[2].z, v[3].z), mx(v[0].w, v[1].w, v[2].w, v[3].w));
+}
+
 static inline unsigned blocks_for(long long items, int per_block) {
   return (unsigned)((items + per_block - 1) / per_block);
 }
@@ -501,7 +550,8 @@ extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, in
   dim3 grid(blocks_for((long long)W * CV, EW_THREADS), (H + BLUR_ROWS - 1) / BLUR_ROWS, N);
   HWG_REQUIRE(grid.y <= 65535 && N <= 65535, "hwg_blur_noise_act_stats: H=%d / N=%d too large", H, N);
   auto k = (noise_w && !noise) ? blur_noise_act_stats_kernel<true> : blur_noise_act_stats_kernel<false>;
-  k<<<grid, EW_THREADS, (size_t)C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+  HWG_SMEM_OPTIN(k);
+  k<<<grid, EW_THREADS, blur_tile_bytes(CV) + (size_t)C * 2 * sizeof(float) + 16, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, cv_shift, noise, noise_w, noise_seed,
       noise_subseq, reinterpret_cast<const unsigned long long*>(noise_seed_dev), act, slope, stats);
   return check_launch("blur_noise_act_stats_kernel");
@@ -532,6 +582,11 @@ extern "C" int hwg_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int
   HWG_REQUIRE(Ho == (H + 2 * ph - kh) / sh + 1 && Wo == (W + 2 * pw - kw) / sw + 1,
               "hwg_maxpool_nhwc: Ho/Wo do not match the pooling geometry");
   const long long items = (long long)N * Ho * Wo * (C / 8);
+  if (kh == 2 && kw == 2) {
+    maxpool22_nhwc_kernel<<<blocks_for(items, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), N, H, W, C, sh, sw, ph, pw, Ho, Wo);
+    return check_launch("maxpool22_nhwc_kernel");
+  }
   maxpool_nhwc_kernel<<<blocks_for(items, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), N, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo);
   return check_launch("maxpool_nhwc_kernel");

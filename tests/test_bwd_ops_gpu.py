@@ -72,7 +72,9 @@ def test_relu_maxpool_bwd(geom, N, C, H, W):
     (gpre_ref,) = torch.autograd.grad(a, pre, g)
     gc, db = ops.relu_maxpool_bwd(_nhwc(g), _nhwc(c.detach()), k, s, p)
     assert _rel(gc.float().permute(0, 3, 1, 2).cpu(), gpre_ref) <= 1e-2
-    assert _rel(db.cpu(), gpre_ref.sum((0, 2, 3))) <= 2e-3
+    # the bias gradient sums the bf16 gradient tensor the pass writes (the values the convolution's weight gradient reads
+    # too): one 2^-9 rounding per element, which only averages out over many pixels — the 7x9 case keeps 4e-3
+    assert _rel(db.cpu(), gpre_ref.sum((0, 2, 3))) <= (2e-3 if H * W >= 512 else 4e-3)
 
 
 def test_relu_maxpool_bwd_ties_first_max_wins():
@@ -95,6 +97,35 @@ def test_relu_maxpool_bwd_ties_overlapping_windows():
     (ref,) = torch.autograd.grad(a, c, g)
     gc, _ = ops.relu_maxpool_bwd(_nhwc(g), _nhwc(c.detach()), (2, 2), (2, 1), (0, 1))
     assert torch.equal(gc.float().permute(0, 3, 1, 2).cpu().double(), ref)
+
+
+@pytest.mark.parametrize("geom", [((2, 2), (2, 2), (0, 0)), ((2, 2), (2, 1), (0, 1))])
+@pytest.mark.parametrize("N,C,H,W", [(2, 64, 8, 21), (1, 256, 5, 12)])
+def test_relu_maxpool_bwd_many_ties_bit_exact(geom, N, C, H, W):
+    """Small-integer activations: most windows hold ties, and zero maxima meet the ReLU mask.  Integer-valued gradients keep
+    every sum exact, so the CUDA result must EQUAL autograd's (first maximum in scan order takes the gradient)."""
+    from handwriting_line_generation_b200 import ops
+    k, s, p = geom
+    g0 = torch.Generator().manual_seed(7 * C + W + s[1])
+    pre = torch.randint(-1, 3, (N, C, H, W), generator=g0).double().requires_grad_()
+    c = F.relu(pre)
+    a = F.max_pool2d(c, k, s, p)
+    g = torch.randint(-8, 9, a.shape, generator=g0).double()
+    (ref,) = torch.autograd.grad(a, pre, g)
+    gc, db = ops.relu_maxpool_bwd(_nhwc(g), _nhwc(c.detach()), k, s, p)
+    assert torch.equal(gc.float().permute(0, 3, 1, 2).cpu().double(), ref)
+    assert torch.equal(db.cpu().double(), ref.sum((0, 2, 3)))
+
+
+@pytest.mark.parametrize("geom", [((2, 2), (2, 2), (0, 0)), ((2, 2), (2, 1), (0, 1))])
+@pytest.mark.parametrize("N,C,H,W", [(2, 128, 32, 64), (3, 256, 16, 65), (1, 64, 7, 9)])
+def test_maxpool_nhwc_forward_bit_exact(geom, N, C, H, W):
+    from handwriting_line_generation_b200 import ops
+    k, s, p = geom
+    x = _bf(torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(C + H)))
+    ref = F.max_pool2d(x, k, s, p)
+    y = ops.maxpool_nhwc(_nhwc(x), k, s, p)
+    assert torch.equal(y.float().permute(0, 3, 1, 2).cpu().double(), ref)
 
 
 @pytest.mark.parametrize("N,H,W", [(2, 64, 128), (3, 64, 260)])

@@ -110,3 +110,31 @@ def test_backward_regenerates_the_forward_noise(site):
     _, _, _, _, dnw_tensor = ops.adain_lrelu_bwd(g, a, save, coef, 0.2, noise=z.contiguous())
     _, _, _, _, dnw_regen = ops.adain_lrelu_bwd(g, a, save, coef, 0.2, noise=None, seed=seed, subseq=subseq, row_subseq=row)
     assert _rel(dnw_regen.cpu(), dnw_tensor.cpu()) <= (2e-2 if site == "blur" else 1e-4)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 64, 200), (3, 128, 8, 37), (2, 64, 13, 70), (1, 32, 1, 9), (2, 16, 9, 1),
+                                     (2, 256, 5, 40)])
+@pytest.mark.parametrize("with_noise", [False, True])
+def test_blur_noise_act_stats_matches_torch(N, C, H, W, with_noise):
+    """`Blur` ([1,2,1] x [1,2,1] / 16 depthwise, zero padding; reference model/pure_gen.py Blur) + NoiseInjection with a
+    given noise tensor + LeakyReLU + per-(n,c) sums, on tiles that are ragged in every direction (rows not a multiple
+    of 8, row segments not a multiple of 256 items, one-row and one-column lines)."""
+    from handwriting_line_generation_b200 import _lib, ops
+    g = torch.Generator().manual_seed(N * 1000 + C + H + W)
+    x = _bf(torch.randn(N, C, H, W, generator=g))
+    k = torch.tensor([1.0, 2.0, 1.0], dtype=torch.float64)
+    k = (k[:, None] * k[None, :] / 16.0).expand(C, 1, 3, 3).contiguous()
+    ref = F.conv2d(x, k, padding=1, groups=C)
+    noise = nw = None
+    if with_noise:
+        noise = torch.randn(N, C, H, W, generator=g)
+        nw = torch.randn(C, generator=g)
+        ref = ref + nw.double()[None, :, None, None] * noise.double()
+    ref = F.leaky_relu(ref, 0.2)
+    stats = torch.zeros(N, C, 2, device="cuda")
+    y = ops.blur_noise_act_stats(_nhwc(x), None if noise is None else _nhwc(noise, torch.float32),
+                                 None if nw is None else nw.cuda(), stats, _lib.ACT_LRELU, 0.2)
+    y = y.float().permute(0, 3, 1, 2).cpu().double()
+    assert _rel(y, ref) <= 6e-3                                          # one bf16 rounding of the output
+    assert _rel(stats[..., 0].cpu(), ref.sum((2, 3))) <= 5e-3
+    assert _rel(stats[..., 1].cpu(), (ref * ref).sum((2, 3))) <= 5e-3
