@@ -284,12 +284,7 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
           float4 z0 = zp[0], z1 = zp[1];
           z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
         } else {
-          const unsigned long long e2 = ((unsigned long long)n * total + item) * 4ull;   // pair index of channel 0
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 zz = normal_pair(nkey, e2 + q);
-            z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
-          }
+          normal_oct(nkey, ((unsigned long long)n * total + item) * 4ull, z);   // pair index of channel 0
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);

@@ -596,11 +596,7 @@ adain_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a,
       } else {
         e = ((unsigned long long)n * total + item) * 8ull;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 zz = normal_pair(key, (e >> 1) + q);
-        z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
-      }
+      normal_oct(key, e >> 1, z);   // e is a multiple of 8
     }
     ld8s(kc, A); ld8s(kc + C, P); ld8s(kc + 2 * C, Q);
 #pragma unroll

@@ -28,8 +28,10 @@ __device__ __forceinline__ uint2 noise_key(unsigned long long seed, unsigned lon
 // element for the noise alone), so the generator was trimmed: the second 32-bit word is ONE odd multiply + xorshift of the
 // (already avalanched) first word instead of a second two-round hash, and the logarithm is lg2.approx.ftz (u1 >= 2^-25 is
 // never subnormal, so the compiler's denormal guard around __log2f was dead weight).
-__device__ __forceinline__ float2 normal_pair(uint2 key, unsigned long long pair) {
-  const uint32_t x = fmix32(((uint32_t)pair ^ key.x) + (uint32_t)(pair >> 32) * 0x9E3779B1u);
+// (lo, him) = low word of the pair index and its high word times 0x9E3779B1 (a per-item constant for callers that draw
+// several consecutive pairs)
+__device__ __forceinline__ float2 normal_pair_lh(uint2 key, uint32_t lo, uint32_t him) {
+  const uint32_t x = fmix32((lo ^ key.x) + him);
   uint32_t y = (x ^ key.y) * 0x2C1B3C6Du;
   y ^= y >> 16;
   const float u1 = fmaf((float)(x >> 8), 5.9604645e-8f, 2.9802322e-8f);   // (0,1): (k + 0.5) / 2^24
@@ -40,6 +42,19 @@ __device__ __forceinline__ float2 normal_pair(uint2 key, unsigned long long pair
   float s, c;
   __sincosf(ang, &s, &c);
   return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ float2 normal_pair(uint2 key, unsigned long long pair) {
+  return normal_pair_lh(key, (uint32_t)pair, (uint32_t)(pair >> 32) * 0x9E3779B1u);
+}
+// the eight normals of pairs pair0 .. pair0+3, pair0 a multiple of 4 (one 16-byte vector of 8 channels): the +q never
+// carries into the high word, so the index arithmetic per pair is one 32-bit add
+__device__ __forceinline__ void normal_oct(uint2 key, unsigned long long pair0, float (&z)[8]) {
+  const uint32_t lo = (uint32_t)pair0, him = (uint32_t)(pair0 >> 32) * 0x9E3779B1u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 zz = normal_pair_lh(key, lo + (uint32_t)q, him);
+    z[2 * q] = zz.x; z[2 * q + 1] = zz.y;
+  }
 }
 
 __device__ __forceinline__ float normal_one(uint2 key, unsigned long long idx) {
