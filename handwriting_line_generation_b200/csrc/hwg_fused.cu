@@ -203,27 +203,26 @@ scale_shift_act_stream_kernel(const uint4* __restrict__ x, uint4* __restrict__ y
 // kept three loads per thread outstanding and measured 2.2 TB/s.  A thread then owns one channel vector of one
 // image column and walks the rows downwards with a separable rolling window (l + 2c + r per row, combined over the
 // rows above / at / below), all from shared memory.
+// ncu on that version (round 2): 76-83 % issue activity at 275 (plain blur) / 437 (with noise) instructions per item —
+// the edge selects of every tap, the runtime activation / statistics / noise options and the register rotation of the
+// rolled row loop.  Now the halo OUTSIDE the image is zero-filled in shared memory by the border blocks (no selects in
+// the taps), the row loop is unrolled (the rotation is renaming) and the two shapes of the hot path are compile-time
+// MODEs: 1 = generator forward (in-kernel noise, LeakyReLU, statistics), 2 = adjoint in the backward (plain blur);
+// 0 keeps every option at run time.
 constexpr int BLUR_ROWS = 8;
 
-__device__ __forceinline__ void blur_hrow(const uint4* __restrict__ tile, int r, bool valid, int pitch, int CV,
-                                          bool has_l, bool has_r, float (&hb)[8]) {
-  if (!valid) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hb[j] = 0.f;
-    return;
-  }
-  const uint4* p = tile + r * pitch + CV + threadIdx.x;
+__device__ __forceinline__ void blur_hrow(const uint4* __restrict__ p, int CV, float (&hb)[8]) {
   float c[8], l[8], q[8];
   unpack8(p[0], c);
-  if (has_l) unpack8(p[-CV], l);
-  if (has_r) unpack8(p[CV], q);
+  unpack8(p[-CV], l);
+  unpack8(p[CV], q);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) hb[j] = 2.f * c[j] + (has_l ? l[j] : 0.f) + (has_r ? q[j] : 0.f);
+  for (int j = 0; j < 8; ++j) hb[j] = fmaf(2.f, c[j], l[j] + q[j]);
 }
 
 __host__ __device__ constexpr size_t blur_tile_bytes(int CV) { return (size_t)(BLUR_ROWS + 2) * (EW_THREADS + 2 * CV) * 16; }
 
-template <bool RNG>
+template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS, 3)
 blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C, int cv_shift,
                             const float* __restrict__ noise, const float* __restrict__ noise_w,
@@ -231,8 +230,12 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
                             const unsigned long long* __restrict__ seed_dev, int act, float slope,
                             float* __restrict__ stats) {
   extern __shared__ __align__(128) unsigned char blur_smem[];
+  const bool has_noise = MODE == 1 || (MODE == 0 && noise_w != nullptr);
+  const bool use_rng = MODE == 1 || (MODE == 0 && noise == nullptr);
+  const bool has_stats = MODE == 1 || (MODE == 0 && stats != nullptr);
+  const int actv = MODE == 1 ? HWG_ACT_LRELU : (MODE == 2 ? HWG_ACT_NONE : act);
   const int n = blockIdx.z, CV = C / 8, pitch = EW_THREADS + 2 * CV;
-  const uint4* tile = reinterpret_cast<const uint4*>(blur_smem);          // [BLUR_ROWS + 2][pitch]
+  uint4* tile = reinterpret_cast<uint4*>(blur_smem);                      // [BLUR_ROWS + 2][pitch]
   float* sacc = reinterpret_cast<float*>(blur_smem + blur_tile_bytes(CV));   // [C][2] block-level statistics
   uint64_t* bar = reinterpret_cast<uint64_t*>(sacc + 2 * C);
   const long long row_items = (long long)W * CV;
@@ -240,72 +243,99 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
   const int seg0 = blockIdx.x * EW_THREADS;
   const int h0 = blockIdx.y * BLUR_ROWS, h1 = min(H, h0 + BLUR_ROWS);
   const uint4* xn = x + (size_t)n * total;
+  // items [s0, s1) of image rows [r0, r1) are copied; tile column of item i is i - (seg0 - CV)
+  const long long s0 = max(seg0 - CV, 0), s1 = min((long long)seg0 + EW_THREADS + CV, row_items);
+  const int r0 = max(h0 - 1, 0), r1 = min(h1 + 1, H);
   if (threadIdx.x == 0) {
     sm100::mbar_init(bar, 1);
     sm100::fence_barrier_init();
-    const long long s0 = max(seg0 - CV, 0), s1 = min((long long)seg0 + EW_THREADS + CV, row_items);
-    const int r0 = max(h0 - 1, 0), r1 = min(h1 + 1, H);
     const uint32_t row_bytes = (uint32_t)(s1 - s0) * 16u;
     sm100::mbar_expect_tx(bar, row_bytes * (uint32_t)(r1 - r0));
     for (int h = r0; h < r1; ++h)
       bulk_load_1d(blur_smem + ((size_t)(h - (h0 - 1)) * pitch + (s0 - (seg0 - CV))) * 16, xn + (long long)h * row_items + s0,
                    row_bytes, bar);
   }
-  if (stats)
+  // border blocks: the halo outside the image is zero (the blur's zero padding); disjoint from what the copies write
+  const uint4 Z = make_uint4(0u, 0u, 0u, 0u);
+  if (h0 == 0)                                         // row above the image
+    for (int i = threadIdx.x; i < pitch; i += EW_THREADS) tile[i] = Z;
+  if (h1 == H)                                         // row below the image
+    for (int i = threadIdx.x; i < pitch; i += EW_THREADS) tile[(size_t)(H - (h0 - 1)) * pitch + i] = Z;
+  if (seg0 == 0)                                       // pixel left of the image
+    for (int i = threadIdx.x; i < (BLUR_ROWS + 2) * CV; i += EW_THREADS) tile[(size_t)(i >> cv_shift) * pitch + (i & (CV - 1))] = Z;
+  const int c1 = (int)(s1 - (seg0 - CV));              // first tile column the copies do not reach
+  if (c1 < pitch) {                                    // pixel right of the image (and the tail of a ragged last segment)
+    const int nz = pitch - c1;
+    for (int i = threadIdx.x; i < (BLUR_ROWS + 2) * nz; i += EW_THREADS) {
+      const int r = i / nz;
+      tile[(size_t)r * pitch + c1 + (i - r * nz)] = Z;
+    }
+  }
+  if (has_stats)
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int ci = seg0 + threadIdx.x;   // (w, cv) inside a row
   const int cv = ci & (CV - 1);
-  float s1[8], s2[8];
+  float s1a[8], s2a[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { s1a[j] = 0.f; s2a[j] = 0.f; }
   float nw[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) nw[j] = noise_w ? noise_w[cv * 8 + j] : 0.f;
+  for (int j = 0; j < 8; ++j) nw[j] = has_noise ? noise_w[cv * 8 + j] : 0.f;
   const uint2 nkey = noise_key(seed + (seed_dev ? *seed_dev : 0ull), subseq);
   sm100::mbar_wait(bar, 0);
   if (ci < row_items) {
-    const int w = ci >> cv_shift;
-    const bool has_l = w > 0, has_r = w < W - 1;
-    uint4* yn = y + (size_t)n * total;
+    // running pointers / indices of this thread's column: one 64-bit add per row instead of a multiply chain
+    uint4* yp = y + (size_t)n * total + (long long)h0 * row_items + ci;
+    const float* zp0 = noise + ((size_t)n * total + (long long)h0 * row_items + ci) * 8;    // used only when noise != nullptr
+    unsigned long long pair0 = ((unsigned long long)n * total + (unsigned long long)h0 * row_items + ci) * 4ull;   // channel 0's pair
+    const uint4* tp = tile + CV + threadIdx.x;
     float prev[8], cur[8], nxt[8];
-    blur_hrow(tile, 0, h0 > 0, pitch, CV, has_l, has_r, prev);
-    blur_hrow(tile, 1, true, pitch, CV, has_l, has_r, cur);
-    for (int h = h0; h < h1; ++h) {
-      blur_hrow(tile, h - h0 + 2, h + 1 < H, pitch, CV, has_l, has_r, nxt);
-      const long long item = (long long)h * row_items + ci;
+    blur_hrow(tp, CV, prev);
+    blur_hrow(tp + pitch, CV, cur);
+#pragma unroll
+    for (int r = 0; r < BLUR_ROWS; ++r) {
+      // straight-line over the 8 rows (the rotation below is register renaming); rows past a ragged bottom tile compute
+      // on whatever the unstaged tile rows hold and are dropped at the store / statistics
+      const bool live = h0 + r < h1;
+      blur_hrow(tp + (r + 2) * pitch, CV, nxt);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = (prev[j] + 2.f * cur[j] + nxt[j]) * (1.f / 16.f);
-      if (noise_w) {
+      if (has_noise) {
         float z[8];
-        if (!RNG) {
-          const float4* zp = reinterpret_cast<const float4*>(noise + ((size_t)n * total + item) * 8);
-          float4 z0 = zp[0], z1 = zp[1];
+        if (!use_rng) {
+          float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+          if (live) { z0 = reinterpret_cast<const float4*>(zp0)[0]; z1 = reinterpret_cast<const float4*>(zp0)[1]; }
           z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
         } else {
-          normal_oct(nkey, ((unsigned long long)n * total + item) * 4ull, z);   // pair index of channel 0
+          normal_oct(nkey, pair0, z);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(nw[j], z[j], acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = act_fn(acc[j], act, slope);
-        s1[j] += acc[j]; s2[j] += acc[j] * acc[j];
-        prev[j] = cur[j]; cur[j] = nxt[j];
+      for (int j = 0; j < 8; ++j) acc[j] = act_fn(acc[j], actv, slope);
+      if (live) {
+        if (has_stats) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1a[j] += acc[j]; s2a[j] += acc[j] * acc[j]; }
+        }
+        *yp = pack8(acc);
       }
-      yn[item] = pack8(acc);
+      yp += row_items; zp0 += row_items * 8; pair0 += (unsigned long long)row_items * 4ull;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { prev[j] = cur[j]; cur[j] = nxt[j]; }
     }
   }
-  if (stats) {
+  if (has_stats) {
     // lanes congruent mod CV hold the same channels: fold them, then one shared atomic per warp
     if (CV <= 32) {
       for (int off = 16; off >= CV; off >>= 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+          s1a[j] += __shfl_xor_sync(0xffffffffu, s1a[j], off);
+          s2a[j] += __shfl_xor_sync(0xffffffffu, s2a[j], off);
         }
       }
     }
@@ -313,8 +343,8 @@ blur_noise_act_stats_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, 
     if (CV > 32 || lane < CV) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sacc[2 * (cv * 8 + j)], s1[j]);
-        atomicAdd(&sacc[2 * (cv * 8 + j) + 1], s2[j]);
+        atomicAdd(&sacc[2 * (cv * 8 + j)], s1a[j]);
+        atomicAdd(&sacc[2 * (cv * 8 + j) + 1], s2a[j]);
       }
     }
     __syncthreads();
@@ -544,7 +574,10 @@ extern "C" int hwg_blur_noise_act_stats(const void* x, void* y, int N, int H, in
   while ((1 << cv_shift) < CV) ++cv_shift;
   dim3 grid(blocks_for((long long)W * CV, EW_THREADS), (H + BLUR_ROWS - 1) / BLUR_ROWS, N);
   HWG_REQUIRE(grid.y <= 65535 && N <= 65535, "hwg_blur_noise_act_stats: H=%d / N=%d too large", H, N);
-  auto k = (noise_w && !noise) ? blur_noise_act_stats_kernel<true> : blur_noise_act_stats_kernel<false>;
+  // the two shapes of the hot path are compile-time specialisations (see the kernel's header)
+  auto k = blur_noise_act_stats_kernel<0>;
+  if (noise_w && !noise && stats && act == HWG_ACT_LRELU) k = blur_noise_act_stats_kernel<1>;
+  else if (!noise_w && !stats && act == HWG_ACT_NONE) k = blur_noise_act_stats_kernel<2>;
   HWG_SMEM_OPTIN(k);
   k<<<grid, EW_THREADS, blur_tile_bytes(CV) + (size_t)C * 2 * sizeof(float) + 16, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C, cv_shift, noise, noise_w, noise_seed,
