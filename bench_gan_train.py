@@ -167,7 +167,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    steps = min(args.steps, 8)
+    steps = min(args.steps, 16)               # bounded: ~11 s of CPU work at 0.65 s per 4-line step
     t0 = time.time()
     sample_B = 4
     B, scaling = per_gpu_batch(max(1, args.gpus))
@@ -610,7 +610,7 @@ def main(args, rank, world, local_rank, load_peaks, ClockSampler):
         if not os.environ.get("HWG_BENCH_NO_CPU_BASELINE"):
             torch.set_num_threads(os.cpu_count() or 1)
             tb = time.time()
-            lps, times = cpu_lines_per_s(4, 4)
+            lps, times = cpu_lines_per_s(4, 14)      # ~10 s of CPU work (0.65 s per 4-line step on the box's 16 threads)
             line["cpu_baseline"] = {"value": lps, "unit": "lines/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{len(times)} timed optimizer steps on a 4-line sample of the batch (T_s={Ts}), "
                                               f"stock torch fp32, {time.time() - tb:.1f}s of CPU work"}
