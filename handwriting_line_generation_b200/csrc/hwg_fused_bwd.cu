@@ -933,7 +933,9 @@ extern "C" int hwg_relu_maxpool_bwd(const void* ga, const void* c, int N, int H,
   if (kh == 2 && kw == 2 && sh == 2 && ph == 0 && ((sw == 2 && pw == 0) || (sw == 1 && pw == 1)) && cv_ok(C)) {
     const int mode = sw == 2 ? 0 : 1;
     const long long items = (long long)N * ((H + 1) / 2) * (mode == 0 ? (W + 1) / 2 : W) * (C / 8);
-    const bool small = items < (1LL << 31) - (long long)BW_THREADS * BW_ITER * 148 * 4;
+    // 32-bit item indices and per-image offsets (IDX = unsigned, OFF = int) when both fit
+    const bool small = items < (1LL << 31) - (long long)BW_THREADS * BW_ITER * 148 * 4 &&
+                       (long long)H * W * (C / 8) < (1LL << 31);
     auto kern = small ? (mode == 0 ? relu_maxpool_bwd_win_kernel<0, unsigned> : relu_maxpool_bwd_win_kernel<1, unsigned>)
                       : (mode == 0 ? relu_maxpool_bwd_win_kernel<0, long long> : relu_maxpool_bwd_win_kernel<1, long long>);
     kern<<<bw_blocks_persistent(items, BW_THREADS * BW_ITER, 1, 3), BW_THREADS, (size_t)C * sizeof(float), (cudaStream_t)stream>>>(
